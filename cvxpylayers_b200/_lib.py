@@ -1,0 +1,89 @@
+"""ctypes binding of libbcone.so (the C ABI declared in include/bcone.h).
+
+There is no CPU fallback: if the CUDA library is missing or no CUDA device is present the
+engine raises.  The library is built in-tree by ``cvxpylayers_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libbcone.so"
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+EXPORTS = [
+    "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary",
+    "bcone_ingest", "bcone_emit", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info",
+]
+
+
+class BconeDesc(C.Structure):
+    _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("nnzA", C.c_int32), ("nnzP", C.c_int32),
+                ("A_indptr", _i32p), ("A_indices", _i32p), ("P_indptr", _i32p), ("P_indices", _i32p),
+                ("z", C.c_int32), ("l", C.c_int32), ("nq", C.c_int32), ("ns", C.c_int32),
+                ("ep", C.c_int32), ("ed", C.c_int32), ("q", _i32p), ("s", _i32p),
+                ("device", C.c_int32), ("max_batch", C.c_int32)]
+
+
+class BconeSettings(C.Structure):
+    _fields_ = [("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_infeas", C.c_double),
+                ("alpha", C.c_double), ("rho_x", C.c_double), ("scale", C.c_double),
+                ("lsqr_atol", C.c_double), ("lsqr_btol", C.c_double), ("lsqr_conlim", C.c_double),
+                ("max_iters", C.c_int32), ("normalize", C.c_int32), ("adaptive_scale", C.c_int32),
+                ("check_interval", C.c_int32), ("ruiz_passes", C.c_int32), ("lsqr_iter_lim", C.c_int32),
+                ("lsqr_precond", C.c_int32), ("reserved1", C.c_int32)]
+
+
+class EngineUnavailable(RuntimeError):
+    """libbcone.so is missing / cannot be loaded. There is deliberately no fallback."""
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EngineUnavailable(
+            f"{LIB_PATH} not found: build it with `python -m cvxpylayers_b200.build` (nvcc, sm_100a). "
+            "The engine has no CPU or PyTorch fallback.")
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover
+        raise EngineUnavailable(f"cannot load {LIB_PATH}: {e}") from e
+    vp = C.c_void_p
+    lib.bcone_default_settings.argtypes = [C.POINTER(BconeSettings)]
+    lib.bcone_default_settings.restype = None
+    lib.bcone_create.argtypes = [C.POINTER(BconeDesc), C.POINTER(vp)]
+    lib.bcone_create.restype = C.c_int
+    lib.bcone_destroy.argtypes = [vp]
+    lib.bcone_destroy.restype = None
+    lib.bcone_last_error.argtypes = [vp]
+    lib.bcone_last_error.restype = C.c_char_p
+    lib.bcone_set_boundary.argtypes = [vp, C.c_int32, _i32p, C.c_int32, _i32p]
+    lib.bcone_set_boundary.restype = C.c_int
+    lib.bcone_ingest.argtypes = [vp, C.c_int32] + [vp] * 8
+    lib.bcone_ingest.restype = C.c_int
+    lib.bcone_emit.argtypes = [vp, C.c_int32] + [vp] * 8
+    lib.bcone_emit.restype = C.c_int
+    lib.bcone_solve.argtypes = [vp, C.c_int32] + [vp] * 10 + [C.POINTER(BconeSettings), vp]
+    lib.bcone_solve.restype = C.c_int
+    lib.bcone_vjp.argtypes = [vp, C.c_int32] + [vp] * 14 + [C.POINTER(BconeSettings), vp]
+    lib.bcone_vjp.restype = C.c_int
+    lib.bcone_launch_count.argtypes = [vp]
+    lib.bcone_launch_count.restype = C.c_int64
+    lib.bcone_kernel_info.argtypes = [vp] + [_i32p] * 6
+    lib.bcone_kernel_info.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def default_settings() -> BconeSettings:
+    st = BconeSettings()
+    load().bcone_default_settings(C.byref(st))
+    return st

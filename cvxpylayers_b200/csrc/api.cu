@@ -1,0 +1,272 @@
+// api.cu -- the C ABI of libbcone.so (declared in include/bcone.h): handle management,
+// structure upload, launch geometry, and the five entry points the reference-side binding
+// calls.  No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+// ---- kernels / launchers implemented in fwd.cu, bwd.cu, pack.cu ----
+extern "C" {
+size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd);
+cudaError_t bc_fwd_configure(int dense, size_t smem);
+cudaError_t bc_fwd_occupancy(int dense, int threads, size_t smem, int *ctas);
+cudaError_t bc_fwd_launch(const FwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
+size_t bc_bwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int psd_total);
+cudaError_t bc_bwd_configure(int dense, size_t smem);
+cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
+cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
+cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
+}
+
+namespace {
+struct Handle {
+  DevStruct S{};
+  int device = 0, max_batch = 0, num_sms = 0;
+  std::vector<void *> allocs;
+  int *counters = nullptr;  // [0] forward, [1] backward work queues
+  int nnz_aug = 0, nb = 0;
+  int *d_gather = nullptr, *d_bidx = nullptr;
+  int fwd_threads = 0, bwd_threads = 0, fwd_ctas = 0, bwd_ctas = 0;
+  size_t fwd_smem = 0, bwd_smem = 0;
+  int tma_ok = 0, psd_total = 0;
+  long long launches = 0;
+  std::string err;
+};
+thread_local std::string g_create_err;
+
+template <class T>
+T *upload(Handle *h, const std::vector<T> &v) {
+  if (v.empty()) return nullptr;
+  void *p = nullptr;
+  if (cudaMalloc(&p, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+  h->allocs.push_back(p);
+  cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return (T *)p;
+}
+int fail(Handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+int cuda_fail(Handle *h, cudaError_t e, const char *where) {
+  return fail(h, BCONE_ECUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+}  // namespace
+
+extern "C" void bcone_default_settings(bcone_settings *st) {
+  st->eps_abs = 1e-4; st->eps_rel = 1e-4; st->eps_infeas = 1e-7;
+  st->alpha = 1.5; st->rho_x = 1e-6; st->scale = 0.1;
+  st->lsqr_atol = 1e-8; st->lsqr_btol = 1e-8; st->lsqr_conlim = 1e8;
+  st->max_iters = 100000; st->normalize = 1; st->adaptive_scale = 1; st->check_interval = 25;
+  st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->lsqr_precond = 0; st->reserved1 = 0;
+}
+
+extern "C" const char *bcone_last_error(void *handle) {
+  return handle ? ((Handle *)handle)->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int bcone_create(const bcone_desc *d, void **out) {
+  if (!d || !out) return fail(nullptr, BCONE_EINVAL, "null argument");
+  *out = nullptr;
+  if (d->n <= 0 || d->m < 0 || d->nnzA < 0 || !d->A_indptr || (d->nnzA > 0 && !d->A_indices))
+    return fail(nullptr, BCONE_EINVAL, "bad dimensions / missing A structure");
+  if (d->ep != 0 || d->ed != 0)
+    return fail(nullptr, BCONE_EUNSUPPORTED, "exponential cones are not built yet (DESIGN.md: out of round-1 scope)");
+  const int n = d->n, m = d->m;
+  long long rows = d->z + d->l;
+  int max_psd = 0, psd_total = 0;
+  for (int i = 0; i < d->nq; i++) rows += d->q[i];
+  for (int i = 0; i < d->ns; i++) { int k = d->s[i]; rows += (long long)k * (k + 1) / 2; max_psd = std::max(max_psd, k); psd_total += k * k + k; }
+  if (rows != m) return fail(nullptr, BCONE_EINVAL, "cone dimensions do not add up to m");
+  if (d->A_indptr[0] != 0 || d->A_indptr[m] != d->nnzA) return fail(nullptr, BCONE_EINVAL, "A_indptr inconsistent with nnzA");
+  if (cudaSetDevice(d->device) != cudaSuccess) return fail(nullptr, BCONE_ECUDA, "cudaSetDevice failed (no CUDA device?)");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) return fail(nullptr, BCONE_ECUDA, "cudaGetDeviceProperties failed");
+
+  Handle *h = new Handle();
+  h->device = d->device; h->max_batch = d->max_batch; h->num_sms = prop.multiProcessorCount;
+  h->psd_total = psd_total;
+  DevStruct &S = h->S;
+  S.n = n; S.m = m; S.nnzA = d->nnzA; S.nnzP = d->P_indptr ? d->nnzP : 0;
+  S.z = d->z; S.l = d->l; S.nq = d->nq; S.ns = d->ns; S.max_psd = max_psd;
+  // --- host-side structure analysis ---
+  std::vector<int> indptr(d->A_indptr, d->A_indptr + m + 1), indices(d->A_indices, d->A_indices + d->nnzA);
+  std::vector<int> rowof(d->nnzA), colptr(n + 1, 0), rowidx(d->nnzA), perm(d->nnzA);
+  bool dense = (long long)d->nnzA == (long long)m * n && d->nnzA > 0;
+  for (int i = 0; i < m; i++) {
+    if (indptr[i + 1] < indptr[i]) { delete h; return fail(nullptr, BCONE_EINVAL, "A_indptr not monotone"); }
+    for (int k = indptr[i]; k < indptr[i + 1]; k++) {
+      int j = indices[k];
+      if (j < 0 || j >= n) { delete h; return fail(nullptr, BCONE_EINVAL, "A column index out of range"); }
+      rowof[k] = i; colptr[j + 1]++;
+      if (dense && j != k - indptr[i]) dense = false;
+    }
+    if (dense && indptr[i + 1] - indptr[i] != n) dense = false;
+  }
+  for (int j = 0; j < n; j++) colptr[j + 1] += colptr[j];
+  {
+    std::vector<int> fill(colptr.begin(), colptr.end() - 1);
+    for (int k = 0; k < d->nnzA; k++) { int p = fill[indices[k]]++; rowidx[p] = rowof[k]; perm[p] = k; }
+  }
+  S.dense = dense ? 1 : 0;
+  std::vector<int> ctype, cstart, csize, corder;
+  {
+    int off = d->z + d->l;
+    for (int i = 0; i < d->nq; i++) { ctype.push_back(BC_CSOC); cstart.push_back(off); csize.push_back(d->q[i]); corder.push_back(0); off += d->q[i]; }
+    for (int i = 0; i < d->ns; i++) { int k = d->s[i], sz = k * (k + 1) / 2; ctype.push_back(BC_CPSD); cstart.push_back(off); csize.push_back(sz); corder.push_back(k); off += sz; }
+  }
+  S.ncones = (int)ctype.size();
+  S.A_indptr = upload(h, indptr); S.A_indices = upload(h, indices); S.A_rowof = upload(h, rowof);
+  S.At_colptr = upload(h, colptr); S.At_rowidx = upload(h, rowidx); S.At_perm = upload(h, perm);
+  S.cone_type = upload(h, ctype); S.cone_start = upload(h, cstart); S.cone_size = upload(h, csize); S.cone_order = upload(h, corder);
+  if (S.nnzP > 0) {
+    std::vector<int> pptr(d->P_indptr, d->P_indptr + n + 1), pidx(d->P_indices, d->P_indices + S.nnzP), prow(S.nnzP);
+    for (int i = 0; i < n; i++) for (int k = pptr[i]; k < pptr[i + 1]; k++) {
+      if (pidx[k] < i || pidx[k] >= n) { bcone_destroy(h); return fail(nullptr, BCONE_EINVAL, "P must be upper triangular CSR"); }
+      prow[k] = i;
+    }
+    S.P_indptr = upload(h, pptr); S.P_indices = upload(h, pidx); S.P_rowof = upload(h, prow);
+  }
+  if (cudaMalloc((void **)&h->counters, 2 * sizeof(int)) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc counters"); }
+  h->allocs.push_back(h->counters);
+
+  // --- launch geometry: threads by problem size, shared memory must hold the whole instance ---
+  const size_t smem_cap = prop.sharedMemPerBlockOptin;
+  int threads = d->nnzA >= 8192 ? 512 : (d->nnzA >= 1024 ? 256 : 128);
+  while (threads < 512 && threads < n) threads *= 2;  // transposed products want one lane per column
+  auto pick = [&](bool fwd, int &thr, size_t &smem) -> bool {
+    for (int tt = threads; tt >= 64; tt /= 2) {
+      size_t sm = fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd) : bc_bwd_smem_bytes(n, m, d->nnzA, tt, max_psd, psd_total);
+      if (sm <= smem_cap) { thr = tt; smem = sm; return true; }
+    }
+    return false;
+  };
+  if (!pick(true, h->fwd_threads, h->fwd_smem) || !pick(false, h->bwd_threads, h->bwd_smem)) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
+             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, d->nnzA, 64, max_psd, psd_total), smem_cap);
+    bcone_destroy(h);
+    return fail(nullptr, BCONE_EUNSUPPORTED, buf);
+  }
+  cudaError_t e;
+  if ((e = bc_fwd_configure(S.dense, h->fwd_smem)) != cudaSuccess || (e = bc_bwd_configure(S.dense, h->bwd_smem)) != cudaSuccess) {
+    std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+    bcone_destroy(h);
+    return fail(nullptr, BCONE_ECUDA, msg);
+  }
+  bc_fwd_occupancy(S.dense, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
+  bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
+  if (h->fwd_ctas < 1) h->fwd_ctas = 1;
+  if (h->bwd_ctas < 1) h->bwd_ctas = 1;
+  h->tma_ok = (d->nnzA > 0 && (d->nnzA % 2) == 0 && (size_t)d->nnzA * 8 < (1u << 20)) ? 1 : 0;
+  *out = h;
+  return BCONE_OK;
+}
+
+extern "C" void bcone_destroy(void *handle) {
+  if (!handle) return;
+  Handle *h = (Handle *)handle;
+  cudaSetDevice(h->device);
+  for (void *p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int bcone_set_boundary(void *handle, int32_t nnz_aug, const int32_t *gather, int32_t nb, const int32_t *b_idx) {
+  Handle *h = (Handle *)handle;
+  if (!h) return BCONE_EINVAL;
+  if (nnz_aug != h->S.nnzA + nb || (h->S.nnzA > 0 && !gather) || (nb > 0 && !b_idx)) return fail(h, BCONE_EINVAL, "set_boundary: inconsistent sizes");
+  for (int k = 0; k < h->S.nnzA; k++) if (gather[k] < 0 || gather[k] >= h->S.nnzA) return fail(h, BCONE_EINVAL, "set_boundary: gather out of range");
+  for (int r = 0; r < nb; r++) if (b_idx[r] < 0 || b_idx[r] >= h->S.m) return fail(h, BCONE_EINVAL, "set_boundary: b_idx out of range");
+  cudaSetDevice(h->device);
+  h->nnz_aug = nnz_aug; h->nb = nb;
+  h->d_gather = upload(h, std::vector<int>(gather, gather + h->S.nnzA));
+  h->d_bidx = upload(h, std::vector<int>(b_idx, b_idx + nb));
+  return BCONE_OK;
+}
+
+#define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, where); } while (0)
+
+extern "C" int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_eval, const double *P_eval,
+                            double *A_vals, double *P_vals, double *b, double *c, void *stream) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !A_eval || !q_eval || !A_vals || !b || !c) return fail(h, BCONE_EINVAL, "ingest: null argument");
+  if (h->nnz_aug == 0 && h->S.nnzA + h->nb != 0) return fail(h, BCONE_EINVAL, "ingest: call bcone_set_boundary first");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevStruct &S = h->S;
+  CK(bc_b2e(A_eval, A_vals, S.nnzA, B, S.nnzA, 0, h->d_gather, nullptr, -1.0, st), "ingest A");
+  CK(cudaMemsetAsync(b, 0, (size_t)B * S.m * sizeof(double), st), "ingest b memset");
+  CK(bc_b2e(A_eval, b, h->nb, B, S.m, S.nnzA, nullptr, h->d_bidx, 1.0, st), "ingest b");
+  CK(bc_b2e(q_eval, c, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "ingest c");
+  h->launches += 3;
+  if (P_eval && P_vals && S.nnzP > 0) { CK(bc_b2e(P_eval, P_vals, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, st), "ingest P"); h->launches++; }
+  return BCONE_OK;
+}
+
+extern "C" int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
+                          const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *stream) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !dA_vals || !db || !dc || !dA_eval || !dq_eval) return fail(h, BCONE_EINVAL, "emit: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevStruct &S = h->S;
+  CK(bc_e2b(dA_vals, dA_eval, S.nnzA, B, S.nnzA, 0, nullptr, h->d_gather, -1.0, st), "emit dA");
+  CK(bc_e2b(db, dA_eval, h->nb, B, S.m, S.nnzA, h->d_bidx, nullptr, 1.0, st), "emit db");
+  CK(bc_e2b(dc, dq_eval, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "emit dc");
+  CK(cudaMemsetAsync(dq_eval + (size_t)S.n * B, 0, (size_t)B * sizeof(double), st), "emit dq tail");
+  h->launches += 3;
+  if (dP_vals && dP_eval && S.nnzP > 0) { CK(bc_e2b(dP_vals, dP_eval, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, st), "emit dP"); h->launches++; }
+  return BCONE_OK;
+}
+
+extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,
+                           const double *c, double *x, double *y, double *s, int32_t *status, int32_t *iters,
+                           double *resid, const bcone_settings *stg, void *stream) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !A_vals || !b || !c || !x || !y || !s || !status || !iters || !stg) return fail(h, BCONE_EINVAL, "solve: null argument");
+  if (h->S.nnzP > 0 && !P_vals) return fail(h, BCONE_EINVAL, "solve: structure has P but P_vals is NULL");
+  if (stg->check_interval <= 0 || stg->max_iters <= 0) return fail(h, BCONE_EINVAL, "solve: check_interval and max_iters must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdArgs a;
+  a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
+  a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
+  a.counter = h->counters; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
+  CK(cudaMemsetAsync(h->counters, 0, sizeof(int), st), "solve counter");
+  const int grid = std::min(B, h->num_sms * h->fwd_ctas);
+  CK(bc_fwd_launch(&a, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
+  h->launches++;
+  return BCONE_OK;
+}
+
+extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,
+                         const double *c, const double *x, const double *y, const double *s, const double *dx,
+                         const double *dy, double *dA_vals, double *dP_vals, double *db, double *dc,
+                         int32_t *lsqr_iters, const bcone_settings *stg, void *stream) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !A_vals || !b || !c || !x || !y || !s || !dx || !dy || !dA_vals || !db || !dc || !stg)
+    return fail(h, BCONE_EINVAL, "vjp: null argument");
+  if (h->S.nnzP > 0 && !P_vals) return fail(h, BCONE_EINVAL, "vjp: structure has P but P_vals is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdArgs a;
+  a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
+  a.x = x; a.y = y; a.s = s; a.dx = dx; a.dy = dy; a.dA = dA_vals; a.dP = dP_vals; a.db = db; a.dc = dc;
+  a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = h->counters + 1;
+  a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total;
+  CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(int), st), "vjp counter");
+  const int grid = std::min(B, h->num_sms * h->bwd_ctas);
+  CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch");
+  h->launches++;
+  return BCONE_OK;
+}
+
+extern "C" int64_t bcone_launch_count(void *handle) { return handle ? ((Handle *)handle)->launches : 0; }
+
+extern "C" int bcone_kernel_info(void *handle, int32_t *ft, int32_t *fs, int32_t *fc, int32_t *bt, int32_t *bs, int32_t *bcx) {
+  Handle *h = (Handle *)handle;
+  if (!h) return BCONE_EINVAL;
+  if (ft) *ft = h->fwd_threads; if (fs) *fs = (int32_t)h->fwd_smem; if (fc) *fc = h->fwd_ctas;
+  if (bt) *bt = h->bwd_threads; if (bs) *bs = (int32_t)h->bwd_smem; if (bcx) *bcx = h->bwd_ctas;
+  return BCONE_OK;
+}

@@ -1,0 +1,382 @@
+// bwd.cu -- backward kernel: adjoint of the cone-program solution map (what the reference gets
+// from diffcp's adjoint closure at src/cvxpylayers/interfaces/diffcp_if.py:86; rows B1-B4 of
+// SURVEY.md section 8a).  One persistent CTA per instance:
+//   v = y - s, pi_y = Pi_{K*}(v), D = DPi_{K*}(v)           (cone Jacobian, block diagonal)
+//   dz = [dx ; D dy ; -(x'dx + y'dy)]                        (ds = 0, diffcp_if.py:84)
+//   r  = LSQR(M', dz),  M = (DQ - I) blkdiag(I, D, 1) + I    (Paige-Saunders, SciPy stopping rules)
+//   dA_ij = x_j r_{n+i} - pi_y,i r_j  on EVERY structural entry;  db = pi_y r_tau - r_y;
+//   dc = x r_tau - r_x;  dP_ij = (r_tau x_i - r_x,i) x_j (+ transpose term off the diagonal)
+// The instance's CSR values are staged once by TMA and stay in shared memory for all LSQR
+// iterations (each applies A and A' twice); P values are read from L2.
+#include "common.cuh"
+
+struct BwdSmem {
+  double *Av, *x, *piy, *v, *b, *c, *px2c, *U, *V, *W, *X, *t1, *t2, *Lsc, *Rsc, *part, *red, *psdVL, *psdscr;
+  uint64_t *bar;
+  int *ibuf;
+};
+
+__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd, int psd_total) {
+  size_t N = (size_t)n + m + 1;
+  size_t d = (((size_t)nnzA + 1) & ~(size_t)1) + 3 * (size_t)n + 3 * (size_t)m + 8 * N + threads + 8 * 32 + 4;
+  if (max_psd > 0) d += psd_total + (size_t)(threads / 32) * (3 * (size_t)max_psd * max_psd + max_psd);
+  return d;
+}
+
+__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, int nnzA, int threads, int max_psd, int psd_total) {
+  const int N = n + m + 1;
+  double *q = base;
+  M.bar = (uint64_t *)q; q += 2;
+  M.ibuf = (int *)q; q += 2;
+  M.Av = q; q += (nnzA + 1) & ~1;
+  M.x = q; q += n; M.c = q; q += n; M.px2c = q; q += n;
+  M.piy = q; q += m; M.v = q; q += m; M.b = q; q += m;
+  M.U = q; q += N; M.V = q; q += N; M.W = q; q += N; M.X = q; q += N; M.t1 = q; q += N; M.t2 = q; q += N;
+  M.Lsc = q; q += N; M.Rsc = q; q += N;
+  M.part = q; q += threads; M.red = q; q += 8 * 32;
+  M.psdVL = q; q += psd_total;
+  M.psdscr = q;
+}
+
+// out_y = D in_y  (D = DPi_{K*}(v)); zero rows identity, nonneg rows mask, SOC closed form,
+// PSD  V (B o (V' dX V)) V'  with V, lambda precomputed in psdVL.  Ends with __syncthreads().
+__device__ __forceinline__ void apply_D(const DevStruct &S, const BwdSmem &M, const double *in, double *out) {
+  const int T = blockDim.x, t = threadIdx.x, pl = S.z + S.l;
+  for (int i = t; i < pl; i += T) out[i] = (i < S.z || M.v[i] > 0) ? in[i] : 0.0;
+  if (S.ncones > 0) {
+    const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+    int psd_off = 0;
+    for (int cb = 0; cb < S.ncones; cb++) {
+      const int ty = __ldg(S.cone_type + cb), s0 = __ldg(S.cone_start + cb), sz = __ldg(S.cone_size + cb);
+      const int k = __ldg(S.cone_order + cb);
+      const int my_off = psd_off;
+      if (ty == BC_CPSD) psd_off += k * k + k;
+      if (cb % nw != warp) continue;
+      const double *vb = M.v + s0, *ib = in + s0;
+      double *ob = out + s0;
+      if (ty == BC_CSOC) {
+        if (sz == 1) { if (lane == 0) ob[0] = vb[0] > 0 ? ib[0] : 0.0; continue; }
+        double ss = 0, xd = 0;
+        for (int i = 1 + lane; i < sz; i += 32) { ss = fma(vb[i], vb[i], ss); xd = fma(vb[i], ib[i], xd); }
+        ss = warp_sum(ss); xd = warp_sum(xd);
+        const double nx = sqrt(ss), tt = vb[0], d0 = ib[0];
+        if (nx <= tt) { for (int i = lane; i < sz; i += 32) ob[i] = ib[i]; }
+        else if (nx <= -tt) { for (int i = lane; i < sz; i += 32) ob[i] = 0.0; }
+        else {
+          const double h = 0.5 / nx;
+          for (int i = 1 + lane; i < sz; i += 32) ob[i] = (vb[i] * d0 + (tt + nx) * ib[i] - tt * vb[i] * xd / (nx * nx)) * h;
+          if (lane == 0) ob[0] = 0.5 * (d0 + xd / nx);
+        }
+      } else {
+        const double *Vm = M.psdVL + my_off, *lam = Vm + k * k;
+        double *Xd = M.psdscr + warp * (3 * S.max_psd * S.max_psd + S.max_psd), *T1 = Xd + k * k, *T2 = T1 + k * k;
+        svec_to_mat_warp(k, ib, Xd);
+        __syncwarp();
+        for (int e = lane; e < k * k; e += 32) {  // T1 = Xd V
+          const int i = e / k, j = e % k; double acc = 0;
+          for (int q = 0; q < k; q++) acc = fma(Xd[i * k + q], Vm[q * k + j], acc);
+          T1[e] = acc;
+        }
+        __syncwarp();
+        for (int e = lane; e < k * k; e += 32) {  // T2 = B o (V' T1)
+          const int i = e / k, j = e % k; double acc = 0;
+          for (int q = 0; q < k; q++) acc = fma(Vm[q * k + i], T1[q * k + j], acc);
+          const double li = lam[i], lj = lam[j];
+          double bij;
+          if (li > 0 && lj > 0) bij = 1.0; else if (li <= 0 && lj <= 0) bij = 0.0;
+          else { const double lp = li > 0 ? li : lj, ln = li > 0 ? lj : li; bij = lp / (lp - ln); }
+          T2[e] = acc * bij;
+        }
+        __syncwarp();
+        for (int e = lane; e < k * k; e += 32) {  // T1 = V T2
+          const int i = e / k, j = e % k; double acc = 0;
+          for (int q = 0; q < k; q++) acc = fma(Vm[i * k + q], T2[q * k + j], acc);
+          T1[e] = acc;
+        }
+        __syncwarp();
+        for (int e = lane; e < k * k; e += 32) {  // Xd = T1 V'
+          const int i = e / k, j = e % k; double acc = 0;
+          for (int q = 0; q < k; q++) acc = fma(T1[i * k + q], Vm[j * k + q], acc);
+          Xd[e] = acc;
+        }
+        __syncwarp();
+        mat_to_svec_warp(k, Xd, ob);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// sym-upper P times vector through shared-memory atomics (P values in global/L2, scaled access).
+__device__ __forceinline__ void P_mul_add(const DevStruct &S, const double *Pg, const double *x, double *acc) {
+  for (int k = threadIdx.x; k < S.nnzP; k += blockDim.x) {
+    const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
+    const double v = __ldg(Pg + k);
+    atomicAdd(&acc[i], v * x[j]);
+    if (i != j) atomicAdd(&acc[j], v * x[i]);
+  }
+}
+
+// out = M' in  (B = M' is the LSQR system matrix).  in/out length N; uses t1, t2.
+template <bool DENSE>
+__device__ __forceinline__ void op_MT(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx,
+                                      const double *in, double *out) {
+  const DevStruct &S = a.S;
+  const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
+  const double it = in[n + m];
+  // out_x = -A' in_y + P in_x - (2Px + c) in_tau
+  AT_mul<DENSE>(S, M.Av, in + n, M.part, [&](int j, double v) { out[j] = -v - M.px2c[j] * it; });
+  if (Pg) { P_mul_add(S, Pg, in, out); }
+  // t1_y = A in_x - b in_tau - in_y ; out_y = D t1_y + in_y
+  A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { M.t1[i] = v - M.b[i] * it - in[n + i]; });
+  double d2[2] = {0, 0};
+  for (int j = t; j < n; j += T) d2[0] = fma(M.c[j], in[j], d2[0]);
+  for (int i = t; i < m; i += T) d2[1] = fma(M.b[i], in[n + i], d2[1]);
+  block_reduce<2, false>(d2, M.red);  // (syncs: t1 complete)
+  apply_D(S, M, M.t1, M.t2);
+  for (int i = t; i < m; i += T) out[n + i] = M.t2[i] + in[n + i];
+  if (t == 0) out[n + m] = d2[0] + d2[1] + xPx * it;
+  __syncthreads();
+}
+
+// out = M in
+template <bool DENSE>
+__device__ __forceinline__ void op_M(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx,
+                                     const double *in, double *out) {
+  const DevStruct &S = a.S;
+  const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
+  const double it = in[n + m];
+  apply_D(S, M, in + n, M.t2);  // t2 = D in_y
+  // out_x = A' t2 + P in_x + c in_tau
+  AT_mul<DENSE>(S, M.Av, M.t2, M.part, [&](int j, double v) { out[j] = v + M.c[j] * it; });
+  if (Pg) { P_mul_add(S, Pg, in, out); }
+  // out_y = -A in_x + b in_tau - t2 + in_y
+  A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { out[n + i] = -v + M.b[i] * it - M.t2[i] + in[n + i]; });
+  double d2[2] = {0, 0};
+  for (int j = t; j < n; j += T) d2[0] = fma(M.px2c[j], in[j], d2[0]);
+  for (int i = t; i < m; i += T) d2[1] = fma(M.b[i], M.t2[i], d2[1]);
+  block_reduce<2, false>(d2, M.red);
+  if (t == 0) out[n + m] = -d2[0] - d2[1] + xPx * it;
+  __syncthreads();
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const DevStruct &S = a.S;
+  const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
+  const bcone_settings &st = a.st;
+  BwdSmem M;
+  carve_b(M, smem, n, m, S.nnzA, T, S.max_psd, a.psd_total);
+  if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  uint32_t tma_phase = 0;
+
+  for (;;) {
+    if (t == 0) M.ibuf[0] = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int inst = M.ibuf[0];
+    if (inst >= a.B) break;
+    const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
+    const double *Pg = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
+    if (a.use_tma) {
+      if (t == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(M.bar, (uint32_t)(S.nnzA * sizeof(double)));
+        tma_bulk_g2s(M.Av, Ag, (uint32_t)(S.nnzA * sizeof(double)), M.bar);
+      }
+    } else {
+      for (int k = t; k < S.nnzA; k += T) M.Av[k] = Ag[k];
+    }
+    const double *dxg = a.dx + (size_t)inst * n, *dyg = a.dy + (size_t)inst * m;
+    for (int j = t; j < n; j += T) {
+      M.x[j] = a.x[(size_t)inst * n + j]; M.c[j] = a.c[(size_t)inst * n + j]; M.px2c[j] = 0.0;
+    }
+    for (int i = t; i < m; i += T) {
+      const double yi = a.y[(size_t)inst * m + i], si = a.s[(size_t)inst * m + i];
+      const double vi = yi - si;
+      M.v[i] = vi; M.b[i] = a.b[(size_t)inst * m + i];
+      M.piy[i] = (i >= S.z && i < S.z + S.l) ? fmax(vi, 0.0) : vi;
+      M.t1[i] = dyg[i];
+    }
+    if (a.use_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }
+    __syncthreads();
+    // ---- cone Jacobian set-up: pi_y on SOC/PSD blocks, eigen-decompositions for PSD blocks ----
+    if (S.ncones > 0) {
+      const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+      int psd_off = 0;
+      for (int cb = 0; cb < S.ncones; cb++) {
+        const int ty = __ldg(S.cone_type + cb), s0 = __ldg(S.cone_start + cb), k = __ldg(S.cone_order + cb);
+        const int my_off = psd_off;
+        if (ty == BC_CPSD) psd_off += k * k + k;
+        if (cb % nw != warp) continue;
+        if (ty == BC_CSOC) project_soc_warp(M.piy + s0, __ldg(S.cone_size + cb));
+        else {
+          double *Vm = M.psdVL + my_off, *lam = Vm + k * k;
+          double *Xd = M.psdscr + warp * (3 * S.max_psd * S.max_psd + S.max_psd);
+          svec_to_mat_warp(k, M.v + s0, Xd);
+          __syncwarp();
+          jacobi_eig_warp(k, Xd, Vm);
+          for (int i = lane; i < k; i += 32) lam[i] = Xd[i * k + i];
+          __syncwarp();
+          for (int e = lane; e < k * k; e += 32) {  // pi = V max(lam,0) V'
+            const int i = e / k, j = e % k; double acc = 0;
+            for (int q = 0; q < k; q++) acc = fma(Vm[i * k + q] * fmax(lam[q], 0.0), Vm[j * k + q], acc);
+            Xd[k * k + e] = acc;
+          }
+          __syncwarp();
+          mat_to_svec_warp(k, Xd + k * k, M.piy + s0);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- 2Px + c, x'Px ----
+    double xPx = 0;
+    if (Pg) {
+      P_mul_add(S, Pg, M.x, M.px2c);
+      __syncthreads();
+      double d1[1] = {0};
+      for (int j = t; j < n; j += T) d1[0] = fma(M.x[j], M.px2c[j], d1[0]);
+      block_reduce<1, false>(d1, M.red);
+      xPx = d1[0];
+    }
+    for (int j = t; j < n; j += T) M.px2c[j] = 2.0 * M.px2c[j] + M.c[j];
+    // ---- dz -> U ----
+    apply_D(S, M, M.t1, M.t2);  // t2 = D dy   (also syncs px2c)
+    double d3[3] = {0, 0, 0};
+    for (int j = t; j < n; j += T) { const double d = dxg[j]; M.U[j] = d; d3[0] = fma(M.x[j], d, d3[0]); d3[1] = fmax(d3[1], fabs(d)); }
+    for (int i = t; i < m; i += T) {
+      const double yi = a.y[(size_t)inst * m + i];
+      M.U[n + i] = M.t2[i]; d3[0] = fma(yi, M.t1[i], d3[0]); d3[1] = fmax(d3[1], fabs(M.t2[i]));
+    }
+    {
+      double s1[1] = {d3[0]}; block_reduce<1, false>(s1, M.red);
+      double m1[1] = {d3[1]}; block_reduce<1, true>(m1, M.red);
+      if (t == 0) M.U[N - 1] = -s1[0];
+      d3[1] = fmax(m1[0], fabs(s1[0]));
+    }
+    __syncthreads();
+    int itn = 0;
+    for (int k = t; k < N; k += T) M.X[k] = 0.0;
+    if (d3[1] > 1e-8) {
+      // ================= LSQR on B = M' (Paige & Saunders; SciPy stopping rules, damp = 0) ====
+      const double eps = 2.220446049250313e-16;
+      const double atol = st.lsqr_atol, btol = st.lsqr_btol;
+      const double ctol = st.lsqr_conlim > 0 ? 1.0 / st.lsqr_conlim : 0.0;
+      const int iter_lim = st.lsqr_iter_lim < 0 ? 2 * N : st.lsqr_iter_lim;
+      double r1[1] = {0};
+      for (int k = t; k < N; k += T) r1[0] = fma(M.U[k], M.U[k], r1[0]);
+      block_reduce<1, false>(r1, M.red);
+      const double bnorm = sqrt(r1[0]);
+      double beta = bnorm, alfa = 0;
+      for (int k = t; k < N; k += T) M.U[k] /= beta;
+      __syncthreads();
+      op_M<DENSE>(a, M, Pg, xPx, M.U, M.V);  // v = B' u = M u
+      r1[0] = 0;
+      for (int k = t; k < N; k += T) r1[0] = fma(M.V[k], M.V[k], r1[0]);
+      block_reduce<1, false>(r1, M.red);
+      alfa = sqrt(r1[0]);
+      if (alfa > 0) for (int k = t; k < N; k += T) { const double q = M.V[k] / alfa; M.V[k] = q; M.W[k] = q; }
+      __syncthreads();
+      double rhobar = alfa, phibar = beta, anorm = 0, ddnorm = 0, xxnorm = 0, z = 0, cs2 = -1, sn2 = 0;
+      if (alfa * beta != 0.0) {
+        while (itn < iter_lim) {
+          itn++;
+          // u = B v - alfa u
+          op_MT<DENSE>(a, M, Pg, xPx, M.V, M.Lsc);  // B v -> Lsc (scratch)
+          r1[0] = 0;
+          for (int k = t; k < N; k += T) { const double q = M.Lsc[k] - alfa * M.U[k]; M.U[k] = q; r1[0] = fma(q, q, r1[0]); }
+          block_reduce<1, false>(r1, M.red);
+          beta = sqrt(r1[0]);
+          if (beta > 0) {
+            for (int k = t; k < N; k += T) M.U[k] /= beta;
+            anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta);
+            __syncthreads();
+            op_M<DENSE>(a, M, Pg, xPx, M.U, M.Lsc);  // B' u -> Lsc
+            r1[0] = 0;
+            for (int k = t; k < N; k += T) { const double q = M.Lsc[k] - beta * M.V[k]; M.V[k] = q; r1[0] = fma(q, q, r1[0]); }
+            block_reduce<1, false>(r1, M.red);
+            alfa = sqrt(r1[0]);
+            if (alfa > 0) for (int k = t; k < N; k += T) M.V[k] /= alfa;
+          }
+          const double rho = hypot(rhobar, beta), cs = rhobar / rho, sn = beta / rho;
+          const double theta = sn * alfa;
+          rhobar = -cs * alfa;
+          const double phi = cs * phibar;
+          phibar = sn * phibar;
+          const double tau = sn * phi;
+          const double t1c = phi / rho, t2c = -theta / rho;
+          __syncthreads();  // V normalised
+          r1[0] = 0;
+          for (int k = t; k < N; k += T) {
+            const double wk = M.W[k], dk = wk / rho;
+            r1[0] = fma(dk, dk, r1[0]);
+            M.X[k] = fma(t1c, wk, M.X[k]);
+            M.W[k] = fma(t2c, wk, M.V[k]);
+          }
+          block_reduce<1, false>(r1, M.red);
+          ddnorm += r1[0];
+          const double delta = sn2 * rho, gambar = -cs2 * rho, rhs = phi - delta * z, zbar = rhs / gambar;
+          const double xnorm = sqrt(xxnorm + zbar * zbar);
+          const double gamma = hypot(gambar, theta);
+          cs2 = gambar / gamma; sn2 = theta / gamma; z = rhs / gamma; xxnorm += z * z;
+          const double acond = anorm * sqrt(ddnorm), rnorm = phibar, arnorm = alfa * fabs(tau);
+          const double test1 = rnorm / bnorm, test2 = arnorm / (anorm * rnorm + eps), test3 = 1.0 / (acond + eps);
+          const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm), rtol = btol + atol * anorm * xnorm / bnorm;
+          int istop = 0;
+          if (itn >= iter_lim) istop = 7;
+          if (1.0 + test3 <= 1.0) istop = 6;
+          if (1.0 + test2 <= 1.0) istop = 5;
+          if (1.0 + tt1 <= 1.0) istop = 4;
+          if (test3 <= ctol) istop = 3;
+          if (test2 <= atol) istop = 2;
+          if (test1 <= rtol) istop = 1;
+          if (istop) break;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- gradient assembly (every structural entry; SURVEY.md 8a B4 + the A.nonzero() hazard) ----
+    {
+      const double rt = M.X[N - 1];
+      double *dAo = a.dA + (size_t)inst * S.nnzA;
+      if (DENSE) {
+        for (int k = t; k < S.nnzA; k += T) { const int i = k / n, j = k % n; dAo[k] = M.x[j] * M.X[n + i] - M.piy[i] * M.X[j]; }
+      } else {
+        for (int k = t; k < S.nnzA; k += T) {
+          const int i = __ldg(S.A_rowof + k), j = __ldg(S.A_indices + k);
+          dAo[k] = M.x[j] * M.X[n + i] - M.piy[i] * M.X[j];
+        }
+      }
+      for (int i = t; i < m; i += T) a.db[(size_t)inst * m + i] = M.piy[i] * rt - M.X[n + i];
+      for (int j = t; j < n; j += T) a.dc[(size_t)inst * n + j] = M.x[j] * rt - M.X[j];
+      if (a.dP && S.nnzP > 0) {
+        double *dPo = a.dP + (size_t)inst * S.nnzP;
+        for (int k = t; k < S.nnzP; k += T) {
+          const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
+          const double gij = (rt * M.x[i] - M.X[i]) * M.x[j], gji = (rt * M.x[j] - M.X[j]) * M.x[i];
+          dPo[k] = (i == j) ? gij : gij + gji;
+        }
+      }
+      if (t == 0 && a.lsqr_iters) a.lsqr_iters[inst] = itn;
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" size_t bc_bwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int psd_total) {
+  return bwd_smem_doubles(n, m, nnzA, threads, max_psd, psd_total) * sizeof(double);
+}
+extern "C" cudaError_t bc_bwd_configure(int dense, size_t smem) {
+  if (dense) return cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+extern "C" cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas_per_sm) {
+  if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_kernel<true>, threads, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_kernel<false>, threads, smem);
+}
+extern "C" cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t stream) {
+  if (a->S.dense) bwd_kernel<true><<<grid, threads, smem, stream>>>(*a);
+  else bwd_kernel<false><<<grid, threads, smem, stream>>>(*a);
+  return cudaGetLastError();
+}

@@ -1,0 +1,379 @@
+// common.cuh -- device-side building blocks shared by the forward (fwd.cu) and backward
+// (bwd.cu) kernels of the batched cone engine.  sm_100a only.
+//
+// Execution model: ONE CTA PER PROBLEM INSTANCE, persistent CTAs pulling instance ids from a
+// global atomic counter (iteration counts vary 10x across a batch, a static grid would leave
+// SMs idle in the tail).  All per-instance state lives in shared memory for the whole solve;
+// HBM is touched once on the way in (TMA bulk copy of the instance's CSR values) and once on
+// the way out.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bcone.h"
+
+#define BC_TAU_FACTOR 10.0
+#define BC_ZERO_CONE_FACTOR 1000.0
+#define BC_MIN_SCALE 1e-4
+#define BC_MAX_SCALE 1e4
+#define BC_RESCALE_MIN_ITERS 100
+#define BC_EQ_MIN 1e-4
+#define BC_EQ_MAX 1e4
+
+enum { BC_CZERO = 0, BC_CNONNEG = 1, BC_CSOC = 2, BC_CPSD = 3 };
+
+// Structure of the batch, device-resident (built once in bcone_create).
+struct DevStruct {
+  int n, m, nnzA, nnzP;
+  int z, l, nq, ns;
+  int dense;                 // A pattern is the full m x n rectangle, row-major
+  int ncones;                // non-polyhedral cone blocks (SOC + PSD)
+  int max_psd;               // largest PSD order
+  const int *A_indptr, *A_indices;         // CSR
+  const int *At_colptr, *At_rowidx, *At_perm; // CSC view: value k of column j is A_vals[At_perm[k]]
+  const int *A_rowof;        // row of each CSR slot [nnzA]
+  const int *P_indptr, *P_indices, *P_rowof; // upper-tri CSR (+ row of each slot)
+  const int *cone_type, *cone_start, *cone_size, *cone_order; // [ncones], rows are offsets in y
+};
+
+// Kernel argument blocks (passed by value as __grid_constant__).
+struct FwdArgs {
+  DevStruct S;
+  int B;
+  const double *A_vals, *P_vals, *b, *c;
+  double *x, *y, *s;
+  int *status, *iters;
+  double *resid;
+  bcone_settings st;
+  int *counter;
+  int use_tma;
+};
+
+struct BwdArgs {
+  DevStruct S;
+  int B;
+  const double *A_vals, *P_vals, *b, *c, *x, *y, *s, *dx, *dy;
+  double *dA, *dP, *db, *dc;
+  int *lsqr_iters;
+  bcone_settings st;
+  int *counter;
+  int use_tma;
+  int psd_total;  // sum over PSD blocks of k^2 + k
+};
+
+// ----------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reduction of K values at once; every thread returns the same bits (fixed order).
+// red must hold K * 32 doubles.  Contains two __syncthreads().
+template <int K, bool MAX>
+__device__ __forceinline__ void block_reduce(double (&v)[K], double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) v[k] = MAX ? warp_max(v[k]) : warp_sum(v[k]);
+  __syncthreads();  // protects red against readers of a previous reduction
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) red[k * 32 + warp] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double a = MAX ? 0.0 : 0.0;
+    for (int w = 0; w < nw; w++) a = MAX ? fmax(a, red[k * 32 + w]) : a + red[k * 32 + w];
+    v[k] = a;
+  }
+}
+
+// ----------------------------------------------------------------------------- matrix layouts
+// Row-oriented storage with a per-row offset/length: dense row-major, packed lower triangle, CSR.
+struct DenseLayout {
+  int ncols;
+  __device__ __forceinline__ int off(int i) const { return i * ncols; }
+  __device__ __forceinline__ int len(int) const { return ncols; }
+};
+struct PackedLowerLayout {  // row i holds columns 0..i at i(i+1)/2
+  __device__ __forceinline__ int off(int i) const { return (i * (i + 1)) >> 1; }
+  __device__ __forceinline__ int len(int i) const { return i + 1; }
+};
+
+// out_i = sum_j M[i][j] * x[j] for "dense-like" layouts: one warp per row, lanes across columns
+// (conflict-free for any row stride), four rows reduced together with a halving butterfly
+// (6 double shuffles per 4 rows instead of 20).  ep(i, value) is called by exactly one lane.
+template <class Layout, class Epi>
+__device__ __forceinline__ void matvec_rows(const double *__restrict__ M, Layout lay, int nrows, int ncols,
+                                            const double *__restrict__ x, Epi ep) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i0 = warp * 4; i0 < nrows; i0 += nw * 4) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const int i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3;
+    const int o0 = lay.off(i0), l0 = lay.len(i0);
+    const int o1 = i1 < nrows ? lay.off(i1) : 0, l1 = i1 < nrows ? lay.len(i1) : 0;
+    const int o2 = i2 < nrows ? lay.off(i2) : 0, l2 = i2 < nrows ? lay.len(i2) : 0;
+    const int o3 = i3 < nrows ? lay.off(i3) : 0, l3 = i3 < nrows ? lay.len(i3) : 0;
+    const int lmax = max(max(l0, l1), max(l2, l3));
+    for (int c = lane; c < lmax; c += 32) {
+      const double xv = x[c];
+      if (c < l0) a0 = fma(M[o0 + c], xv, a0);
+      if (c < l1) a1 = fma(M[o1 + c], xv, a1);
+      if (c < l2) a2 = fma(M[o2 + c], xv, a2);
+      if (c < l3) a3 = fma(M[o3 + c], xv, a3);
+    }
+    // 4 -> 2
+    const bool hi = lane & 16;
+    double k0 = hi ? a2 : a0, k1 = hi ? a3 : a1, s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    // 2 -> 1
+    const bool hi2 = lane & 8;
+    double k = hi2 ? k1 : k0, s = hi2 ? k0 : k1;
+    k += __shfl_xor_sync(0xffffffffu, s, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    if ((lane & 7) == 0) {
+      const int r = i0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+      if (r < nrows) ep(r, k);
+    }
+  }
+}
+
+// out_j = sum_i M[i][j] * y[i] (transposed product).  Thread (j, chunk): lanes across columns
+// (coalesced, conflict-free), row range split in chunks, partials combined through `part`
+// (needs blockDim.x doubles).  Contains two __syncthreads(); ep(j, value) called once per column.
+template <class Layout, class Epi>
+__device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout lay, int nrows, int ncols,
+                                            const double *__restrict__ y, double *part, Epi ep) {
+  const int T = blockDim.x, t = threadIdx.x;
+  if (ncols <= T) {
+    const int CH = T / ncols;
+    const int j = t % ncols, c = t / ncols;
+    if (c < CH) {
+      const int lo = (int)(((long long)c * nrows) / CH), hi = (int)(((long long)(c + 1) * nrows) / CH);
+      double a0 = 0, a1 = 0;
+      int i = lo;
+      for (; i + 1 < hi; i += 2) {
+        if (j < lay.len(i)) a0 = fma(M[lay.off(i) + j], y[i], a0);
+        if (j < lay.len(i + 1)) a1 = fma(M[lay.off(i + 1) + j], y[i + 1], a1);
+      }
+      if (i < hi && j < lay.len(i)) a0 = fma(M[lay.off(i) + j], y[i], a0);
+      part[t] = a0 + a1;
+    }
+    __syncthreads();
+    if (t < ncols) {
+      double a = 0;
+      for (int cc = 0; cc < CH; cc++) a += part[cc * ncols + t];
+      ep(t, a);
+    }
+    __syncthreads();
+  } else {
+    for (int j = t; j < ncols; j += T) {
+      double a = 0;
+      for (int i = 0; i < nrows; i++)
+        if (j < lay.len(i)) a = fma(M[lay.off(i) + j], y[i], a);
+      ep(j, a);
+    }
+    __syncthreads();
+  }
+}
+
+// CSR products for arbitrary patterns (index arrays stay in global memory: they are shared by
+// every CTA of the grid and sit in L1/L2).  Sub-warp groups of G lanes per row.
+template <class Epi>
+__device__ __forceinline__ void csr_rows(const double *__restrict__ vals, const int *__restrict__ indptr,
+                                         const int *__restrict__ indices, int nrows,
+                                         const double *__restrict__ x, Epi ep) {
+  constexpr int G = 4;
+  const int g = threadIdx.x % G, grp = threadIdx.x / G, ngrp = blockDim.x / G;
+  for (int base = 0; base < nrows; base += ngrp) {  // block-uniform trip count (full-mask shuffles below)
+    const int i = base + grp;
+    double a = 0;
+    if (i < nrows) {
+      const int e = __ldg(indptr + i + 1);
+      for (int k = __ldg(indptr + i) + g; k < e; k += G) a = fma(vals[k], x[__ldg(indices + k)], a);
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (g == 0 && i < nrows) ep(i, a);
+  }
+}
+template <class Epi>
+__device__ __forceinline__ void csr_cols(const double *__restrict__ vals, const int *__restrict__ colptr,
+                                         const int *__restrict__ rowidx, const int *__restrict__ perm, int ncols,
+                                         const double *__restrict__ y, Epi ep) {
+  constexpr int G = 4;
+  const int g = threadIdx.x % G, grp = threadIdx.x / G, ngrp = blockDim.x / G;
+  for (int base = 0; base < ncols; base += ngrp) {
+    const int j = base + grp;
+    double a = 0;
+    if (j < ncols) {
+      const int e = __ldg(colptr + j + 1);
+      for (int k = __ldg(colptr + j) + g; k < e; k += G) a = fma(vals[__ldg(perm + k)], y[__ldg(rowidx + k)], a);
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (g == 0 && j < ncols) ep(j, a);
+  }
+}
+
+// A x  and  A' y  for the instance's (scaled) values in shared memory.
+template <bool DENSE, class Epi>
+__device__ __forceinline__ void A_mul(const DevStruct &S, const double *Av, const double *x, Epi ep) {
+  if (DENSE) matvec_rows(Av, DenseLayout{S.n}, S.m, S.n, x, ep);
+  else csr_rows(Av, S.A_indptr, S.A_indices, S.m, x, ep);
+}
+// NOTE: ends with a __syncthreads() in the dense case; callers sync themselves in the CSR case.
+template <bool DENSE, class Epi>
+__device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, const double *y, double *part, Epi ep) {
+  if (DENSE) matvec_cols(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep);
+  else { csr_cols(Av, S.At_colptr, S.At_rowidx, S.At_perm, S.n, y, ep); __syncthreads(); }
+}
+
+// ----------------------------------------------------------------------------- cone projections
+// Projection of the non-polyhedral blocks of v (length m, y-space) onto K*; zero rows untouched,
+// nonneg rows are handled elementwise by the caller.  One warp per cone block.
+// scratch: per-warp workspace of 2*max_psd^2 + max_psd doubles (only touched for PSD blocks).
+__device__ void jacobi_eig_warp(int k, double *X, double *V);
+
+__device__ __forceinline__ void project_soc_warp(double *v, int sz) {
+  const int lane = threadIdx.x & 31;
+  if (sz == 1) { if (lane == 0 && v[0] < 0) v[0] = 0; return; }
+  double ss = 0;
+  for (int i = 1 + lane; i < sz; i += 32) ss += v[i] * v[i];
+  ss = warp_sum(ss);
+  const double nx = sqrt(ss), t = v[0];
+  if (nx <= t) return;
+  if (nx <= -t) { for (int i = lane; i < sz; i += 32) v[i] = 0; return; }
+  const double a = 0.5 * (1.0 + t / nx);
+  __syncwarp();
+  for (int i = 1 + lane; i < sz; i += 32) v[i] *= a;
+  if (lane == 0) v[0] = a * nx;
+}
+
+// svec index helpers (lower triangle, column-major, off-diagonals scaled by sqrt2;
+// reference layout: src/cvxpylayers/torch/cvxpylayer.py:201-222)
+__device__ __forceinline__ void svec_to_mat_warp(int k, const double *v, double *X) {
+  const int lane = threadIdx.x & 31;
+  const double is2 = 0.70710678118654752440;
+  for (int e = lane; e < k * k; e += 32) {
+    int i = e / k, j = e % k;
+    int r = max(i, j), c = min(i, j);
+    int idx = c * k - (c * (c - 1)) / 2 + (r - c);
+    X[e] = (i == j) ? v[idx] : v[idx] * is2;
+  }
+}
+__device__ __forceinline__ void mat_to_svec_warp(int k, const double *X, double *v) {
+  const int lane = threadIdx.x & 31;
+  const double s2 = 1.41421356237309504880;
+  for (int e = lane; e < k * k; e += 32) {
+    int i = e / k, j = e % k;
+    if (i < j) continue;
+    int idx = j * k - (j * (j - 1)) / 2 + (i - j);
+    v[idx] = (i == j) ? X[i * k + i] : 0.5 * (X[i * k + j] + X[j * k + i]) * s2;
+  }
+}
+
+// Cyclic Jacobi on a k x k symmetric matrix by one warp (row-major X, eigenvectors in V's columns).
+__device__ inline void jacobi_eig_warp(int k, double *X, double *V) {
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < k * k; e += 32) V[e] = (e / k == e % k) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0, dg = 0;
+    for (int e = lane; e < k * k; e += 32) { double a = X[e]; if (e / k == e % k) dg += a * a; else off += a * a; }
+    off = warp_sum(off); dg = warp_sum(dg);
+    if (off <= 1e-30 * (dg + off) || off == 0.0) break;
+    for (int p = 0; p < k - 1; p++) for (int q = p + 1; q < k; q++) {
+      const double apq = X[p * k + q];
+      if (apq == 0.0) continue;  // warp-uniform (same smem word)
+      const double app = X[p * k + p], aqq = X[q * k + q];
+      const double theta = (aqq - app) / (2.0 * apq);
+      const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      __syncwarp();
+      for (int r = lane; r < k; r += 32) {
+        double xp = X[r * k + p], xq = X[r * k + q];
+        X[r * k + p] = c * xp - s * xq; X[r * k + q] = s * xp + c * xq;
+        double vp = V[r * k + p], vq = V[r * k + q];
+        V[r * k + p] = c * vp - s * vq; V[r * k + q] = s * vp + c * vq;
+      }
+      __syncwarp();
+      for (int r = lane; r < k; r += 32) {
+        double xp = X[p * k + r], xq = X[q * k + r];
+        X[p * k + r] = c * xp - s * xq; X[q * k + r] = s * xp + c * xq;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+}
+
+__device__ inline void project_psd_warp(double *v, int k, double *scr) {
+  const int lane = threadIdx.x & 31;
+  double *X = scr, *V = scr + k * k, *lam = V + k * k;
+  svec_to_mat_warp(k, v, X);
+  __syncwarp();
+  jacobi_eig_warp(k, X, V);
+  for (int i = lane; i < k; i += 32) lam[i] = fmax(X[i * k + i], 0.0);
+  __syncwarp();
+  for (int e = lane; e < k * k; e += 32) {
+    int i = e / k, j = e % k;
+    double a = 0;
+    for (int q = 0; q < k; q++) a = fma(V[i * k + q] * lam[q], V[j * k + q], a);
+    X[e] = a;
+  }
+  __syncwarp();
+  mat_to_svec_warp(k, X, v);
+  __syncwarp();
+}
+
+// v (y-space, length m) <- Pi_{K*}(v) for the SOC/PSD blocks; warps stride over cone blocks.
+__device__ __forceinline__ void project_cones(const DevStruct &S, double *v, double *psd_scr) {
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int scr_stride = 2 * S.max_psd * S.max_psd + S.max_psd;
+  for (int cb = warp; cb < S.ncones; cb += nw) {
+    const int ty = __ldg(S.cone_type + cb), st = __ldg(S.cone_start + cb);
+    if (ty == BC_CSOC) project_soc_warp(v + st, __ldg(S.cone_size + cb));
+    else project_psd_warp(v + st, __ldg(S.cone_order + cb), psd_scr + warp * scr_stride);
+  }
+}

@@ -1,0 +1,452 @@
+// fwd.cu -- forward solve kernel: operator splitting on the homogeneous self-dual embedding
+// (the work diffcp/SCS do for the reference at src/cvxpylayers/interfaces/diffcp_if.py:365,369;
+// rows F3-F6 of SURVEY.md section 8a).  One persistent CTA per instance; the instance's CSR
+// values (TMA bulk copy), the packed inverse Cholesky factor of the reduced normalised KKT
+// matrix and every iterate vector stay in shared memory for the whole solve.
+//
+// Per iteration (all on-chip):
+//   t_n  = rho_x w_x - A' w_y                         (transposed product, lanes across columns)
+//   p_x  = Linv' (Linv t_n)                            (two packed-triangular products)
+//   p_y  = w_y + (A p_x) / r_y                         (row product, warp per row, butterfly reduce)
+//   tau~ = positive root of the embedding's quadratic  (four fused R-weighted dot products)
+//   u    = Pi_{R^n x K* x R+}(2 u~ - w),  w += alpha (u - u~)
+// Every check_interval iterations: SCS termination quantities on the un-normalised data,
+// infeasibility certificates, adaptive scale (re-factorisation on chip).
+#include "common.cuh"
+
+struct FwdSmem {
+  double *Av, *Li, *w, *u, *ut, *g, *bh, *ch, *Dm, *En, *tn, *tn2, *tm, *part, *red, *psd;
+  uint64_t *bar;
+  int *ibuf;
+};
+
+__host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd) {
+  size_t N = (size_t)n + m + 1;
+  size_t nA = ((size_t)nnzA + 1) & ~(size_t)1;
+  size_t d = nA + (size_t)n * (n + 1) / 2 + 3 * N + (n + m) + m + n + m + n + n + n + m + threads + 8 * 32;
+  if (max_psd > 0) d += (size_t)(threads / 32) * (2 * (size_t)max_psd * max_psd + max_psd);
+  return d + 2 /*mbarrier*/ + 2 /*ibuf*/;
+}
+
+__device__ __forceinline__ void carve(FwdSmem &M, double *base, int n, int m, int nnzA, int threads, int max_psd) {
+  const int N = n + m + 1;
+  double *q = base;
+  M.bar = (uint64_t *)q; q += 2;
+  M.ibuf = (int *)q; q += 2;
+  M.Av = q; q += (nnzA + 1) & ~1;
+  M.Li = q; q += n * (n + 1) / 2;
+  M.w = q; q += N; M.u = q; q += N; M.ut = q; q += N;
+  M.g = q; q += n + m; M.bh = q; q += m; M.ch = q; q += n; M.Dm = q; q += m; M.En = q; q += n;
+  M.tn = q; q += n; M.tn2 = q; q += n; M.tm = q; q += m;
+  M.part = q; q += threads; M.red = q; q += 8 * 32;
+  M.psd = q;
+}
+
+__device__ __forceinline__ double inv_ry(const DevStruct &S, int i, double scale) {
+  return i < S.z ? BC_ZERO_CONE_FACTOR * scale : scale;
+}
+
+// K = rho_x I + P^ + A^' R_y^{-1} A^ (packed lower) -> Cholesky -> in-place inverse Linv;
+// then g = (R_z + M)^{-1} h and g'Rg.  Returns false if the factorisation broke down.
+template <bool DENSE>
+__device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, double &gRg) {
+  const DevStruct &S = a.S;
+  const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
+  const int npk = n * (n + 1) / 2;
+  double *K = M.Li;
+  if (DENSE) {
+    for (int e = t; e < npk; e += T) {
+      int j = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while ((j + 1) * (j + 2) / 2 <= e) j++;
+      while (j * (j + 1) / 2 > e) j--;
+      const int k = e - j * (j + 1) / 2;
+      double acc0 = 0, acc1 = 0;
+      const double *cj = M.Av + j, *ck = M.Av + k;
+      int i = 0;
+      for (; i < S.z; i++) acc0 = fma(cj[i * n], ck[i * n], acc0);
+      for (; i < m; i++) acc1 = fma(cj[i * n], ck[i * n], acc1);
+      K[e] = (acc0 * BC_ZERO_CONE_FACTOR + acc1) * scale + (j == k ? rho_x : 0.0);
+    }
+    __syncthreads();
+  } else {
+    for (int e = t; e < npk; e += T) K[e] = 0.0;
+    __syncthreads();
+    for (int e = t; e < n; e += T) K[e * (e + 1) / 2 + e] = rho_x;
+    for (int k = t; k < S.nnzA; k += T) {
+      const int i = __ldg(S.A_rowof + k), ja = __ldg(S.A_indices + k);
+      const double va = M.Av[k] * inv_ry(S, i, scale);
+      const int e = __ldg(S.A_indptr + i + 1);
+      for (int k2 = __ldg(S.A_indptr + i); k2 < e; k2++) {
+        const int jb = __ldg(S.A_indices + k2);
+        if (jb <= ja) atomicAdd(&K[ja * (ja + 1) / 2 + jb], va * M.Av[k2]);
+      }
+    }
+    __syncthreads();
+  }
+  if (Pv) {
+    for (int k = t; k < S.nnzP; k += T) {
+      const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);  // j >= i
+      atomicAdd(&K[j * (j + 1) / 2 + i], Pv[k] * M.En[i] * M.En[j]);
+    }
+    __syncthreads();
+  }
+  // ---- in-place packed Cholesky (right-looking) ----
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    const double dkk = K[k * (k + 1) / 2 + k];
+    if (!(dkk > 0)) { ok = false; break; }  // block-uniform: all threads read the same word
+    const double lkk = sqrt(dkk);
+    __syncthreads();
+    if (t == 0) K[k * (k + 1) / 2 + k] = lkk;
+    for (int i = k + 1 + t; i < n; i += T) K[i * (i + 1) / 2 + k] /= lkk;
+    __syncthreads();
+    const int r = n - k - 1, cnt = r * (r + 1) / 2;
+    for (int e = t; e < cnt; e += T) {
+      int ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while ((ii + 1) * (ii + 2) / 2 <= e) ii++;
+      while (ii * (ii + 1) / 2 > e) ii--;
+      const int jj = e - ii * (ii + 1) / 2;
+      const int i = k + 1 + ii, j = k + 1 + jj;
+      K[i * (i + 1) / 2 + j] -= K[i * (i + 1) / 2 + k] * K[j * (j + 1) / 2 + k];
+    }
+    __syncthreads();
+  }
+  if (!ok) return false;
+  // ---- in-place inverse of the packed lower factor, row by row ----
+  // X[i][j] = -(1/l_ii) sum_{k=j}^{i-1} L[i][k] X[k][j]; rows < i already hold X.
+  for (int i = 0; i < n; i++) {
+    const int ro = i * (i + 1) / 2;
+    for (int k = t; k <= i; k += T) M.tn[k] = K[ro + k];  // original row i of L
+    __syncthreads();
+    const double il = 1.0 / M.tn[i];
+    for (int j = t; j <= i; j += T) {
+      double acc = 0;
+      for (int k = j; k < i; k++) acc = fma(M.tn[k], K[k * (k + 1) / 2 + j], acc);
+      K[ro + j] = (j == i) ? il : -acc * il;
+    }
+    __syncthreads();
+  }
+  // ---- g = (R_z + M)^{-1} h, h = (c^, b^) ----
+  for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
+  __syncthreads();
+  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; });
+  if (DENSE) { /* AT_mul ended with a sync */ }
+  matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
+  __syncthreads();
+  matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.g[j] = v; });
+  A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); });
+  __syncthreads();
+  double acc[1] = {0};
+  for (int k = t; k < n + m; k += T) {
+    const double r = k < n ? rho_x : 1.0 / inv_ry(S, k - n, scale);
+    acc[0] = fma(r * M.g[k], M.g[k], acc[0]);
+  }
+  block_reduce<1, false>(acc, M.red);
+  gRg = acc[0];
+  return true;
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const DevStruct &S = a.S;
+  const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
+  const bcone_settings &st = a.st;
+  FwdSmem M;
+  carve(M, smem, n, m, S.nnzA, T, S.max_psd);
+  if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  uint32_t tma_phase = 0;
+  const double rho_x = st.rho_x, alpha = st.alpha, dtau = BC_TAU_FACTOR;
+
+  for (;;) {
+    if (t == 0) M.ibuf[0] = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int inst = M.ibuf[0];
+    if (inst >= a.B) break;
+    const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
+    const double *Pg = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
+    const double *bg = a.b + (size_t)inst * m, *cg = a.c + (size_t)inst * n;
+
+    // ---- stage the instance: one TMA bulk copy for the CSR values, plain loads for b, c ----
+    if (a.use_tma) {
+      if (t == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(M.bar, (uint32_t)(S.nnzA * sizeof(double)));
+        tma_bulk_g2s(M.Av, Ag, (uint32_t)(S.nnzA * sizeof(double)), M.bar);
+      }
+    } else {
+      for (int k = t; k < S.nnzA; k += T) M.Av[k] = Ag[k];
+    }
+    double nb0 = 0, nc0 = 0;
+    for (int i = t; i < m; i += T) { const double v = bg[i]; M.bh[i] = v; M.Dm[i] = 1.0; nb0 = fmax(nb0, fabs(v)); }
+    for (int j = t; j < n; j += T) { const double v = cg[j]; M.ch[j] = v; M.En[j] = 1.0; nc0 = fmax(nc0, fabs(v)); }
+    if (a.use_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }
+    __syncthreads();
+
+    // ---- Ruiz equilibration: A^ = D A E, P^ = E P E ----
+    if (st.normalize) {
+      for (int pass = 0; pass < st.ruiz_passes; pass++) {
+        // row and column inf-norms of the current A^ (and P^)
+        if (DENSE) {
+          const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+          for (int i = warp; i < m; i += nw) {
+            double r = 0;
+            for (int c = lane; c < n; c += 32) r = fmax(r, fabs(M.Av[i * n + c]));
+            r = warp_max(r);
+            if (lane == 0) M.tm[i] = r;
+          }
+          const int CH = max(1, T / n);
+          const int j = t % n, c = t / n;
+          if (c < CH && n <= T) {
+            const int lo = (int)(((long long)c * m) / CH), hi = (int)(((long long)(c + 1) * m) / CH);
+            double r = 0;
+            for (int i = lo; i < hi; i++) r = fmax(r, fabs(M.Av[i * n + j]));
+            M.part[t] = r;
+          }
+          __syncthreads();
+          if (n <= T) {
+            if (t < n) { double r = 0; for (int cc = 0; cc < CH; cc++) r = fmax(r, M.part[cc * n + t]); M.tn[t] = r; }
+          } else {
+            for (int jj = t; jj < n; jj += T) { double r = 0; for (int i = 0; i < m; i++) r = fmax(r, fabs(M.Av[i * n + jj])); M.tn[jj] = r; }
+          }
+          __syncthreads();
+        } else {
+          for (int i = t; i < m; i += T) {
+            double r = 0;
+            for (int k = __ldg(S.A_indptr + i); k < __ldg(S.A_indptr + i + 1); k++) r = fmax(r, fabs(M.Av[k]));
+            M.tm[i] = r;
+          }
+          for (int j = t; j < n; j += T) {
+            double r = 0;
+            for (int k = __ldg(S.At_colptr + j); k < __ldg(S.At_colptr + j + 1); k++) r = fmax(r, fabs(M.Av[__ldg(S.At_perm + k)]));
+            M.tn[j] = r;
+          }
+          __syncthreads();
+        }
+        if (Pg) {
+          for (int k = t; k < S.nnzP; k += T) {
+            const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
+            const double v = fabs(Pg[k] * M.En[i] * M.En[j]);
+            atomicMax((unsigned long long *)&M.tn[i], (unsigned long long)__double_as_longlong(v));
+            atomicMax((unsigned long long *)&M.tn[j], (unsigned long long)__double_as_longlong(v));
+          }
+          __syncthreads();
+        }
+        for (int i = t; i < m; i += T) { const double r = M.tm[i]; M.tm[i] = fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
+        for (int j = t; j < n; j += T) { const double r = M.tn[j]; M.tn[j] = fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
+        __syncthreads();
+        if (S.ncones > 0) {  // one scale per non-separable cone: the block mean
+          const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+          for (int cb = warp; cb < S.ncones; cb += nw) {
+            const int s0 = __ldg(S.cone_start + cb), sz = __ldg(S.cone_size + cb);
+            double sum = 0;
+            for (int i = lane; i < sz; i += 32) sum += M.tm[s0 + i];
+            sum = warp_sum(sum) / sz;
+            for (int i = lane; i < sz; i += 32) M.tm[s0 + i] = sum;
+          }
+          __syncthreads();
+        }
+        if (DENSE) {
+          for (int k = t; k < S.nnzA; k += T) M.Av[k] *= M.tm[k / n] * M.tn[k % n];
+        } else {
+          for (int k = t; k < S.nnzA; k += T) M.Av[k] *= M.tm[__ldg(S.A_rowof + k)] * M.tn[__ldg(S.A_indices + k)];
+        }
+        for (int i = t; i < m; i += T) M.Dm[i] *= M.tm[i];
+        for (int j = t; j < n; j += T) M.En[j] *= M.tn[j];
+        __syncthreads();
+      }
+    }
+    double sigma;
+    {
+      double v[4] = {nb0, nc0, 0, 0};
+      for (int i = t; i < m; i += T) { const double q = M.Dm[i] * M.bh[i]; M.bh[i] = q; v[2] = fmax(v[2], fabs(q)); }
+      for (int j = t; j < n; j += T) { const double q = M.En[j] * M.ch[j]; M.ch[j] = q; v[3] = fmax(v[3], fabs(q)); }
+      block_reduce<4, true>(v, M.red);
+      nb0 = v[0]; nc0 = v[1];
+      sigma = fmax(v[2], v[3]);
+      sigma = (!st.normalize || sigma < 1e-6) ? 1.0 : 1.0 / sigma;
+      for (int i = t; i < m; i += T) M.bh[i] *= sigma;
+      for (int j = t; j < n; j += T) M.ch[j] *= sigma;
+      __syncthreads();
+    }
+
+    double scale = st.scale, gRg = 0;
+    int status = BCONE_INACCURATE, it = 0;
+    bool okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg);
+    for (int k = t; k < N; k += T) { M.w[k] = (k == N - 1) ? 1.0 : 0.0; M.u[k] = 0; M.ut[k] = 0; }
+    __syncthreads();
+    double sum_log = 0, rp = nan(""), rd = nan(""), gap = nan("");
+    int n_log = 0, last_up = 0;
+    if (!okf) status = BCONE_FAILED;
+
+    for (it = 1; okf && it <= st.max_iters; it++) {
+      // ---- affine step ----
+      AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; });
+      matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
+      __syncthreads();
+      matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; });
+      A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) { M.ut[n + i] = M.w[n + i] + v * inv_ry(S, i, scale); });
+      __syncthreads();
+      double d4[4] = {0, 0, 0, 0};  // mu'g, p'Rg, p'Rp, p'mu
+      for (int k = t; k < n + m; k += T) {
+        const double r = k < n ? rho_x : 1.0 / inv_ry(S, k - n, scale);
+        const double pk = M.ut[k], wk = M.w[k], gk = M.g[k];
+        d4[0] = fma(r * wk, gk, d4[0]); d4[1] = fma(r * pk, gk, d4[1]);
+        d4[2] = fma(r * pk, pk, d4[2]); d4[3] = fma(r * pk, wk, d4[3]);
+      }
+      block_reduce<4, false>(d4, M.red);
+      const double qa = dtau + gRg, qb = d4[0] - 2.0 * d4[1] - dtau * M.w[N - 1], qc = d4[2] - d4[3];
+      double disc = qb * qb - 4.0 * qa * qc;
+      if (disc < 0) disc = 0;
+      const double tau_t = (-qb + sqrt(disc)) / (2.0 * qa);
+      const bool check = (it % st.check_interval == 0) || it == st.max_iters;
+      __syncthreads();  // everyone has read w[N-1] / ut before they are overwritten
+      // ---- cone step + relaxation (fused when the cone is polyhedral and no check is due) ----
+      const bool fused = (S.ncones == 0) && !check;
+      for (int k = t; k < N; k += T) {
+        const double utk = (k == N - 1) ? tau_t : M.ut[k] - tau_t * M.g[k];
+        const double wk = M.w[k];
+        double uk = 2.0 * utk - wk;
+        if (k >= n + S.z && k < n + S.z + S.l) uk = fmax(uk, 0.0);
+        if (k == N - 1) uk = fmax(uk, 0.0);
+        M.ut[k] = utk; M.u[k] = uk;
+        if (fused) M.w[k] = wk + alpha * (uk - utk);
+      }
+      __syncthreads();
+      if (S.ncones > 0) { project_cones(S, M.u + n, M.psd); __syncthreads(); }
+
+      if (check) {
+        // ---- termination quantities on the un-normalised data ----
+        const double tau = M.u[N - 1];
+        A_mul<DENSE>(S, M.Av, M.u, [&](int i, double v) { M.tm[i] = v; });
+        AT_mul<DENSE>(S, M.Av, M.u + n, M.part, [&](int j, double v) { M.tn[j] = v; });
+        for (int j = t; j < n; j += T) M.tn2[j] = 0.0;
+        __syncthreads();
+        if (Pg) {
+          for (int k = t; k < S.nnzP; k += T) {
+            const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
+            const double v = Pg[k] * M.En[i] * M.En[j];
+            atomicAdd(&M.tn2[i], v * M.u[j]);
+            if (i != j) atomicAdd(&M.tn2[j], v * M.u[i]);
+          }
+          __syncthreads();
+        }
+        double sm[3] = {0, 0, 0};   // xPx_u, ctx_u, bty_u
+        double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // rp, nAx, nS, nAxs, rd, nPx, nATy
+        for (int i = t; i < m; i += T) {
+          const int k = n + i;
+          const double rsk = (M.u[k] - (2.0 * M.ut[k] - M.w[k])) / inv_ry(S, i, scale);
+          const double sc = 1.0 / (M.Dm[i] * sigma), ax = M.tm[i];
+          mx[0] = fmax(mx[0], fabs(ax + rsk - M.bh[i] * tau) * sc);
+          mx[1] = fmax(mx[1], fabs(ax) * sc); mx[2] = fmax(mx[2], fabs(rsk) * sc);
+          mx[3] = fmax(mx[3], fabs(ax + rsk) * sc);
+          sm[2] = fma(M.bh[i], M.u[k], sm[2]);
+        }
+        for (int j = t; j < n; j += T) {
+          const double sc = 1.0 / (M.En[j] * sigma), px = M.tn2[j], aty = M.tn[j];
+          mx[4] = fmax(mx[4], fabs(px + aty + M.ch[j] * tau) * sc);
+          mx[5] = fmax(mx[5], fabs(px) * sc); mx[6] = fmax(mx[6], fabs(aty) * sc);
+          sm[0] = fma(M.u[j], px, sm[0]); sm[1] = fma(M.ch[j], M.u[j], sm[1]);
+        }
+        block_reduce<3, false>(sm, M.red);
+        block_reduce<7, true>(mx, M.red);
+        const double s2 = sigma * sigma;
+        bool done = false;
+        if (tau > 1e-12) {
+          const double itau = 1.0 / tau;
+          const double xPx = sm[0] * itau * itau / s2, ctx = sm[1] * itau / s2, bty = sm[2] * itau / s2;
+          rp = mx[0] * itau; rd = mx[4] * itau; gap = fabs(xPx + ctx + bty);
+          const double np_ = fmax(fmax(mx[1] * itau, mx[2] * itau), nb0);
+          const double nd_ = fmax(fmax(mx[5] * itau, mx[6] * itau), nc0);
+          const double tp = st.eps_abs + st.eps_rel * np_, td = st.eps_abs + st.eps_rel * nd_;
+          const double tg = st.eps_abs + st.eps_rel * fmax(fmax(fabs(xPx), fabs(ctx)), fabs(bty));
+          if (rp <= tp && rd <= td && gap <= tg) { status = BCONE_SOLVED; done = true; }
+          else if (st.adaptive_scale) {
+            const double relp = rp / fmax(np_, 1e-18), reld = rd / fmax(nd_, 1e-18);
+            if (relp > 0 && reld > 0) { sum_log += log(relp) - log(reld); n_log++; }
+          }
+        }
+        if (!done) {
+          const double bty_c = sm[2] / s2, ctx_c = sm[1] / s2;
+          if (bty_c < 0 && mx[6] / (-bty_c) <= st.eps_infeas) { status = BCONE_INFEASIBLE; done = true; }
+          else if (ctx_c < 0 && fmax(mx[5], mx[3]) / (-ctx_c) <= st.eps_infeas) { status = BCONE_UNBOUNDED; done = true; }
+        }
+        if (done) break;
+        if (st.adaptive_scale && n_log > 0 && it - last_up >= BC_RESCALE_MIN_ITERS) {
+          const double fac = sqrt(exp(sum_log / n_log));
+          if (fac > 3.1622776601683795 || fac < 0.31622776601683794) {
+            const double ns = fmin(fmax(scale * fac, BC_MIN_SCALE), BC_MAX_SCALE);
+            if (ns != scale) {
+              // keep R (w + u - 2 u~) invariant across the metric change (y block only)
+              const double ratio = ns / scale;  // r_old / r_new
+              for (int i = t; i < m; i += T) {
+                const int k = n + i;
+                M.w[k] = ratio * (M.w[k] + M.u[k] - 2.0 * M.ut[k]) + 2.0 * M.ut[k] - M.u[k];
+              }
+              scale = ns;
+              __syncthreads();
+              okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg);
+              if (!okf) { status = BCONE_FAILED; break; }
+              sum_log = 0; n_log = 0; last_up = it;
+            }
+          }
+        }
+      }
+      if (!fused && it < st.max_iters) {  // (the last iterate keeps w so that s = R(u - t) is recoverable)
+        for (int k = t; k < N; k += T) M.w[k] += alpha * (M.u[k] - M.ut[k]);
+        __syncthreads();
+      }
+    }
+    if (it > st.max_iters) it = st.max_iters;
+
+    // ---- write back ----
+    {
+      double *xo = a.x + (size_t)inst * n, *yo = a.y + (size_t)inst * m, *so = a.s + (size_t)inst * m;
+      if (status == BCONE_SOLVED || status == BCONE_INACCURATE) {
+        double tau = M.u[N - 1];
+        if (!(tau > 1e-12)) tau = 1e-12;
+        const double k0 = 1.0 / (sigma * tau);
+        for (int j = t; j < n; j += T) xo[j] = M.En[j] * M.u[j] * k0;
+        for (int i = t; i < m; i += T) {
+          const int k = n + i;
+          const double rsk = (M.u[k] - (2.0 * M.ut[k] - M.w[k])) / inv_ry(S, i, scale);
+          yo[i] = M.Dm[i] * M.u[k] * k0;
+          so[i] = rsk * k0 / M.Dm[i];
+        }
+      } else {
+        const double qn = nan("");
+        for (int j = t; j < n; j += T) xo[j] = qn;
+        for (int i = t; i < m; i += T) { yo[i] = qn; so[i] = qn; }
+      }
+      if (t == 0) {
+        a.status[inst] = status; a.iters[inst] = it;
+        if (a.resid) { a.resid[inst * 3 + 0] = rp; a.resid[inst * 3 + 1] = rd; a.resid[inst * 3 + 2] = gap; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------- host launcher
+extern "C" size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd) {
+  return fwd_smem_doubles(n, m, nnzA, threads, max_psd) * sizeof(double);
+}
+
+extern "C" cudaError_t bc_fwd_configure(int dense, size_t smem) {
+  cudaError_t e;
+  if (dense) e = cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else e = cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return e;
+}
+
+extern "C" cudaError_t bc_fwd_occupancy(int dense, int threads, size_t smem, int *ctas_per_sm) {
+  if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fwd_kernel<true>, threads, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fwd_kernel<false>, threads, smem);
+}
+
+extern "C" cudaError_t bc_fwd_launch(const FwdArgs *a, int grid, int threads, size_t smem, cudaStream_t stream) {
+  if (a->S.dense) fwd_kernel<true><<<grid, threads, smem, stream>>>(*a);
+  else fwd_kernel<false><<<grid, threads, smem, stream>>>(*a);
+  return cudaGetLastError();
+}

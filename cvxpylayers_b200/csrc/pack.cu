@@ -1,0 +1,93 @@
+// pack.cu -- boundary layout <-> engine layout.
+//
+// The reference hands its solver interface value matrices with the BATCH AXIS CONTIGUOUS
+// (A_eval[nnz_aug, B], q_eval[n+1, B]; src/cvxpylayers/torch/cvxpylayer.py:441-451) and then
+// walks them in a per-instance Python loop (diffcp_if.py:57-68).  The engine wants one
+// instance's values contiguous so a CTA can stage them with a single TMA bulk copy.  These two
+// kernels are that re-packing, fused with the sign flip (A = -A_cvx), the CSC->CSR gather and
+// the b_idx scatter: HBM-bound tiled transposes, 128-bit loads along the batch axis.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TK 32  // rows of the boundary matrix per tile
+#define TI 64  // batch entries per tile
+
+// out[i * ldo + dmap(k)] = sign * in[(roff + smap(k)) * B + i],  k in [0,K), i in [0,B)
+__global__ void __launch_bounds__(256) b2e_kernel(const double *__restrict__ in, double *__restrict__ out, int K, int B,
+                                                  int ldo, int roff, const int *__restrict__ smap,
+                                                  const int *__restrict__ dmap, double sign) {
+  __shared__ double tile[TK][TI + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
+  const bool vec = ((B & 1) == 0);
+  for (int kk = ty; kk < TK; kk += 8) {
+    const int k = k0 + kk;
+    if (k >= K) continue;
+    const int r = roff + (smap ? __ldg(smap + k) : k);
+    const int i = i0 + 2 * tx;
+    const double *p = in + (size_t)r * B + i;
+    if (vec && i + 1 < B) {
+      const double2 v = *reinterpret_cast<const double2 *>(p);
+      tile[kk][2 * tx] = v.x; tile[kk][2 * tx + 1] = v.y;
+    } else {
+      if (i < B) tile[kk][2 * tx] = p[0];
+      if (i + 1 < B) tile[kk][2 * tx + 1] = p[1];
+    }
+  }
+  __syncthreads();
+  const int k = k0 + tx;
+  if (k < K) {
+    const int d = dmap ? __ldg(dmap + k) : k;
+    for (int ii = ty; ii < TI; ii += 8) {
+      const int i = i0 + ii;
+      if (i < B) out[(size_t)i * ldo + d] = sign * tile[tx][ii];
+    }
+  }
+}
+
+// out[(roff + dmap(k)) * B + i] = sign * in[i * ldi + smap(k)]
+__global__ void __launch_bounds__(256) e2b_kernel(const double *__restrict__ in, double *__restrict__ out, int K, int B,
+                                                  int ldi, int roff, const int *__restrict__ smap,
+                                                  const int *__restrict__ dmap, double sign) {
+  __shared__ double tile[TK][TI + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
+  const int k = k0 + tx;
+  if (k < K) {
+    const int s = smap ? __ldg(smap + k) : k;
+    for (int ii = ty; ii < TI; ii += 8) {
+      const int i = i0 + ii;
+      if (i < B) tile[tx][ii] = in[(size_t)i * ldi + s];
+    }
+  }
+  __syncthreads();
+  const bool vec = ((B & 1) == 0);
+  for (int kk = ty; kk < TK; kk += 8) {
+    const int kq = k0 + kk;
+    if (kq >= K) continue;
+    const int r = roff + (dmap ? __ldg(dmap + kq) : kq);
+    const int i = i0 + 2 * tx;
+    double *p = out + (size_t)r * B + i;
+    if (vec && i + 1 < B) {
+      *reinterpret_cast<double2 *>(p) = make_double2(sign * tile[kk][2 * tx], sign * tile[kk][2 * tx + 1]);
+    } else {
+      if (i < B) p[0] = sign * tile[kk][2 * tx];
+      if (i + 1 < B) p[1] = sign * tile[kk][2 * tx + 1];
+    }
+  }
+}
+
+extern "C" cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap,
+                              const int *dmap, double sign, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
+  b2e_kernel<<<grid, 256, 0, st>>>(in, out, K, B, ldo, roff, smap, dmap, sign);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap,
+                              const int *dmap, double sign, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
+  e2b_kernel<<<grid, 256, 0, st>>>(in, out, K, B, ldi, roff, smap, dmap, sign);
+  return cudaGetLastError();
+}

@@ -1,0 +1,231 @@
+"""Drop-in solver interface: the B200 twin of ``cvxpylayers/interfaces/diffcp_if.py``.
+
+Mirrors, name for name and argument for argument, what the reference's torch layer expects of a
+backend:
+
+* ``B200_ctx(objective_structure, constraint_structure, dims, lower_bounds, upper_bounds, options)``
+  -- same constructor as ``DIFFCP_ctx`` (``diffcp_if.py:105-120``): the CSC structure
+  ``(indices, indptr, (m, n+1))`` of ``[A_cvx | b]`` and cvxpy's cone dims.
+* ``_CvxpyLayer.apply(P_eval, q_eval, A_eval, cl_ctx, solver_args, needs_grad, warm_start)``
+  -> ``(primal[B,n], dual[B,m], opaque, opaque)`` -- same call the layer makes at
+  ``torch/cvxpylayer.py:475-483``; backward returns the 7-tuple of ``diffcp_if.py:403``.
+
+Differences from DIFFCP, all deliberate and documented in DESIGN.md: tensors stay on the GPU
+(CPU inputs are copied in and results copied back, so outputs live where the inputs live,
+as ``tests/test_moreau.py:787-815`` requires of a GPU backend); a native quadratic ``P`` is accepted
+(``moreau_if.py:400-426`` convention, upper triangle); the gradient covers *every* structural
+entry of ``A`` (the reference's ``dA.data`` drops exact zeros, SURVEY.md 8a note).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Any
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+from .engine import STATUS, Engine, make_settings
+from .structure import ConeSpec, Structure
+
+try:  # raise the reference's own exception type when diffcp is importable (tests/test_torch.py:299-316)
+    from diffcp import SolverError as _SolverErrorBase  # type: ignore
+except Exception:  # noqa: BLE001
+    _SolverErrorBase = Exception
+
+
+class SolverError(_SolverErrorBase):
+    """Raised when an instance is infeasible / unbounded / failed, like ``diffcp.SolverError``."""
+
+
+def dims_to_solver_dict(dims: Any) -> dict:
+    """cvxpy ``ConeDims`` -> {"z","l","q","s","ep","ed","p"} (the conversion the reference imports
+    from cvxpy at ``diffcp_if.py:8``); plain dicts pass through."""
+    if isinstance(dims, dict):
+        return dims
+    if isinstance(dims, ConeSpec):
+        return dims.to_dict()
+    out = {"z": int(getattr(dims, "zero", 0)), "l": int(getattr(dims, "nonneg", 0)),
+           "q": [int(v) for v in getattr(dims, "soc", [])], "s": [int(v) for v in getattr(dims, "psd", [])],
+           "ep": int(getattr(dims, "exp", 0)), "ed": 0}
+    p3d = getattr(dims, "p3d", [])
+    if len(p3d):
+        out["p"] = list(p3d)
+    return out
+
+
+def _detect_batch_size(con_values: torch.Tensor) -> tuple[int, bool]:
+    """Same rule as ``diffcp_if.py:34-43``: 1-D values = one unbatched instance."""
+    if con_values.dim() == 1:
+        return 1, True
+    return con_values.shape[1], False
+
+
+class B200_ctx:
+    """Per-layer solver context (twin of ``DIFFCP_ctx``, ``diffcp_if.py:99-120``)."""
+
+    def __init__(self, objective_structure, constraint_structure, dims, lower_bounds=None, upper_bounds=None,
+                 options=None, device: str | torch.device | None = None):
+        con_indices, con_ptr, (m, np1) = constraint_structure
+        con_indices = np.asarray(con_indices)
+        con_ptr = np.asarray(con_ptr)
+        n = np1 - 1
+        self.A_structure = (con_indices, con_ptr)
+        self.A_shape = (m, np1)
+        self.b_idx = con_indices[con_ptr[-2]: con_ptr[-1]]
+        self.dims = dims
+        self.options = options or {}
+        self.device = device
+        nnzA = int(con_ptr[-2])
+        # CSC (boundary order) -> CSR (engine order): gather[k] = boundary row feeding CSR slot k
+        csc = sp.csc_matrix((np.arange(1, nnzA + 1), con_indices[:nnzA], con_ptr[:-1]), shape=(m, n))
+        csr = csc.tocsr()
+        csr.sort_indices()
+        self.gather = (csr.data - 1).astype(np.int32)
+        P_indptr = P_indices = None
+        self.nnzP = 0
+        if objective_structure is not None:
+            p_indices, p_ptr, _ = objective_structure
+            p_indices, p_ptr = np.asarray(p_indices), np.asarray(p_ptr)
+            # accepted convention: CSR of the upper triangle (values arrive already CSR-ordered, as the
+            # reference arranges for its QP-capable backends, interfaces/__init__.py:38-42)
+            rows = np.repeat(np.arange(n), np.diff(p_ptr))
+            if np.any(p_indices < rows):
+                raise NotImplementedError("P must be passed as the CSR upper triangle")
+            P_indptr, P_indices = p_ptr.astype(np.int32), p_indices.astype(np.int32)
+            self.nnzP = int(P_indices.size)
+        cones = ConeSpec.from_dict(dims_to_solver_dict(dims))
+        self.structure = Structure(n, m, csr.indptr.astype(np.int32), csr.indices.astype(np.int32), cones,
+                                   P_indptr, P_indices)
+        self._engines: dict[torch.device, Engine] = {}
+
+    def engine(self, device: torch.device) -> Engine:
+        eng = self._engines.get(device)
+        if eng is None:
+            eng = Engine(self.structure, device)
+            eng.set_boundary(self.gather, np.asarray(self.b_idx, dtype=np.int32))
+            self._engines[device] = eng
+        return eng
+
+    def compute_device(self, t: torch.Tensor) -> torch.device:
+        if t.is_cuda:
+            return t.device
+        if self.device is not None:
+            return torch.device(self.device)
+        if not torch.cuda.is_available():
+            raise _lib.EngineUnavailable("no CUDA device: the B200 backend has no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+
+
+class _Saved:
+    """Opaque carrier for the tensors the backward needs (kept out of autograd's sight)."""
+
+    def __init__(self, *items):
+        self.items = items
+
+
+def _to_dev(t: torch.Tensor | None, dev: torch.device) -> torch.Tensor | None:
+    if t is None:
+        return None
+    return t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+
+
+class _CvxpyLayer(torch.autograd.Function):
+    """Twin of ``diffcp_if._CvxpyLayer`` (``diffcp_if.py:327-403``)."""
+
+    @staticmethod
+    def forward(P_eval, q_eval, A_eval, cl_ctx, solver_args, needs_grad=True, warm_start=None):
+        ctx: B200_ctx = cl_ctx.solver_ctx
+        batch_size, originally_unbatched = _detect_batch_size(A_eval)
+        if originally_unbatched:
+            A_eval = A_eval.unsqueeze(1)
+            q_eval = q_eval.unsqueeze(1)
+            P_eval = P_eval.unsqueeze(1) if P_eval is not None else None
+        in_device, in_dtype = A_eval.device, A_eval.dtype
+        dev = ctx.compute_device(A_eval)
+        eng = ctx.engine(dev)
+        merged = {**ctx.options}
+        if solver_args:
+            merged.update(solver_args)
+        settings = make_settings(merged)
+        use_P = P_eval is not None and ctx.nnzP > 0
+        with torch.cuda.device(dev):
+            A_vals, P_vals, b, c = eng.ingest(_to_dev(A_eval, dev), _to_dev(q_eval, dev),
+                                              _to_dev(P_eval, dev) if use_P else None)
+            sol = eng.solve(A_vals, b, c, P_vals, settings)
+            status = sol.status.cpu()  # the one host sync of the forward: per-instance status
+        bad = (status != 1) & (status != 2)
+        if bool(bad.any()):
+            i = int(torch.nonzero(bad)[0])
+            raise SolverError(f"instance {i}: solver returned status {STATUS.get(int(status[i]), int(status[i]))}")
+        if bool((status == 2).any()):
+            warnings.warn("Solved/Inaccurate.", stacklevel=2)
+        primal = sol.x.to(device=in_device, dtype=in_dtype)
+        dual = sol.y.to(device=in_device, dtype=in_dtype)
+        saved = _Saved(eng, settings, A_vals, P_vals, b, c, sol.x, sol.y, sol.s) if needs_grad else None
+        return primal, dual, saved, (batch_size, originally_unbatched, in_device, in_dtype, use_P)
+
+    @staticmethod
+    def setup_context(ctx: Any, inputs: tuple, outputs: tuple) -> None:
+        _, _, saved, backward_data = outputs
+        ctx.saved = saved
+        ctx.backward_data = backward_data
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx: Any, dprimal, ddual, _saved, _data):
+        batch_size, originally_unbatched, in_device, in_dtype, use_P = ctx.backward_data
+        if ctx.saved is None:
+            raise RuntimeError("backward called on a forward pass run with needs_grad=False")
+        eng, settings, A_vals, P_vals, b, c, x, y, s = ctx.saved.items
+        dev = eng.device
+        with torch.cuda.device(dev):
+            dx = _to_dev(dprimal, dev).reshape(batch_size, -1)
+            dy = _to_dev(ddual, dev).reshape(batch_size, -1)
+            dA_vals, dP_vals, db, dc, _ = eng.vjp(A_vals, b, c, x, y, s, dx, dy, P_vals, settings)
+            dA_eval, dq_eval, dP_eval = eng.emit(dA_vals, dP_vals if use_P else None, db, dc)
+        dA_eval = dA_eval.to(device=in_device, dtype=in_dtype)
+        dq_eval = dq_eval.to(device=in_device, dtype=in_dtype)
+        dP_eval = dP_eval.to(device=in_device, dtype=in_dtype) if dP_eval is not None else None
+        if originally_unbatched:
+            dq_eval = dq_eval.squeeze(1)
+            dA_eval = dA_eval.squeeze(1)
+            dP_eval = dP_eval.squeeze(1) if dP_eval is not None else None
+        return dP_eval, dq_eval, dA_eval, None, None, None, None
+
+
+def get_solver_ctx(solver, param_prob, cone_dims, data, kwargs, verbose=False):
+    """Twin of ``cvxpylayers.interfaces.get_solver_ctx`` (``interfaces/__init__.py:13-69``) for the
+    solver name "B200"; see INTEGRATION.md for the two-line patch that registers it."""
+    if solver != "B200":
+        raise RuntimeError("Unknown solver. Check if your solver is supported by CVXPYlayers")
+    options = dict(kwargs) if kwargs else {}
+    return B200_ctx(None, param_prob.reduced_A.problem_data_index, cone_dims,
+                    data.get("lower_bound"), data.get("upper_bound"), options)
+
+
+def get_torch_cvxpylayer(solver):
+    """Twin of ``cvxpylayers.interfaces.get_torch_cvxpylayer`` (``interfaces/__init__.py:72-101``)."""
+    if solver != "B200":
+        raise RuntimeError("Unknown solver. Check if your solver is supported by CVXPYlayers")
+    return _CvxpyLayer
+
+
+def register() -> None:
+    """Patch an importable ``cvxpylayers`` so ``CvxpyLayer(problem, ..., solver="B200")`` dispatches
+    here (the reference's dispatch is a closed ``match``; INTEGRATION.md shows the same change as a
+    source patch).  cvxpy's canonicalisation for DIFFCP is reused (``parse_args.py:447-462``)."""
+    import cvxpylayers.interfaces as ifs  # noqa: PLC0415
+
+    orig_ctx, orig_layer = ifs.get_solver_ctx, ifs.get_torch_cvxpylayer
+
+    def _ctx(solver, param_prob, cone_dims, data, kwargs, verbose=False):
+        if solver == "B200":
+            return get_solver_ctx(solver, param_prob, cone_dims, data, kwargs, verbose)
+        return orig_ctx(solver, param_prob, cone_dims, data, kwargs, verbose)
+
+    def _layer(solver):
+        return _CvxpyLayer if solver == "B200" else orig_layer(solver)
+
+    ifs.get_solver_ctx, ifs.get_torch_cvxpylayer = _ctx, _layer

@@ -1,0 +1,96 @@
+/*
+ * bcone.h -- C ABI of the B200-native batched cone-program solve-and-differentiate
+ * engine (libbcone.so).  Plain pointers and sizes only; every data pointer is the
+ * CALLER'S DEVICE MEMORY unless stated, every call is asynchronous on the given
+ * CUDA stream, every function returns 0 on success and a negative code on error
+ * (message via bcone_last_error); nothing throws across this boundary.
+ *
+ * What each entry point replaces in the reference (cvxpy/cvxpylayers @ f0b1c15):
+ *   bcone_create   <- DIFFCP_ctx.__init__            src/cvxpylayers/interfaces/diffcp_if.py:105-120
+ *                     (captures the sparsity structure + cone dims once per layer;
+ *                      CSR twin: MOREAU_ctx.__init__ moreau_if.py:181-222)
+ *   bcone_ingest   <- _build_diffcp_matrices         diffcp_if.py:46-70   (per-instance Python loop
+ *                     turning the [nnz,B] boundary tensors into solver data A=-A_cvx, b, c)
+ *   bcone_solve    <- diffcp.solve_and_derivative_batch / solve_only_batch
+ *                                                    diffcp_if.py:365, :369 (SCS forward solve)
+ *   bcone_vjp      <- the adjoint closure adj_batch  diffcp_if.py:86      (diffcp adjoint_derivative)
+ *   bcone_emit     <- _compute_gradients re-packing  diffcp_if.py:88-94 + stacks :396-397
+ *                     (dA_eval = [-dA ; db[b_idx]], dq_eval = [dc ; 0])
+ *
+ * Solver form (SCS / diffcp convention):  min 1/2 x'Px + c'x  s.t.  Ax + s = b, s in K,
+ * dual y in K*.  K = zero(z) x nonneg(l) x SOC(q[0..nq)) x PSD(s[0..ns)) in that row order.
+ * All floating point data is fp64.
+ */
+#ifndef BCONE_H
+#define BCONE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int32_t n, m, nnzA, nnzP;
+  const int32_t *A_indptr, *A_indices; /* HOST pointers, CSR of A (m+1 / nnzA); copied        */
+  const int32_t *P_indptr, *P_indices; /* HOST pointers, CSR upper triangle of P, or NULL     */
+  int32_t z, l, nq, ns, ep, ed;        /* cone spec; ep/ed must be 0 (exp cones: not built)   */
+  const int32_t *q, *s;                /* HOST: SOC sizes [nq], PSD orders [ns]               */
+  int32_t device;                      /* CUDA device ordinal                                 */
+  int32_t max_batch;                   /* workspace is sized for this many instances          */
+} bcone_desc;
+
+typedef struct {
+  double eps_abs, eps_rel, eps_infeas; /* SCS termination (defaults 1e-4, 1e-4, 1e-7)         */
+  double alpha, rho_x, scale;          /* over-relaxation 1.5, 1e-6, 0.1                      */
+  double lsqr_atol, lsqr_btol, lsqr_conlim; /* 1e-8, 1e-8, 1e8 (diffcp / SciPy LSQR rules)    */
+  int32_t max_iters, normalize, adaptive_scale, check_interval;
+  int32_t ruiz_passes, lsqr_iter_lim;  /* lsqr_iter_lim < 0 -> 2N like diffcp                 */
+  int32_t lsqr_precond;                /* 0 plain LSQR (reference semantics), 1 equilibrated  */
+  int32_t reserved1;
+} bcone_settings;
+
+enum { BCONE_SOLVED = 1, BCONE_INACCURATE = 2, BCONE_UNBOUNDED = -1, BCONE_INFEASIBLE = -2, BCONE_FAILED = -4 };
+enum { BCONE_OK = 0, BCONE_EINVAL = -1, BCONE_ECUDA = -2, BCONE_ENOMEM = -3, BCONE_EUNSUPPORTED = -4 };
+
+void bcone_default_settings(bcone_settings *st);
+
+int bcone_create(const bcone_desc *desc, void **handle);
+void bcone_destroy(void *handle);
+const char *bcone_last_error(void *handle); /* handle may be NULL: last create() error */
+
+/* Boundary layout -> engine layout.  A_eval[nnz_aug, B], q_eval[n+1, B], P_eval[nnzP, B] are the
+ * reference's batch-contiguous value matrices; gather[k] (HOST int32 [nnzA], given once at
+ * bcone_set_boundary) is the row of A_eval feeding CSR slot k.  Outputs: A_vals[B,nnzA] = -A_eval,
+ * b[B,m] (zeros off b_idx), c[B,n], P_vals[B,nnzP]. */
+int bcone_set_boundary(void *handle, int32_t nnz_aug, const int32_t *gather, int32_t nb, const int32_t *b_idx);
+int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_eval, const double *P_eval,
+                 double *A_vals, double *P_vals, double *b, double *c, void *cuda_stream);
+/* Engine gradients -> boundary layout: dA_eval[nnz_aug,B] = [-dA (boundary order) ; db[b_idx]],
+ * dq_eval[n+1,B] = [dc ; 0], dP_eval[nnzP,B]. */
+int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
+               const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *cuda_stream);
+
+/* Forward: instance-contiguous inputs A_vals[B,nnzA] (CSR order), P_vals[B,nnzP] or NULL, b[B,m], c[B,n];
+ * outputs x[B,n], y[B,m], s[B,m], status[B], iters[B] (int32), resid[B,3] or NULL. */
+int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,
+                const double *c, double *x, double *y, double *s, int32_t *status, int32_t *iters,
+                double *resid, const bcone_settings *st, void *cuda_stream);
+
+/* Backward (stateless): adjoint of the solution map at (x,y,s) applied to (dx,dy), ds = 0.
+ * Outputs dA_vals[B,nnzA] (every structural entry), dP_vals[B,nnzP] or NULL, db[B,m], dc[B,n],
+ * lsqr_iters[B] or NULL. */
+int bcone_vjp(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,
+              const double *c, const double *x, const double *y, const double *s, const double *dx,
+              const double *dy, double *dA_vals, double *dP_vals, double *db, double *dc,
+              int32_t *lsqr_iters, const bcone_settings *st, void *cuda_stream);
+
+/* Introspection for benchmarks/tests: kernel launches issued by this handle so far, and the
+ * launch geometry chosen for the forward / backward kernels. */
+int64_t bcone_launch_count(void *handle);
+int bcone_kernel_info(void *handle, int32_t *fwd_threads, int32_t *fwd_smem, int32_t *fwd_ctas_per_sm,
+                      int32_t *bwd_threads, int32_t *bwd_smem, int32_t *bwd_ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

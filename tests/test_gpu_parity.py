@@ -1,0 +1,73 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances (north_star): solutions to the solver's own eps_abs/eps_rel -- checked through the
+solver-independent SCS termination residuals on the original data -- and gradients to 1e-4
+relative against the oracle run on the same (x, y, s).
+"""
+import numpy as np
+import pytest
+import torch
+
+from cvxpylayers_b200 import problems as pr
+from cvxpylayers_b200.engine import Engine, make_settings
+from oracle import np_ref
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("C1", 4), ("C2", 6), ("C3", 6), ("C5", 4)]
+
+
+def _t(a, dev):
+    return None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+
+
+def _solve_gpu(bt, dev, **args):
+    eng = Engine(bt.structure, dev)
+    sol = eng.solve(_t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(bt.P_vals, dev), make_settings(args))
+    torch.cuda.synchronize()
+    return eng, sol
+
+
+@pytest.mark.parametrize("name,B", CASES)
+@pytest.mark.parametrize("eps", [1e-4, 1e-8])
+def test_forward_certificates_and_oracle(name, B, eps, cuda_device):
+    bt = pr.CONFIGS[name](B=B)
+    st = bt.structure
+    eng, sol = _solve_gpu(bt, cuda_device, eps=eps, max_iters=20000)
+    x, y, s = sol.x.cpu().numpy(), sol.y.cpu().numpy(), sol.s.cpu().numpy()
+    assert (sol.status.cpu().numpy() == 1).all(), sol.status
+    xo, yo, so, sto, ito = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=eps, max_iters=20000)
+    assert (sto == 1).all()
+    for i in range(B):
+        P = bt.P_dense(i) if bt.P_vals is not None else None
+        r = np_ref.kkt_residuals(bt.A_dense(i), P, bt.b[i], bt.c[i], x[i], y[i], s[i])
+        assert np_ref.is_converged(r, eps, eps, 1.001), (i, r)
+    # same algorithm, same data: the two implementations agree far inside the solver tolerance
+    scale = max(1.0, np.abs(xo).max())
+    assert np.abs(x - xo).max() <= 20 * eps * scale
+    # iteration counts track the oracle's (same checks every 25 iterations)
+    assert np.abs(sol.iters.cpu().numpy() - ito).max() <= 50
+
+
+@pytest.mark.parametrize("name,B", CASES)
+def test_backward_matches_oracle(name, B, cuda_device):
+    bt = pr.CONFIGS[name](B=B)
+    st = bt.structure
+    dev = cuda_device
+    xo, yo, so, sto, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-10, max_iters=100000)
+    rng = np.random.default_rng(5)
+    dx, dy = rng.standard_normal(xo.shape), rng.standard_normal(yo.shape)
+    lim = 40 * (st.n + st.m + 1)
+    eng = Engine(st, dev)
+    dA, dP, db, dc, its = eng.vjp(_t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(xo, dev), _t(yo, dev), _t(so, dev),
+                                  _t(dx, dev), _t(dy, dev), _t(bt.P_vals, dev), make_settings({"lsqr_iter_lim": lim}))
+    torch.cuda.synchronize()
+    rA, rP, rb, rc, rits = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, xo, yo, so, dx, dy, bt.P_vals, lsqr_iter_lim=lim)
+
+    def rel(a, b_):
+        return np.abs(a.cpu().numpy() - b_).max() / max(np.abs(b_).max(), 1e-30)
+
+    assert rel(db, rb) < 1e-4 and rel(dc, rc) < 1e-4 and rel(dA, rA) < 1e-4, (rel(dA, rA), rel(db, rb), rel(dc, rc), its, rits)
+    if rP is not None:
+        assert rel(dP, rP) < 1e-4
