@@ -15,7 +15,7 @@ size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd);
 cudaError_t bc_fwd_configure(int dense, size_t smem);
 cudaError_t bc_fwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_fwd_launch(const FwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
-size_t bc_bwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int psd_total);
+size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total);
 cudaError_t bc_bwd_configure(int dense, size_t smem);
 cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
@@ -33,7 +33,7 @@ struct Handle {
   int *d_gather = nullptr, *d_bidx = nullptr;
   int fwd_threads = 0, bwd_threads = 0, fwd_ctas = 0, bwd_ctas = 0;
   size_t fwd_smem = 0, bwd_smem = 0;
-  int tma_ok = 0, psd_total = 0;
+  int tma_ok = 0, psd_total = 0, p_in_smem = 0;
   long long launches = 0;
   std::string err;
 };
@@ -130,6 +130,17 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
       prow[k] = i;
     }
     S.P_indptr = upload(h, pptr); S.P_indices = upload(h, pidx); S.P_rowof = upload(h, prow);
+    // CSC view of the upper triangle + dense-pattern detection (row-major full upper triangle)
+    std::vector<int> pc(n + 1, 0), pr(S.nnzP), pp(S.nnzP);
+    bool pd = (long long)S.nnzP == (long long)n * (n + 1) / 2;
+    for (int i = 0; i < n; i++) {
+      if (pd && pptr[i + 1] - pptr[i] != n - i) pd = false;
+      for (int k = pptr[i]; k < pptr[i + 1]; k++) { pc[pidx[k] + 1]++; if (pd && pidx[k] != i + (k - pptr[i])) pd = false; }
+    }
+    for (int j = 0; j < n; j++) pc[j + 1] += pc[j];
+    { std::vector<int> fill(pc.begin(), pc.end() - 1); for (int k = 0; k < S.nnzP; k++) { int p = fill[pidx[k]]++; pr[p] = prow[k]; pp[p] = k; } }
+    S.Pt_colptr = upload(h, pc); S.Pt_rowidx = upload(h, pr); S.Pt_perm = upload(h, pp);
+    S.p_dense = pd ? 1 : 0;
   }
   if (cudaMalloc((void **)&h->counters, 2 * sizeof(int)) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc counters"); }
   h->allocs.push_back(h->counters);
@@ -138,17 +149,27 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
   int threads = d->nnzA >= 8192 ? 512 : (d->nnzA >= 1024 ? 256 : 128);
   while (threads < 512 && threads < n) threads *= 2;  // transposed products want one lane per column
-  auto pick = [&](bool fwd, int &thr, size_t &smem) -> bool {
+  const int npoly = d->z + d->l;
+  auto pick_fwd = [&]() -> bool {
     for (int tt = threads; tt >= 64; tt /= 2) {
-      size_t sm = fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd) : bc_bwd_smem_bytes(n, m, d->nnzA, tt, max_psd, psd_total);
-      if (sm <= smem_cap) { thr = tt; smem = sm; return true; }
+      size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd);
+      if (sm <= smem_cap) { h->fwd_threads = tt; h->fwd_smem = sm; return true; }
     }
     return false;
   };
-  if (!pick(true, h->fwd_threads, h->fwd_smem) || !pick(false, h->bwd_threads, h->bwd_smem)) {
+  auto pick_bwd = [&]() -> bool {   // prefer P staged in shared memory, fall back to P read from L2
+    for (int psm = (S.nnzP > 0 ? 1 : 0); psm >= 0; psm--)
+      for (int tt = threads; tt >= 64; tt /= 2) {
+        size_t sm = bc_bwd_smem_bytes(n, m, npoly, d->nnzA, psm ? S.nnzP : 0, tt, max_psd, psd_total);
+        if (sm <= smem_cap) { h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = psm; return true; }
+        if (psm) break;  // do not trade threads for P residency
+      }
+    return false;
+  };
+  if (!pick_fwd() || !pick_bwd()) {
     char buf[256];
     snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
-             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, d->nnzA, 64, max_psd, psd_total), smem_cap);
+             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total), smem_cap);
     bcone_destroy(h);
     return fail(nullptr, BCONE_EUNSUPPORTED, buf);
   }
@@ -253,7 +274,7 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.dx = dx; a.dy = dy; a.dA = dA_vals; a.dP = dP_vals; a.db = db; a.dc = dc;
   a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = h->counters + 1;
-  a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total;
+  a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
   CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(int), st), "vjp counter");
   const int grid = std::min(B, h->num_sms * h->bwd_ctas);
   CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch");

@@ -11,29 +11,34 @@
 #include "common.cuh"
 
 struct BwdSmem {
-  double *Av, *x, *piy, *v, *b, *c, *px2c, *U, *V, *W, *X, *t1, *t2, *Lsc, *Rsc, *part, *red, *psdVL, *psdscr;
+  double *Av, *Pv, *x, *piy, *v, *b, *c, *px2c, *U, *V, *W, *X, *t1, *t2, *Lsc, *Rsc, *tin, *part, *red, *psdVL, *psdscr;
   uint64_t *bar;
   int *ibuf;
 };
 
-__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd, int psd_total) {
+// v is only kept for the non-polyhedral rows (nonneg rows use pi_y > 0 <=> v > 0 as their mask).
+__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total) {
   size_t N = (size_t)n + m + 1;
-  size_t d = (((size_t)nnzA + 1) & ~(size_t)1) + 3 * (size_t)n + 3 * (size_t)m + 8 * N + threads + 8 * 32 + 4;
+  size_t d = 4 + (((size_t)nnzA + 1) & ~(size_t)1) + (((size_t)nnzP_smem + 1) & ~(size_t)1) + 3 * (size_t)n + 2 * (size_t)m + (m - npoly) +
+             7 * N + 2 * (size_t)m + threads + 2 * 32;
   if (max_psd > 0) d += psd_total + (size_t)(threads / 32) * (3 * (size_t)max_psd * max_psd + max_psd);
   return d;
 }
 
-__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, int nnzA, int threads, int max_psd, int psd_total) {
+__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total) {
   const int N = n + m + 1;
   double *q = base;
   M.bar = (uint64_t *)q; q += 2;
   M.ibuf = (int *)q; q += 2;
   M.Av = q; q += (nnzA + 1) & ~1;
+  M.Pv = q; q += (nnzP_smem + 1) & ~1;
   M.x = q; q += n; M.c = q; q += n; M.px2c = q; q += n;
-  M.piy = q; q += m; M.v = q; q += m; M.b = q; q += m;
-  M.U = q; q += N; M.V = q; q += N; M.W = q; q += N; M.X = q; q += N; M.t1 = q; q += N; M.t2 = q; q += N;
-  M.Lsc = q; q += N; M.Rsc = q; q += N;
-  M.part = q; q += threads; M.red = q; q += 8 * 32;
+  M.piy = q; q += m; M.b = q; q += m;
+  M.v = q - npoly; q += m - npoly;  // indexed by the original row i >= npoly
+  M.U = q; q += N; M.V = q; q += N; M.W = q; q += N; M.X = q; q += N;
+  M.Lsc = q; q += N; M.Rsc = q; q += N; M.tin = q; q += N;
+  M.t1 = q; q += m; M.t2 = q; q += m;
+  M.part = q; q += threads; M.red = q; q += 2 * 32;
   M.psdVL = q; q += psd_total;
   M.psdscr = q;
 }
@@ -42,7 +47,7 @@ __device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, 
 // PSD  V (B o (V' dX V)) V'  with V, lambda precomputed in psdVL.  Ends with __syncthreads().
 __device__ __forceinline__ void apply_D(const DevStruct &S, const BwdSmem &M, const double *in, double *out) {
   const int T = blockDim.x, t = threadIdx.x, pl = S.z + S.l;
-  for (int i = t; i < pl; i += T) out[i] = (i < S.z || M.v[i] > 0) ? in[i] : 0.0;
+  for (int i = t; i < pl; i += T) out[i] = (i < S.z || M.piy[i] > 0) ? in[i] : 0.0;
   if (S.ncones > 0) {
     const int lane = t & 31, warp = t >> 5, nw = T >> 5;
     int psd_off = 0;
@@ -107,57 +112,106 @@ __device__ __forceinline__ void apply_D(const DevStruct &S, const BwdSmem &M, co
   __syncthreads();
 }
 
-// sym-upper P times vector through shared-memory atomics (P values in global/L2, scaled access).
-__device__ __forceinline__ void P_mul_add(const DevStruct &S, const double *Pg, const double *x, double *acc) {
-  for (int k = threadIdx.x; k < S.nnzP; k += blockDim.x) {
-    const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
-    const double v = __ldg(Pg + k);
-    atomicAdd(&acc[i], v * x[j]);
-    if (i != j) atomicAdd(&acc[j], v * x[i]);
-  }
-}
-
-// out = M' in  (B = M' is the LSQR system matrix).  in/out length N; uses t1, t2.
+// out += sc o (M' in)   (B = M' is the LSQR system matrix; sc = left scaling or nullptr).  in/out length N.
 template <bool DENSE>
 __device__ __forceinline__ void op_MT(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx,
-                                      const double *in, double *out) {
+                                      const double *in, double *out, const double *sc) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const double it = in[n + m];
-  // out_x = -A' in_y + P in_x - (2Px + c) in_tau
-  AT_mul<DENSE>(S, M.Av, in + n, M.part, [&](int j, double v) { out[j] = -v - M.px2c[j] * it; });
-  if (Pg) { P_mul_add(S, Pg, in, out); }
-  // t1_y = A in_x - b in_tau - in_y ; out_y = D t1_y + in_y
+  // x rows: -A' in_y + P in_x - (2Px + c) in_tau
+  AT_mul<DENSE>(S, M.Av, in + n, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * (-v - M.px2c[j] * it); });
+  if (Pg) P_mul(S, Pg, in, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * v; });
+  // t1_y = A in_x - b in_tau - in_y ; y rows: D t1_y + in_y
   A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { M.t1[i] = v - M.b[i] * it - in[n + i]; });
   double d2[2] = {0, 0};
   for (int j = t; j < n; j += T) d2[0] = fma(M.c[j], in[j], d2[0]);
   for (int i = t; i < m; i += T) d2[1] = fma(M.b[i], in[n + i], d2[1]);
   block_reduce<2, false>(d2, M.red);  // (syncs: t1 complete)
   apply_D(S, M, M.t1, M.t2);
-  for (int i = t; i < m; i += T) out[n + i] = M.t2[i] + in[n + i];
-  if (t == 0) out[n + m] = d2[0] + d2[1] + xPx * it;
+  for (int i = t; i < m; i += T) out[n + i] += (sc ? sc[n + i] : 1.0) * (M.t2[i] + in[n + i]);
+  if (t == 0) out[n + m] += (sc ? sc[n + m] : 1.0) * (d2[0] + d2[1] + xPx * it);
   __syncthreads();
 }
 
-// out = M in
+// out += sc o (M in)
 template <bool DENSE>
 __device__ __forceinline__ void op_M(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx,
-                                     const double *in, double *out) {
+                                     const double *in, double *out, const double *sc) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const double it = in[n + m];
   apply_D(S, M, in + n, M.t2);  // t2 = D in_y
-  // out_x = A' t2 + P in_x + c in_tau
-  AT_mul<DENSE>(S, M.Av, M.t2, M.part, [&](int j, double v) { out[j] = v + M.c[j] * it; });
-  if (Pg) { P_mul_add(S, Pg, in, out); }
-  // out_y = -A in_x + b in_tau - t2 + in_y
-  A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { out[n + i] = -v + M.b[i] * it - M.t2[i] + in[n + i]; });
+  // x rows: A' t2 + P in_x + c in_tau
+  AT_mul<DENSE>(S, M.Av, M.t2, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * (v + M.c[j] * it); });
+  if (Pg) P_mul(S, Pg, in, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * v; });
+  // y rows: -A in_x + b in_tau - t2 + in_y
+  A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { out[n + i] += (sc ? sc[n + i] : 1.0) * (-v + M.b[i] * it - M.t2[i] + in[n + i]); });
   double d2[2] = {0, 0};
   for (int j = t; j < n; j += T) d2[0] = fma(M.px2c[j], in[j], d2[0]);
   for (int i = t; i < m; i += T) d2[1] = fma(M.b[i], M.t2[i], d2[1]);
   block_reduce<2, false>(d2, M.red);
-  if (t == 0) out[n + m] = -d2[0] - d2[1] + xPx * it;
+  if (t == 0) out[n + m] += (sc ? sc[n + m] : 1.0) * (-d2[0] - d2[1] + xPx * it);
   __syncthreads();
+}
+
+// 2-norm Ruiz scaling of a 0/1-skeleton surrogate of M' (see oracle/cone_oracle.c lsqr_equilibrate):
+// Lsc / Rsc <- left / right diagonal scalings; inactive nonneg rows get 0 (their unknown is dz_i = 0).
+// Row / column sums of squares need four products with the elementwise-squared A per pass.
+template <bool DENSE>
+__device__ void equilibrate(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx, int passes) {
+  const DevStruct &S = a.S;
+  const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
+  const int lo = S.z, hi = S.z + S.l;
+  double *L = M.Lsc, *R = M.Rsc, *rs = M.V, *cs = M.W, *sq = M.X;  // V, W, X are free before LSQR starts
+  for (int k = t; k < N; k += T) {
+    double v = 1.0;
+    if (k >= n && k < n + m) { const int i = k - n; if (i >= lo && i < hi && !(M.piy[i] > 0)) v = 0.0; }
+    L[k] = v; R[k] = v;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < passes; pass++) {
+    const double Lt = L[N - 1], Rt = R[N - 1];
+    // ---- vector terms + tau row / column (reductions) ----
+    double s4[2] = {0, 0};  // rs[tau], cs[tau]
+    for (int j = t; j < n; j += T) {
+      const double e1 = M.px2c[j] * M.px2c[j] * L[j] * L[j] * Rt * Rt;
+      const double e2 = M.c[j] * M.c[j] * Lt * Lt * R[j] * R[j];
+      rs[j] = e1; cs[j] = e2; s4[1] += e1; s4[0] += e2;
+    }
+    for (int i = t; i < m; i += T) {
+      const int k = n + i;
+      const double b2 = M.b[i] * M.b[i];
+      const double e1 = b2 * L[k] * L[k] * Rt * Rt, e2 = b2 * Lt * Lt * R[k] * R[k];
+      const double e3 = (i >= hi ? 1.0 : 0.0) * L[k] * L[k] * R[k] * R[k];
+      rs[k] = e1 + e3; cs[k] = e2 + e3; s4[1] += e1; s4[0] += e2;
+    }
+    block_reduce<2, false>(s4, M.red);
+    const double ett = xPx * xPx * Lt * Lt * Rt * Rt;
+    // ---- A block: four products with A.^2 ----
+    for (int k = t; k < N; k += T) sq[k] = R[k] * R[k];
+    __syncthreads();
+    AT_mul<DENSE, true>(S, M.Av, sq + n, M.part, [&](int j, double v) { rs[j] += v * L[j] * L[j]; });       // (x-row j, y-col i)
+    A_mul<DENSE, true>(S, M.Av, sq, [&](int i, double v) { rs[n + i] += v * L[n + i] * L[n + i]; });          // (y-row i, x-col j)
+    __syncthreads();
+    for (int k = t; k < N; k += T) sq[k] = L[k] * L[k];
+    __syncthreads();
+    A_mul<DENSE, true>(S, M.Av, sq, [&](int i, double v) { cs[n + i] += v * R[n + i] * R[n + i]; });          // (x-row j, y-col i)
+    AT_mul<DENSE, true>(S, M.Av, sq + n, M.part, [&](int j, double v) { cs[j] += v * R[j] * R[j]; });         // (y-row i, x-col j)
+    if (Pg) {  // P.^2 block (x rows, x cols): rs_i += L_i^2 (P.^2 R_x^2)_i ; cs_j += R_j^2 (P.^2 L_x^2)_j
+      P_mul<true>(S, Pg, sq, M.part, [&](int j, double v) { cs[j] += v * R[j] * R[j]; });
+      for (int k = t; k < n; k += T) sq[k] = R[k] * R[k];
+      __syncthreads();
+      P_mul<true>(S, Pg, sq, M.part, [&](int j, double v) { rs[j] += v * L[j] * L[j]; });
+    }
+    __syncthreads();
+    for (int k = t; k < N; k += T) {
+      const double r = (k == N - 1) ? s4[0] + ett : rs[k], c = (k == N - 1) ? s4[1] + ett : cs[k];
+      if (L[k] > 0 && r > 1e-300) L[k] /= sqrt(sqrt(r));
+      if (R[k] > 0 && c > 1e-300) R[k] /= sqrt(sqrt(c));
+    }
+    __syncthreads();
+  }
 }
 
 template <bool DENSE>
@@ -167,7 +221,7 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
   const bcone_settings &st = a.st;
   BwdSmem M;
-  carve_b(M, smem, n, m, S.nnzA, T, S.max_psd, a.psd_total);
+  carve_b(M, smem, n, m, S.z + S.l, S.nnzA, a.p_in_smem ? S.nnzP : 0, T, S.max_psd, a.psd_total);
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
@@ -178,16 +232,20 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
     const int inst = M.ibuf[0];
     if (inst >= a.B) break;
     const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
-    const double *Pg = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
+    const double *Pglob = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
+    const double *Pg = (Pglob && a.p_in_smem) ? M.Pv : Pglob;
+    const bool tmaP = a.use_tma && Pglob && a.p_in_smem && (S.nnzP % 2 == 0) && ((((size_t)inst * S.nnzP) & 1) == 0);
     if (a.use_tma) {
       if (t == 0) {
         fence_proxy_async();
-        mbar_expect_tx(M.bar, (uint32_t)(S.nnzA * sizeof(double)));
+        mbar_expect_tx(M.bar, (uint32_t)((S.nnzA + (tmaP ? S.nnzP : 0)) * sizeof(double)));
         tma_bulk_g2s(M.Av, Ag, (uint32_t)(S.nnzA * sizeof(double)), M.bar);
+        if (tmaP) tma_bulk_g2s(M.Pv, Pglob, (uint32_t)(S.nnzP * sizeof(double)), M.bar);
       }
     } else {
       for (int k = t; k < S.nnzA; k += T) M.Av[k] = Ag[k];
     }
+    if (Pglob && a.p_in_smem && !tmaP) for (int k = t; k < S.nnzP; k += T) M.Pv[k] = Pglob[k];
     const double *dxg = a.dx + (size_t)inst * n, *dyg = a.dy + (size_t)inst * m;
     for (int j = t; j < n; j += T) {
       M.x[j] = a.x[(size_t)inst * n + j]; M.c[j] = a.c[(size_t)inst * n + j]; M.px2c[j] = 0.0;
@@ -195,7 +253,8 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
     for (int i = t; i < m; i += T) {
       const double yi = a.y[(size_t)inst * m + i], si = a.s[(size_t)inst * m + i];
       const double vi = yi - si;
-      M.v[i] = vi; M.b[i] = a.b[(size_t)inst * m + i];
+      if (i >= S.z + S.l) M.v[i] = vi;
+      M.b[i] = a.b[(size_t)inst * m + i];
       M.piy[i] = (i >= S.z && i < S.z + S.l) ? fmax(vi, 0.0) : vi;
       M.t1[i] = dyg[i];
     }
@@ -233,8 +292,7 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
     // ---- 2Px + c, x'Px ----
     double xPx = 0;
     if (Pg) {
-      P_mul_add(S, Pg, M.x, M.px2c);
-      __syncthreads();
+      P_mul(S, Pg, M.x, M.part, [&](int j, double v) { M.px2c[j] += v; });
       double d1[1] = {0};
       for (int j = t; j < n; j += T) d1[0] = fma(M.x[j], M.px2c[j], d1[0]);
       block_reduce<1, false>(d1, M.red);
@@ -264,14 +322,32 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
       const double atol = st.lsqr_atol, btol = st.lsqr_btol;
       const double ctol = st.lsqr_conlim > 0 ? 1.0 / st.lsqr_conlim : 0.0;
       const int iter_lim = st.lsqr_iter_lim < 0 ? 2 * N : st.lsqr_iter_lim;
+      const bool pc = st.lsqr_precond != 0;
+      if (pc) {
+        equilibrate<DENSE>(a, M, Pg, xPx, st.ruiz_passes > 0 ? st.ruiz_passes : 10);
+        for (int k = t; k < N; k += T) { M.U[k] *= M.Lsc[k]; M.X[k] = 0.0; }
+        __syncthreads();
+      }
+      // B = diag(Lsc) M' diag(Rsc)  (identity scalings when lsqr_precond = 0); both products accumulate
+      auto acc_B = [&](const double *in, double *out) {   // out += B in
+        const double *src = in;
+        if (pc) { for (int k = t; k < N; k += T) M.tin[k] = M.Rsc[k] * in[k]; src = M.tin; }
+        __syncthreads();
+        op_MT<DENSE>(a, M, Pg, xPx, src, out, pc ? M.Lsc : nullptr);
+      };
+      auto acc_BT = [&](const double *in, double *out) {  // out += B' in
+        const double *src = in;
+        if (pc) { for (int k = t; k < N; k += T) M.tin[k] = M.Lsc[k] * in[k]; src = M.tin; }
+        __syncthreads();
+        op_M<DENSE>(a, M, Pg, xPx, src, out, pc ? M.Rsc : nullptr);
+      };
       double r1[1] = {0};
       for (int k = t; k < N; k += T) r1[0] = fma(M.U[k], M.U[k], r1[0]);
       block_reduce<1, false>(r1, M.red);
       const double bnorm = sqrt(r1[0]);
       double beta = bnorm, alfa = 0;
-      for (int k = t; k < N; k += T) M.U[k] /= beta;
-      __syncthreads();
-      op_M<DENSE>(a, M, Pg, xPx, M.U, M.V);  // v = B' u = M u
+      for (int k = t; k < N; k += T) { M.U[k] /= beta; M.V[k] = 0.0; }
+      acc_BT(M.U, M.V);  // v = B' u
       r1[0] = 0;
       for (int k = t; k < N; k += T) r1[0] = fma(M.V[k], M.V[k], r1[0]);
       block_reduce<1, false>(r1, M.red);
@@ -282,19 +358,18 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
       if (alfa * beta != 0.0) {
         while (itn < iter_lim) {
           itn++;
-          // u = B v - alfa u
-          op_MT<DENSE>(a, M, Pg, xPx, M.V, M.Lsc);  // B v -> Lsc (scratch)
+          for (int k = t; k < N; k += T) M.U[k] *= -alfa;   // u = B v - alfa u
+          acc_B(M.V, M.U);
           r1[0] = 0;
-          for (int k = t; k < N; k += T) { const double q = M.Lsc[k] - alfa * M.U[k]; M.U[k] = q; r1[0] = fma(q, q, r1[0]); }
+          for (int k = t; k < N; k += T) r1[0] = fma(M.U[k], M.U[k], r1[0]);
           block_reduce<1, false>(r1, M.red);
           beta = sqrt(r1[0]);
           if (beta > 0) {
-            for (int k = t; k < N; k += T) M.U[k] /= beta;
+            for (int k = t; k < N; k += T) { M.U[k] /= beta; M.V[k] *= -beta; }   // v = B' u - beta v
             anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta);
-            __syncthreads();
-            op_M<DENSE>(a, M, Pg, xPx, M.U, M.Lsc);  // B' u -> Lsc
+            acc_BT(M.U, M.V);
             r1[0] = 0;
-            for (int k = t; k < N; k += T) { const double q = M.Lsc[k] - beta * M.V[k]; M.V[k] = q; r1[0] = fma(q, q, r1[0]); }
+            for (int k = t; k < N; k += T) r1[0] = fma(M.V[k], M.V[k], r1[0]);
             block_reduce<1, false>(r1, M.red);
             alfa = sqrt(r1[0]);
             if (alfa > 0) for (int k = t; k < N; k += T) M.V[k] /= alfa;
@@ -334,6 +409,7 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
           if (istop) break;
         }
       }
+      if (pc) { __syncthreads(); for (int k = t; k < N; k += T) M.X[k] *= M.Rsc[k]; }
     }
     __syncthreads();
     // ---- gradient assembly (every structural entry; SURVEY.md 8a B4 + the A.nonzero() hazard) ----
@@ -364,8 +440,8 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
   }
 }
 
-extern "C" size_t bc_bwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int psd_total) {
-  return bwd_smem_doubles(n, m, nnzA, threads, max_psd, psd_total) * sizeof(double);
+extern "C" size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total) {
+  return bwd_smem_doubles(n, m, npoly, nnzA, nnzP_smem, threads, max_psd, psd_total) * sizeof(double);
 }
 extern "C" cudaError_t bc_bwd_configure(int dense, size_t smem) {
   if (dense) return cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -32,6 +32,8 @@ struct DevStruct {
   const int *At_colptr, *At_rowidx, *At_perm; // CSC view: value k of column j is A_vals[At_perm[k]]
   const int *A_rowof;        // row of each CSR slot [nnzA]
   const int *P_indptr, *P_indices, *P_rowof; // upper-tri CSR (+ row of each slot)
+  const int *Pt_colptr, *Pt_rowidx, *Pt_perm; // CSC view of the upper triangle
+  int p_dense;               // P pattern is the full upper triangle in row-major order
   const int *cone_type, *cone_start, *cone_size, *cone_order; // [ncones], rows are offsets in y
 };
 
@@ -58,6 +60,7 @@ struct BwdArgs {
   int *counter;
   int use_tma;
   int psd_total;  // sum over PSD blocks of k^2 + k
+  int p_in_smem;  // P values staged in shared memory (they fit) instead of read from L2
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -129,35 +132,48 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], double *red) {
 // Row-oriented storage with a per-row offset/length: dense row-major, packed lower triangle, CSR.
 struct DenseLayout {
   int ncols;
-  __device__ __forceinline__ int off(int i) const { return i * ncols; }
-  __device__ __forceinline__ int len(int) const { return ncols; }
+  __device__ __forceinline__ int base(int i) const { return i * ncols; }
+  __device__ __forceinline__ int beg(int) const { return 0; }
+  __device__ __forceinline__ int end(int) const { return ncols; }
 };
 struct PackedLowerLayout {  // row i holds columns 0..i at i(i+1)/2
-  __device__ __forceinline__ int off(int i) const { return (i * (i + 1)) >> 1; }
-  __device__ __forceinline__ int len(int i) const { return i + 1; }
+  __device__ __forceinline__ int base(int i) const { return (i * (i + 1)) >> 1; }
+  __device__ __forceinline__ int beg(int) const { return 0; }
+  __device__ __forceinline__ int end(int i) const { return i + 1; }
+};
+// Upper triangle stored row by row (row i holds columns i..n-1): the CSR order of a dense
+// upper-triangular pattern.  STRICT drops the diagonal (used for the transposed half of a
+// symmetric product so the diagonal is not counted twice).
+template <bool STRICT>
+struct PackedUpperLayout {
+  int n;
+  __device__ __forceinline__ int base(int i) const { return i * n - ((i * (i + 1)) >> 1); }
+  __device__ __forceinline__ int beg(int i) const { return STRICT ? i + 1 : i; }
+  __device__ __forceinline__ int end(int) const { return n; }
 };
 
 // out_i = sum_j M[i][j] * x[j] for "dense-like" layouts: one warp per row, lanes across columns
 // (conflict-free for any row stride), four rows reduced together with a halving butterfly
 // (6 double shuffles per 4 rows instead of 20).  ep(i, value) is called by exactly one lane.
-template <class Layout, class Epi>
+template <bool SQ = false, class Layout, class Epi>
 __device__ __forceinline__ void matvec_rows(const double *__restrict__ M, Layout lay, int nrows, int ncols,
                                             const double *__restrict__ x, Epi ep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int i0 = warp * 4; i0 < nrows; i0 += nw * 4) {
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     const int i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3;
-    const int o0 = lay.off(i0), l0 = lay.len(i0);
-    const int o1 = i1 < nrows ? lay.off(i1) : 0, l1 = i1 < nrows ? lay.len(i1) : 0;
-    const int o2 = i2 < nrows ? lay.off(i2) : 0, l2 = i2 < nrows ? lay.len(i2) : 0;
-    const int o3 = i3 < nrows ? lay.off(i3) : 0, l3 = i3 < nrows ? lay.len(i3) : 0;
+    const int o0 = lay.base(i0), b0 = lay.beg(i0), l0 = lay.end(i0);
+    const int o1 = i1 < nrows ? lay.base(i1) : 0, b1 = i1 < nrows ? lay.beg(i1) : 0, l1 = i1 < nrows ? lay.end(i1) : 0;
+    const int o2 = i2 < nrows ? lay.base(i2) : 0, b2 = i2 < nrows ? lay.beg(i2) : 0, l2 = i2 < nrows ? lay.end(i2) : 0;
+    const int o3 = i3 < nrows ? lay.base(i3) : 0, b3 = i3 < nrows ? lay.beg(i3) : 0, l3 = i3 < nrows ? lay.end(i3) : 0;
     const int lmax = max(max(l0, l1), max(l2, l3));
-    for (int c = lane; c < lmax; c += 32) {
+    const int bmin = min(b0, lmax) & ~31;  // rows are visited in increasing order: row i0 starts first
+    for (int c = bmin + lane; c < lmax; c += 32) {
       const double xv = x[c];
-      if (c < l0) a0 = fma(M[o0 + c], xv, a0);
-      if (c < l1) a1 = fma(M[o1 + c], xv, a1);
-      if (c < l2) a2 = fma(M[o2 + c], xv, a2);
-      if (c < l3) a3 = fma(M[o3 + c], xv, a3);
+      if (c >= b0 && c < l0) { const double q = M[o0 + c]; a0 = fma(SQ ? q * q : q, xv, a0); }
+      if (c >= b1 && c < l1) { const double q = M[o1 + c]; a1 = fma(SQ ? q * q : q, xv, a1); }
+      if (c >= b2 && c < l2) { const double q = M[o2 + c]; a2 = fma(SQ ? q * q : q, xv, a2); }
+      if (c >= b3 && c < l3) { const double q = M[o3 + c]; a3 = fma(SQ ? q * q : q, xv, a3); }
     }
     // 4 -> 2
     const bool hi = lane & 16;
@@ -181,7 +197,7 @@ __device__ __forceinline__ void matvec_rows(const double *__restrict__ M, Layout
 // out_j = sum_i M[i][j] * y[i] (transposed product).  Thread (j, chunk): lanes across columns
 // (coalesced, conflict-free), row range split in chunks, partials combined through `part`
 // (needs blockDim.x doubles).  Contains two __syncthreads(); ep(j, value) called once per column.
-template <class Layout, class Epi>
+template <bool SQ = false, class Layout, class Epi>
 __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout lay, int nrows, int ncols,
                                             const double *__restrict__ y, double *part, Epi ep) {
   const int T = blockDim.x, t = threadIdx.x;
@@ -193,10 +209,10 @@ __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout
       double a0 = 0, a1 = 0;
       int i = lo;
       for (; i + 1 < hi; i += 2) {
-        if (j < lay.len(i)) a0 = fma(M[lay.off(i) + j], y[i], a0);
-        if (j < lay.len(i + 1)) a1 = fma(M[lay.off(i + 1) + j], y[i + 1], a1);
+        if (j >= lay.beg(i) && j < lay.end(i)) { const double q = M[lay.base(i) + j]; a0 = fma(SQ ? q * q : q, y[i], a0); }
+        if (j >= lay.beg(i + 1) && j < lay.end(i + 1)) { const double q = M[lay.base(i + 1) + j]; a1 = fma(SQ ? q * q : q, y[i + 1], a1); }
       }
-      if (i < hi && j < lay.len(i)) a0 = fma(M[lay.off(i) + j], y[i], a0);
+      if (i < hi && j >= lay.beg(i) && j < lay.end(i)) { const double q = M[lay.base(i) + j]; a0 = fma(SQ ? q * q : q, y[i], a0); }
       part[t] = a0 + a1;
     }
     __syncthreads();
@@ -210,7 +226,7 @@ __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout
     for (int j = t; j < ncols; j += T) {
       double a = 0;
       for (int i = 0; i < nrows; i++)
-        if (j < lay.len(i)) a = fma(M[lay.off(i) + j], y[i], a);
+        if (j >= lay.beg(i) && j < lay.end(i)) { const double q = M[lay.base(i) + j]; a = fma(SQ ? q * q : q, y[i], a); }
       ep(j, a);
     }
     __syncthreads();
@@ -219,7 +235,7 @@ __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout
 
 // CSR products for arbitrary patterns (index arrays stay in global memory: they are shared by
 // every CTA of the grid and sit in L1/L2).  Sub-warp groups of G lanes per row.
-template <class Epi>
+template <bool SQ = false, class Epi>
 __device__ __forceinline__ void csr_rows(const double *__restrict__ vals, const int *__restrict__ indptr,
                                          const int *__restrict__ indices, int nrows,
                                          const double *__restrict__ x, Epi ep) {
@@ -230,14 +246,14 @@ __device__ __forceinline__ void csr_rows(const double *__restrict__ vals, const 
     double a = 0;
     if (i < nrows) {
       const int e = __ldg(indptr + i + 1);
-      for (int k = __ldg(indptr + i) + g; k < e; k += G) a = fma(vals[k], x[__ldg(indices + k)], a);
+      for (int k = __ldg(indptr + i) + g; k < e; k += G) { const double q = vals[k]; a = fma(SQ ? q * q : q, x[__ldg(indices + k)], a); }
     }
     a += __shfl_xor_sync(0xffffffffu, a, 1);
     a += __shfl_xor_sync(0xffffffffu, a, 2);
     if (g == 0 && i < nrows) ep(i, a);
   }
 }
-template <class Epi>
+template <bool SQ = false, class Epi>
 __device__ __forceinline__ void csr_cols(const double *__restrict__ vals, const int *__restrict__ colptr,
                                          const int *__restrict__ rowidx, const int *__restrict__ perm, int ncols,
                                          const double *__restrict__ y, Epi ep) {
@@ -248,7 +264,7 @@ __device__ __forceinline__ void csr_cols(const double *__restrict__ vals, const 
     double a = 0;
     if (j < ncols) {
       const int e = __ldg(colptr + j + 1);
-      for (int k = __ldg(colptr + j) + g; k < e; k += G) a = fma(vals[__ldg(perm + k)], y[__ldg(rowidx + k)], a);
+      for (int k = __ldg(colptr + j) + g; k < e; k += G) { const double q = vals[__ldg(perm + k)]; a = fma(SQ ? q * q : q, y[__ldg(rowidx + k)], a); }
     }
     a += __shfl_xor_sync(0xffffffffu, a, 1);
     a += __shfl_xor_sync(0xffffffffu, a, 2);
@@ -257,16 +273,50 @@ __device__ __forceinline__ void csr_cols(const double *__restrict__ vals, const 
 }
 
 // A x  and  A' y  for the instance's (scaled) values in shared memory.
-template <bool DENSE, class Epi>
+template <bool DENSE, bool SQ = false, class Epi>
 __device__ __forceinline__ void A_mul(const DevStruct &S, const double *Av, const double *x, Epi ep) {
-  if (DENSE) matvec_rows(Av, DenseLayout{S.n}, S.m, S.n, x, ep);
-  else csr_rows(Av, S.A_indptr, S.A_indices, S.m, x, ep);
+  if (DENSE) matvec_rows<SQ>(Av, DenseLayout{S.n}, S.m, S.n, x, ep);
+  else csr_rows<SQ>(Av, S.A_indptr, S.A_indices, S.m, x, ep);
 }
 // NOTE: ends with a __syncthreads() in the dense case; callers sync themselves in the CSR case.
-template <bool DENSE, class Epi>
+template <bool DENSE, bool SQ = false, class Epi>
 __device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, const double *y, double *part, Epi ep) {
-  if (DENSE) matvec_cols(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep);
-  else { csr_cols(Av, S.At_colptr, S.At_rowidx, S.At_perm, S.n, y, ep); __syncthreads(); }
+  if (DENSE) matvec_cols<SQ>(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep);
+  else { csr_cols<SQ>(Av, S.At_colptr, S.At_rowidx, S.At_perm, S.n, y, ep); __syncthreads(); }
+}
+
+// out[i] += (P x)[i] for symmetric P given by its upper triangle (values Pv in shared or global
+// memory): row pass over the upper triangle, then the transposed pass over the strict upper part.
+// No atomics: every out[i] has a single writer per pass.  Ends with __syncthreads().
+template <bool SQ = false, class Epi>
+__device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, const double *x, double *part, Epi ep) {
+  const int n = S.n;
+  if (S.p_dense) {
+    matvec_rows<SQ>(Pv, PackedUpperLayout<false>{n}, n, n, x, ep);
+    __syncthreads();
+    matvec_cols<SQ>(Pv, PackedUpperLayout<true>{n}, n, n, x, part, ep);
+  } else {
+    csr_rows<SQ>(Pv, S.P_indptr, S.P_indices, n, x, ep);
+    __syncthreads();
+    // CSC view of the upper triangle; the diagonal entry (row == col) is skipped here
+    constexpr int G = 4;
+    const int g = threadIdx.x % G, grp = threadIdx.x / G, ngrp = blockDim.x / G;
+    for (int base = 0; base < n; base += ngrp) {
+      const int j = base + grp;
+      double a = 0;
+      if (j < n) {
+        const int e = __ldg(S.Pt_colptr + j + 1);
+        for (int k = __ldg(S.Pt_colptr + j) + g; k < e; k += G) {
+          const int i = __ldg(S.Pt_rowidx + k);
+          if (i != j) { const double q = Pv[__ldg(S.Pt_perm + k)]; a = fma(SQ ? q * q : q, x[i], a); }
+        }
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (g == 0 && j < n) ep(j, a);
+    }
+    __syncthreads();
+  }
 }
 
 // ----------------------------------------------------------------------------- cone projections

@@ -15,7 +15,7 @@
 #include "common.cuh"
 
 struct FwdSmem {
-  double *Av, *Li, *w, *u, *ut, *g, *bh, *ch, *Dm, *En, *tn, *tn2, *tm, *part, *red, *psd;
+  double *Av, *Li, *w, *u, *ut, *g, *bh, *ch, *Dm, *En, *tn, *tn2, *tn3, *tm, *part, *red, *psd;
   uint64_t *bar;
   int *ibuf;
 };
@@ -23,7 +23,7 @@ struct FwdSmem {
 __host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd) {
   size_t N = (size_t)n + m + 1;
   size_t nA = ((size_t)nnzA + 1) & ~(size_t)1;
-  size_t d = nA + (size_t)n * (n + 1) / 2 + 3 * N + (n + m) + m + n + m + n + n + n + m + threads + 8 * 32;
+  size_t d = nA + (size_t)n * (n + 1) / 2 + 3 * N + (n + m) + m + n + m + n + n + n + n + m + threads + 8 * 32;
   if (max_psd > 0) d += (size_t)(threads / 32) * (2 * (size_t)max_psd * max_psd + max_psd);
   return d + 2 /*mbarrier*/ + 2 /*ibuf*/;
 }
@@ -37,7 +37,7 @@ __device__ __forceinline__ void carve(FwdSmem &M, double *base, int n, int m, in
   M.Li = q; q += n * (n + 1) / 2;
   M.w = q; q += N; M.u = q; q += N; M.ut = q; q += N;
   M.g = q; q += n + m; M.bh = q; q += m; M.ch = q; q += n; M.Dm = q; q += m; M.En = q; q += n;
-  M.tn = q; q += n; M.tn2 = q; q += n; M.tm = q; q += m;
+  M.tn = q; q += n; M.tn2 = q; q += n; M.tn3 = q; q += n; M.tm = q; q += m;
   M.part = q; q += threads; M.red = q; q += 8 * 32;
   M.psd = q;
 }
@@ -321,15 +321,11 @@ __global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArg
         const double tau = M.u[N - 1];
         A_mul<DENSE>(S, M.Av, M.u, [&](int i, double v) { M.tm[i] = v; });
         AT_mul<DENSE>(S, M.Av, M.u + n, M.part, [&](int j, double v) { M.tn[j] = v; });
-        for (int j = t; j < n; j += T) M.tn2[j] = 0.0;
+        for (int j = t; j < n; j += T) { M.tn2[j] = 0.0; M.tn3[j] = M.En[j] * M.u[j]; }
         __syncthreads();
-        if (Pg) {
-          for (int k = t; k < S.nnzP; k += T) {
-            const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
-            const double v = Pg[k] * M.En[i] * M.En[j];
-            atomicAdd(&M.tn2[i], v * M.u[j]);
-            if (i != j) atomicAdd(&M.tn2[j], v * M.u[i]);
-          }
+        if (Pg) {  // P^ u_x = E (P (E u_x)); no atomics
+          P_mul(S, Pg, M.tn3, M.part, [&](int j, double v) { M.tn2[j] += v; });
+          for (int j = t; j < n; j += T) M.tn2[j] *= M.En[j];
           __syncthreads();
         }
         double sm[3] = {0, 0, 0};   // xPx_u, ctx_u, bty_u

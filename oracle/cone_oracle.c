@@ -40,7 +40,7 @@ void orc_default_settings(orc_settings *st) {
   st->alpha = 1.5; st->rho_x = 1e-6; st->scale = 0.1;
   st->lsqr_atol = 1e-8; st->lsqr_btol = 1e-8; st->lsqr_conlim = 1e8;
   st->max_iters = 100000; st->normalize = 1; st->adaptive_scale = 1; st->check_interval = 25;
-  st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->reserved0 = 0; st->reserved1 = 0;
+  st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->lsqr_precond = 0; st->reserved1 = 0;
 }
 
 int orc_max_threads(void) {
@@ -555,6 +555,7 @@ typedef struct {
   const double *Av, *Pv, *b, *c, *v, *x;
   double xPx; double *Px2c; /* 2 P x + c */
   const cblock *CB; int ncb;
+  double *Ls, *Rs, *t4; /* diagonal equilibration of the LSQR system (lsqr_precond) */
   double *t1, *t2, *t3;
 } bwd_ctx;
 
@@ -596,14 +597,78 @@ static void op_MT(void *c_, const double *in, double *out) {
   for (int i = 0; i < N; i++) out[i] = k->t2[i] + in[i];
 }
 
+/* B' = diag(Ls) M' diag(Rs) and its transpose */
+static void op_Bs(void *c_, const double *in, double *out) {
+  bwd_ctx *k = (bwd_ctx *)c_; int N = k->n + k->m + 1;
+  for (int i = 0; i < N; i++) k->t4[i] = k->Rs[i] * in[i];
+  op_MT(c_, k->t4, out);
+  for (int i = 0; i < N; i++) out[i] *= k->Ls[i];
+}
+static void op_BsT(void *c_, const double *in, double *out) {
+  bwd_ctx *k = (bwd_ctx *)c_; int N = k->n + k->m + 1;
+  for (int i = 0; i < N; i++) k->t4[i] = k->Ls[i] * in[i];
+  op_M(c_, k->t4, out);
+  for (int i = 0; i < N; i++) out[i] *= k->Rs[i];
+}
+
+/* 2-norm Ruiz scaling of a surrogate of M' (cone Jacobian replaced by its 0/1 skeleton:
+ * zero rows and active nonneg rows 1, inactive nonneg rows dropped -- their unknown is exactly
+ * dz_i = 0 --, SOC/PSD rows 1 with a unit diagonal standing in for I - D).  A diagonally
+ * rescaled system has the same solution wherever the solution map is differentiable. */
+static void lsqr_equilibrate(bwd_ctx *k, const double *piy_unused, int passes) {
+  const orc_desc *d = k->d; int n = k->n, m = k->m, N = n + m + 1;
+  double *L = k->Ls, *R = k->Rs;
+  double *rs = (double *)calloc(2 * (size_t)N + m, sizeof(double)), *cs = rs + N, *dg = cs + N;
+  int lo = d->z, hi = d->z + d->l;
+  for (int i = 0; i < N; i++) { L[i] = 1.0; R[i] = 1.0; }
+  for (int i = 0; i < m; i++) {
+    int live = !(i >= lo && i < hi) || k->v[i] > 0;
+    if (!live) { L[n + i] = 0.0; R[n + i] = 0.0; }
+    dg[i] = (i >= hi) ? 1.0 : 0.0; /* surrogate of (I - D) on non-polyhedral rows */
+  }
+  for (int pass = 0; pass < passes; pass++) {
+    for (int i = 0; i < 2 * N; i++) rs[i] = 0;
+    /* A block: x-row j / y-col i carry -A_ij ; y-row i / x-col j carry A_ij */
+    for (int i = 0; i < m; i++) for (int a = d->A_indptr[i]; a < d->A_indptr[i + 1]; a++) {
+      int j = d->A_indices[a]; double v2 = k->Av[a] * k->Av[a];
+      double e1 = v2 * L[j] * L[j] * R[n + i] * R[n + i];       /* (x-row j, y-col i) */
+      double e2 = v2 * L[n + i] * L[n + i] * R[j] * R[j];       /* (y-row i, x-col j) */
+      rs[j] += e1; cs[n + i] += e1; rs[n + i] += e2; cs[j] += e2;
+    }
+    if (d->P_indptr) for (int i = 0; i < n; i++) for (int a = d->P_indptr[i]; a < d->P_indptr[i + 1]; a++) {
+      int j = d->P_indices[a]; double v2 = k->Pv[a] * k->Pv[a];
+      double e1 = v2 * L[i] * L[i] * R[j] * R[j];
+      rs[i] += e1; cs[j] += e1;
+      if (i != j) { double e2 = v2 * L[j] * L[j] * R[i] * R[i]; rs[j] += e2; cs[i] += e2; }
+    }
+    for (int j = 0; j < n; j++) {
+      double e1 = k->Px2c[j] * k->Px2c[j] * L[j] * L[j] * R[N - 1] * R[N - 1]; rs[j] += e1; cs[N - 1] += e1;
+      double e2 = k->c[j] * k->c[j] * L[N - 1] * L[N - 1] * R[j] * R[j]; rs[N - 1] += e2; cs[j] += e2;
+    }
+    for (int i = 0; i < m; i++) {
+      double b2 = k->b[i] * k->b[i];
+      double e1 = b2 * L[n + i] * L[n + i] * R[N - 1] * R[N - 1]; rs[n + i] += e1; cs[N - 1] += e1;
+      double e2 = b2 * L[N - 1] * L[N - 1] * R[n + i] * R[n + i]; rs[N - 1] += e2; cs[n + i] += e2;
+      double e3 = dg[i] * L[n + i] * L[n + i] * R[n + i] * R[n + i]; rs[n + i] += e3; cs[n + i] += e3;
+    }
+    { double e = k->xPx * k->xPx * L[N - 1] * L[N - 1] * R[N - 1] * R[N - 1]; rs[N - 1] += e; cs[N - 1] += e; }
+    for (int i = 0; i < N; i++) {
+      if (L[i] > 0 && rs[i] > 1e-300) L[i] /= sqrt(sqrt(rs[i]));
+      if (R[i] > 0 && cs[i] > 1e-300) R[i] /= sqrt(sqrt(cs[i]));
+    }
+  }
+  free(rs);
+}
+
 int orc_vjp(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
             const double *x, const double *y, const double *s, const double *dx, const double *dy,
             double *dAv, double *dPv, double *db, double *dc, const orc_settings *st) {
   int n = d->n, m = d->m, N = n + m + 1;
-  double *buf = (double *)calloc((size_t)8 * N + 4 * n + 2 * m, sizeof(double)), *q = buf;
+  double *buf = (double *)calloc((size_t)12 * N + 4 * n + 2 * m, sizeof(double)), *q = buf;
   double *v = q; q += m; double *piy = q; q += m; double *dz = q; q += N; double *r = q; q += N;
   bwd_ctx K; K.d = d; K.n = n; K.m = m; K.Av = Av; K.Pv = Pv; K.b = b; K.c = c; K.v = v; K.x = x;
   K.t1 = q; q += N; K.t2 = q; q += N; K.t3 = q; q += N; K.Px2c = q; q += n;
+  K.Ls = q; q += N; K.Rs = q; q += N; K.t4 = q; q += N;
   cblock *CB; K.ncb = cone_blocks(d, &CB); K.CB = CB;
   for (int i = 0; i < m; i++) { v[i] = y[i] - s[i]; piy[i] = v[i]; }
   orc_proj_dual_cone(d, piy);
@@ -615,7 +680,13 @@ int orc_vjp(const orc_desc *d, const double *Av, const double *Pv, const double 
   dz[N - 1] = -(dot(n, x, dx) + dot(m, y, dy));
   int its = 0, allz = 1;
   for (int i = 0; i < N; i++) if (fabs(dz[i]) > 1e-8) { allz = 0; break; }
-  if (!allz) its = lsqr_core(N, N, op_MT, op_M, &K, dz, r, st->lsqr_atol, st->lsqr_btol, st->lsqr_conlim, st->lsqr_iter_lim);
+  if (!allz && st->lsqr_precond) {
+    lsqr_equilibrate(&K, piy, st->ruiz_passes > 0 ? st->ruiz_passes : 10);
+    for (int i = 0; i < N; i++) dz[i] *= K.Ls[i];
+    its = lsqr_core(N, N, op_Bs, op_BsT, &K, dz, r, st->lsqr_atol, st->lsqr_btol, st->lsqr_conlim, st->lsqr_iter_lim);
+    for (int i = 0; i < N; i++) r[i] *= K.Rs[i];
+  } else if (!allz)
+    its = lsqr_core(N, N, op_MT, op_M, &K, dz, r, st->lsqr_atol, st->lsqr_btol, st->lsqr_conlim, st->lsqr_iter_lim);
   /* gradient assembly on EVERY structural entry (SURVEY.md 8a row B4 and the A.nonzero() hazard note) */
   double rt = r[N - 1];
   for (int i = 0; i < m; i++) for (int k = d->A_indptr[i]; k < d->A_indptr[i + 1]; k++) {
