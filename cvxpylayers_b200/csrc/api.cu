@@ -19,6 +19,10 @@ size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int t
 cudaError_t bc_bwd_configure(int dense, size_t smem);
 cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
+size_t bc_bwdf_smem_bytes(int n, int m, int nnzA, int nnzP, int threads);
+cudaError_t bc_bwdf_configure(size_t smem);
+cudaError_t bc_bwdf_occupancy(int threads, size_t smem, int *ctas);
+cudaError_t bc_bwdf_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
 cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
 }
@@ -34,6 +38,7 @@ struct Handle {
   int fwd_threads = 0, bwd_threads = 0, fwd_ctas = 0, bwd_ctas = 0;
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
+  int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
   std::string err;
 };
@@ -166,7 +171,14 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
       }
     return false;
   };
-  if (!pick_fwd() || !pick_bwd()) {
+  // fast backward path: same launch geometry fields, different kernel
+  if (S.dense && S.ncones == 0 && n <= 128 && (S.nnzP == 0 || S.p_dense)) {
+    for (int tt = threads; tt >= 64; tt /= 2) {
+      size_t sm = bc_bwdf_smem_bytes(n, m, d->nnzA, S.nnzP, tt);
+      if (sm <= smem_cap) { h->fast_bwd = 1; h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = S.nnzP > 0; break; }
+    }
+  }
+  if (!pick_fwd() || (!h->fast_bwd && !pick_bwd())) {
     char buf[256];
     snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
              bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total), smem_cap);
@@ -174,13 +186,15 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     return fail(nullptr, BCONE_EUNSUPPORTED, buf);
   }
   cudaError_t e;
-  if ((e = bc_fwd_configure(S.dense, h->fwd_smem)) != cudaSuccess || (e = bc_bwd_configure(S.dense, h->bwd_smem)) != cudaSuccess) {
+  if ((e = bc_fwd_configure(S.dense, h->fwd_smem)) != cudaSuccess ||
+      (e = (h->fast_bwd ? bc_bwdf_configure(h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
   bc_fwd_occupancy(S.dense, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
-  bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
+  if (h->fast_bwd) bc_bwdf_occupancy(h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
+  else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;
   h->tma_ok = (d->nnzA > 0 && (d->nnzA % 2) == 0 && (size_t)d->nnzA * 8 < (1u << 20)) ? 1 : 0;
@@ -277,7 +291,8 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
   CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(int), st), "vjp counter");
   const int grid = std::min(B, h->num_sms * h->bwd_ctas);
-  CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch");
+  if (h->fast_bwd) CK(bc_bwdf_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch (fast)");
+  else CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch");
   h->launches++;
   return BCONE_OK;
 }

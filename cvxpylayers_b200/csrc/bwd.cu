@@ -115,13 +115,13 @@ __device__ __forceinline__ void apply_D(const DevStruct &S, const BwdSmem &M, co
 // out += sc o (M' in)   (B = M' is the LSQR system matrix; sc = left scaling or nullptr).  in/out length N.
 template <bool DENSE>
 __device__ __forceinline__ void op_MT(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx,
-                                      const double *in, double *out, const double *sc) {
+                                      const double *in, double *out, const double *sc, const ColPlan &plA, const ColPlan &plN) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const double it = in[n + m];
   // x rows: -A' in_y + P in_x - (2Px + c) in_tau
-  AT_mul<DENSE>(S, M.Av, in + n, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * (-v - M.px2c[j] * it); });
-  if (Pg) P_mul(S, Pg, in, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * v; });
+  AT_mul<DENSE>(S, M.Av, in + n, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * (-v - M.px2c[j] * it); }, plA);
+  if (Pg) P_mul(S, Pg, in, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * v; }, plN);
   // t1_y = A in_x - b in_tau - in_y ; y rows: D t1_y + in_y
   A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { M.t1[i] = v - M.b[i] * it - in[n + i]; });
   double d2[2] = {0, 0};
@@ -137,14 +137,14 @@ __device__ __forceinline__ void op_MT(const BwdArgs &a, const BwdSmem &M, const 
 // out += sc o (M in)
 template <bool DENSE>
 __device__ __forceinline__ void op_M(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx,
-                                     const double *in, double *out, const double *sc) {
+                                     const double *in, double *out, const double *sc, const ColPlan &plA, const ColPlan &plN) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const double it = in[n + m];
   apply_D(S, M, in + n, M.t2);  // t2 = D in_y
   // x rows: A' t2 + P in_x + c in_tau
-  AT_mul<DENSE>(S, M.Av, M.t2, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * (v + M.c[j] * it); });
-  if (Pg) P_mul(S, Pg, in, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * v; });
+  AT_mul<DENSE>(S, M.Av, M.t2, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * (v + M.c[j] * it); }, plA);
+  if (Pg) P_mul(S, Pg, in, M.part, [&](int j, double v) { out[j] += (sc ? sc[j] : 1.0) * v; }, plN);
   // y rows: -A in_x + b in_tau - t2 + in_y
   A_mul<DENSE>(S, M.Av, in, [&](int i, double v) { out[n + i] += (sc ? sc[n + i] : 1.0) * (-v + M.b[i] * it - M.t2[i] + in[n + i]); });
   double d2[2] = {0, 0};
@@ -159,7 +159,8 @@ __device__ __forceinline__ void op_M(const BwdArgs &a, const BwdSmem &M, const d
 // Lsc / Rsc <- left / right diagonal scalings; inactive nonneg rows get 0 (their unknown is dz_i = 0).
 // Row / column sums of squares need four products with the elementwise-squared A per pass.
 template <bool DENSE>
-__device__ void equilibrate(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx, int passes) {
+__device__ void equilibrate(const BwdArgs &a, const BwdSmem &M, const double *Pg, double xPx, int passes,
+                            const ColPlan &plA, const ColPlan &plN) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
   const int lo = S.z, hi = S.z + S.l;
@@ -191,18 +192,18 @@ __device__ void equilibrate(const BwdArgs &a, const BwdSmem &M, const double *Pg
     // ---- A block: four products with A.^2 ----
     for (int k = t; k < N; k += T) sq[k] = R[k] * R[k];
     __syncthreads();
-    AT_mul<DENSE, true>(S, M.Av, sq + n, M.part, [&](int j, double v) { rs[j] += v * L[j] * L[j]; });       // (x-row j, y-col i)
+    AT_mul<DENSE, true>(S, M.Av, sq + n, M.part, [&](int j, double v) { rs[j] += v * L[j] * L[j]; }, plA);       // (x-row j, y-col i)
     A_mul<DENSE, true>(S, M.Av, sq, [&](int i, double v) { rs[n + i] += v * L[n + i] * L[n + i]; });          // (y-row i, x-col j)
     __syncthreads();
     for (int k = t; k < N; k += T) sq[k] = L[k] * L[k];
     __syncthreads();
     A_mul<DENSE, true>(S, M.Av, sq, [&](int i, double v) { cs[n + i] += v * R[n + i] * R[n + i]; });          // (x-row j, y-col i)
-    AT_mul<DENSE, true>(S, M.Av, sq + n, M.part, [&](int j, double v) { cs[j] += v * R[j] * R[j]; });         // (y-row i, x-col j)
+    AT_mul<DENSE, true>(S, M.Av, sq + n, M.part, [&](int j, double v) { cs[j] += v * R[j] * R[j]; }, plA);         // (y-row i, x-col j)
     if (Pg) {  // P.^2 block (x rows, x cols): rs_i += L_i^2 (P.^2 R_x^2)_i ; cs_j += R_j^2 (P.^2 L_x^2)_j
-      P_mul<true>(S, Pg, sq, M.part, [&](int j, double v) { cs[j] += v * R[j] * R[j]; });
+      P_mul<true>(S, Pg, sq, M.part, [&](int j, double v) { cs[j] += v * R[j] * R[j]; }, plN);
       for (int k = t; k < n; k += T) sq[k] = R[k] * R[k];
       __syncthreads();
-      P_mul<true>(S, Pg, sq, M.part, [&](int j, double v) { rs[j] += v * L[j] * L[j]; });
+      P_mul<true>(S, Pg, sq, M.part, [&](int j, double v) { rs[j] += v * L[j] * L[j]; }, plN);
     }
     __syncthreads();
     for (int k = t; k < N; k += T) {
@@ -215,7 +216,7 @@ __device__ void equilibrate(const BwdArgs &a, const BwdSmem &M, const double *Pg
 }
 
 template <bool DENSE>
-__global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
+  const ColPlan plA = make_colplan(m, n), plN = make_colplan(n, n);
 
   for (;;) {
     if (t == 0) M.ibuf[0] = atomicAdd(a.counter, 1);
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
     // ---- 2Px + c, x'Px ----
     double xPx = 0;
     if (Pg) {
-      P_mul(S, Pg, M.x, M.part, [&](int j, double v) { M.px2c[j] += v; });
+      P_mul(S, Pg, M.x, M.part, [&](int j, double v) { M.px2c[j] += v; }, plN);
       double d1[1] = {0};
       for (int j = t; j < n; j += T) d1[0] = fma(M.x[j], M.px2c[j], d1[0]);
       block_reduce<1, false>(d1, M.red);
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
       const int iter_lim = st.lsqr_iter_lim < 0 ? 2 * N : st.lsqr_iter_lim;
       const bool pc = st.lsqr_precond != 0;
       if (pc) {
-        equilibrate<DENSE>(a, M, Pg, xPx, st.ruiz_passes > 0 ? st.ruiz_passes : 10);
+        equilibrate<DENSE>(a, M, Pg, xPx, st.ruiz_passes > 0 ? st.ruiz_passes : 10, plA, plN);
         for (int k = t; k < N; k += T) { M.U[k] *= M.Lsc[k]; M.X[k] = 0.0; }
         __syncthreads();
       }
@@ -333,13 +335,13 @@ __global__ void __launch_bounds__(512) bwd_kernel(const __grid_constant__ BwdArg
         const double *src = in;
         if (pc) { for (int k = t; k < N; k += T) M.tin[k] = M.Rsc[k] * in[k]; src = M.tin; }
         __syncthreads();
-        op_MT<DENSE>(a, M, Pg, xPx, src, out, pc ? M.Lsc : nullptr);
+        op_MT<DENSE>(a, M, Pg, xPx, src, out, pc ? M.Lsc : nullptr, plA, plN);
       };
       auto acc_BT = [&](const double *in, double *out) {  // out += B' in
         const double *src = in;
         if (pc) { for (int k = t; k < N; k += T) M.tin[k] = M.Lsc[k] * in[k]; src = M.tin; }
         __syncthreads();
-        op_M<DENSE>(a, M, Pg, xPx, src, out, pc ? M.Rsc : nullptr);
+        op_M<DENSE>(a, M, Pg, xPx, src, out, pc ? M.Rsc : nullptr, plA, plN);
       };
       double r1[1] = {0};
       for (int k = t; k < N; k += T) r1[0] = fma(M.U[k], M.U[k], r1[0]);

@@ -129,69 +129,135 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], double *red) {
 }
 
 // ----------------------------------------------------------------------------- matrix layouts
-// Row-oriented storage with a per-row offset/length: dense row-major, packed lower triangle, CSR.
+// Row-oriented storage: element (i, c) lives at base(i) + c for beg(i) <= c < end(i).
+// step(i) = base(i+1) - base(i); column j is present in rows [row_lo(j), row_hi(j, nrows)).
 struct DenseLayout {
+  static constexpr bool kFullRows = true;
   int ncols;
   __device__ __forceinline__ int base(int i) const { return i * ncols; }
+  __device__ __forceinline__ int step(int) const { return ncols; }
   __device__ __forceinline__ int beg(int) const { return 0; }
   __device__ __forceinline__ int end(int) const { return ncols; }
+  __device__ __forceinline__ int row_lo(int) const { return 0; }
+  __device__ __forceinline__ int row_hi(int, int nrows) const { return nrows; }
 };
 struct PackedLowerLayout {  // row i holds columns 0..i at i(i+1)/2
+  static constexpr bool kFullRows = false;
   __device__ __forceinline__ int base(int i) const { return (i * (i + 1)) >> 1; }
+  __device__ __forceinline__ int step(int i) const { return i + 1; }
   __device__ __forceinline__ int beg(int) const { return 0; }
   __device__ __forceinline__ int end(int i) const { return i + 1; }
+  __device__ __forceinline__ int row_lo(int j) const { return j; }
+  __device__ __forceinline__ int row_hi(int, int nrows) const { return nrows; }
 };
 // Upper triangle stored row by row (row i holds columns i..n-1): the CSR order of a dense
 // upper-triangular pattern.  STRICT drops the diagonal (used for the transposed half of a
 // symmetric product so the diagonal is not counted twice).
 template <bool STRICT>
 struct PackedUpperLayout {
+  static constexpr bool kFullRows = false;
   int n;
   __device__ __forceinline__ int base(int i) const { return i * n - ((i * (i + 1)) >> 1); }
+  __device__ __forceinline__ int step(int i) const { return n - i - 1; }
   __device__ __forceinline__ int beg(int i) const { return STRICT ? i + 1 : i; }
   __device__ __forceinline__ int end(int) const { return n; }
+  __device__ __forceinline__ int row_lo(int) const { return 0; }
+  __device__ __forceinline__ int row_hi(int j, int nrows) const { return min(nrows, STRICT ? j : j + 1); }
 };
 
-// out_i = sum_j M[i][j] * x[j] for "dense-like" layouts: one warp per row, lanes across columns
-// (conflict-free for any row stride), four rows reduced together with a halving butterfly
-// (6 double shuffles per 4 rows instead of 20).  ep(i, value) is called by exactly one lane.
+// 4 row sums -> one value per 8-lane group with a halving butterfly (6 double shuffles instead
+// of 20).  Returns the total of row ((lane>>4)&1)*2 + ((lane>>3)&1) in every lane of that group.
+__device__ __forceinline__ double butterfly4(double a0, double a1, double a2, double a3, int lane) {
+  const bool hi = lane & 16;
+  double k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
+  const double s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const bool hi2 = lane & 8;
+  double k = hi2 ? k1 : k0;
+  const double s = hi2 ? k0 : k1;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
+}
+
+// out_i = sum_j M[i][j] * x[j]: one warp per row, lanes across columns (conflict-free for any
+// row stride), x held in registers (ncols <= 128), four rows reduced together.
+// ep(i, value) is called by exactly one lane.
 template <bool SQ = false, class Layout, class Epi>
 __device__ __forceinline__ void matvec_rows(const double *__restrict__ M, Layout lay, int nrows, int ncols,
                                             const double *__restrict__ x, Epi ep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i0 = warp * 4; i0 < nrows; i0 += nw * 4) {
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    const int i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3;
-    const int o0 = lay.base(i0), b0 = lay.beg(i0), l0 = lay.end(i0);
-    const int o1 = i1 < nrows ? lay.base(i1) : 0, b1 = i1 < nrows ? lay.beg(i1) : 0, l1 = i1 < nrows ? lay.end(i1) : 0;
-    const int o2 = i2 < nrows ? lay.base(i2) : 0, b2 = i2 < nrows ? lay.beg(i2) : 0, l2 = i2 < nrows ? lay.end(i2) : 0;
-    const int o3 = i3 < nrows ? lay.base(i3) : 0, b3 = i3 < nrows ? lay.beg(i3) : 0, l3 = i3 < nrows ? lay.end(i3) : 0;
-    const int lmax = max(max(l0, l1), max(l2, l3));
-    const int bmin = min(b0, lmax) & ~31;  // rows are visited in increasing order: row i0 starts first
-    for (int c = bmin + lane; c < lmax; c += 32) {
-      const double xv = x[c];
-      if (c >= b0 && c < l0) { const double q = M[o0 + c]; a0 = fma(SQ ? q * q : q, xv, a0); }
-      if (c >= b1 && c < l1) { const double q = M[o1 + c]; a1 = fma(SQ ? q * q : q, xv, a1); }
-      if (c >= b2 && c < l2) { const double q = M[o2 + c]; a2 = fma(SQ ? q * q : q, xv, a2); }
-      if (c >= b3 && c < l3) { const double q = M[o3 + c]; a3 = fma(SQ ? q * q : q, xv, a3); }
+  if (ncols <= 128) {
+    double xr[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; xr[k] = c < ncols ? x[c] : 0.0; }
+    for (int i0 = warp * 4; i0 < nrows; i0 += nw * 4) {
+      int o[4], b[4], e[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int i = i0 + r; const bool ok = i < nrows;
+        o[r] = ok ? lay.base(i) : 0; b[r] = ok ? lay.beg(i) : 0; e[r] = ok ? lay.end(i) : 0;
+      }
+      double a[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = lane + 32 * k;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (c >= b[r] && c < e[r]) { const double q = M[o[r] + c]; a[r] = fma(SQ ? q * q : q, xr[k], a[r]); }
+      }
+      const double k = butterfly4(a[0], a[1], a[2], a[3], lane);
+      if ((lane & 7) == 0) {
+        const int r = i0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        if (r < nrows) ep(r, k);
+      }
     }
-    // 4 -> 2
-    const bool hi = lane & 16;
-    double k0 = hi ? a2 : a0, k1 = hi ? a3 : a1, s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
-    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-    // 2 -> 1
-    const bool hi2 = lane & 8;
-    double k = hi2 ? k1 : k0, s = hi2 ? k0 : k1;
-    k += __shfl_xor_sync(0xffffffffu, s, 8);
-    k += __shfl_xor_sync(0xffffffffu, k, 4);
-    k += __shfl_xor_sync(0xffffffffu, k, 2);
-    k += __shfl_xor_sync(0xffffffffu, k, 1);
-    if ((lane & 7) == 0) {
-      const int r = i0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
-      if (r < nrows) ep(r, k);
+  } else {
+    for (int i0 = warp * 4; i0 < nrows; i0 += nw * 4) {
+      int o[4], b[4], e[4];
+      int lmax = 0, bmin = 1 << 30;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int i = i0 + r; const bool ok = i < nrows;
+        o[r] = ok ? lay.base(i) : 0; b[r] = ok ? lay.beg(i) : 0; e[r] = ok ? lay.end(i) : 0;
+        lmax = max(lmax, e[r]); if (ok) bmin = min(bmin, b[r]);
+      }
+      double a[4] = {0, 0, 0, 0};
+      for (int c = (min(bmin, lmax) & ~31) + lane; c < lmax; c += 32) {
+        const double xv = x[c];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if (c >= b[r] && c < e[r]) { const double q = M[o[r] + c]; a[r] = fma(SQ ? q * q : q, xv, a[r]); }
+      }
+      const double k = butterfly4(a[0], a[1], a[2], a[3], lane);
+      if ((lane & 7) == 0) {
+        const int r = i0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        if (r < nrows) ep(r, k);
+      }
     }
   }
+}
+
+// Work split of a transposed product over the block, computed once per kernel (integer
+// divisions are expensive): thread -> (column j, row chunk [lo, hi)).
+struct ColPlan {
+  int j, lo, hi, CH;
+  bool active, fits;
+};
+__device__ __forceinline__ ColPlan make_colplan(int nrows, int ncols) {
+  ColPlan p;
+  const int T = blockDim.x, t = threadIdx.x;
+  p.fits = ncols <= T;
+  p.CH = p.fits ? T / ncols : 1;
+  p.j = p.fits ? t % ncols : t;
+  const int c = p.fits ? t / ncols : 0;
+  p.active = p.fits && c < p.CH;
+  p.lo = (c * nrows) / p.CH;
+  p.hi = ((c + 1) * nrows) / p.CH;
+  return p;
 }
 
 // out_j = sum_i M[i][j] * y[i] (transposed product).  Thread (j, chunk): lanes across columns
@@ -199,34 +265,49 @@ __device__ __forceinline__ void matvec_rows(const double *__restrict__ M, Layout
 // (needs blockDim.x doubles).  Contains two __syncthreads(); ep(j, value) called once per column.
 template <bool SQ = false, class Layout, class Epi>
 __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout lay, int nrows, int ncols,
-                                            const double *__restrict__ y, double *part, Epi ep) {
+                                            const double *__restrict__ y, double *part, Epi ep, const ColPlan &pl) {
   const int T = blockDim.x, t = threadIdx.x;
-  if (ncols <= T) {
-    const int CH = T / ncols;
-    const int j = t % ncols, c = t / ncols;
-    if (c < CH) {
-      const int lo = (int)(((long long)c * nrows) / CH), hi = (int)(((long long)(c + 1) * nrows) / CH);
+  if (pl.fits) {
+    if (pl.active) {
+      const int j = pl.j;
+      int i = max(pl.lo, lay.row_lo(j));
+      const int hi = min(pl.hi, lay.row_hi(j, nrows));
       double a0 = 0, a1 = 0;
-      int i = lo;
-      for (; i + 1 < hi; i += 2) {
-        if (j >= lay.beg(i) && j < lay.end(i)) { const double q = M[lay.base(i) + j]; a0 = fma(SQ ? q * q : q, y[i], a0); }
-        if (j >= lay.beg(i + 1) && j < lay.end(i + 1)) { const double q = M[lay.base(i + 1) + j]; a1 = fma(SQ ? q * q : q, y[i + 1], a1); }
+      if (i < hi) {
+        const double *p = M + lay.base(i) + j;
+        if (Layout::kFullRows) {
+          const int st = lay.step(0);
+          for (; i + 3 < hi; i += 4) {
+            const double q0 = p[0], q1 = p[st], q2 = p[2 * st], q3 = p[3 * st];
+            a0 = fma(SQ ? q0 * q0 : q0, y[i], a0); a1 = fma(SQ ? q1 * q1 : q1, y[i + 1], a1);
+            a0 = fma(SQ ? q2 * q2 : q2, y[i + 2], a0); a1 = fma(SQ ? q3 * q3 : q3, y[i + 3], a1);
+            p += 4 * st;
+          }
+          for (; i < hi; i++) { const double q = p[0]; a0 = fma(SQ ? q * q : q, y[i], a0); p += st; }
+        } else {
+          for (; i + 1 < hi; i += 2) {
+            const int s0 = lay.step(i);
+            const double q0 = p[0], q1 = p[s0];
+            a0 = fma(SQ ? q0 * q0 : q0, y[i], a0); a1 = fma(SQ ? q1 * q1 : q1, y[i + 1], a1);
+            p += s0 + lay.step(i + 1);
+          }
+          if (i < hi) { const double q = p[0]; a0 = fma(SQ ? q * q : q, y[i], a0); }
+        }
       }
-      if (i < hi && j >= lay.beg(i) && j < lay.end(i)) { const double q = M[lay.base(i) + j]; a0 = fma(SQ ? q * q : q, y[i], a0); }
       part[t] = a0 + a1;
     }
     __syncthreads();
     if (t < ncols) {
       double a = 0;
-      for (int cc = 0; cc < CH; cc++) a += part[cc * ncols + t];
+      for (int cc = 0; cc < pl.CH; cc++) a += part[cc * ncols + t];
       ep(t, a);
     }
     __syncthreads();
   } else {
     for (int j = t; j < ncols; j += T) {
       double a = 0;
-      for (int i = 0; i < nrows; i++)
-        if (j >= lay.beg(i) && j < lay.end(i)) { const double q = M[lay.base(i) + j]; a = fma(SQ ? q * q : q, y[i], a); }
+      const int hi = lay.row_hi(j, nrows);
+      for (int i = lay.row_lo(j); i < hi; i++) { const double q = M[lay.base(i) + j]; a = fma(SQ ? q * q : q, y[i], a); }
       ep(j, a);
     }
     __syncthreads();
@@ -280,8 +361,8 @@ __device__ __forceinline__ void A_mul(const DevStruct &S, const double *Av, cons
 }
 // NOTE: ends with a __syncthreads() in the dense case; callers sync themselves in the CSR case.
 template <bool DENSE, bool SQ = false, class Epi>
-__device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, const double *y, double *part, Epi ep) {
-  if (DENSE) matvec_cols<SQ>(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep);
+__device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, const double *y, double *part, Epi ep, const ColPlan &plA) {
+  if (DENSE) matvec_cols<SQ>(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep, plA);
   else { csr_cols<SQ>(Av, S.At_colptr, S.At_rowidx, S.At_perm, S.n, y, ep); __syncthreads(); }
 }
 
@@ -289,12 +370,12 @@ __device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, con
 // memory): row pass over the upper triangle, then the transposed pass over the strict upper part.
 // No atomics: every out[i] has a single writer per pass.  Ends with __syncthreads().
 template <bool SQ = false, class Epi>
-__device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, const double *x, double *part, Epi ep) {
+__device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, const double *x, double *part, Epi ep, const ColPlan &plN) {
   const int n = S.n;
   if (S.p_dense) {
     matvec_rows<SQ>(Pv, PackedUpperLayout<false>{n}, n, n, x, ep);
     __syncthreads();
-    matvec_cols<SQ>(Pv, PackedUpperLayout<true>{n}, n, n, x, part, ep);
+    matvec_cols<SQ>(Pv, PackedUpperLayout<true>{n}, n, n, x, part, ep, plN);
   } else {
     csr_rows<SQ>(Pv, S.P_indptr, S.P_indices, n, x, ep);
     __syncthreads();

@@ -49,7 +49,8 @@ __device__ __forceinline__ double inv_ry(const DevStruct &S, int i, double scale
 // K = rho_x I + P^ + A^' R_y^{-1} A^ (packed lower) -> Cholesky -> in-place inverse Linv;
 // then g = (R_z + M)^{-1} h and g'Rg.  Returns false if the factorisation broke down.
 template <bool DENSE>
-__device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, double &gRg) {
+__device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, double &gRg,
+                             const ColPlan &plA, const ColPlan &plN) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const int npk = n * (n + 1) / 2;
@@ -129,11 +130,11 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   // ---- g = (R_z + M)^{-1} h, h = (c^, b^) ----
   for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
   __syncthreads();
-  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; });
+  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; }, plA);
   if (DENSE) { /* AT_mul ended with a sync */ }
   matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
   __syncthreads();
-  matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.g[j] = v; });
+  matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.g[j] = v; }, plN);
   A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); });
   __syncthreads();
   double acc[1] = {0};
@@ -147,7 +148,7 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
 }
 
 template <bool DENSE>
-__global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArg
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
+  const ColPlan plA = make_colplan(m, n), plN = make_colplan(n, n);
   const double rho_x = st.rho_x, alpha = st.alpha, dtau = BC_TAU_FACTOR;
 
   for (;;) {
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArg
 
     double scale = st.scale, gRg = 0;
     int status = BCONE_INACCURATE, it = 0;
-    bool okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg);
+    bool okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg, plA, plN);
     for (int k = t; k < N; k += T) { M.w[k] = (k == N - 1) ? 1.0 : 0.0; M.u[k] = 0; M.ut[k] = 0; }
     __syncthreads();
     double sum_log = 0, rp = nan(""), rd = nan(""), gap = nan("");
@@ -282,10 +284,10 @@ __global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArg
 
     for (it = 1; okf && it <= st.max_iters; it++) {
       // ---- affine step ----
-      AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; });
+      AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; }, plA);
       matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
       __syncthreads();
-      matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; });
+      matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; }, plN);
       A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) { M.ut[n + i] = M.w[n + i] + v * inv_ry(S, i, scale); });
       __syncthreads();
       double d4[4] = {0, 0, 0, 0};  // mu'g, p'Rg, p'Rp, p'mu
@@ -320,11 +322,11 @@ __global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArg
         // ---- termination quantities on the un-normalised data ----
         const double tau = M.u[N - 1];
         A_mul<DENSE>(S, M.Av, M.u, [&](int i, double v) { M.tm[i] = v; });
-        AT_mul<DENSE>(S, M.Av, M.u + n, M.part, [&](int j, double v) { M.tn[j] = v; });
+        AT_mul<DENSE>(S, M.Av, M.u + n, M.part, [&](int j, double v) { M.tn[j] = v; }, plA);
         for (int j = t; j < n; j += T) { M.tn2[j] = 0.0; M.tn3[j] = M.En[j] * M.u[j]; }
         __syncthreads();
         if (Pg) {  // P^ u_x = E (P (E u_x)); no atomics
-          P_mul(S, Pg, M.tn3, M.part, [&](int j, double v) { M.tn2[j] += v; });
+          P_mul(S, Pg, M.tn3, M.part, [&](int j, double v) { M.tn2[j] += v; }, plN);
           for (int j = t; j < n; j += T) M.tn2[j] *= M.En[j];
           __syncthreads();
         }
@@ -382,7 +384,7 @@ __global__ void __launch_bounds__(512) fwd_kernel(const __grid_constant__ FwdArg
               }
               scale = ns;
               __syncthreads();
-              okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg);
+              okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg, plA, plN);
               if (!okf) { status = BCONE_FAILED; break; }
               sum_log = 0; n_log = 0; last_up = it;
             }
