@@ -186,13 +186,13 @@ def run_ours(a):
         return sol, its, e
 
     def step_e2e():
-        A = hA.clone().requires_grad_(True) if False else hA.detach().requires_grad_(True)
+        A = hA.detach().requires_grad_(True)
         q = hq.detach().requires_grad_(True)
         P = hP.detach().requires_grad_(True)
         primal, dual, _, _ = _CvxpyLayer.apply(P, q, A, cl_ctx, {}, True, None)
         loss = (primal * dxh).sum() + (dual * dyh).sum()
         loss.backward()
-        return float(loss), A.grad, q.grad, P.grad
+        return float(loss.detach()), A.grad, q.grad, P.grad
 
     def sync():
         if world > 1:

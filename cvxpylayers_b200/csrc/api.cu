@@ -20,8 +20,8 @@ cudaError_t bc_bwd_configure(int dense, size_t smem);
 cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
 size_t bc_bwdf_smem_bytes(int n, int m, int nnzA, int nnzP, int threads);
-cudaError_t bc_bwdf_configure(size_t smem);
-cudaError_t bc_bwdf_occupancy(int threads, size_t smem, int *ctas);
+cudaError_t bc_bwdf_configure(int n, size_t smem);
+cudaError_t bc_bwdf_occupancy(int n, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwdf_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
 cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
@@ -172,7 +172,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     return false;
   };
   // fast backward path: same launch geometry fields, different kernel
-  if (S.dense && S.ncones == 0 && n <= 128 && (S.nnzP == 0 || S.p_dense)) {
+  if (S.dense && S.ncones == 0 && n <= 128 && (n % 2) == 0 && (S.nnzP == 0 || S.p_dense)) {
     for (int tt = threads; tt >= 64; tt /= 2) {
       size_t sm = bc_bwdf_smem_bytes(n, m, d->nnzA, S.nnzP, tt);
       if (sm <= smem_cap) { h->fast_bwd = 1; h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = S.nnzP > 0; break; }
@@ -187,13 +187,13 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   }
   cudaError_t e;
   if ((e = bc_fwd_configure(S.dense, h->fwd_smem)) != cudaSuccess ||
-      (e = (h->fast_bwd ? bc_bwdf_configure(h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
+      (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
   bc_fwd_occupancy(S.dense, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
-  if (h->fast_bwd) bc_bwdf_occupancy(h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
+  if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;

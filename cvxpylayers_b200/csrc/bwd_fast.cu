@@ -16,7 +16,7 @@
 #include "common.cuh"
 
 struct FastSmem {
-  double *Av, *Pv, *x, *c, *px2c, *piy, *b, *U, *V, *W, *X, *Lsc, *Rsc, *prow, *part, *red;
+  double *Av, *Pv, *x, *c, *px2c, *piy, *b, *U, *V, *W, *X, *Lsc, *Rsc, *ein, *prow, *part, *red;
   int *rows;
   uint64_t *bar;
   int *ibuf;
@@ -25,8 +25,8 @@ struct FastSmem {
 __host__ __device__ inline size_t bwdf_smem_doubles(int n, int m, int nnzA, int nnzP, int threads) {
   const size_t N = (size_t)n + m + 1;
   const size_t part = (size_t)8 * n > (size_t)threads ? (size_t)8 * n : (size_t)threads;
-  return 4 + (((size_t)nnzA + 1) & ~(size_t)1) + (((size_t)nnzP + 1) & ~(size_t)1) + 3 * (size_t)n + 2 * (size_t)m + 6 * N + n + part +
-         4 * 32 + ((size_t)m + n + 2) / 2;
+  return 4 + (((size_t)nnzA + 1) & ~(size_t)1) + (((size_t)nnzP + 1) & ~(size_t)1) + 3 * (size_t)n + 2 * (size_t)m + 6 * N + ((N + 1) & ~(size_t)1) + n + part +
+         3 * 32 + ((size_t)m + n + 2) / 2 + 4;
 }
 
 __device__ __forceinline__ void carve_f(FastSmem &M, double *base, int n, int m, int nnzA, int nnzP, int threads) {
@@ -36,25 +36,33 @@ __device__ __forceinline__ void carve_f(FastSmem &M, double *base, int n, int m,
   M.ibuf = (int *)q; q += 2;
   M.Av = q; q += (nnzA + 1) & ~1;
   M.Pv = q; q += (nnzP + 1) & ~1;
+  M.ein = q; q += (N + 1) & ~1;                     // 16-byte aligned (double2 loads)
+  M.part = q; q += (8 * n > threads ? 8 * n : threads);
   M.x = q; q += n; M.c = q; q += n; M.px2c = q; q += n;
   M.piy = q; q += m; M.b = q; q += m;
   M.U = q; q += N; M.V = q; q += N; M.W = q; q += N; M.X = q; q += N; M.Lsc = q; q += N; M.Rsc = q; q += N;
   M.prow = q; q += n;
-  M.part = q; q += (8 * n > threads ? 8 * n : threads);
-  M.red = q; q += 4 * 32;
+  M.red = q; q += 3 * 32;
   M.rows = (int *)q;
 }
 
-// One fused pass over the row list.  xr[] = effective x-part of the input (registers);
-// ymul(i) = multiplier of A row i in the column accumulation; P row i uses xin(i).
+// One fused pass over the row list.  ex = x-part of the effective input in shared memory
+// (16-byte aligned); lanes own column PAIRS (2*lane + 64k, +1): A rows are read with 128-bit
+// loads, P rows (packed upper triangle, row starts not 16-byte aligned) with 64-bit loads.
+// ymul(i) = multiplier of A row i in the column accumulation; P row i uses ex[i].
 // repi(row_code, value) is called by one lane per listed row (row_code < m: A row, else P row m+i);
 // cepi(j, column_total) once per column by thread j (P's row part is added by the caller via prow).
-template <bool SQ, class XIn, class YMul, class RowEpi, class ColEpi>
-__device__ __forceinline__ void fused_pass(const FastSmem &M, int n, int m, int nlist, XIn xin, YMul ymul, RowEpi repi, ColEpi cepi) {
+// n must be even and <= 64*NCH.
+template <bool SQ, int NCH, class YMul, class RowEpi, class ColEpi>
+__device__ __forceinline__ void fused_pass(const FastSmem &M, int n, int m, int nlist, const double *ex, YMul ymul, RowEpi repi, ColEpi cepi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, t = threadIdx.x;
-  double xr[4], acc[4] = {0, 0, 0, 0};
+  double2 xr[NCH], acc[NCH];
+  const bool tail_ok = 2 * lane + 64 * (NCH - 1) < n;   // the last chunk may be partial
 #pragma unroll
-  for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; xr[k] = c < n ? xin(c) : 0.0; }
+  for (int k = 0; k < NCH; k++) {
+    acc[k] = make_double2(0.0, 0.0);
+    xr[k] = (k < NCH - 1 || tail_ok) ? *reinterpret_cast<const double2 *>(ex + 2 * lane + 64 * k) : make_double2(0.0, 0.0);
+  }
   const int ngroups = (nlist + 3) >> 2;
   for (int g = warp; g < ngroups; g += nw) {
     double a[4] = {0, 0, 0, 0};
@@ -65,20 +73,33 @@ __device__ __forceinline__ void fused_pass(const FastSmem &M, int n, int m, int 
         const int row = M.rows[idx];
         if (row < m) {
           const double mul = ymul(row);
-          const double *p = M.Av + row * n;
+          const double2 *p2 = reinterpret_cast<const double2 *>(M.Av + row * n) + lane;
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int c = lane + 32 * k;
-            if (c < n) { double q = p[c]; if (SQ) q *= q; a[r] = fma(q, xr[k], a[r]); acc[k] = fma(q, mul, acc[k]); }
+          for (int k = 0; k < NCH; k++) {
+            if (k < NCH - 1 || tail_ok) {
+              double2 q = p2[32 * k];
+              if (SQ) { q.x *= q.x; q.y *= q.y; }
+              a[r] = fma(q.x, xr[k].x, a[r]); a[r] = fma(q.y, xr[k].y, a[r]);
+              acc[k].x = fma(q.x, mul, acc[k].x); acc[k].y = fma(q.y, mul, acc[k].y);
+            }
           }
         } else {
           const int i = row - m;
-          const double mul = xin(i);
+          const double mul = ex[i];
           const double *p = M.Pv + (i * n - ((i * (i + 1)) >> 1));
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int c = lane + 32 * k;
-            if (c >= i && c < n) { double q = p[c]; if (SQ) q *= q; a[r] = fma(q, xr[k], a[r]); if (c > i) acc[k] = fma(q, mul, acc[k]); }
+          for (int k = 0; k < NCH; k++) {
+            const int c0 = 2 * lane + 64 * k, c1 = c0 + 1;
+            if (c1 >= i && (k < NCH - 1 || tail_ok)) {
+              double q1 = p[c1]; if (SQ) q1 *= q1;
+              a[r] = fma(q1, xr[k].y, a[r]);
+              if (c1 > i) acc[k].y = fma(q1, mul, acc[k].y);
+              if (c0 >= i) {
+                double q0 = p[c0]; if (SQ) q0 *= q0;
+                a[r] = fma(q0, xr[k].x, a[r]);
+                if (c0 > i) acc[k].x = fma(q0, mul, acc[k].x);
+              }
+            }
           }
         }
       }
@@ -93,12 +114,17 @@ __device__ __forceinline__ void fused_pass(const FastSmem &M, int n, int m, int 
   const int slot = warp & 7;
   if (warp < 8) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; if (c < n) M.part[slot * n + c] = acc[k]; }
+    for (int k = 0; k < NCH; k++)
+      if (k < NCH - 1 || tail_ok) *reinterpret_cast<double2 *>(M.part + slot * n + 2 * lane + 64 * k) = acc[k];
   }
   __syncthreads();
   if (warp >= 8) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; if (c < n) M.part[slot * n + c] += acc[k]; }
+    for (int k = 0; k < NCH; k++)
+      if (k < NCH - 1 || tail_ok) {
+        double2 *q = reinterpret_cast<double2 *>(M.part + slot * n + 2 * lane + 64 * k);
+        double2 v = *q; v.x += acc[k].x; v.y += acc[k].y; *q = v;
+      }
   }
   __syncthreads();
   if (t < n) {
@@ -112,29 +138,30 @@ __device__ __forceinline__ void fused_pass(const FastSmem &M, int n, int m, int 
 // out <- osc o (Op e) + coef * out, with e = in o isc * iscal (the effective input);
 // TRANS: Op = M' (the LSQR system matrix B), else Op = M.  Returns ||out||^2; wn2 is block-summed in place.
 // D = diag(d): d_i = 1 on zero rows, [pi_y,i > 0] on nonneg rows.
-template <bool TRANS>
+template <bool TRANS, int NCH>
 __device__ __forceinline__ double fast_op(const FastSmem &M, const DevStruct &S, int nlist, double xPx, const double *in,
                                           const double *isc, double iscal, double *out, const double *osc, double coef,
                                           double &wn2) {
-  const int n = S.n, m = S.m, N = n + m + 1, t = threadIdx.x;
-  auto ex = [&](int c) { return in[c] * (isc ? isc[c] : 1.0) * iscal; };
-  const double et = in[N - 1] * (isc ? isc[N - 1] : 1.0) * iscal;
+  const int n = S.n, m = S.m, N = n + m + 1, t = threadIdx.x, T = blockDim.x;
+  for (int k = t; k < N; k += T) M.ein[k] = in[k] * (isc ? isc[k] : 1.0) * iscal;   // effective input
+  const double out_t = out[N - 1];
+  __syncthreads();
+  const double *e = M.ein;
+  const double et = e[N - 1];
   double dot = 0, nrm = 0;
   auto ymul = [&](int i) {
-    const double ey = in[n + i] * (isc ? isc[n + i] : 1.0) * iscal;
-    if (TRANS) return -ey;
-    const double d = (i < S.z || M.piy[i] > 0) ? 1.0 : 0.0;
-    return d * ey;
+    if (TRANS) return -e[n + i];
+    return (i < S.z || M.piy[i] > 0) ? e[n + i] : 0.0;
   };
   auto repi = [&](int row, double v) {
     if (row < m) {
       const int i = row, k = n + i;
-      const double ey = in[k] * (isc ? isc[k] : 1.0) * iscal;
-      const double d = (i < S.z || M.piy[i] > 0) ? 1.0 : 0.0;
+      const double ey = e[k], bi = M.b[i];
+      const bool d = (i < S.z || M.piy[i] > 0);
       double val;
-      if (TRANS) { val = d * (v - M.b[i] * et - ey) + ey; dot = fma(M.b[i], ey, dot); }
-      else { val = -v + M.b[i] * et - d * ey + ey; dot = fma(-M.b[i], d * ey, dot); }
-      const double o = (osc ? osc[k] : 1.0) * val + coef * out[k];
+      if (TRANS) { val = d ? v - bi * et : ey; dot = fma(bi, ey, dot); }
+      else { const double dey = d ? ey : 0.0; val = -v + bi * et - dey + ey; dot = fma(-bi, dey, dot); }
+      const double o = fma(osc ? osc[k] : 1.0, val, coef * out[k]);
       out[k] = o; nrm = fma(o, o, nrm);
     } else {
       M.prow[row - m] = v;
@@ -142,23 +169,22 @@ __device__ __forceinline__ double fast_op(const FastSmem &M, const DevStruct &S,
   };
   const bool hasP = S.nnzP > 0;
   auto cepi = [&](int j, double s) {
-    const double e = ex(j);
     double val = s + (hasP ? M.prow[j] : 0.0);
-    if (TRANS) { val -= M.px2c[j] * et; dot = fma(M.c[j], e, dot); }
-    else { val += M.c[j] * et; dot = fma(-M.px2c[j], e, dot); }
-    const double o = (osc ? osc[j] : 1.0) * val + coef * out[j];
+    if (TRANS) { val -= M.px2c[j] * et; dot = fma(M.c[j], e[j], dot); }
+    else { val += M.c[j] * et; dot = fma(-M.px2c[j], e[j], dot); }
+    const double o = fma(osc ? osc[j] : 1.0, val, coef * out[j]);
     out[j] = o; nrm = fma(o, o, nrm);
   };
-  fused_pass<false>(M, n, m, nlist, ex, ymul, repi, cepi);
+  fused_pass<false, NCH>(M, n, m, nlist, e, ymul, repi, cepi);
   double r3[3] = {dot, nrm, wn2};
   block_reduce<3, false>(r3, M.red);
-  const double ot = (osc ? osc[N - 1] : 1.0) * (r3[0] + xPx * et) + coef * out[N - 1];
-  __syncthreads();  // everyone has read out[N-1]
+  const double ot = fma(osc ? osc[N - 1] : 1.0, r3[0] + xPx * et, coef * out_t);
   if (t == 0) out[N - 1] = ot;
   wn2 = r3[2];
   return r3[1] + ot * ot;
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   const DevStruct &S = a.S;
@@ -236,9 +262,11 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
       const int *saved = M.rows;
       M.rows = (int *)saved + nA;
       double acc1 = 0;
-      fused_pass<false>(M, n, m, n, [&](int c) { return M.x[c]; }, [&](int) { return 0.0; },
-                        [&](int row, double v) { M.prow[row - m] = v; },
-                        [&](int j, double s) { const double px = s + M.prow[j]; M.px2c[j] = 2.0 * px + M.c[j]; acc1 = fma(M.x[j], px, acc1); });
+      for (int j = t; j < n; j += T) M.ein[j] = M.x[j];
+      __syncthreads();
+      fused_pass<false, NCH>(M, n, m, n, M.ein, [&](int) { return 0.0; },
+                             [&](int row, double v) { M.prow[row - m] = v; },
+                             [&](int j, double s) { const double px = s + M.prow[j]; M.px2c[j] = 2.0 * px + M.c[j]; acc1 = fma(M.x[j], px, acc1); });
       M.rows = (int *)saved;
       double s1[1] = {acc1}; block_reduce<1, false>(s1, M.red);
       xPx = s1[0];
@@ -262,7 +290,9 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
           const double Lt = L[N - 1], Rt = R[N - 1];
           double s2[2] = {0, 0};  // rs[tau], cs[tau]
           // pass 1: in = R.^2  -> row sums of squares (x rows via columns, y rows via row results)
-          fused_pass<true>(M, n, m, nlist, [&](int c) { return R[c] * R[c]; }, [&](int i) { return R[n + i] * R[n + i]; },
+          for (int k = t; k < N; k += T) M.ein[k] = R[k] * R[k];
+          __syncthreads();
+          fused_pass<true, NCH>(M, n, m, nlist, M.ein, [&](int i) { return M.ein[n + i]; },
                            [&](int row, double v) {
                              if (row < m) { const int k = n + row; const double e1 = M.b[row] * M.b[row] * L[k] * L[k] * Rt * Rt;
                                rs[k] = v * L[k] * L[k] + e1; s2[1] += e1; }
@@ -271,7 +301,9 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
                              rs[j] = (s + (hasP ? M.prow[j] : 0.0)) * L[j] * L[j] + e1; s2[1] += e1; });
           __syncthreads();
           // pass 2: in = L.^2  -> column sums of squares
-          fused_pass<true>(M, n, m, nlist, [&](int c) { return L[c] * L[c]; }, [&](int i) { return L[n + i] * L[n + i]; },
+          for (int k = t; k < N; k += T) M.ein[k] = L[k] * L[k];
+          __syncthreads();
+          fused_pass<true, NCH>(M, n, m, nlist, M.ein, [&](int i) { return M.ein[n + i]; },
                            [&](int row, double v) {
                              if (row < m) { const int k = n + row; const double e2 = M.b[row] * M.b[row] * Lt * Lt * R[k] * R[k];
                                cs[k] = v * R[k] * R[k] + e2; s2[0] += e2; }
@@ -299,11 +331,11 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
       double r1[1] = {0};
       for (int k = t; k < N; k += T) { r1[0] = fma(M.U[k], M.U[k], r1[0]); M.V[k] = 0.0; }
       block_reduce<1, false>(r1, M.red);
-      const double bnorm = sqrt(r1[0]);
+      const double bnorm = sqrt(r1[0]), ibnorm = bnorm > 0 ? 1.0 / bnorm : 0.0;
       double beta = bnorm, alfa = 0, wn2 = 0;
       if (beta > 0) {
         __syncthreads();
-        alfa = sqrt(fast_op<false>(M, S, nlist, xPx, M.U, Ls, 1.0 / beta, M.V, Rs, 0.0, wn2));   // V = B' u
+        alfa = sqrt(fast_op<false, NCH>(M, S, nlist, xPx, M.U, Ls, 1.0 / beta, M.V, Rs, 0.0, wn2));   // V = B' u
         __syncthreads();
       }
       if (alfa > 0) for (int k = t; k < N; k += T) M.W[k] = M.V[k] / alfa;
@@ -314,24 +346,27 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
         while (itn < iter_lim) {
           itn++;
           // U = B v - alfa u
-          const double nb2 = fast_op<true>(M, S, nlist, xPx, M.V, Rs, 1.0 / alfa, M.U, Ls, -alfa / beta, wn2);
+          const double nb2 = fast_op<true, NCH>(M, S, nlist, xPx, M.V, Rs, 1.0 / alfa, M.U, Ls, -alfa / beta, wn2);
           const double wnorm2 = wn2;   // ||w_k||^2 of the current w
           beta = sqrt(nb2);
           __syncthreads();
           if (beta > 0) {
             anorm = sqrt(anorm * anorm + alfa * alfa + beta * beta);
             double dummy = 0;
-            const double na2 = fast_op<false>(M, S, nlist, xPx, M.U, Ls, 1.0 / beta, M.V, Rs, -beta / alfa, dummy);  // V = B' u - beta v
+            const double na2 = fast_op<false, NCH>(M, S, nlist, xPx, M.U, Ls, 1.0 / beta, M.V, Rs, -beta / alfa, dummy);  // V = B' u - beta v
             alfa = sqrt(na2);
             __syncthreads();
           }
-          const double rho = hypot(rhobar, beta), cs = rhobar / rho, sn = beta / rho;
+          // scalar recurrences of LSQR (same quantities as SciPy's; reciprocals shared, stopping
+          // ratios compared by cross-multiplication to keep fp64 divisions off the critical path)
+          const double rho = sqrt(fma(rhobar, rhobar, beta * beta)), irho = 1.0 / rho;
+          const double cs = rhobar * irho, sn = beta * irho;
           const double theta = sn * alfa;
           rhobar = -cs * alfa;
           const double phi = cs * phibar;
           phibar = sn * phibar;
           const double tau = sn * phi;
-          const double t1c = phi / rho, t2c = -theta / rho, ialfa = alfa > 0 ? 1.0 / alfa : 0.0;
+          const double t1c = phi * irho, t2c = -theta * irho, ialfa = alfa > 0 ? 1.0 / alfa : 0.0;
           wn2 = 0;
           for (int k = t; k < N; k += T) {
             const double wk = M.W[k];
@@ -339,21 +374,22 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
             const double wnew = fma(t2c, wk, M.V[k] * ialfa);
             M.W[k] = wnew; wn2 = fma(wnew, wnew, wn2);
           }
-          ddnorm += wnorm2 / (rho * rho);
+          ddnorm = fma(wnorm2, irho * irho, ddnorm);
           const double delta = sn2 * rho, gambar = -cs2 * rho, rhs = phi - delta * z, zbar = rhs / gambar;
-          const double xnorm = sqrt(xxnorm + zbar * zbar);
-          const double gamma = hypot(gambar, theta);
-          cs2 = gambar / gamma; sn2 = theta / gamma; z = rhs / gamma; xxnorm += z * z;
+          const double xnorm = sqrt(fma(zbar, zbar, xxnorm));
+          const double gamma = sqrt(fma(gambar, gambar, theta * theta)), igamma = 1.0 / gamma;
+          cs2 = gambar * igamma; sn2 = theta * igamma; z = rhs * igamma; xxnorm = fma(z, z, xxnorm);
           const double acond = anorm * sqrt(ddnorm), rnorm = phibar, arnorm = alfa * fabs(tau);
-          const double test1 = rnorm / bnorm, test2 = arnorm / (anorm * rnorm + eps), test3 = 1.0 / (acond + eps);
-          const double tt1 = test1 / (1.0 + anorm * xnorm / bnorm), rtol = btol + atol * anorm * xnorm / bnorm;
+          const double test1 = rnorm * ibnorm, den2 = fma(anorm, rnorm, eps), den3 = acond + eps;
+          const double axb = anorm * xnorm * ibnorm, rtol = fma(atol, axb, btol);
+          const double u = 1.1102230246251565e-16;   // 1 + t <= 1  <=>  t <= 2^-53
           int istop = 0;
           if (itn >= iter_lim) istop = 7;
-          if (1.0 + test3 <= 1.0) istop = 6;
-          if (1.0 + test2 <= 1.0) istop = 5;
-          if (1.0 + tt1 <= 1.0) istop = 4;
-          if (test3 <= ctol) istop = 3;
-          if (test2 <= atol) istop = 2;
+          if (1.0 <= u * den3) istop = 6;
+          if (arnorm <= u * den2) istop = 5;
+          if (test1 <= u * (1.0 + axb)) istop = 4;
+          if (1.0 <= ctol * den3) istop = 3;
+          if (arnorm <= atol * den2) istop = 2;
           if (test1 <= rtol) istop = 1;
           if (istop || !(alfa > 0) || !(beta > 0)) break;
         }
@@ -388,13 +424,16 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
 extern "C" size_t bc_bwdf_smem_bytes(int n, int m, int nnzA, int nnzP, int threads) {
   return bwdf_smem_doubles(n, m, nnzA, nnzP, threads) * sizeof(double);
 }
-extern "C" cudaError_t bc_bwdf_configure(size_t smem) {
-  return cudaFuncSetAttribute(bwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+extern "C" cudaError_t bc_bwdf_configure(int n, size_t smem) {
+  if (n <= 64) return cudaFuncSetAttribute(bwd_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(bwd_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-extern "C" cudaError_t bc_bwdf_occupancy(int threads, size_t smem, int *ctas_per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_fast_kernel, threads, smem);
+extern "C" cudaError_t bc_bwdf_occupancy(int n, int threads, size_t smem, int *ctas_per_sm) {
+  if (n <= 64) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_fast_kernel<1>, threads, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_fast_kernel<2>, threads, smem);
 }
 extern "C" cudaError_t bc_bwdf_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t stream) {
-  bwd_fast_kernel<<<grid, threads, smem, stream>>>(*a);
+  if (a->S.n <= 64) bwd_fast_kernel<1><<<grid, threads, smem, stream>>>(*a);
+  else bwd_fast_kernel<2><<<grid, threads, smem, stream>>>(*a);
   return cudaGetLastError();
 }

@@ -120,11 +120,12 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], double *red) {
     for (int k = 0; k < K; k++) red[k * 32 + warp] = v[k];
   }
   __syncthreads();
+  // second stage: every warp combines the per-warp partials with the same shuffle tree,
+  // so all threads end with identical bits
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    double a = MAX ? 0.0 : 0.0;
-    for (int w = 0; w < nw; w++) a = MAX ? fmax(a, red[k * 32 + w]) : a + red[k * 32 + w];
-    v[k] = a;
+    const double a = lane < nw ? red[k * 32 + lane] : 0.0;
+    v[k] = MAX ? warp_max(a) : warp_sum(a);
   }
 }
 

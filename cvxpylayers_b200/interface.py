@@ -126,9 +126,23 @@ class _Saved:
 
 
 def _to_dev(t: torch.Tensor | None, dev: torch.device) -> torch.Tensor | None:
+    """Host -> device (asynchronous DMA when the caller's tensor is pinned)."""
     if t is None:
         return None
-    return t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+    return t.detach().to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+
+
+def _to_host_like(t: torch.Tensor | None, device: torch.device, dtype: torch.dtype) -> torch.Tensor | None:
+    """Device -> the caller's device.  CPU results land in pinned memory (torch's caching host
+    allocator recycles the blocks) so the copy is one asynchronous DMA instead of a staged
+    pageable copy; the stream is synchronised before the tensor is handed out."""
+    if t is None:
+        return None
+    if device.type != "cpu":
+        return t.to(device=device, dtype=dtype)
+    out = torch.empty(t.shape, dtype=dtype, pin_memory=True)
+    out.copy_(t if t.dtype == dtype else t.to(dtype), non_blocking=True)
+    return out
 
 
 class _CvxpyLayer(torch.autograd.Function):
@@ -161,8 +175,11 @@ class _CvxpyLayer(torch.autograd.Function):
             raise SolverError(f"instance {i}: solver returned status {STATUS.get(int(status[i]), int(status[i]))}")
         if bool((status == 2).any()):
             warnings.warn("Solved/Inaccurate.", stacklevel=2)
-        primal = sol.x.to(device=in_device, dtype=in_dtype)
-        dual = sol.y.to(device=in_device, dtype=in_dtype)
+        with torch.cuda.device(dev):
+            primal = _to_host_like(sol.x, in_device, in_dtype)
+            dual = _to_host_like(sol.y, in_device, in_dtype)
+            if in_device.type == "cpu":
+                torch.cuda.current_stream(dev).synchronize()
         saved = _Saved(eng, settings, A_vals, P_vals, b, c, sol.x, sol.y, sol.s) if needs_grad else None
         return primal, dual, saved, (batch_size, originally_unbatched, in_device, in_dtype, use_P)
 
@@ -185,9 +202,11 @@ class _CvxpyLayer(torch.autograd.Function):
             dy = _to_dev(ddual, dev).reshape(batch_size, -1)
             dA_vals, dP_vals, db, dc, _ = eng.vjp(A_vals, b, c, x, y, s, dx, dy, P_vals, settings)
             dA_eval, dq_eval, dP_eval = eng.emit(dA_vals, dP_vals if use_P else None, db, dc)
-        dA_eval = dA_eval.to(device=in_device, dtype=in_dtype)
-        dq_eval = dq_eval.to(device=in_device, dtype=in_dtype)
-        dP_eval = dP_eval.to(device=in_device, dtype=in_dtype) if dP_eval is not None else None
+            dA_eval = _to_host_like(dA_eval, in_device, in_dtype)
+            dq_eval = _to_host_like(dq_eval, in_device, in_dtype)
+            dP_eval = _to_host_like(dP_eval, in_device, in_dtype)
+            if in_device.type == "cpu":
+                torch.cuda.current_stream(dev).synchronize()
         if originally_unbatched:
             dq_eval = dq_eval.squeeze(1)
             dA_eval = dA_eval.squeeze(1)

@@ -177,6 +177,24 @@ def dense_qp(B: int, n: int, m: int, z: int, seed: int = 0, with_P: bool = True,
     return plant(st, A, P_vals, rng, name=f"dense_qp_n{n}_m{m}_z{z}", active_frac=active_frac)
 
 
+def dense_lp(B: int, n: int, m: int, seed: int = 0) -> Batch:
+    """Dense LP with a planted NON-DEGENERATE vertex: exactly n of the m nonneg rows are active
+    (strict complementarity), so the optimum is unique and the solution map differentiable."""
+    rng = np.random.default_rng(seed)
+    st = Structure.dense(n, m, ConeSpec(l=m))
+    A = rng.standard_normal((B, m * n)) / np.sqrt(n)
+    x = rng.standard_normal((B, n))
+    z = -np.abs(rng.standard_normal((B, m))) - 0.1
+    for i in range(B):
+        act = rng.choice(m, size=n, replace=False)
+        z[i, act] = np.abs(z[i, act])
+    y = np.maximum(z, 0.0)
+    s = y - z
+    b = _apply_A(st, A, x) + s
+    c = -_apply_AT(st, A, y)
+    return Batch(st, A, b, c, None, x, y, s, f"dense_lp_n{n}_m{m}")
+
+
 def config_c1(seed: int = 0) -> Batch:
     return dense_qp(1, 10, 20, 0, seed)
 

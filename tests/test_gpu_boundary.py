@@ -1,0 +1,172 @@
+"""GPU tests through the reference-facing boundary and the C-ABI pack kernels, plus the committed
+golden fixtures and size-independent properties at the headline batch size."""
+import warnings
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from cvxpylayers_b200 import problems as pr
+from cvxpylayers_b200.engine import Engine, make_settings
+from cvxpylayers_b200.interface import B200_ctx, SolverError, _CvxpyLayer
+from cvxpylayers_b200.structure import ConeSpec, Structure
+from oracle import oracle as orc
+from tests.util import GOLDEN_CASES, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+
+
+def _layer(bt, **opts):
+    st = bt.structure
+    bd = pr.to_boundary(bt)
+    pstruct = (st.P_indices, st.P_indptr, (st.n, st.n)) if st.P_indptr is not None else None
+    ctx = B200_ctx(pstruct, (bd.con_indices, bd.con_ptr, bd.shape), bd.dims, options=opts)
+    return ctx, bd, SimpleNamespace(solver_ctx=ctx)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixtures_through_c_abi(name, cuda_device):
+    bt, g = load_golden(name)
+    st, dev = bt.structure, cuda_device
+    eng = Engine(st, dev)
+    sol = eng.solve(_t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(bt.P_vals, dev), make_settings({"eps": 1e-9, "max_iters": 200000}))
+    assert (sol.status.cpu().numpy() == 1).all()
+    scale = max(1.0, np.abs(g["x"]).max())
+    assert np.abs(sol.x.cpu().numpy() - g["x"]).max() < 1e-6 * scale
+    assert np.abs(sol.y.cpu().numpy() - g["y"]).max() < 1e-6 * max(1.0, np.abs(g["y"]).max())
+    dA, dP, db, dc, _ = eng.vjp(_t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(g["x"], dev), _t(g["y"], dev), _t(g["s"], dev),
+                                _t(g["dx"], dev), _t(g["dy"], dev), _t(bt.P_vals, dev),
+                                make_settings({"lsqr_precond": 1, "lsqr_iter_lim": 100000}))
+    tol = 1e-4
+    assert rel_err(dA.cpu().numpy(), g["dA"]) < tol and rel_err(db.cpu().numpy(), g["db"]) < tol and rel_err(dc.cpu().numpy(), g["dc"]) < tol
+    if dP is not None:
+        assert rel_err(dP.cpu().numpy(), g["dP"]) < tol
+
+
+@pytest.mark.parametrize("name,B", [("C1", 5), ("C3", 4), ("C5", 3)])
+def test_pack_kernels_roundtrip(name, B, cuda_device):
+    """bcone_ingest == the reference's per-instance re-packing (diffcp_if.py:57-68), bcone_emit == :88-94."""
+    bt = pr.CONFIGS[name](B=B)
+    ctx, bd, _ = _layer(bt)
+    eng = ctx.engine(cuda_device)
+    A_vals, P_vals, b, c = eng.ingest(_t(bd.A_eval, cuda_device), _t(bd.q_eval, cuda_device), _t(bd.P_eval, cuda_device))
+    assert np.array_equal(A_vals.cpu().numpy(), bt.A_vals) and np.array_equal(b.cpu().numpy(), bt.b) and np.array_equal(c.cpu().numpy(), bt.c)
+    if bt.P_vals is not None:
+        assert np.array_equal(P_vals.cpu().numpy(), bt.P_vals)
+    rng = np.random.default_rng(0)
+    gA, gb, gc = rng.standard_normal(bt.A_vals.shape), rng.standard_normal(bt.b.shape), rng.standard_normal(bt.c.shape)
+    dA_eval, dq_eval, _ = eng.emit(_t(gA, cuda_device), None, _t(gb, cuda_device), _t(gc, cuda_device))
+    dA_eval, dq_eval = dA_eval.cpu().numpy(), dq_eval.cpu().numpy()
+    st = bt.structure
+    assert np.array_equal(-dA_eval[ctx.gather].T, gA)               # con_grad = [-dA.data ; db[b_idx]]
+    assert np.array_equal(dA_eval[st.nnzA:].T, gb[:, np.asarray(ctx.b_idx)])
+    assert np.array_equal(dq_eval[:-1].T, gc) and not dq_eval[-1].any()  # lin_grad = [dc ; 0]
+
+
+@pytest.mark.parametrize("host_inputs", [False, True])
+def test_layer_forward_backward_matches_oracle(host_inputs, cuda_device):
+    bt = pr.dense_qp(6, 10, 20, 3, seed=5)
+    st = bt.structure
+    args = {"eps": 1e-9, "max_iters": 100000, "lsqr_precond": 1}
+    ctx, bd, cl = _layer(bt, **args)
+    dev = torch.device("cpu") if host_inputs else cuda_device
+    A = torch.tensor(bd.A_eval, device=dev, requires_grad=True)
+    q = torch.tensor(bd.q_eval, device=dev, requires_grad=True)
+    P = torch.tensor(bd.P_eval, device=dev, requires_grad=True)
+    if host_inputs:
+        ctx.device = cuda_device
+    primal, dual, _, _ = _CvxpyLayer.apply(P, q, A, cl, {}, True, None)
+    assert primal.device.type == dev.type and primal.shape == (6, st.n) and dual.shape == (6, st.m)  # outputs live where inputs live
+    rng = np.random.default_rng(1)
+    dx, dy = rng.standard_normal(primal.shape), rng.standard_normal(dual.shape)
+    ((primal * torch.tensor(dx, device=dev)).sum() + (dual * torch.tensor(dy, device=dev)).sum()).backward()
+    xo, yo, so, sto, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+    assert np.abs(primal.detach().cpu().numpy() - xo).max() < 1e-6 and np.abs(dual.detach().cpu().numpy() - yo).max() < 1e-6
+    gA, gP, gb, gc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, xo, yo, so, dx, dy, bt.P_vals, **args)
+    dAe, dqe, dPe = A.grad.cpu().numpy(), q.grad.cpu().numpy(), P.grad.cpu().numpy()
+    assert rel_err(-dAe[ctx.gather].T, gA) < 1e-4 and rel_err(dAe[st.nnzA:].T, gb) < 1e-4
+    assert rel_err(dqe[:-1].T, gc) < 1e-4 and not dqe[-1].any() and rel_err(dPe.T, gP) < 1e-4
+
+
+def test_unbatched_inputs_keep_the_reference_shapes(cuda_device):
+    """1-D inputs = one instance; outputs stay 2-D [1, n] (torch/cvxpylayer.py:247-250), grads are 1-D."""
+    bt = pr.dense_qp(1, 6, 9, 2, seed=6)
+    ctx, bd, cl = _layer(bt, eps=1e-8)
+    A = torch.tensor(bd.A_eval[:, 0], device=cuda_device, requires_grad=True)
+    q = torch.tensor(bd.q_eval[:, 0], device=cuda_device, requires_grad=True)
+    P = torch.tensor(bd.P_eval[:, 0], device=cuda_device, requires_grad=True)
+    primal, dual, _, _ = _CvxpyLayer.apply(P, q, A, cl, {}, True, None)
+    assert primal.shape == (1, 6) and dual.shape == (1, 9)
+    primal.sum().backward()
+    assert A.grad.shape == A.shape and q.grad.shape == q.shape and P.grad.shape == P.shape
+
+
+def test_no_grad_path_and_solver_args_override(cuda_device):
+    bt = pr.dense_qp(2, 6, 9, 2, seed=7)
+    ctx, bd, cl = _layer(bt, eps=1e-8)
+    A, q, P = _t(bd.A_eval, cuda_device), _t(bd.q_eval, cuda_device), _t(bd.P_eval, cuda_device)
+    primal, dual, saved, _ = _CvxpyLayer.apply(P, q, A, cl, {}, False, None)
+    assert saved is None and np.abs(primal.cpu().numpy() - bt.x_star).max() < 1e-5
+    with warnings.catch_warnings(record=True) as w:  # per-call override reaches the solver (tests/test_torch.py:705-752)
+        warnings.simplefilter("always")
+        p1, _, _, _ = _CvxpyLayer.apply(P, q, A, cl, {"max_iters": 1}, False, None)
+    assert any("Inaccurate" in str(x.message) for x in w)
+    assert np.abs(p1.cpu().numpy() - bt.x_star).max() > 1e-2
+
+
+def test_infeasible_raises_solver_error(cuda_device):
+    """tests/test_torch.py:299-316: infeasible / unbounded problems raise."""
+    st = Structure.dense(1, 2, ConeSpec(l=2))
+    bt = pr.Batch(st, np.array([[1.0, -1.0]]), np.array([[-1.0, -1.0]]), np.array([[0.0]]))
+    ctx, bd, cl = _layer(bt)
+    with pytest.raises(SolverError):
+        _CvxpyLayer.apply(None, _t(bd.q_eval, cuda_device), _t(bd.A_eval, cuda_device), cl, {}, False, None)
+
+
+def test_headline_batch_properties(cuda_device):
+    """BASELINE.json configs[1] at full size (B=4096): every instance satisfies the termination
+    criteria on the original data (evaluated with torch on the device), the adjoint is linear in
+    (dx, dy) and vanishes for dz = 0."""
+    B = 4096
+    bt = pr.config_c2(B=B, seed=1)
+    st, dev = bt.structure, cuda_device
+    eng = Engine(st, dev)
+    eps = 1e-4
+    A, b, c, P = _t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(bt.P_vals, dev)
+    sol = eng.solve(A, b, c, P, make_settings({"eps": eps, "max_iters": 10000}))
+    assert int((sol.status == 1).sum()) == B
+    Am = A.view(B, st.m, st.n)
+    iu = torch.triu_indices(st.n, st.n, device=dev)
+    Pm = torch.zeros((B, st.n, st.n), dtype=torch.float64, device=dev)
+    Pm[:, iu[0], iu[1]] = P
+    Pm = Pm + Pm.transpose(1, 2) - torch.diag_embed(torch.diagonal(Pm, dim1=1, dim2=2))
+    Ax = torch.bmm(Am, sol.x.unsqueeze(2)).squeeze(2)
+    Px = torch.bmm(Pm, sol.x.unsqueeze(2)).squeeze(2)
+    ATy = torch.bmm(Am.transpose(1, 2), sol.y.unsqueeze(2)).squeeze(2)
+    mx = lambda t: t.abs().amax(dim=1)  # noqa: E731
+    rp, rd = mx(Ax + sol.s - b), mx(Px + ATy + c)
+    xPx, ctx_, bty = (sol.x * Px).sum(1), (c * sol.x).sum(1), (b * sol.y).sum(1)
+    tp = eps + eps * torch.maximum(torch.maximum(mx(Ax), mx(sol.s)), mx(b))
+    td = eps + eps * torch.maximum(torch.maximum(mx(Px), mx(ATy)), mx(c))
+    tg = eps + eps * torch.maximum(torch.maximum(xPx.abs(), ctx_.abs()), bty.abs())
+    assert bool((rp <= 1.001 * tp).all()) and bool((rd <= 1.001 * td).all()) and bool(((xPx + ctx_ + bty).abs() <= 1.001 * tg).all())
+    assert bool((sol.s[:, st.cones.z:] >= 0).all()) and bool((sol.y[:, st.cones.z:] >= 0).all())  # cone membership
+    # adjoint: linearity and the zero shortcut, on a slice (tight LSQR so linearity is not masked by its tolerance)
+    k = 64
+    sl = lambda t: t[:k].contiguous()  # noqa: E731
+    g = torch.Generator(device="cpu").manual_seed(0)
+    d1x, d1y = torch.randn((k, st.n), dtype=torch.float64, generator=g).to(dev), torch.randn((k, st.m), dtype=torch.float64, generator=g).to(dev)
+    d2x, d2y = torch.randn((k, st.n), dtype=torch.float64, generator=g).to(dev), torch.randn((k, st.m), dtype=torch.float64, generator=g).to(dev)
+    tight = make_settings({"lsqr_precond": 1, "lsqr_atol": 1e-13, "lsqr_btol": 1e-13, "lsqr_iter_lim": 5000})
+    run = lambda dx, dy: eng.vjp(sl(A), sl(b), sl(c), sl(sol.x), sl(sol.y), sl(sol.s), dx, dy, sl(P), tight)  # noqa: E731
+    g1, g2, g12 = run(d1x, d1y), run(d2x, d2y), run(d1x + 2 * d2x, d1y + 2 * d2y)
+    for a1, a2, a12 in zip(g1[:4], g2[:4], g12[:4]):
+        ref = a1 + 2 * a2
+        assert float((a12 - ref).abs().max() / ref.abs().max()) < 1e-5
+    z = run(torch.zeros_like(d1x), torch.zeros_like(d1y))
+    assert not z[0].any() and not z[2].any() and not z[3].any() and not z[4].any()

@@ -1,0 +1,129 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol declared in
+include/bcone.h (no compute calls without a GPU), settings mapping, structure checks, the
+boundary re-packing maps, and the world_size-2 gather path over gloo."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from cvxpylayers_b200 import _lib, dist as bdist, problems as pr
+from cvxpylayers_b200.engine import make_settings
+from cvxpylayers_b200.interface import B200_ctx, dims_to_solver_dict
+from cvxpylayers_b200.structure import ConeSpec, Structure
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "bcone.h")).read()
+    declared = set(re.findall(r"\b(bcone_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_settings_struct_matches_header_defaults():
+    st = _lib.default_settings()
+    assert (st.eps_abs, st.eps_rel, st.eps_infeas) == (1e-4, 1e-4, 1e-7)  # SCS defaults
+    assert (st.alpha, st.rho_x, st.scale) == (1.5, 1e-6, 0.1)
+    assert (st.lsqr_atol, st.lsqr_btol, st.lsqr_conlim) == (1e-8, 1e-8, 1e8)  # diffcp / SciPy LSQR rules
+    assert st.max_iters == 100000 and st.check_interval == 25 and st.lsqr_iter_lim == -1
+
+
+def test_solver_args_mapping_follows_the_reference_keys():
+    st = make_settings({"eps": 1e-10, "max_iters": 10000, "acceleration_lookback": 0, "verbose": True})  # tests/test_torch.py:401-405
+    assert st.eps_abs == 1e-10 and st.eps_rel == 1e-10 and st.max_iters == 10000
+    with pytest.raises(ValueError):
+        make_settings({"not_a_solver_arg": 1})
+    with pytest.raises(ValueError):
+        make_settings({"mode": "dense"})
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from cvxpylayers_b200.engine import Engine
+
+    with pytest.raises(_lib.EngineUnavailable):
+        Engine(Structure.dense(4, 6, ConeSpec(l=6)), "cuda")
+
+
+def test_structure_validation():
+    with pytest.raises(ValueError):
+        Structure(3, 2, [0, 1, 2], [0, 5], ConeSpec(l=2))  # column out of range
+    with pytest.raises(ValueError):
+        Structure(3, 2, [0, 1, 2], [0, 1], ConeSpec(l=3))  # cone rows != m
+    with pytest.raises(ValueError):
+        Structure(2, 1, [0, 1], [0], ConeSpec(l=1), [0, 1, 2], [1, 0])  # P not upper triangular
+    with pytest.raises(NotImplementedError):
+        ConeSpec.from_dict({"l": 1, "p": [0.5]})
+    assert Structure.dense(5, 7, ConeSpec(z=2, l=5)).is_dense_A
+    assert ConeSpec(z=1, l=2, q=[3, 4], s=[3]).m == 1 + 2 + 7 + 6
+
+
+def test_dims_conversion_accepts_cvxpy_like_objects():
+    class Dims:  # attribute names of cvxpy's ConeDims
+        zero, nonneg, soc, psd, exp, p3d = 2, 3, [4], [3], 0, []
+
+    assert dims_to_solver_dict(Dims()) == {"z": 2, "l": 3, "q": [4], "s": [3], "ep": 0, "ed": 0}
+
+
+@pytest.mark.parametrize("name", ["C1", "C3", "C5"])
+def test_boundary_roundtrip(name):
+    """to_boundary() builds the [A_cvx | b] CSC tensors of diffcp_if.py:46-70; B200_ctx must recover the
+    engine's CSR structure and the gather map that inverts the re-packing."""
+    bt = pr.CONFIGS[name](B=3)
+    st = bt.structure
+    bd = pr.to_boundary(bt)
+    ctx = B200_ctx(None, (bd.con_indices, bd.con_ptr, bd.shape), bd.dims)
+    assert np.array_equal(ctx.structure.A_indptr, st.A_indptr) and np.array_equal(ctx.structure.A_indices, st.A_indices)
+    # reference semantics: A = -A_aug[:, :-1], b = A_aug[:, -1]
+    for i in range(bt.B):
+        A_aug = sp.csc_matrix((bd.A_eval[:, i], bd.con_indices, bd.con_ptr), shape=bd.shape)
+        assert np.allclose((-A_aug[:, :-1]).toarray(), bt.A_dense(i))
+        assert np.allclose(A_aug[:, -1].toarray().ravel(), bt.b[i])
+        assert np.allclose(-bd.A_eval[ctx.gather, i], bt.A_vals[i])
+    assert np.array_equal(ctx.b_idx, np.arange(st.m))
+
+
+def test_shard_ranges_partition_the_batch():
+    for B, w in [(4096, 8), (10, 3), (5, 8), (7, 1)]:
+        seen = []
+        for r in range(w):
+            lo, hi = bdist.shard_range(B, r, w)
+            seen += list(range(lo, hi))
+        assert seen == list(range(B))
+        assert sum(bdist.shard_sizes(B, w)) == B
+
+
+def _gloo_worker(rank, world, port, B, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = bdist.shard_range(B, rank, world)
+    full = torch.arange(B * 3, dtype=torch.float64).reshape(B, 3)
+    local = full[lo:hi].clone()
+    g0 = bdist.gather_rows(local, B, dst=0)
+    ga = bdist.gather_rows(local, B, dst=None)
+    ok = bool(torch.equal(ga, full)) and ((rank != 0 and g0 is None) or (rank == 0 and torch.equal(g0, full)))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [8, 7])
+def test_gather_rows_world_size_2_gloo(B):
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 500) + B
+    mp.spawn(_gloo_worker, args=(2, port, B, out), nprocs=2, join=True)
+    assert out[0] and out[1]

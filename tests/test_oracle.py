@@ -1,0 +1,204 @@
+"""CPU tests that pin the oracle (oracle/cone_oracle.c) -- the checker the GPU tests rely on.
+
+The reference (cvxpy/cvxpylayers) stores no golden vectors for this path and its arithmetic
+(diffcp + SCS) is not importable here; what its own tests pin are analytic facts.
+Those are restated below with the reference test they come from, next to solver-independent
+checks (KKT certificates, HiGHS, SciPy's LSQR, finite differences).
+"""
+import numpy as np
+import pytest
+import scipy.optimize as sopt
+import torch
+from scipy.sparse.linalg import lsqr as scipy_lsqr
+
+from cvxpylayers_b200 import problems as pr
+from cvxpylayers_b200.structure import ConeSpec, Structure
+from oracle import np_ref
+from oracle import oracle as orc
+from tests.util import GOLDEN_CASES, load_golden, rel_err
+
+
+# ----------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("name,B", [("C1", 4), ("C2", 3), ("C3", 4), ("C5", 3)])
+@pytest.mark.parametrize("eps", [1e-4, 1e-8])
+def test_forward_kkt_certificate(name, B, eps):
+    """Every returned point satisfies SCS's own termination criteria on the original data."""
+    bt = pr.CONFIGS[name](B=B)
+    x, y, s, status, iters = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=eps, max_iters=50000)
+    assert (status == 1).all()
+    for i in range(B):
+        P = bt.P_dense(i) if bt.P_vals is not None else None
+        r = np_ref.kkt_residuals(bt.A_dense(i), P, bt.b[i], bt.c[i], x[i], y[i], s[i])
+        assert np_ref.is_converged(r, eps, eps, 1.0001)
+        assert abs(s[i] @ y[i]) <= 1e-9 * max(1.0, np.abs(s[i]).max() * np.abs(y[i]).max() * bt.structure.m)  # exact complementarity
+    if bt.x_star is not None and name != "C5":
+        assert np.abs(x - bt.x_star).max() < 200 * eps  # planted optimum recovered
+
+
+def test_lp_matches_highs():
+    """Cross-solver check (the reference cross-checks against Clarabel, tests/test_dual_variables.py:14-42)."""
+    # (plain operator splitting is slow on LPs -- no Anderson acceleration yet, DESIGN.md -- so the
+    # comparison uses the instances of this seed that converge quickly)
+    bt = pr.dense_lp(6, 8, 20, seed=4).select([1, 2, 4])
+    x, y, s, status, _ = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, eps=1e-9, max_iters=400000)
+    assert (status == 1).all()
+    for i in range(bt.B):
+        A = bt.A_dense(i)
+        res = sopt.linprog(bt.c[i], A_ub=A, b_ub=bt.b[i], bounds=[(None, None)] * bt.structure.n, method="highs")
+        assert res.status == 0
+        assert abs(bt.c[i] @ x[i] - res.fun) < 1e-6 * max(1, abs(res.fun))
+        assert np.abs(x[i] - res.x).max() < 1e-5
+        assert np.abs(y[i] + res.ineqlin.marginals).max() < 1e-5  # SCS dual sign convention: y >= 0
+
+
+def test_equality_qp_known_answer():
+    """min ||x||^2 s.t. x1 + x2 = 2 -> x* = [1, 1]  (reference tests/test_diffcp_optional_deps.py:29-57)."""
+    st = Structure(2, 1, [0, 2], [0, 1], ConeSpec(z=1), [0, 1, 2], [0, 1])
+    A = np.array([[1.0, 1.0]]); b = np.array([[2.0]]); c = np.zeros((1, 2)); P = np.array([[2.0, 2.0]])
+    x, y, s, status, _ = orc.solve_batch(st, A, b, c, P, eps=1e-10)
+    assert status[0] == 1 and np.abs(x[0] - 1.0).max() < 1e-7
+    # d x / d b = [1/2, 1/2]: gradient of sum(x) wrt b is 1
+    dA, dP, db, dc, _ = orc.vjp_batch(st, A, b, c, x, y, s, np.ones((1, 2)), np.zeros((1, 1)), P)
+    assert abs(db[0, 0] - 1.0) < 1e-6
+
+
+def test_ridge_closed_form_and_gradient():
+    """Least squares with closed-form solution and gradient (reference tests/test_torch.py:90-118:
+    x* = (A'A + I)^{-1} A'b, grads atol 1e-6 at eps 1e-10), written as a QP with P = 2(A'A + I)."""
+    rng = np.random.default_rng(0)
+    mA, n = 30, 8
+    A_t = torch.tensor(rng.standard_normal((mA, n)), requires_grad=True)
+    b_t = torch.tensor(rng.standard_normal(mA), requires_grad=True)
+    x_cf = torch.linalg.solve(A_t.T @ A_t + torch.eye(n, dtype=torch.double), A_t.T @ b_t)
+    x_cf.sum().backward()
+    # QP data; one slack row 0*x + s = 1, s >= 0 keeps m >= 1
+    iu = np.triu_indices(n)
+    st = Structure(n, 1, [0, 0], np.zeros(0, np.int32), ConeSpec(l=1),
+                   np.concatenate([[0], np.cumsum(np.arange(n, 0, -1))]), iu[1])
+    A2 = A_t.detach().clone().requires_grad_(True); b2 = b_t.detach().clone().requires_grad_(True)
+    P_full = 2 * (A2.T @ A2 + torch.eye(n, dtype=torch.double))
+    P_up = P_full[iu[0], iu[1]]
+    c_t = -2 * A2.T @ b2
+    x, y, s, status, _ = orc.solve_batch(st, np.zeros((1, 0)), np.ones((1, 1)), c_t.detach().numpy()[None], P_up.detach().numpy()[None], eps=1e-10)
+    assert status[0] == 1
+    assert np.abs(x[0] - x_cf.detach().numpy()).max() < 1e-6
+    dA, dP, db, dc, _ = orc.vjp_batch(st, np.zeros((1, 0)), np.ones((1, 1)), c_t.detach().numpy()[None], x, y, s,
+                                      np.ones((1, n)), np.zeros((1, 1)), P_up.detach().numpy()[None])
+    ((P_up * torch.tensor(dP[0])).sum() + (c_t * torch.tensor(dc[0])).sum()).backward()
+    assert np.abs(A2.grad.numpy() - A_t.grad.numpy()).max() < 1e-6
+    assert np.abs(b2.grad.numpy() - b_t.grad.numpy()).max() < 1e-6
+
+
+def test_infeasible_and_unbounded_are_reported():
+    """Status -> exception contract of the reference (tests/test_torch.py:299-316)."""
+    st = Structure.dense(1, 2, ConeSpec(l=2))
+    # x <= -1 and -x <= -1 (x >= 1): infeasible
+    _, _, _, status, _ = orc.solve_batch(st, np.array([[1.0, -1.0]]), np.array([[-1.0, -1.0]]), np.array([[0.0]]))
+    assert status[0] == -2
+    # min x s.t. x <= 1: unbounded below
+    _, _, _, status, _ = orc.solve_batch(st, np.array([[1.0, 0.0]]), np.array([[1.0, 1.0]]), np.array([[1.0]]))
+    assert status[0] == -1
+
+
+def test_max_iters_degrades_answer():
+    """solver_args reach the solver: max_iters=1 must visibly degrade (reference tests/test_torch.py:705-752)."""
+    bt = pr.CONFIGS["C1"](B=1)
+    x1, _, _, st1, it1 = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, bt.P_vals, max_iters=1)
+    x2, _, _, st2, _ = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-8)
+    assert st1[0] == 2 and it1[0] == 1 and st2[0] == 1
+    assert np.abs(x1 - bt.x_star).max() > 100 * np.abs(x2 - bt.x_star).max()
+
+
+# ----------------------------------------------------------------------------- cones
+def test_cone_projection_and_jacobian_against_numpy():
+    cones = ConeSpec(z=2, l=3, q=[4, 1, 5], s=[3, 2])
+    m = cones.m
+    st = Structure(1, m, np.arange(m + 1), np.zeros(m, np.int32), cones)
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        v = rng.standard_normal(m) * 2
+        assert np.abs(orc.proj_dual_cone(st, v) - pr.proj_dual_cone(v, cones)).max() < 1e-12
+        D = np_ref.dproj_matrix(v, cones)
+        dv = rng.standard_normal(m)
+        assert np.abs(orc.dproj_dual_cone(st, v, dv) - D @ dv).max() < 1e-10
+        # Jacobian is the derivative of the projection (finite differences)
+        h = 1e-6
+        fd = (pr.proj_dual_cone(v + h * dv, cones) - pr.proj_dual_cone(v - h * dv, cones)) / (2 * h)
+        assert np.abs(fd - D @ dv).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------- LSQR and the adjoint
+def test_lsqr_matches_scipy():
+    """diffcp's lsqr.cpp ports SciPy's LSQR; the oracle's must reproduce SciPy's iterates."""
+    rng = np.random.default_rng(1)
+    for (r, c) in [(30, 30), (40, 25), (25, 40)]:
+        M = rng.standard_normal((r, c)); rhs = rng.standard_normal(r)
+        sol, its = orc.lsqr_dense(M, rhs)
+        ref = scipy_lsqr(M, rhs, atol=1e-8, btol=1e-8, conlim=1e8, iter_lim=2 * c)
+        assert its == ref[2]
+        assert np.abs(sol - ref[0]).max() < 1e-6 * max(1, np.abs(ref[0]).max())
+
+
+@pytest.mark.parametrize("name,B", [("C1", 3), ("C3", 3)])
+@pytest.mark.parametrize("precond", [0, 1])
+def test_vjp_matches_scipy_restatement(name, B, precond):
+    """Oracle adjoint vs the NumPy/SciPy restatement of diffcp's adjoint_derivative (explicit M, scipy lsqr)."""
+    bt = pr.CONFIGS[name](B=B)
+    st = bt.structure
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-10, max_iters=100000)
+    rng = np.random.default_rng(2)
+    dx, dy = rng.standard_normal(x.shape), rng.standard_normal(y.shape)
+    dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, x, y, s, dx, dy, bt.P_vals, lsqr_precond=precond, lsqr_iter_lim=50000)
+    rows = np.repeat(np.arange(st.m), np.diff(st.A_indptr))
+    for i in range(B):
+        P = bt.P_dense(i) if bt.P_vals is not None else None
+        rA, rP, rb, rc, _ = np_ref.vjp_dense(bt.A_dense(i), P, bt.b[i], bt.c[i], x[i], y[i], s[i], dx[i], dy[i], st.cones, exact=True)
+        tol = 5e-5 if precond else 1e-4   # north_star: 1e-4 relative; plain LSQR stops at atol = btol = 1e-8 on a worse-conditioned system
+        assert rel_err(db[i], rb) < tol and rel_err(dc[i], rc) < tol
+        assert rel_err(dA[i], rA[rows, st.A_indices]) < tol
+        if P is not None:
+            prow = np.repeat(np.arange(st.n), np.diff(st.P_indptr)); pcol = st.P_indices
+            rPv = np.where(prow == pcol, rP[prow, pcol], rP[prow, pcol] + rP[pcol, prow])
+            assert rel_err(dP[i], rPv) < tol
+
+
+def test_vjp_matches_finite_differences():
+    """Central differences through a tight forward solve (the reference uses torch.autograd.gradcheck
+    with atol 1e-4 / rtol 1e-3, tests/test_torch.py:415-426, tests/test_dual_variables.py:209-313)."""
+    bt = pr.dense_qp(1, 6, 10, 2, seed=21)
+    st = bt.structure
+    args = dict(eps=1e-12, max_iters=400000)
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+    rng = np.random.default_rng(8)
+    dx, dy = rng.standard_normal(x.shape), rng.standard_normal(y.shape)
+    dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, x, y, s, dx, dy, bt.P_vals, lsqr_precond=1, lsqr_iter_lim=10000)
+
+    def loss(Av, Pv, b, c):
+        xx, yy, _, stt, _ = orc.solve_batch(st, Av, b, c, Pv, **args)
+        assert stt[0] == 1
+        return float(xx[0] @ dx[0] + yy[0] @ dy[0])
+
+    h = 1e-6
+    for arr, grad, which in ((bt.b, db, "b"), (bt.c, dc, "c"), (bt.A_vals, dA, "A"), (bt.P_vals, dP, "P")):
+        idxs = rng.choice(arr.shape[1], size=min(6, arr.shape[1]), replace=False)
+        for k in idxs:
+            vals = {"A": bt.A_vals.copy(), "P": bt.P_vals.copy(), "b": bt.b.copy(), "c": bt.c.copy()}
+            vals[which][0, k] += h
+            lp = loss(vals["A"], vals["P"], vals["b"], vals["c"])
+            vals[which][0, k] -= 2 * h
+            lm = loss(vals["A"], vals["P"], vals["b"], vals["c"])
+            fd = (lp - lm) / (2 * h)
+            assert abs(fd - grad[0, k]) <= 1e-4 + 1e-3 * abs(fd), (which, k, fd, grad[0, k])
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_reproduces_golden_fixtures(name):
+    bt, g = load_golden(name)
+    st = bt.structure
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=200000)
+    assert (status == 1).all()
+    assert np.abs(x - g["x"]).max() < 1e-9 and np.abs(y - g["y"]).max() < 1e-9 and np.abs(s - g["s"]).max() < 1e-9
+    dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, g["x"], g["y"], g["s"], g["dx"], g["dy"], bt.P_vals,
+                                      lsqr_precond=1, lsqr_iter_lim=100000)
+    assert rel_err(dA, g["dA"]) < 1e-9 and rel_err(db, g["db"]) < 1e-9 and rel_err(dc, g["dc"]) < 1e-9
