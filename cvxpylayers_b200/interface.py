@@ -18,6 +18,9 @@ entry of ``A`` (the reference's ``dA.data`` drops exact zeros, SURVEY.md 8a note
 """
 from __future__ import annotations
 
+import os
+import sys
+import time
 import warnings
 from typing import Any
 
@@ -33,6 +36,9 @@ try:  # raise the reference's own exception type when diffcp is importable (test
     from diffcp import SolverError as _SolverErrorBase  # type: ignore
 except Exception:  # noqa: BLE001
     _SolverErrorBase = Exception
+
+
+_TRACE = bool(os.environ.get("B200_TRACE"))
 
 
 class SolverError(_SolverErrorBase):
@@ -197,6 +203,7 @@ class _CvxpyLayer(torch.autograd.Function):
             raise RuntimeError("backward called on a forward pass run with needs_grad=False")
         eng, settings, A_vals, P_vals, b, c, x, y, s = ctx.saved.items
         dev = eng.device
+        _tb = time.perf_counter() if _TRACE else 0.0
         with torch.cuda.device(dev):
             dx = _to_dev(dprimal, dev).reshape(batch_size, -1)
             dy = _to_dev(ddual, dev).reshape(batch_size, -1)
@@ -207,6 +214,8 @@ class _CvxpyLayer(torch.autograd.Function):
             dP_eval = _to_host_like(dP_eval, in_device, in_dtype)
             if in_device.type == "cpu":
                 torch.cuda.current_stream(dev).synchronize()
+        if _TRACE:
+            print(f"[b200] backward body {1e3 * (time.perf_counter() - _tb):.1f} ms", file=sys.stderr)
         if originally_unbatched:
             dq_eval = dq_eval.squeeze(1)
             dA_eval = dA_eval.squeeze(1)
