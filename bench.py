@@ -32,6 +32,9 @@ METRIC = "QP problems/sec fwd+bwd (batch=4096, n=100, m=200, zero+nonneg cones)"
 UNIT = "problems/s"
 # Solver settings shared by both arms (SCS defaults for the forward; LSQR rules of diffcp).
 SOLVER_ARGS = {"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 1}
+# DRAM bytes per instance measured by ncu --set full on 296-instance launches (profiles/):
+# bwd_fast_kernel 62.17 MB read + 7.17 MB written; fwd_kernel 60.3 MB read + 0.2 MB written.
+NCU_DRAM_BYTES_PER_INSTANCE = {"bwd": (62.166016e6 + 7.173376e6) / 296, "fwd": (60.317696e6 + 0.20608e6) / 296}
 # Algorithmic HBM bytes per instance: fwd reads A,P,b,c + writes x,y,s;
 # bwd re-reads data + x,y,s + dx,dy and writes dA,dP,db,dc.
 def algo_bytes(n, m, nnzA, nnzP):
@@ -85,9 +88,21 @@ def make_workload(batch: int, seed: int):
     return bt, pr.to_boundary(bt)
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
 def cpu_arm(bt, sample: int, steps: int, warmup: int, threads: int = 0):
-    """Times the oracle (reference algorithm on host cores): forward + adjoint on `sample` instances."""
+    """Times the oracle (reference algorithm on host cores): forward + adjoint on `sample` instances.
+    The thread count is passed explicitly (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin
+    the baseline to one core)."""
     from oracle import oracle as orc
+
+    if threads <= 0:
+        threads = host_cores()
 
     st = bt.structure
     sub = bt.select(slice(0, sample))
@@ -106,7 +121,7 @@ def cpu_arm(bt, sample: int, steps: int, warmup: int, threads: int = 0):
     for _ in range(steps):
         status = step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    cores = orc.max_threads() if threads <= 0 else threads
+    cores = threads
     return sample / dt, dt, cores, int((status == 1).sum())
 
 
@@ -283,7 +298,8 @@ def run_ours(a):
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "traffic": None,
+                             "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_INSTANCE.get(dom, 0) * B / 1e9 or None,
+                             "traffic_unit": "GB per launch (ncu dram__bytes_read+write per instance, profiles/prof_*_r1*.txt, x B)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                              "note": "on-chip iterative solve: HBM is touched once in/out per instance, the loop runs in shared memory"},
                 "kernel_ms": {k: round(v, 3) for k, v in kt.items()},

@@ -15,7 +15,7 @@ size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd);
 cudaError_t bc_fwd_configure(int dense, size_t smem);
 cudaError_t bc_fwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_fwd_launch(const FwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
-size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total);
+size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp);
 cudaError_t bc_bwd_configure(int dense, size_t smem);
 cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
@@ -79,13 +79,14 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   *out = nullptr;
   if (d->n <= 0 || d->m < 0 || d->nnzA < 0 || !d->A_indptr || (d->nnzA > 0 && !d->A_indices))
     return fail(nullptr, BCONE_EINVAL, "bad dimensions / missing A structure");
-  if (d->ep != 0 || d->ed != 0)
-    return fail(nullptr, BCONE_EUNSUPPORTED, "exponential cones are not built yet (DESIGN.md: out of round-1 scope)");
+  if (d->ep < 0 || d->ed < 0) return fail(nullptr, BCONE_EINVAL, "negative cone count");
   const int n = d->n, m = d->m;
   long long rows = d->z + d->l;
   int max_psd = 0, psd_total = 0;
   for (int i = 0; i < d->nq; i++) rows += d->q[i];
   for (int i = 0; i < d->ns; i++) { int k = d->s[i]; rows += (long long)k * (k + 1) / 2; max_psd = std::max(max_psd, k); psd_total += k * k + k; }
+  const int exp_start = (int)rows;
+  rows += 3LL * (d->ep + d->ed);
   if (rows != m) return fail(nullptr, BCONE_EINVAL, "cone dimensions do not add up to m");
   if (d->A_indptr[0] != 0 || d->A_indptr[m] != d->nnzA) return fail(nullptr, BCONE_EINVAL, "A_indptr inconsistent with nnzA");
   if (cudaSetDevice(d->device) != cudaSuccess) return fail(nullptr, BCONE_ECUDA, "cudaSetDevice failed (no CUDA device?)");
@@ -98,6 +99,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   DevStruct &S = h->S;
   S.n = n; S.m = m; S.nnzA = d->nnzA; S.nnzP = d->P_indptr ? d->nnzP : 0;
   S.z = d->z; S.l = d->l; S.nq = d->nq; S.ns = d->ns; S.max_psd = max_psd;
+  S.ep = d->ep; S.ed = d->ed; S.exp_start = exp_start;
   // --- host-side structure analysis ---
   std::vector<int> indptr(d->A_indptr, d->A_indptr + m + 1), indices(d->A_indices, d->A_indices + d->nnzA);
   std::vector<int> rowof(d->nnzA), colptr(n + 1, 0), rowidx(d->nnzA), perm(d->nnzA);
@@ -165,14 +167,14 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   auto pick_bwd = [&]() -> bool {   // prefer P staged in shared memory, fall back to P read from L2
     for (int psm = (S.nnzP > 0 ? 1 : 0); psm >= 0; psm--)
       for (int tt = threads; tt >= 64; tt /= 2) {
-        size_t sm = bc_bwd_smem_bytes(n, m, npoly, d->nnzA, psm ? S.nnzP : 0, tt, max_psd, psd_total);
+        size_t sm = bc_bwd_smem_bytes(n, m, npoly, d->nnzA, psm ? S.nnzP : 0, tt, max_psd, psd_total, d->ep + d->ed);
         if (sm <= smem_cap) { h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = psm; return true; }
         if (psm) break;  // do not trade threads for P residency
       }
     return false;
   };
   // fast backward path: same launch geometry fields, different kernel
-  if (S.dense && S.ncones == 0 && n <= 128 && (n % 2) == 0 && (S.nnzP == 0 || S.p_dense)) {
+  if (S.dense && S.ncones == 0 && d->ep + d->ed == 0 && n <= 128 && (n % 2) == 0 && (S.nnzP == 0 || S.p_dense)) {
     for (int tt = threads; tt >= 64; tt /= 2) {
       size_t sm = bc_bwdf_smem_bytes(n, m, d->nnzA, S.nnzP, tt);
       if (sm <= smem_cap) { h->fast_bwd = 1; h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = S.nnzP > 0; break; }
@@ -181,7 +183,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   if (!pick_fwd() || (!h->fast_bwd && !pick_bwd())) {
     char buf[256];
     snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
-             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total), smem_cap);
+             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total, d->ep + d->ed), smem_cap);
     bcone_destroy(h);
     return fail(nullptr, BCONE_EUNSUPPORTED, buf);
   }

@@ -11,21 +11,21 @@
 #include "common.cuh"
 
 struct BwdSmem {
-  double *Av, *Pv, *x, *piy, *v, *b, *c, *px2c, *U, *V, *W, *X, *t1, *t2, *Lsc, *Rsc, *tin, *part, *red, *psdVL, *psdscr;
+  double *Av, *Pv, *x, *piy, *v, *b, *c, *px2c, *U, *V, *W, *X, *t1, *t2, *Lsc, *Rsc, *tin, *part, *red, *psdVL, *psdscr, *expJ;
   uint64_t *bar;
   int *ibuf;
 };
 
 // v is only kept for the non-polyhedral rows (nonneg rows use pi_y > 0 <=> v > 0 as their mask).
-__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total) {
+__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
   size_t N = (size_t)n + m + 1;
   size_t d = 4 + (((size_t)nnzA + 1) & ~(size_t)1) + (((size_t)nnzP_smem + 1) & ~(size_t)1) + 3 * (size_t)n + 2 * (size_t)m + (m - npoly) +
              7 * N + 2 * (size_t)m + threads + 2 * 32;
   if (max_psd > 0) d += psd_total + (size_t)(threads / 32) * (3 * (size_t)max_psd * max_psd + max_psd);
-  return d;
+  return d + 9 * (size_t)nexp;
 }
 
-__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total) {
+__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
   const int N = n + m + 1;
   double *q = base;
   M.bar = (uint64_t *)q; q += 2;
@@ -39,6 +39,7 @@ __device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, 
   M.Lsc = q; q += N; M.Rsc = q; q += N; M.tin = q; q += N;
   M.t1 = q; q += m; M.t2 = q; q += m;
   M.part = q; q += threads; M.red = q; q += 2 * 32;
+  M.expJ = q; q += 9 * nexp;
   M.psdVL = q; q += psd_total;
   M.psdscr = q;
 }
@@ -108,6 +109,12 @@ __device__ __forceinline__ void apply_D(const DevStruct &S, const BwdSmem &M, co
         mat_to_svec_warp(k, Xd, ob);
       }
     }
+  }
+  for (int e = t; e < S.ep + S.ed; e += T) {
+    const double *J = M.expJ + 9 * e, *ib = in + S.exp_start + 3 * e;
+    double *ob = out + S.exp_start + 3 * e;
+    const double i0 = ib[0], i1 = ib[1], i2 = ib[2];
+    ob[0] = J[0] * i0 + J[1] * i1 + J[2] * i2; ob[1] = J[3] * i0 + J[4] * i1 + J[5] * i2; ob[2] = J[6] * i0 + J[7] * i1 + J[8] * i2;
   }
   __syncthreads();
 }
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
   const bcone_settings &st = a.st;
   BwdSmem M;
-  carve_b(M, smem, n, m, S.z + S.l, S.nnzA, a.p_in_smem ? S.nnzP : 0, T, S.max_psd, a.psd_total);
+  carve_b(M, smem, n, m, S.z + S.l, S.nnzA, a.p_in_smem ? S.nnzP : 0, T, S.max_psd, a.psd_total, S.ep + S.ed);
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
@@ -288,6 +295,14 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
           __syncwarp();
           mat_to_svec_warp(k, Xd + k * k, M.piy + s0);
         }
+      }
+      __syncthreads();
+    }
+    if (S.ep + S.ed > 0) {   // exponential cones: pi_y and the 3x3 Jacobians, one cone per thread
+      for (int e = t; e < S.ep + S.ed; e += T) {
+        const int s0 = S.exp_start + 3 * e;
+        dproj_exp_dualblock_mat(M.v + s0, e < S.ep, M.expJ + 9 * e);
+        proj_exp_dualblock(M.piy + s0, e < S.ep);
       }
       __syncthreads();
     }
@@ -442,8 +457,8 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
   }
 }
 
-extern "C" size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total) {
-  return bwd_smem_doubles(n, m, npoly, nnzA, nnzP_smem, threads, max_psd, psd_total) * sizeof(double);
+extern "C" size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
+  return bwd_smem_doubles(n, m, npoly, nnzA, nnzP_smem, threads, max_psd, psd_total, nexp) * sizeof(double);
 }
 extern "C" cudaError_t bc_bwd_configure(int dense, size_t smem) {
   if (dense) return cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -25,6 +25,7 @@ enum { BC_CZERO = 0, BC_CNONNEG = 1, BC_CSOC = 2, BC_CPSD = 3 };
 struct DevStruct {
   int n, m, nnzA, nnzP;
   int z, l, nq, ns;
+  int ep, ed, exp_start;     // exponential cones: ep primal + ed dual triples starting at row exp_start
   int dense;                 // A pattern is the full m x n rectangle, row-major
   int ncones;                // non-polyhedral cone blocks (SOC + PSD)
   int max_psd;               // largest PSD order
@@ -450,14 +451,13 @@ __device__ inline void jacobi_eig_warp(int k, double *X, double *V) {
   const int lane = threadIdx.x & 31;
   for (int e = lane; e < k * k; e += 32) V[e] = (e / k == e % k) ? 1.0 : 0.0;
   __syncwarp();
-  for (int sweep = 0; sweep < 60; sweep++) {
-    double off = 0, dg = 0;
-    for (int e = lane; e < k * k; e += 32) { double a = X[e]; if (e / k == e % k) dg += a * a; else off += a * a; }
-    off = warp_sum(off); dg = warp_sum(dg);
-    if (off <= 1e-30 * (dg + off) || off == 0.0) break;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    int rotations = 0;   // warp-uniform: every lane reads the same shared-memory words
     for (int p = 0; p < k - 1; p++) for (int q = p + 1; q < k; q++) {
       const double apq = X[p * k + q];
-      if (apq == 0.0) continue;  // warp-uniform (same smem word)
+      // skip negligible off-diagonals; the sweep loop ends when a whole sweep rotates nothing
+      if (fabs(apq) <= 1e-17 * (fabs(X[p * k + p]) + fabs(X[q * k + q])) || apq == 0.0) continue;
+      rotations++;
       const double app = X[p * k + p], aqq = X[q * k + q];
       const double theta = (aqq - app) / (2.0 * apq);
       const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
@@ -476,6 +476,7 @@ __device__ inline void jacobi_eig_warp(int k, double *X, double *V) {
       }
       __syncwarp();
     }
+    if (rotations == 0) break;
   }
   __syncwarp();
 }
@@ -499,6 +500,120 @@ __device__ inline void project_psd_warp(double *v, int k, double *scr) {
   __syncwarp();
 }
 
+// ----------------------------------------------------------------------------- exponential cone
+// K_exp = cl{(x,y,z): y > 0, y e^{x/y} <= z}.  Thread-level projection (one cone per thread):
+// closed-form cases, else bisection on the dual variable with an inner 1-D Newton (Parikh & Boyd,
+// Proximal Algorithms 6.3.4) and a Newton polish of the univariate optimality condition in
+// rho = x/y; Jacobian by implicit differentiation of the projection's KKT system (4x4 solve).
+__device__ inline double exp_newton_one_d(double rho, double yh, double zh) {
+  double t = fmax(-zh, 1e-6);
+  for (int i = 0; i < 100; i++) {
+    const double f = t * (t + zh) / rho / rho - yh / rho + log(t / rho) + 1.0;
+    const double fp = (2.0 * t + zh) / rho / rho + 1.0 / t;
+    t -= f / fp;
+    if (t <= -zh) return 0.0;
+    if (t <= 0.0) return zh;
+    if (fabs(f) < 1e-13) break;
+  }
+  return t + zh;
+}
+__device__ inline double exp_calc_grad(const double *v, double *x, double rho) {
+  x[2] = exp_newton_one_d(rho, v[1], v[2]);
+  x[1] = (x[2] - v[2]) * x[2] / rho;
+  x[0] = v[0] - rho;
+  if (x[1] <= 1e-12) return x[0];
+  return x[0] + x[1] * log(x[1] / x[2]);
+}
+__device__ inline double exp_h(double r, double s, double t, double rho, double *y, double *mu) {
+  const double E = exp(rho);
+  *y = (r + t * E) / (rho + E * E);
+  *mu = *y * E - t;
+  return *y + *mu * E * (1.0 - rho) - s;
+}
+// v <- Pi_{K_exp}(v); returns the case (0 inside, 1 polar, 2 analytic face, 3 iterative)
+__device__ inline int proj_exp(double *v) {
+  const double r = v[0], s = v[1], t = v[2];
+  if ((s > 0 && s * exp(fmin(r / s, 700.0)) - t <= 1e-13) || (r <= 0 && s == 0 && t >= 0)) return 0;
+  if ((r > 0 && r * exp(fmin(s / r, 700.0)) + 2.718281828459045 * t <= 1e-13) || (r == 0 && s <= 0 && t <= 0)) { v[0] = v[1] = v[2] = 0; return 1; }
+  if (r < 0 && s < 0) { v[1] = 0.0; v[2] = fmax(t, 0.0); return 2; }
+  double x[3], lb = 0.0, ub = 0.125;
+  while (exp_calc_grad(v, x, ub) > 0 && ub < 1e300) { lb = ub; ub *= 2.0; }
+  for (int i = 0; i < 200; i++) {
+    const double rho = 0.5 * (ub + lb), g = exp_calc_grad(v, x, rho);
+    if (g > 0) lb = rho; else ub = rho;
+    if (ub - lb < 1e-10 * fmax(1.0, rho)) break;
+  }
+  if (x[1] > 1e-12) {
+    double rr = x[0] / x[1], y, mu, hv = exp_h(r, s, t, rr, &y, &mu);
+    for (int it = 0; it < 8; it++) {
+      const double d = 1e-7 * fmax(1.0, fabs(rr));
+      double y2, m2;
+      const double dh = (exp_h(r, s, t, rr + d, &y2, &m2) - exp_h(r, s, t, rr - d, &y2, &m2)) / (2.0 * d);
+      if (dh == 0.0) break;
+      double yn, mn;
+      const double rn = rr - hv / dh, hn = exp_h(r, s, t, rn, &yn, &mn);
+      if (!(fabs(hn) < fabs(hv) && yn > 0 && mn >= 0)) break;
+      rr = rn; hv = hn; y = yn; mu = mn;
+    }
+    if (y > 0 && mu >= 0) { x[0] = y * rr; x[1] = y; x[2] = y * exp(rr); }
+  }
+  v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+  return 3;
+}
+// J (3x3 row-major) = D Pi_{K_exp}(v)
+__device__ inline void dproj_exp_mat(const double *v, double *J) {
+  double p[3] = {v[0], v[1], v[2]};
+  const int cs = proj_exp(p);
+  for (int i = 0; i < 9; i++) J[i] = 0;
+  if (cs == 0) { J[0] = J[4] = J[8] = 1.0; return; }
+  if (cs == 1) return;
+  if (cs == 2) { J[0] = 1.0; J[8] = v[2] > 0 ? 1.0 : 0.0; return; }
+  if (!(p[1] > 1e-12)) { J[0] = v[0] < 0 ? 1.0 : 0.0; J[8] = p[2] > 0 ? 1.0 : 0.0; return; }
+  const double rho = p[0] / p[1], E = exp(rho), mu = p[2] - v[2], a = mu * E / p[1];
+  double K[4][7] = {{1.0 + a, -a * rho, 0.0, E, 1, 0, 0},
+                    {-a * rho, 1.0 + a * rho * rho, 0.0, E * (1.0 - rho), 0, 1, 0},
+                    {0.0, 0.0, 1.0, -1.0, 0, 0, 1},
+                    {E, E * (1.0 - rho), -1.0, 0.0, 0, 0, 0}};
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    int pv = c;
+#pragma unroll
+    for (int r2 = c + 1; r2 < 4; r2++) if (fabs(K[r2][c]) > fabs(K[pv][c])) pv = r2;
+#pragma unroll
+    for (int r2 = 0; r2 < 4; r2++) if (r2 == pv && pv != c) {
+#pragma unroll
+      for (int k = 0; k < 7; k++) { const double tmp = K[c][k]; K[c][k] = K[r2][k]; K[r2][k] = tmp; }
+    }
+    const double ip = 1.0 / K[c][c];
+#pragma unroll
+    for (int k = 0; k < 7; k++) K[c][k] *= ip;
+#pragma unroll
+    for (int r2 = 0; r2 < 4; r2++) if (r2 != c) {
+      const double f = K[r2][c];
+#pragma unroll
+      for (int k = 0; k < 7; k++) K[r2][k] -= f * K[c][k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) J[i * 3 + j] = K[i][4 + j];
+}
+// y-block versions: rows whose primal cone is K_exp project onto K* (Moreau), rows whose primal
+// cone is the dual exponential cone project onto K_exp itself.
+__device__ inline void proj_exp_dualblock(double *v, bool primal_is_exp) {
+  if (primal_is_exp) { double w[3] = {-v[0], -v[1], -v[2]}; proj_exp(w); v[0] += w[0]; v[1] += w[1]; v[2] += w[2]; }
+  else proj_exp(v);
+}
+__device__ inline void dproj_exp_dualblock_mat(const double *v, bool primal_is_exp, double *J) {
+  if (primal_is_exp) {
+    double w[3] = {-v[0], -v[1], -v[2]};
+    dproj_exp_mat(w, J);
+#pragma unroll
+    for (int i = 0; i < 9; i++) J[i] = ((i % 4 == 0) ? 1.0 : 0.0) - J[i];
+  } else dproj_exp_mat(v, J);
+}
+
 // v (y-space, length m) <- Pi_{K*}(v) for the SOC/PSD blocks; warps stride over cone blocks.
 __device__ __forceinline__ void project_cones(const DevStruct &S, double *v, double *psd_scr) {
   const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -508,4 +623,5 @@ __device__ __forceinline__ void project_cones(const DevStruct &S, double *v, dou
     if (ty == BC_CSOC) project_soc_warp(v + st, __ldg(S.cone_size + cb));
     else project_psd_warp(v + st, __ldg(S.cone_order + cb), psd_scr + warp * scr_stride);
   }
+  for (int e = threadIdx.x; e < S.ep + S.ed; e += blockDim.x) proj_exp_dualblock(v + S.exp_start + 3 * e, e < S.ep);
 }

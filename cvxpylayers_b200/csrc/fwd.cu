@@ -238,6 +238,14 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         for (int i = t; i < m; i += T) { const double r = M.tm[i]; M.tm[i] = fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
         for (int j = t; j < n; j += T) { const double r = M.tn[j]; M.tn[j] = fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
         __syncthreads();
+        if (S.ep + S.ed > 0) {
+          for (int e = t; e < S.ep + S.ed; e += T) {
+            double *q = M.tm + S.exp_start + 3 * e;
+            const double mean = (q[0] + q[1] + q[2]) / 3.0;
+            q[0] = mean; q[1] = mean; q[2] = mean;
+          }
+          __syncthreads();
+        }
         if (S.ncones > 0) {  // one scale per non-separable cone: the block mean
           const int lane = t & 31, warp = t >> 5, nw = T >> 5;
           for (int cb = warp; cb < S.ncones; cb += nw) {
@@ -305,7 +313,8 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
       const bool check = (it % st.check_interval == 0) || it == st.max_iters;
       __syncthreads();  // everyone has read w[N-1] / ut before they are overwritten
       // ---- cone step + relaxation (fused when the cone is polyhedral and no check is due) ----
-      const bool fused = (S.ncones == 0) && !check;
+      const bool nonpoly = S.ncones + S.ep + S.ed > 0;
+      const bool fused = !nonpoly && !check;
       for (int k = t; k < N; k += T) {
         const double utk = (k == N - 1) ? tau_t : M.ut[k] - tau_t * M.g[k];
         const double wk = M.w[k];
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         if (fused) M.w[k] = wk + alpha * (uk - utk);
       }
       __syncthreads();
-      if (S.ncones > 0) { project_cones(S, M.u + n, M.psd); __syncthreads(); }
+      if (nonpoly) { project_cones(S, M.u + n, M.psd); __syncthreads(); }
 
       if (check) {
         // ---- termination quantities on the un-normalised data ----

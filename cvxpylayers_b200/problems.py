@@ -88,6 +88,7 @@ class Batch:
     y_star: np.ndarray | None = None
     s_star: np.ndarray | None = None
     name: str = ""
+    aux: dict | None = None
 
     @property
     def B(self) -> int:
@@ -266,12 +267,48 @@ def sdp(B: int = 256, k: int = 10, n_eq: int = 10, seed: int = 0) -> Batch:
     return plant(st, A_vals, None, rng, name=f"sdp_k{k}_eq{n_eq}")
 
 
+def exp_sum(B: int = 64, p: int = 6, k: int = 12, lam: float = 1.0, seed: int = 0) -> Batch:
+    """Exponential-cone workload:  min  sum_i exp(a_i'x + d_i) + c'x + lam/2 ||x||^2  written with
+    k exponential cones (a_i'x + d_i, 1, t_i) in K_exp and the quadratic term as a (diagonal, sparse) P.
+    Variables (x in R^p, t in R^k); the reference's exp-cone tests are the logistic-regression / LML
+    layers of tests/test_torch.py:158-187,219-230."""
+    rng = np.random.default_rng(seed)
+    n, m = p + k, 3 * k
+    rows, cols = [], []
+    for i in range(k):
+        rows += [3 * i] * p
+        cols += list(range(p))
+        rows.append(3 * i + 2)
+        cols.append(p + i)
+    pat = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(m, n))
+    pat.sort_indices()
+    pptr = np.concatenate([np.arange(p + 1), np.full(k, p)]).astype(np.int32)
+    st = Structure(n, m, pat.indptr, pat.indices, ConeSpec(ep=k), pptr, np.arange(p, dtype=np.int32))
+    a = rng.standard_normal((B, k, p)) / np.sqrt(p)
+    d = 0.3 * rng.standard_normal((B, k))
+    A_vals = np.zeros((B, st.nnzA))
+    b = np.zeros((B, m))
+    pos = 0
+    for i in range(k):
+        A_vals[:, pos : pos + p] = -a[:, i, :]
+        pos += p
+        A_vals[:, pos] = -1.0
+        pos += 1
+        b[:, 3 * i] = d[:, i]
+        b[:, 3 * i + 1] = 1.0
+    c = np.concatenate([0.5 * rng.standard_normal((B, p)), np.ones((B, k))], axis=1)
+    bt = Batch(st, A_vals, b, c, np.full((B, p), lam), name=f"exp_sum_p{p}_k{k}")
+    bt.aux = {"a": a, "d": d, "lam": lam, "p": p, "k": k}
+    return bt
+
+
 CONFIGS = {
     "C1": lambda B=1, seed=0: dense_qp(B, 10, 20, 0, seed),
     "C2": lambda B=4096, seed=0: dense_qp(B, 100, 200, 50, seed),
     "C3": lambda B=2048, seed=0: socp_portfolio(B, seed=seed),
     "C4": lambda B=512, seed=0: sparse_lp(B, seed=seed),
     "C5": lambda B=256, seed=0: sdp(B, seed=seed),
+    "EXP": lambda B=64, seed=0: exp_sum(B, seed=seed),
 }
 
 

@@ -18,7 +18,8 @@
  *                     (dA_eval = [-dA ; db[b_idx]], dq_eval = [dc ; 0])
  *
  * Solver form (SCS / diffcp convention):  min 1/2 x'Px + c'x  s.t.  Ax + s = b, s in K,
- * dual y in K*.  K = zero(z) x nonneg(l) x SOC(q[0..nq)) x PSD(s[0..ns)) in that row order.
+ * dual y in K*.  K = zero(z) x nonneg(l) x SOC(q[0..nq)) x PSD(s[0..ns)) x exp(ep) x exp*(ed) in that
+ * row order (exp triples (x,y,z): y e^{x/y} <= z).
  * All floating point data is fp64.
  */
 #ifndef BCONE_H
@@ -33,7 +34,7 @@ typedef struct {
   int32_t n, m, nnzA, nnzP;
   const int32_t *A_indptr, *A_indices; /* HOST pointers, CSR of A (m+1 / nnzA); copied        */
   const int32_t *P_indptr, *P_indices; /* HOST pointers, CSR upper triangle of P, or NULL     */
-  int32_t z, l, nq, ns, ep, ed;        /* cone spec; ep/ed must be 0 (exp cones: not built)   */
+  int32_t z, l, nq, ns, ep, ed;        /* cone spec in SCS row order z, l, q, s, ep, ed        */
   const int32_t *q, *s;                /* HOST: SOC sizes [nq], PSD orders [ns]               */
   int32_t device;                      /* CUDA device ordinal                                 */
   int32_t max_batch;                   /* workspace is sized for this many instances          */

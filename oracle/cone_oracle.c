@@ -76,15 +76,12 @@ static int cone_blocks(const orc_desc *d, cblock **out) {
  * On exit X holds eigenvalues on its diagonal, V the eigenvectors as columns. */
 static void jacobi_eig(int k, double *X, double *V) {
   for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) V[i * k + j] = (i == j);
-  for (int sweep = 0; sweep < 60; sweep++) {
-    double off = 0, diag = 0;
-    for (int i = 0; i < k; i++) for (int j = 0; j < k; j++) {
-      if (i != j) off += X[i * k + j] * X[i * k + j]; else diag += X[i * k + i] * X[i * k + i];
-    }
-    if (off <= 1e-30 * (diag + off) || off == 0.0) break;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    int rotations = 0;
     for (int p = 0; p < k - 1; p++) for (int q = p + 1; q < k; q++) {
       double apq = X[p * k + q];
-      if (apq == 0.0) continue;
+      if (fabs(apq) <= 1e-17 * (fabs(X[p * k + p]) + fabs(X[q * k + q])) || apq == 0.0) continue;
+      rotations++;
       double app = X[p * k + p], aqq = X[q * k + q];
       double theta = (aqq - app) / (2.0 * apq);
       double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
@@ -102,6 +99,7 @@ static void jacobi_eig(int k, double *X, double *V) {
         V[r * k + p] = c * vp - s * vq; V[r * k + q] = s * vp + c * vq;
       }
     }
+    if (rotations == 0) break;
   }
 }
 
@@ -148,6 +146,100 @@ static void proj_psd(int k, double *v) {
   free(lam); free(X);
 }
 
+
+/* ---- exponential cone K_exp = cl{(x,y,z): y > 0, y e^{x/y} <= z} ------------------------------
+ * Projection: the three closed-form cases, otherwise bisection on the dual variable with an inner
+ * 1-D Newton (Parikh & Boyd, "Proximal Algorithms" 6.3.4 -- the scheme of SCS's exp_cone.c), then a
+ * Newton polish of the univariate optimality condition in rho = x/y (Friberg 2023) to full precision.
+ * Jacobian: implicit differentiation of the projection's KKT system (the 4x4 solve of SURVEY.md 8a B1). */
+static double exp_newton_one_d(double rho, double yh, double zh) {
+  double t = fmax(-zh, 1e-6);
+  for (int i = 0; i < 100; i++) {
+    double f = t * (t + zh) / rho / rho - yh / rho + log(t / rho) + 1.0;
+    double fp = (2.0 * t + zh) / rho / rho + 1.0 / t;
+    t -= f / fp;
+    if (t <= -zh) return 0.0;
+    if (t <= 0.0) return zh;
+    if (fabs(f) < 1e-13) break;
+  }
+  return t + zh;
+}
+static double exp_calc_grad(const double *v, double *x, double rho) {
+  x[2] = exp_newton_one_d(rho, v[1], v[2]);
+  x[1] = (x[2] - v[2]) * x[2] / rho;
+  x[0] = v[0] - rho;
+  if (x[1] <= 1e-12) return x[0];
+  return x[0] + x[1] * log(x[1] / x[2]);
+}
+static double exp_h(double r, double s, double t, double rho, double *y, double *mu) {
+  double E = exp(rho);
+  *y = (r + t * E) / (rho + E * E);
+  *mu = *y * E - t;
+  return *y + *mu * E * (1.0 - rho) - s;
+}
+/* returns the case: 0 in K, 1 in polar (-> 0), 2 analytic face, 3 iterative */
+static int proj_exp(double *v) {
+  const double r = v[0], s = v[1], t = v[2];
+  if ((s > 0 && s * exp(fmin(r / s, 700.0)) - t <= 1e-13) || (r <= 0 && s == 0 && t >= 0)) return 0;
+  if ((r > 0 && r * exp(fmin(s / r, 700.0)) + 2.718281828459045 * t <= 1e-13) || (r == 0 && s <= 0 && t <= 0)) { v[0] = v[1] = v[2] = 0; return 1; }
+  if (r < 0 && s < 0) { v[1] = 0.0; v[2] = fmax(t, 0.0); return 2; }
+  double x[3], lb = 0.0, ub = 0.125;
+  while (exp_calc_grad(v, x, ub) > 0 && ub < 1e300) { lb = ub; ub *= 2.0; }
+  for (int i = 0; i < 200; i++) {
+    double rho = 0.5 * (ub + lb), g = exp_calc_grad(v, x, rho);
+    if (g > 0) lb = rho; else ub = rho;
+    if (ub - lb < 1e-10 * fmax(1.0, rho)) break;
+  }
+  if (x[1] > 1e-12) { /* polish */
+    double rr = x[0] / x[1], y, mu, hv = exp_h(r, s, t, rr, &y, &mu);
+    for (int it = 0; it < 8; it++) {
+      double d = 1e-7 * fmax(1.0, fabs(rr)), y2, m2;
+      double dh = (exp_h(r, s, t, rr + d, &y2, &m2) - exp_h(r, s, t, rr - d, &y2, &m2)) / (2.0 * d);
+      if (dh == 0.0) break;
+      double rn = rr - hv / dh, yn, mn, hn = exp_h(r, s, t, rn, &yn, &mn);
+      if (!(fabs(hn) < fabs(hv) && yn > 0 && mn >= 0)) break;
+      rr = rn; hv = hn; y = yn; mu = mn;
+    }
+    if (y > 0 && mu >= 0) { x[0] = y * rr; x[1] = y; x[2] = y * exp(rr); }
+  }
+  v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+  return 3;
+}
+/* J (3x3 row-major) = D Pi_{K_exp}(v) */
+static void dproj_exp_mat(const double *v, double *J) {
+  double p[3] = {v[0], v[1], v[2]};
+  int cs = proj_exp(p);
+  for (int i = 0; i < 9; i++) J[i] = 0;
+  if (cs == 0) { J[0] = J[4] = J[8] = 1.0; return; }
+  if (cs == 1) return;
+  if (cs == 2) { J[0] = 1.0; J[8] = v[2] > 0 ? 1.0 : 0.0; return; }
+  if (!(p[1] > 1e-12)) { J[0] = v[0] < 0 ? 1.0 : 0.0; J[8] = p[2] > 0 ? 1.0 : 0.0; return; } /* landed on the y = 0 face */
+  const double rho = p[0] / p[1], E = exp(rho), mu = p[2] - v[2], a = mu * E / p[1];
+  double K[4][7] = {{1.0 + a, -a * rho, 0.0, E, 1, 0, 0},
+                    {-a * rho, 1.0 + a * rho * rho, 0.0, E * (1.0 - rho), 0, 1, 0},
+                    {0.0, 0.0, 1.0, -1.0, 0, 0, 1},
+                    {E, E * (1.0 - rho), -1.0, 0.0, 0, 0, 0}};
+  for (int c = 0; c < 4; c++) { /* Gauss-Jordan with partial pivoting */
+    int pv = c;
+    for (int r2 = c + 1; r2 < 4; r2++) if (fabs(K[r2][c]) > fabs(K[pv][c])) pv = r2;
+    if (pv != c) for (int k = 0; k < 7; k++) { double tmp = K[c][k]; K[c][k] = K[pv][k]; K[pv][k] = tmp; }
+    double ip = 1.0 / K[c][c];
+    for (int k = 0; k < 7; k++) K[c][k] *= ip;
+    for (int r2 = 0; r2 < 4; r2++) if (r2 != c) { double f = K[r2][c]; if (f != 0) for (int k = 0; k < 7; k++) K[r2][k] -= f * K[c][k]; }
+  }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) J[i * 3 + j] = K[i][4 + j];
+}
+/* dual-cone versions used on the y block: DUALK = 1 for rows whose primal cone K is the exp cone
+ * (project onto K* by Moreau), 0 for rows whose primal cone is the dual exp cone (K* = K_exp). */
+static void proj_exp_dualblock(double *v, int primal_is_exp) {
+  if (primal_is_exp) { double w[3] = {-v[0], -v[1], -v[2]}; proj_exp(w); for (int i = 0; i < 3; i++) v[i] += w[i]; }
+  else proj_exp(v);
+}
+static void dproj_exp_dualblock_mat(const double *v, int primal_is_exp, double *J) {
+  if (primal_is_exp) { double w[3] = {-v[0], -v[1], -v[2]}; dproj_exp_mat(w, J); for (int i = 0; i < 9; i++) J[i] = ((i % 4 == 0) ? 1.0 : 0.0) - J[i]; }
+  else dproj_exp_mat(v, J);
+}
+
 static void proj_dual_blocks(const cblock *B, int nb, double *v) {
   for (int k = 0; k < nb; k++) {
     double *vb = v + B[k].start;
@@ -156,7 +248,9 @@ static void proj_dual_blocks(const cblock *B, int nb, double *v) {
       case CNONNEG: for (int i = 0; i < B[k].size; i++) if (vb[i] < 0) vb[i] = 0; break;
       case CSOC: proj_soc(B[k].size, vb); break;
       case CPSD: proj_psd(B[k].order, vb); break;
-      default: break; /* exponential cones: not built yet (out of round-1 scope) */
+      case CEXP: proj_exp_dualblock(vb, 1); break;
+      case CEXPD: proj_exp_dualblock(vb, 0); break;
+      default: break;
     }
   }
 }
@@ -218,6 +312,11 @@ static void dproj_dual_blocks(const cblock *B, int nb, const double *v, const do
         }
         mat_to_svec(o, Dm, ob);
         free(X);
+        break;
+      }
+      case CEXP: case CEXPD: {
+        double J[9]; dproj_exp_dualblock_mat(vb, B[k].type == CEXP, J);
+        for (int i = 0; i < 3; i++) ob[i] = J[i * 3] * db[0] + J[i * 3 + 1] * db[1] + J[i * 3 + 2] * db[2];
         break;
       }
       default: for (int i = 0; i < sz; i++) ob[i] = 0; break;
@@ -316,7 +415,6 @@ static void set_ry(fwd_ws *w, double scale) {
 int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
               double *x, double *y, double *s, int32_t *iters, double *resid, const orc_settings *st) {
   int n = d->n, m = d->m, N = n + m + 1, nnzA = d->nnzA, nnzP = d->P_indptr ? d->nnzP : 0;
-  if (d->ep > 0 || d->ed > 0) { if (iters) *iters = 0; return ORC_FAILED; }
   size_t tot = (size_t)nnzA + nnzP + 3 * m + 3 * n + (size_t)n * n + (n + m) + n + m + 6 * (size_t)N + 2 * m + 2 * n;
   double *buf = (double *)calloc(tot + 16, sizeof(double)), *q = buf;
   fwd_ws W; W.n = n; W.m = m; W.d = d; W.rho_x = st->rho_x;

@@ -1,1 +1,2 @@
-BENCH_E2E_BREAKDOWN=1 B200_TRACE=1 python bench.py --steps 3 --warmup 3 --cpu-sample 0 2>&1 | grep -v "^{" | tail -20
+python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+python tools/bench_configs.py 2>&1 | tee gpurun_out/configs_r1.jsonl | tail -6

@@ -15,7 +15,7 @@ from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("C1", 4), ("C2", 6), ("C3", 6), ("C5", 4)]
+CASES = [("C1", 4), ("C2", 6), ("C3", 6), ("C5", 4), ("EXP", 5)]
 
 
 def _t(a, dev):

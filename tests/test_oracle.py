@@ -202,3 +202,60 @@ def test_oracle_reproduces_golden_fixtures(name):
     dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, g["x"], g["y"], g["s"], g["dx"], g["dy"], bt.P_vals,
                                       lsqr_precond=1, lsqr_iter_lim=100000)
     assert rel_err(dA, g["dA"]) < 1e-9 and rel_err(db, g["db"]) < 1e-9 and rel_err(dc, g["dc"]) < 1e-9
+
+
+# ----------------------------------------------------------------------------- exponential cone
+def test_exp_cone_projection_certificate_and_jacobian():
+    """Moreau certificate (p in K, v - p in K^o, p'(v - p) = 0) + finite-difference Jacobian."""
+    st_ed = Structure(1, 3, np.arange(4), np.zeros(3, np.int32), ConeSpec(ed=1))   # K* = K_exp
+    st_ep = Structure(1, 3, np.arange(4), np.zeros(3, np.int32), ConeSpec(ep=1))   # K* = dual exp cone
+
+    def in_K(v, tol):
+        r, s_, t_ = v
+        return (s_ > 0 and s_ * np.exp(min(r / s_, 700)) <= t_ + tol) or (r <= tol and abs(s_) <= tol and t_ >= -tol)
+
+    def in_Kstar(u, tol):
+        a, b_, c_ = u
+        return (a < 0 and -a * np.exp(min(b_ / a, 700)) <= np.e * c_ + tol) or (abs(a) <= tol and b_ >= -tol and c_ >= -tol)
+
+    rng = np.random.default_rng(2)
+    jac_bad = 0
+    for _ in range(1500):
+        v = rng.standard_normal(3) * rng.choice([0.1, 1, 10, 100])
+        sc = max(1.0, np.abs(v).max())
+        p = orc.proj_dual_cone(st_ed, v)
+        assert in_K(p, 1e-6 * sc) and in_Kstar(-(v - p), 1e-6 * sc) and abs(p @ (v - p)) <= 1e-6 * sc * sc
+        q = orc.proj_dual_cone(st_ep, v)
+        assert in_Kstar(q, 1e-6 * sc) and in_K(-(v - q), 1e-6 * sc) and abs(q @ (v - q)) <= 1e-6 * sc * sc
+        dv = rng.standard_normal(3)
+        h = 1e-6 * sc
+        fd = (orc.proj_dual_cone(st_ed, v + h * dv) - orc.proj_dual_cone(st_ed, v - h * dv)) / (2 * h)
+        jac_bad += np.abs(fd - orc.dproj_dual_cone(st_ed, v, dv)).max() > 1e-4 * max(1, np.abs(fd).max())
+    assert jac_bad <= 3  # central differences straddle a kink of the projection now and then
+
+
+def test_exp_cone_program_matches_scipy_minimize():
+    """min sum exp(a_i'x + d_i) + c'x + lam/2||x||^2 solved as a cone program vs a smooth solver."""
+    bt = pr.exp_sum(3, p=4, k=7, seed=3)
+    st, aux = bt.structure, bt.aux
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=200000)
+    assert (status == 1).all()
+    for i in range(bt.B):
+        a, d, cx = aux["a"][i], aux["d"][i], bt.c[i, : aux["p"]]
+        f = lambda z: np.exp(a @ z + d).sum() + cx @ z + 0.5 * aux["lam"] * z @ z  # noqa: E731
+        g = lambda z: a.T @ np.exp(a @ z + d) + cx + aux["lam"] * z  # noqa: E731
+        res = sopt.minimize(f, np.zeros(aux["p"]), jac=g, method="BFGS", options={"gtol": 1e-12})
+        assert np.abs(x[i, : aux["p"]] - res.x).max() < 1e-6
+        assert np.abs(x[i, aux["p"]:] - np.exp(a @ res.x + d)).max() < 1e-6
+    # adjoint against finite differences on b (the d_i shifts)
+    rng = np.random.default_rng(0)
+    dx, dy = rng.standard_normal(x.shape), np.zeros_like(y)
+    dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, x, y, s, dx, dy, bt.P_vals, lsqr_precond=1, lsqr_iter_lim=20000)
+    h = 1e-6
+    for k in (0, 3, 6):
+        bp, bm = bt.b.copy(), bt.b.copy()
+        bp[:, k] += h; bm[:, k] -= h
+        xp = orc.solve_batch(st, bt.A_vals, bp, bt.c, bt.P_vals, eps=1e-11, max_iters=400000)[0]
+        xm = orc.solve_batch(st, bt.A_vals, bm, bt.c, bt.P_vals, eps=1e-11, max_iters=400000)[0]
+        fd = ((xp - xm) * dx).sum(1) / (2 * h)
+        assert np.abs(fd - db[:, k]).max() <= 1e-4 + 1e-3 * np.abs(fd).max(), (k, fd, db[:, k])
