@@ -11,11 +11,13 @@
 
 // ---- kernels / launchers implemented in fwd.cu, bwd.cu, pack.cu ----
 extern "C" {
-size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd);
-cudaError_t bc_fwd_configure(int dense, size_t smem);
-cudaError_t bc_fwd_occupancy(int dense, int threads, size_t smem, int *ctas);
-cudaError_t bc_fwd_launch(const FwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
-size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp);
+size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect);
+size_t bc_fwd_ws_doubles(int n, int m);
+cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem);
+cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas);
+cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t st);
+size_t bc_bwd_ws_doubles(int n, int m, int npoly);
+size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp, int vec_global);
 cudaError_t bc_bwd_configure(int dense, size_t smem);
 cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
@@ -38,6 +40,9 @@ struct Handle {
   int fwd_threads = 0, bwd_threads = 0, fwd_ctas = 0, bwd_ctas = 0;
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
+  int fwd_indirect = 0, bwd_vec_global = 0;   // large instances: CG instead of Cholesky, vectors in a global slab
+  double *fwd_ws = nullptr, *bwd_ws = nullptr;
+  size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
   std::string err;
@@ -157,20 +162,22 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   int threads = d->nnzA >= 8192 ? 512 : (d->nnzA >= 1024 ? 256 : 128);
   while (threads < 512 && threads < n) threads *= 2;  // transposed products want one lane per column
   const int npoly = d->z + d->l;
-  auto pick_fwd = [&]() -> bool {
-    for (int tt = threads; tt >= 64; tt /= 2) {
-      size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd);
-      if (sm <= smem_cap) { h->fwd_threads = tt; h->fwd_smem = sm; return true; }
-    }
+  auto pick_fwd = [&]() -> bool {   // DIRECT (Cholesky on chip) if the instance fits, else INDIRECT (CG, vectors in L2)
+    for (int ind = 0; ind <= 1; ind++)
+      for (int tt = threads; tt >= 64; tt /= 2) {
+        size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd, ind);
+        if (sm <= smem_cap) { h->fwd_threads = tt; h->fwd_smem = sm; h->fwd_indirect = ind; return true; }
+      }
     return false;
   };
-  auto pick_bwd = [&]() -> bool {   // prefer P staged in shared memory, fall back to P read from L2
-    for (int psm = (S.nnzP > 0 ? 1 : 0); psm >= 0; psm--)
-      for (int tt = threads; tt >= 64; tt /= 2) {
-        size_t sm = bc_bwd_smem_bytes(n, m, npoly, d->nnzA, psm ? S.nnzP : 0, tt, max_psd, psd_total, d->ep + d->ed);
-        if (sm <= smem_cap) { h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = psm; return true; }
-        if (psm) break;  // do not trade threads for P residency
-      }
+  auto pick_bwd = [&]() -> bool {   // prefer P staged in shared memory, then vectors on chip, then vectors in L2
+    for (int vg = 0; vg <= 1; vg++)
+      for (int psm = (S.nnzP > 0 ? 1 : 0); psm >= 0; psm--)
+        for (int tt = threads; tt >= 64; tt /= 2) {
+          size_t sm = bc_bwd_smem_bytes(n, m, npoly, d->nnzA, psm ? S.nnzP : 0, tt, max_psd, psd_total, d->ep + d->ed, vg);
+          if (sm <= smem_cap) { h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = psm; h->bwd_vec_global = vg; return true; }
+          if (psm) break;  // do not trade threads for P residency
+        }
     return false;
   };
   // fast backward path: same launch geometry fields, different kernel
@@ -183,22 +190,32 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   if (!pick_fwd() || (!h->fast_bwd && !pick_bwd())) {
     char buf[256];
     snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
-             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total, d->ep + d->ed), smem_cap);
+             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, 1), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total, d->ep + d->ed, 1), smem_cap);
     bcone_destroy(h);
     return fail(nullptr, BCONE_EUNSUPPORTED, buf);
   }
   cudaError_t e;
-  if ((e = bc_fwd_configure(S.dense, h->fwd_smem)) != cudaSuccess ||
+  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fwd_smem)) != cudaSuccess ||
       (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
-  bc_fwd_occupancy(S.dense, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
+  bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
   if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;
+  if (h->fwd_indirect) {
+    h->fwd_ws_stride = bc_fwd_ws_doubles(n, m);
+    if (cudaMalloc((void **)&h->fwd_ws, h->fwd_ws_stride * sizeof(double) * h->num_sms * h->fwd_ctas) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc forward workspace"); }
+    h->allocs.push_back(h->fwd_ws);
+  }
+  if (h->bwd_vec_global && !h->fast_bwd) {
+    h->bwd_ws_stride = bc_bwd_ws_doubles(n, m, npoly);
+    if (cudaMalloc((void **)&h->bwd_ws, h->bwd_ws_stride * sizeof(double) * h->num_sms * h->bwd_ctas) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc backward workspace"); }
+    h->allocs.push_back(h->bwd_ws);
+  }
   h->tma_ok = (d->nnzA > 0 && (d->nnzA % 2) == 0 && (size_t)d->nnzA * 8 < (1u << 20)) ? 1 : 0;
   *out = h;
   return BCONE_OK;
@@ -270,9 +287,10 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
   a.counter = h->counters; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
+  a.ws = h->fwd_ws; a.ws_stride = (long long)h->fwd_ws_stride;
   CK(cudaMemsetAsync(h->counters, 0, sizeof(int), st), "solve counter");
   const int grid = std::min(B, h->num_sms * h->fwd_ctas);
-  CK(bc_fwd_launch(&a, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
+  CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
   h->launches++;
   return BCONE_OK;
 }
@@ -291,6 +309,7 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   a.x = x; a.y = y; a.s = s; a.dx = dx; a.dy = dy; a.dA = dA_vals; a.dP = dP_vals; a.db = db; a.dc = dc;
   a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = h->counters + 1;
   a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
+  a.ws = h->fast_bwd ? nullptr : h->bwd_ws; a.ws_stride = (long long)h->bwd_ws_stride;
   CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(int), st), "vjp counter");
   const int grid = std::min(B, h->num_sms * h->bwd_ctas);
   if (h->fast_bwd) CK(bc_bwdf_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch (fast)");

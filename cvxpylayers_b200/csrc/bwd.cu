@@ -17,28 +17,34 @@ struct BwdSmem {
 };
 
 // v is only kept for the non-polyhedral rows (nonneg rows use pi_y > 0 <=> v > 0 as their mask).
-__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
+__host__ __device__ inline size_t bwd_vec_doubles(int n, int m, int npoly) {
   size_t N = (size_t)n + m + 1;
-  size_t d = 4 + (((size_t)nnzA + 1) & ~(size_t)1) + (((size_t)nnzP_smem + 1) & ~(size_t)1) + 3 * (size_t)n + 2 * (size_t)m + (m - npoly) +
-             7 * N + 2 * (size_t)m + threads + 2 * 32;
+  return 3 * (size_t)n + 2 * (size_t)m + (m - npoly) + 7 * N + 2 * (size_t)m;
+}
+// vec_global: large instances keep the LSQR vectors in a per-CTA slab of global memory.
+__host__ __device__ inline size_t bwd_smem_doubles(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp, int vec_global) {
+  size_t d = 4 + (((size_t)nnzA + 1) & ~(size_t)1) + (((size_t)nnzP_smem + 1) & ~(size_t)1) + threads + 2 * 32;
+  if (!vec_global) d += bwd_vec_doubles(n, m, npoly);
   if (max_psd > 0) d += psd_total + (size_t)(threads / 32) * (3 * (size_t)max_psd * max_psd + max_psd);
   return d + 9 * (size_t)nexp;
 }
 
-__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
+__device__ __forceinline__ void carve_b(BwdSmem &M, double *base, double *gws, int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
   const int N = n + m + 1;
   double *q = base;
   M.bar = (uint64_t *)q; q += 2;
   M.ibuf = (int *)q; q += 2;
   M.Av = q; q += (nnzA + 1) & ~1;
   M.Pv = q; q += (nnzP_smem + 1) & ~1;
-  M.x = q; q += n; M.c = q; q += n; M.px2c = q; q += n;
-  M.piy = q; q += m; M.b = q; q += m;
-  M.v = q - npoly; q += m - npoly;  // indexed by the original row i >= npoly
-  M.U = q; q += N; M.V = q; q += N; M.W = q; q += N; M.X = q; q += N;
-  M.Lsc = q; q += N; M.Rsc = q; q += N; M.tin = q; q += N;
-  M.t1 = q; q += m; M.t2 = q; q += m;
   M.part = q; q += threads; M.red = q; q += 2 * 32;
+  double *v = gws ? gws : q;
+  M.x = v; v += n; M.c = v; v += n; M.px2c = v; v += n;
+  M.piy = v; v += m; M.b = v; v += m;
+  M.v = v - npoly; v += m - npoly;  // indexed by the original row i >= npoly
+  M.U = v; v += N; M.V = v; v += N; M.W = v; v += N; M.X = v; v += N;
+  M.Lsc = v; v += N; M.Rsc = v; v += N; M.tin = v; v += N;
+  M.t1 = v; v += m; M.t2 = v; v += m;
+  if (!gws) q = v;
   M.expJ = q; q += 9 * nexp;
   M.psdVL = q; q += psd_total;
   M.psdscr = q;
@@ -229,7 +235,8 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
   const bcone_settings &st = a.st;
   BwdSmem M;
-  carve_b(M, smem, n, m, S.z + S.l, S.nnzA, a.p_in_smem ? S.nnzP : 0, T, S.max_psd, a.psd_total, S.ep + S.ed);
+  carve_b(M, smem, a.ws ? a.ws + (size_t)blockIdx.x * a.ws_stride : nullptr, n, m, S.z + S.l, S.nnzA, a.p_in_smem ? S.nnzP : 0, T, S.max_psd,
+          a.psd_total, S.ep + S.ed);
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
@@ -457,9 +464,10 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
   }
 }
 
-extern "C" size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp) {
-  return bwd_smem_doubles(n, m, npoly, nnzA, nnzP_smem, threads, max_psd, psd_total, nexp) * sizeof(double);
+extern "C" size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp, int vec_global) {
+  return bwd_smem_doubles(n, m, npoly, nnzA, nnzP_smem, threads, max_psd, psd_total, nexp, vec_global) * sizeof(double);
 }
+extern "C" size_t bc_bwd_ws_doubles(int n, int m, int npoly) { return (bwd_vec_doubles(n, m, npoly) + 1) & ~(size_t)1; }
 extern "C" cudaError_t bc_bwd_configure(int dense, size_t smem) {
   if (dense) return cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -49,6 +49,8 @@ struct FwdArgs {
   bcone_settings st;
   int *counter;
   int use_tma;
+  double *ws;            // INDIRECT mode: per-CTA slab of global memory holding the iterate vectors
+  long long ws_stride;   // doubles per CTA
 };
 
 struct BwdArgs {
@@ -62,6 +64,8 @@ struct BwdArgs {
   int use_tma;
   int psd_total;  // sum over PSD blocks of k^2 + k
   int p_in_smem;  // P values staged in shared memory (they fit) instead of read from L2
+  double *ws;            // large instances: LSQR vectors live in a per-CTA slab of global memory (L2)
+  long long ws_stride;
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -190,7 +194,7 @@ __device__ __forceinline__ double butterfly4(double a0, double a1, double a2, do
 // ep(i, value) is called by exactly one lane.
 template <bool SQ = false, class Layout, class Epi>
 __device__ __forceinline__ void matvec_rows(const double *__restrict__ M, Layout lay, int nrows, int ncols,
-                                            const double *__restrict__ x, Epi ep) {
+                                            const double *x, Epi ep) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (ncols <= 128) {
     double xr[4];
@@ -267,7 +271,7 @@ __device__ __forceinline__ ColPlan make_colplan(int nrows, int ncols) {
 // (needs blockDim.x doubles).  Contains two __syncthreads(); ep(j, value) called once per column.
 template <bool SQ = false, class Layout, class Epi>
 __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout lay, int nrows, int ncols,
-                                            const double *__restrict__ y, double *part, Epi ep, const ColPlan &pl) {
+                                            const double *y, double *part, Epi ep, const ColPlan &pl) {
   const int T = blockDim.x, t = threadIdx.x;
   if (pl.fits) {
     if (pl.active) {
@@ -321,7 +325,7 @@ __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout
 template <bool SQ = false, class Epi>
 __device__ __forceinline__ void csr_rows(const double *__restrict__ vals, const int *__restrict__ indptr,
                                          const int *__restrict__ indices, int nrows,
-                                         const double *__restrict__ x, Epi ep) {
+                                         const double *x, Epi ep) {
   constexpr int G = 4;
   const int g = threadIdx.x % G, grp = threadIdx.x / G, ngrp = blockDim.x / G;
   for (int base = 0; base < nrows; base += ngrp) {  // block-uniform trip count (full-mask shuffles below)
@@ -339,7 +343,7 @@ __device__ __forceinline__ void csr_rows(const double *__restrict__ vals, const 
 template <bool SQ = false, class Epi>
 __device__ __forceinline__ void csr_cols(const double *__restrict__ vals, const int *__restrict__ colptr,
                                          const int *__restrict__ rowidx, const int *__restrict__ perm, int ncols,
-                                         const double *__restrict__ y, Epi ep) {
+                                         const double *y, Epi ep) {
   constexpr int G = 4;
   const int g = threadIdx.x % G, grp = threadIdx.x / G, ngrp = blockDim.x / G;
   for (int base = 0; base < ncols; base += ngrp) {

@@ -15,30 +15,40 @@
 #include "common.cuh"
 
 struct FwdSmem {
-  double *Av, *Li, *w, *u, *ut, *g, *bh, *ch, *Dm, *En, *tn, *tn2, *tn3, *tm, *part, *red, *psd;
+  double *Av, *Li, *w, *u, *ut, *g, *bh, *ch, *Dm, *En, *tn, *tn2, *tn3, *tm, *part, *red, *psd, *cr, *cp, *cq, *kd, *cx;
   uint64_t *bar;
   int *ibuf;
 };
 
-__host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd) {
+// Vector block shared by both modes (doubles): iterate + work vectors (+ CG vectors when INDIRECT).
+__host__ __device__ inline size_t fwd_vec_doubles(int n, int m, int indirect) {
   size_t N = (size_t)n + m + 1;
+  return 3 * N + (n + m) + m + n + m + n + n + n + n + m + (indirect ? 5 * (size_t)n : 0);
+}
+// DIRECT: everything on chip.  INDIRECT (instances whose n x n Cholesky does not fit): the CSR values,
+// the reduction scratch and the PSD scratch stay in shared memory, the vectors move to a global slab.
+__host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd, int indirect) {
   size_t nA = ((size_t)nnzA + 1) & ~(size_t)1;
-  size_t d = nA + (size_t)n * (n + 1) / 2 + 3 * N + (n + m) + m + n + m + n + n + n + n + m + threads + 8 * 32;
+  size_t d = 4 + nA + threads + 8 * 32;
+  if (!indirect) d += (size_t)n * (n + 1) / 2 + fwd_vec_doubles(n, m, 0);
   if (max_psd > 0) d += (size_t)(threads / 32) * (2 * (size_t)max_psd * max_psd + max_psd);
-  return d + 2 /*mbarrier*/ + 2 /*ibuf*/;
+  return d;
 }
 
-__device__ __forceinline__ void carve(FwdSmem &M, double *base, int n, int m, int nnzA, int threads, int max_psd) {
+__device__ __forceinline__ void carve(FwdSmem &M, double *base, double *gws, int n, int m, int nnzA, int threads, int max_psd) {
   const int N = n + m + 1;
   double *q = base;
   M.bar = (uint64_t *)q; q += 2;
   M.ibuf = (int *)q; q += 2;
   M.Av = q; q += (nnzA + 1) & ~1;
-  M.Li = q; q += n * (n + 1) / 2;
-  M.w = q; q += N; M.u = q; q += N; M.ut = q; q += N;
-  M.g = q; q += n + m; M.bh = q; q += m; M.ch = q; q += n; M.Dm = q; q += m; M.En = q; q += n;
-  M.tn = q; q += n; M.tn2 = q; q += n; M.tn3 = q; q += n; M.tm = q; q += m;
   M.part = q; q += threads; M.red = q; q += 8 * 32;
+  if (!gws) { M.Li = q; q += n * (n + 1) / 2; } else M.Li = nullptr;
+  double *v = gws ? gws : q;
+  M.w = v; v += N; M.u = v; v += N; M.ut = v; v += N;
+  M.g = v; v += n + m; M.bh = v; v += m; M.ch = v; v += n; M.Dm = v; v += m; M.En = v; v += n;
+  M.tn = v; v += n; M.tn2 = v; v += n; M.tn3 = v; v += n; M.tm = v; v += m;
+  if (gws) { M.cr = v; v += n; M.cp = v; v += n; M.cq = v; v += n; M.kd = v; v += n; M.cx = v; v += n; }
+  else { M.cr = M.cp = M.cq = M.kd = M.cx = nullptr; q = v; }
   M.psd = q;
 }
 
@@ -46,15 +56,96 @@ __device__ __forceinline__ double inv_ry(const DevStruct &S, int i, double scale
   return i < S.z ? BC_ZERO_CONE_FACTOR * scale : scale;
 }
 
+// ----------------------------------------------------------------------------- INDIRECT linear system
+// out = K v,  K = rho_x I + P^ + A^' R_y^{-1} A^   (two sparse products; SCS "indirect" mode)
+template <bool DENSE>
+__device__ void K_mul(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, const double *v, double *out,
+                      const ColPlan &plA, const ColPlan &plN) {
+  const DevStruct &S = a.S;
+  const int n = S.n, T = blockDim.x, t = threadIdx.x;
+  A_mul<DENSE>(S, M.Av, v, [&](int i, double q) { M.tm[i] = q * inv_ry(S, i, scale); });
+  __syncthreads();
+  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double q) { out[j] = q + rho_x * v[j]; }, plA);
+  if (Pv) {
+    for (int j = t; j < n; j += T) M.tn3[j] = M.En[j] * v[j];
+    __syncthreads();
+    P_mul(S, Pv, M.tn3, M.part, [&](int j, double q) { out[j] += M.En[j] * q; }, plN);
+  }
+}
+// Jacobi-preconditioned CG on K x = rhs, warm-started from x; stops at ||r|| <= tol.  Returns iterations.
+template <bool DENSE>
+__device__ int cg_solve(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, const double *rhs, double *x,
+                        double tol, int maxit, const ColPlan &plA, const ColPlan &plN) {
+  const int n = a.S.n, T = blockDim.x, t = threadIdx.x;
+  K_mul<DENSE>(a, M, Pv, scale, rho_x, x, M.cq, plA, plN);
+  double r2[2] = {0, 0};
+  for (int j = t; j < n; j += T) {
+    const double r = rhs[j] - M.cq[j], z = r / M.kd[j];
+    M.cr[j] = r; M.cp[j] = z; r2[0] = fma(r, z, r2[0]); r2[1] = fma(r, r, r2[1]);
+  }
+  block_reduce<2, false>(r2, M.red);
+  double rz = r2[0];
+  int it = 0;
+  while (it < maxit && sqrt(r2[1]) > tol) {
+    it++;
+    __syncthreads();
+    K_mul<DENSE>(a, M, Pv, scale, rho_x, M.cp, M.cq, plA, plN);
+    double pq[1] = {0};
+    for (int j = t; j < n; j += T) pq[0] = fma(M.cp[j], M.cq[j], pq[0]);
+    block_reduce<1, false>(pq, M.red);
+    const double alpha = rz / pq[0];
+    r2[0] = 0; r2[1] = 0;
+    for (int j = t; j < n; j += T) {
+      x[j] = fma(alpha, M.cp[j], x[j]);
+      const double r = fma(-alpha, M.cq[j], M.cr[j]), z = r / M.kd[j];
+      M.cr[j] = r; M.cq[j] = z; r2[0] = fma(r, z, r2[0]); r2[1] = fma(r, r, r2[1]);
+    }
+    block_reduce<2, false>(r2, M.red);
+    const double beta = r2[0] / rz;
+    rz = r2[0];
+    for (int j = t; j < n; j += T) M.cp[j] = fma(beta, M.cp[j], M.cq[j]);
+  }
+  __syncthreads();
+  return it;
+}
+
 // K = rho_x I + P^ + A^' R_y^{-1} A^ (packed lower) -> Cholesky -> in-place inverse Linv;
 // then g = (R_z + M)^{-1} h and g'Rg.  Returns false if the factorisation broke down.
-template <bool DENSE>
+template <bool DENSE, bool INDIRECT>
 __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, double &gRg,
                              const ColPlan &plA, const ColPlan &plN) {
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const int npk = n * (n + 1) / 2;
   double *K = M.Li;
+  if (INDIRECT) {
+    // Jacobi preconditioner diag(K), then g = (R_z + M)^{-1} h by CG at tight tolerance
+    for (int i = t; i < m; i += T) M.tm[i] = inv_ry(S, i, scale);
+    for (int j = t; j < n; j += T) M.tn3[j] = 0.0;
+    __syncthreads();
+    AT_mul<DENSE, true>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.kd[j] = rho_x + v; }, plA);
+    if (Pv) {
+      for (int k = t; k < S.nnzP; k += T) { const int i = __ldg(S.P_rowof + k); if (__ldg(S.P_indices + k) == i) M.kd[i] += Pv[k] * M.En[i] * M.En[i]; }
+      __syncthreads();
+    }
+    for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
+    __syncthreads();
+    AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; M.g[j] = 0.0; }, plA);
+    double nr[1] = {0};
+    for (int j = t; j < n; j += T) nr[0] = fma(M.tn[j], M.tn[j], nr[0]);
+    block_reduce<1, false>(nr, M.red);
+    cg_solve<DENSE>(a, M, Pv, scale, rho_x, M.tn, M.g, 1e-13 * fmax(1.0, sqrt(nr[0])), 10 * n, plA, plN);
+    A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); });
+    __syncthreads();
+    double acc[1] = {0};
+    for (int k = t; k < n + m; k += T) {
+      const double r = k < n ? rho_x : 1.0 / inv_ry(S, k - n, scale);
+      acc[0] = fma(r * M.g[k], M.g[k], acc[0]);
+    }
+    block_reduce<1, false>(acc, M.red);
+    gRg = acc[0];
+    return true;
+  }
   if (DENSE) {
     for (int e = t; e < npk; e += T) {
       int j = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
@@ -147,14 +238,14 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   return true;
 }
 
-template <bool DENSE>
+template <bool DENSE, bool INDIRECT>
 __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
   const bcone_settings &st = a.st;
   FwdSmem M;
-  carve(M, smem, n, m, S.nnzA, T, S.max_psd);
+  carve(M, smem, INDIRECT ? a.ws + (size_t)blockIdx.x * a.ws_stride : nullptr, n, m, S.nnzA, T, S.max_psd);
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
@@ -283,8 +374,9 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
 
     double scale = st.scale, gRg = 0;
     int status = BCONE_INACCURATE, it = 0;
-    bool okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg, plA, plN);
+    bool okf = factor_and_g<DENSE, INDIRECT>(a, M, Pg, scale, rho_x, gRg, plA, plN);
     for (int k = t; k < N; k += T) { M.w[k] = (k == N - 1) ? 1.0 : 0.0; M.u[k] = 0; M.ut[k] = 0; }
+    if (INDIRECT) for (int j = t; j < n; j += T) M.cx[j] = 0.0;
     __syncthreads();
     double sum_log = 0, rp = nan(""), rd = nan(""), gap = nan("");
     int n_log = 0, last_up = 0;
@@ -293,9 +385,20 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     for (it = 1; okf && it <= st.max_iters; it++) {
       // ---- affine step ----
       AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; }, plA);
-      matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
-      __syncthreads();
-      matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; }, plN);
+      if (INDIRECT) {
+        // warm start from the previous p_x = ut_x + tau~ g_x; tolerance tightens with the iteration count
+        double nr[1] = {0};
+        for (int j = t; j < n; j += T) { nr[0] = fma(M.tn[j], M.tn[j], nr[0]); M.ut[j] = M.cx[j]; }
+        block_reduce<1, false>(nr, M.red);
+        const double tol = fmax(1e-13, fmin(1e-6, 0.1 / pow((double)it, 1.5))) * fmax(1.0, sqrt(nr[0]));
+        cg_solve<DENSE>(a, M, Pg, scale, rho_x, M.tn, M.ut, tol, 4 * n, plA, plN);
+        for (int j = t; j < n; j += T) M.cx[j] = M.ut[j];   // keep p_x for the next warm start
+        __syncthreads();
+      } else {
+        matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
+        __syncthreads();
+        matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; }, plN);
+      }
       A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) { M.ut[n + i] = M.w[n + i] + v * inv_ry(S, i, scale); });
       __syncthreads();
       double d4[4] = {0, 0, 0, 0};  // mu'g, p'Rg, p'Rp, p'mu
@@ -393,7 +496,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
               }
               scale = ns;
               __syncthreads();
-              okf = factor_and_g<DENSE>(a, M, Pg, scale, rho_x, gRg, plA, plN);
+              okf = factor_and_g<DENSE, INDIRECT>(a, M, Pg, scale, rho_x, gRg, plA, plN);
               if (!okf) { status = BCONE_FAILED; break; }
               sum_log = 0; n_log = 0; last_up = it;
             }
@@ -436,24 +539,31 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
 }
 
 // ----------------------------------------------------------------------------- host launcher
-extern "C" size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd) {
-  return fwd_smem_doubles(n, m, nnzA, threads, max_psd) * sizeof(double);
+extern "C" size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect) {
+  return fwd_smem_doubles(n, m, nnzA, threads, max_psd, indirect) * sizeof(double);
 }
+extern "C" size_t bc_fwd_ws_doubles(int n, int m) { return (fwd_vec_doubles(n, m, 1) + 1) & ~(size_t)1; }
 
-extern "C" cudaError_t bc_fwd_configure(int dense, size_t smem) {
-  cudaError_t e;
-  if (dense) e = cudaFuncSetAttribute(fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else e = cudaFuncSetAttribute(fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define FWD_DISPATCH(EXPR)                                        \
+  do {                                                            \
+    if (dense && indirect) { auto k = fwd_kernel<true, true>; EXPR; }        \
+    else if (dense) { auto k = fwd_kernel<true, false>; EXPR; }              \
+    else if (indirect) { auto k = fwd_kernel<false, true>; EXPR; }           \
+    else { auto k = fwd_kernel<false, false>; EXPR; }                        \
+  } while (0)
+
+extern "C" cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem) {
+  cudaError_t e = cudaSuccess;
+  FWD_DISPATCH(e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return e;
 }
-
-extern "C" cudaError_t bc_fwd_occupancy(int dense, int threads, size_t smem, int *ctas_per_sm) {
-  if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fwd_kernel<true>, threads, smem);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fwd_kernel<false>, threads, smem);
+extern "C" cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas_per_sm) {
+  cudaError_t e = cudaSuccess;
+  FWD_DISPATCH(e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k, threads, smem));
+  return e;
 }
-
-extern "C" cudaError_t bc_fwd_launch(const FwdArgs *a, int grid, int threads, size_t smem, cudaStream_t stream) {
-  if (a->S.dense) fwd_kernel<true><<<grid, threads, smem, stream>>>(*a);
-  else fwd_kernel<false><<<grid, threads, smem, stream>>>(*a);
+extern "C" cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t stream) {
+  const int dense = a->S.dense;
+  FWD_DISPATCH((k<<<grid, threads, smem, stream>>>(*a)));
   return cudaGetLastError();
 }

@@ -242,13 +242,35 @@ def socp_portfolio(B: int = 2048, n_assets: int = 50, n_soc: int = 5, k: int = 1
 
 
 def sparse_lp(B: int = 512, n: int = 1000, m: int = 2000, density: float = 0.01, seed: int = 0) -> Batch:
-    """C4: sparse LP, one pattern for the whole batch, fresh values per instance."""
+    """C4: sparse LP, one pattern for the whole batch, fresh values per instance; planted
+    non-degenerate vertex (exactly n active rows, strict complementarity)."""
     rng = np.random.default_rng(seed)
     pat = sp.random(m, n, density=density, random_state=np.random.RandomState(seed), format="csr")
     pat.sort_indices()
     st = Structure(n, m, pat.indptr, pat.indices, ConeSpec(l=m))
     A_vals = rng.standard_normal((B, st.nnzA))
-    return plant(st, A_vals, None, rng, name=f"sparse_lp_n{n}_m{m}", active_frac=0.4)
+    x = rng.standard_normal((B, n))
+    z = -np.abs(rng.standard_normal((B, m))) - 0.1
+    for i in range(B):
+        act = rng.choice(m, size=n, replace=False)
+        z[i, act] = np.abs(z[i, act])
+    y = np.maximum(z, 0.0)
+    s = y - z
+    b = _apply_A(st, A_vals, x) + s
+    c = -_apply_AT(st, A_vals, y)
+    return Batch(st, A_vals, b, c, None, x, y, s, f"sparse_lp_n{n}_m{m}")
+
+
+def sparse_qp(B: int = 8, n: int = 300, m: int = 600, density: float = 0.03, seed: int = 0) -> Batch:
+    """Sparse strongly convex QP (diagonal P) too large for the on-chip Cholesky: exercises the
+    CG (indirect) forward path and the L2-resident-vector backward path with a well-defined gradient."""
+    rng = np.random.default_rng(seed)
+    pat = sp.random(m, n, density=density, random_state=np.random.RandomState(seed), format="csr")
+    pat.sort_indices()
+    st = Structure(n, m, pat.indptr, pat.indices, ConeSpec(l=m), np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32))
+    A_vals = rng.standard_normal((B, st.nnzA))
+    P_vals = 0.5 + rng.random((B, n))
+    return plant(st, A_vals, P_vals, rng, name=f"sparse_qp_n{n}_m{m}", active_frac=0.2)
 
 
 def sdp(B: int = 256, k: int = 10, n_eq: int = 10, seed: int = 0) -> Batch:

@@ -1,2 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -6
-python tools/bench_configs.py 2>&1 | tee gpurun_out/configs_r1.jsonl | tail -6
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sparse or C5 or EXP" 2>&1 | tail -12

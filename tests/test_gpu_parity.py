@@ -78,3 +78,39 @@ def test_backward_matches_oracle(name, B, precond, cuda_device):
     assert rel(db, rb) < tol and rel(dc, rc) < tol and rel(dA, rA) < tol, (rel(dA, rA), rel(db, rb), rel(dc, rc), its, rits)
     if rP is not None:
         assert rel(dP, rP) < tol
+
+
+def test_sparse_lp_c4_indirect_forward(cuda_device):
+    """BASELINE config C4 (sparse LP, n=1000, m=2000, 1% dense): the n x n Cholesky does not fit on
+    chip, so the engine switches to CG on the reduced KKT system with the iterate vectors in L2.
+    Un-accelerated operator splitting needs thousands of iterations on LPs, so the check
+    is the solver's own termination certificate at the SCS default tolerance."""
+    B, eps = 4, 1e-4
+    bt = pr.sparse_lp(B=B, seed=3)
+    eng, sol = _solve_gpu(bt, cuda_device, eps=eps, max_iters=100000)
+    assert eng.kernel_info()["fwd_smem"] < 232448
+    assert (sol.status.cpu().numpy() == 1).all(), (sol.status, sol.iters)
+    x, y, s = sol.x.cpu().numpy(), sol.y.cpu().numpy(), sol.s.cpu().numpy()
+    for i in range(B):
+        r = np_ref.kkt_residuals(bt.A_dense(i), None, bt.b[i], bt.c[i], x[i], y[i], s[i])
+        assert np_ref.is_converged(r, eps, eps, 1.001), (i, r)
+    assert (s >= -1e-12).all() and (y >= -1e-12).all() and np.abs((s * y).sum(1)).max() < 1e-8
+
+
+def test_large_sparse_qp_indirect_forward_and_l2_backward(cuda_device):
+    """n=300, m=600 sparse QP: CG forward + L2-resident LSQR vectors, against the oracle."""
+    bt = pr.sparse_qp(B=5, seed=2)
+    st, dev = bt.structure, cuda_device
+    eng, sol = _solve_gpu(bt, dev, eps=1e-8, max_iters=100000)
+    assert (sol.status.cpu().numpy() == 1).all(), (sol.status, sol.iters)
+    assert np.abs(sol.x.cpu().numpy() - bt.x_star).max() < 1e-5
+    xo, yo, so, sto, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-10, max_iters=400000)
+    assert (sto == 1).all()
+    rng = np.random.default_rng(5)
+    dx, dy = rng.standard_normal(xo.shape), rng.standard_normal(yo.shape)
+    lim = 20 * (st.n + st.m + 1)
+    dA, dP, db, dc, its = eng.vjp(_t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(xo, dev), _t(yo, dev), _t(so, dev),
+                                  _t(dx, dev), _t(dy, dev), _t(bt.P_vals, dev), make_settings({"lsqr_iter_lim": lim, "lsqr_precond": 1}))
+    rA, rP, rb, rc, rits = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, xo, yo, so, dx, dy, bt.P_vals, lsqr_iter_lim=lim, lsqr_precond=1)
+    rel = lambda a, b_: np.abs(a.cpu().numpy() - b_).max() / max(np.abs(b_).max(), 1e-30)  # noqa: E731
+    assert rel(db, rb) < 1e-4 and rel(dc, rc) < 1e-4 and rel(dA, rA) < 1e-4 and rel(dP, rP) < 1e-4, (rel(dA, rA), rel(db, rb), rel(dc, rc), its, rits)
