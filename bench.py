@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "QP problems/sec fwd+bwd (batch=4096, n=100, m=200, zero+nonneg cones)"
 UNIT = "problems/s"
 # Solver settings shared by both arms (SCS defaults for the forward; LSQR rules of diffcp).
-SOLVER_ARGS = {"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 1}
+SOLVER_ARGS = {"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 2}
 # DRAM bytes per instance measured by ncu --set full on 296-instance launches (profiles/):
 # bwd_fast_kernel 62.17 MB read + 7.17 MB written; fwd_kernel 60.3 MB read + 0.2 MB written.
 NCU_DRAM_BYTES_PER_INSTANCE = {"bwd": (62.166016e6 + 7.173376e6) / 296, "fwd": (60.317696e6 + 0.20608e6) / 296}

@@ -25,6 +25,9 @@ size_t bc_bwdf_smem_bytes(int n, int m, int nnzA, int nnzP, int threads);
 cudaError_t bc_bwdf_configure(int n, size_t smem);
 cudaError_t bc_bwdf_occupancy(int n, int threads, size_t smem, int *ctas);
 cudaError_t bc_bwdf_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
+size_t bc_bwdb_smem_bytes(int n, int m, int threads);
+cudaError_t bc_bwdb_configure(size_t smem);
+cudaError_t bc_bwdb_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
 cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
 }
@@ -43,6 +46,8 @@ struct Handle {
   int fwd_indirect = 0, bwd_vec_global = 0;   // large instances: CG instead of Cholesky, vectors in a global slab
   double *fwd_ws = nullptr, *bwd_ws = nullptr;
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
+  int block_bwd = 0, blk_threads = 0; size_t blk_smem = 0;   // KKT-block preconditioned backward (lsqr_precond = 2)
+  int *fail_list = nullptr; int fail_cap = 0;
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
   std::string err;
@@ -154,7 +159,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     S.Pt_colptr = upload(h, pc); S.Pt_rowidx = upload(h, pr); S.Pt_perm = upload(h, pp);
     S.p_dense = pd ? 1 : 0;
   }
-  if (cudaMalloc((void **)&h->counters, 2 * sizeof(int)) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc counters"); }
+  if (cudaMalloc((void **)&h->counters, 4 * sizeof(int)) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc counters"); }
   h->allocs.push_back(h->counters);
 
   // --- launch geometry: threads by problem size, shared memory must hold the whole instance ---
@@ -187,6 +192,12 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
       if (sm <= smem_cap) { h->fast_bwd = 1; h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = S.nnzP > 0; break; }
     }
   }
+  if (h->fast_bwd && S.nnzP > 0) {   // block-preconditioned variant for strongly convex QPs
+    for (int tt = threads; tt >= 128; tt /= 2) {
+      size_t sm = bc_bwdb_smem_bytes(n, m, tt);
+      if (sm <= smem_cap) { h->block_bwd = 1; h->blk_threads = tt; h->blk_smem = sm; break; }
+    }
+  }
   if (!pick_fwd() || (!h->fast_bwd && !pick_bwd())) {
     char buf[256];
     snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
@@ -201,6 +212,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
+  if (h->block_bwd && (e = bc_bwdb_configure(h->blk_smem)) != cudaSuccess) h->block_bwd = 0;
   bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
   if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
@@ -310,6 +322,25 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = h->counters + 1;
   a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
   a.ws = h->fast_bwd ? nullptr : h->bwd_ws; a.ws_stride = (long long)h->bwd_ws_stride;
+  a.inst_list = nullptr; a.B_dev = nullptr; a.fail_list = nullptr; a.fail_count = nullptr;
+  if (h->block_bwd && stg->lsqr_precond == 2) {
+    // pass 1: block-preconditioned solve; pass 2: equilibrated LSQR on the instances it rejected
+    if (h->fail_cap < B) {
+      int *p = nullptr;
+      CK(cudaMalloc((void **)&p, (size_t)B * sizeof(int)), "vjp fail list");
+      h->allocs.push_back(p); h->fail_list = p; h->fail_cap = B;
+    }
+    CK(cudaMemsetAsync(h->counters + 1, 0, 3 * sizeof(int), st), "vjp counters");
+    a.fail_list = h->fail_list; a.fail_count = h->counters + 2;
+    CK(bc_bwdb_launch(&a, std::min(B, h->num_sms), h->blk_threads, h->blk_smem, st), "vjp launch (block)");
+    BwdArgs f = a;
+    f.st.lsqr_precond = 1; f.counter = h->counters + 3; f.inst_list = h->fail_list; f.B_dev = h->counters + 2;
+    f.fail_list = nullptr; f.fail_count = nullptr;
+    CK(bc_bwdf_launch(&f, std::min(B, h->num_sms * h->bwd_ctas), h->bwd_threads, h->bwd_smem, st), "vjp launch (fallback)");
+    h->launches += 2;
+    return BCONE_OK;
+  }
+  if (a.st.lsqr_precond == 2) a.st.lsqr_precond = 1;   // block factorisation not available for this structure
   CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(int), st), "vjp counter");
   const int grid = std::min(B, h->num_sms * h->bwd_ctas);
   if (h->fast_bwd) CK(bc_bwdf_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch (fast)");

@@ -200,10 +200,13 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
   const int lo = S.z, hi = S.z + S.l;
 
   for (;;) {
-    if (t == 0) M.ibuf[0] = atomicAdd(a.counter, 1);
+    if (t == 0) {
+      const int k = atomicAdd(a.counter, 1), nwork = a.B_dev ? *a.B_dev : a.B;
+      M.ibuf[0] = k < nwork ? (a.inst_list ? a.inst_list[k] : k) : -1;
+    }
     __syncthreads();
     const int inst = M.ibuf[0];
-    if (inst >= a.B) break;
+    if (inst < 0) break;
     const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
     const double *Pglob = hasP ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
     const bool tmaP = a.use_tma && hasP && (S.nnzP % 2 == 0);

@@ -64,6 +64,9 @@ struct BwdArgs {
   int use_tma;
   int psd_total;  // sum over PSD blocks of k^2 + k
   int p_in_smem;  // P values staged in shared memory (they fit) instead of read from L2
+  const int *inst_list;  // optional: work item k is instance inst_list[k] (fallback pass of the block solver)
+  const int *B_dev;      // optional: number of work items read from device memory
+  int *fail_list, *fail_count;  // block solver: instances it could not handle, for the fallback pass
   double *ws;            // large instances: LSQR vectors live in a per-CTA slab of global memory (L2)
   long long ws_stride;
 };
@@ -154,6 +157,15 @@ struct PackedLowerLayout {  // row i holds columns 0..i at i(i+1)/2
   __device__ __forceinline__ int beg(int) const { return 0; }
   __device__ __forceinline__ int end(int i) const { return i + 1; }
   __device__ __forceinline__ int row_lo(int j) const { return j; }
+  __device__ __forceinline__ int row_hi(int, int nrows) const { return nrows; }
+};
+struct PackedLowerStrictLayout {  // same storage, diagonal excluded (transposed half of a symmetric product)
+  static constexpr bool kFullRows = false;
+  __device__ __forceinline__ int base(int i) const { return (i * (i + 1)) >> 1; }
+  __device__ __forceinline__ int step(int i) const { return i + 1; }
+  __device__ __forceinline__ int beg(int) const { return 0; }
+  __device__ __forceinline__ int end(int i) const { return i; }
+  __device__ __forceinline__ int row_lo(int j) const { return j + 1; }
   __device__ __forceinline__ int row_hi(int, int nrows) const { return nrows; }
 };
 // Upper triangle stored row by row (row i holds columns i..n-1): the CSR order of a dense
@@ -404,6 +416,51 @@ __device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, cons
     }
     __syncthreads();
   }
+}
+
+// ----------------------------------------------------------------------------- packed Cholesky + inverse
+// In-place Cholesky K = L L' of a packed-lower SPD matrix (row i at i(i+1)/2) followed by the
+// in-place inverse L^{-1}: the factor is applied afterwards as two triangular products, which keeps
+// every solve free of sequential substitution.  tmp: n doubles.  Block-uniform result (false: not PD).
+__device__ inline bool chol_inv_packed(double *K, int n, double *tmp) {
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    const int kk = (k * (k + 1)) >> 1;
+    const double dkk = K[kk + k];
+    if (!(dkk > 0)) { ok = false; break; }   // every thread reads the same word
+    const double ilkk = 1.0 / sqrt(dkk);
+    __syncthreads();
+    if (t == 0) K[kk + k] = dkk * ilkk;
+    for (int i = k + 1 + t; i < n; i += T) K[((i * (i + 1)) >> 1) + k] *= ilkk;
+    __syncthreads();
+    // trailing update: warp per row i, lanes across columns j in (k, i]
+    for (int i = k + 1 + warp; i < n; i += nw) {
+      const int ri = (i * (i + 1)) >> 1;
+      const double lik = K[ri + k];
+      for (int j = k + 1 + lane; j <= i; j += 32) K[ri + j] = fma(-lik, K[((j * (j + 1)) >> 1) + k], K[ri + j]);
+    }
+    __syncthreads();
+  }
+  if (!ok) return false;
+  // X = L^{-1}, row by row: X[i][j] = -(1/l_ii) sum_{k=j}^{i-1} L[i][k] X[k][j]; four lanes per output
+  for (int i = 0; i < n; i++) {
+    const int ro = (i * (i + 1)) >> 1;
+    for (int k = t; k <= i; k += T) tmp[k] = K[ro + k];
+    __syncthreads();
+    const double il = 1.0 / tmp[i];
+    const int g = t & 3;
+    for (int base = 0; base <= i; base += T >> 2) {   // block-uniform trip count (full-mask shuffles)
+      const int j = base + (t >> 2);
+      double acc = 0;
+      if (j < i) for (int k = j + g; k < i; k += 4) acc = fma(tmp[k], K[((k * (k + 1)) >> 1) + j], acc);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (g == 0 && j <= i) K[ro + j] = (j == i) ? il : -acc * il;
+    }
+    __syncthreads();
+  }
+  return true;
 }
 
 // ----------------------------------------------------------------------------- cone projections

@@ -182,42 +182,7 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
     }
     __syncthreads();
   }
-  // ---- in-place packed Cholesky (right-looking) ----
-  bool ok = true;
-  for (int k = 0; k < n; k++) {
-    const double dkk = K[k * (k + 1) / 2 + k];
-    if (!(dkk > 0)) { ok = false; break; }  // block-uniform: all threads read the same word
-    const double lkk = sqrt(dkk);
-    __syncthreads();
-    if (t == 0) K[k * (k + 1) / 2 + k] = lkk;
-    for (int i = k + 1 + t; i < n; i += T) K[i * (i + 1) / 2 + k] /= lkk;
-    __syncthreads();
-    const int r = n - k - 1, cnt = r * (r + 1) / 2;
-    for (int e = t; e < cnt; e += T) {
-      int ii = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-      while ((ii + 1) * (ii + 2) / 2 <= e) ii++;
-      while (ii * (ii + 1) / 2 > e) ii--;
-      const int jj = e - ii * (ii + 1) / 2;
-      const int i = k + 1 + ii, j = k + 1 + jj;
-      K[i * (i + 1) / 2 + j] -= K[i * (i + 1) / 2 + k] * K[j * (j + 1) / 2 + k];
-    }
-    __syncthreads();
-  }
-  if (!ok) return false;
-  // ---- in-place inverse of the packed lower factor, row by row ----
-  // X[i][j] = -(1/l_ii) sum_{k=j}^{i-1} L[i][k] X[k][j]; rows < i already hold X.
-  for (int i = 0; i < n; i++) {
-    const int ro = i * (i + 1) / 2;
-    for (int k = t; k <= i; k += T) M.tn[k] = K[ro + k];  // original row i of L
-    __syncthreads();
-    const double il = 1.0 / M.tn[i];
-    for (int j = t; j <= i; j += T) {
-      double acc = 0;
-      for (int k = j; k < i; k++) acc = fma(M.tn[k], K[k * (k + 1) / 2 + j], acc);
-      K[ro + j] = (j == i) ? il : -acc * il;
-    }
-    __syncthreads();
-  }
+  if (!chol_inv_packed(K, n, M.tn)) return false;
   // ---- g = (R_z + M)^{-1} h, h = (c^, b^) ----
   for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
   __syncthreads();

@@ -46,7 +46,8 @@ typedef struct {
   double lsqr_atol, lsqr_btol, lsqr_conlim; /* 1e-8, 1e-8, 1e8 (diffcp / SciPy LSQR rules)    */
   int32_t max_iters, normalize, adaptive_scale, check_interval;
   int32_t ruiz_passes, lsqr_iter_lim;  /* lsqr_iter_lim < 0 -> 2N like diffcp                 */
-  int32_t lsqr_precond;                /* 0 plain LSQR (reference semantics), 1 equilibrated  */
+  int32_t lsqr_precond;                /* 0 plain LSQR (reference semantics), 1 diagonally equilibrated,
+                                          2 KKT-block preconditioned where applicable (else 1) */
   int32_t reserved1;
 } bcone_settings;
 

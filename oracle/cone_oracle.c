@@ -758,6 +758,91 @@ static void lsqr_equilibrate(bwd_ctx *k, const double *piy_unused, int passes) {
   free(rs);
 }
 
+/* ---- lsqr_precond = 2: LSQR right-preconditioned by the exact block factorisation of the KKT part
+ * of the reduced system.  With live rows L (zero rows + active nonneg rows), the reduced matrix is
+ *     B = [[G, -h'], [g', x'Px]],   G = [[P, -A_L'], [A_L, 0]],  h' = (2Px + c ; b_L),  g = (c ; b_L),
+ * and B blkdiag(G,1)^{-1} = [[I, -h'], [(G^{-T} g)', x'Px]] is the identity plus a rank-2 term, so LSQR
+ * converges in a handful of O(N) iterations; the singular homogeneity direction is still resolved by
+ * LSQR's minimum-norm property.  Needs P > 0 and A_L of full row rank (both checked by the Cholesky
+ * factorisations of P and of S = A_L P^{-1} A_L'); otherwise the caller falls back to lsqr_precond = 1.
+ * Returns LSQR iterations, or -1 if the factorisation is not applicable. */
+typedef struct { int nr; const double *hp, *q; double xPx; } border_ctx;
+static void border_mv(void *c_, const double *in, double *out) {   /* C z */
+  border_ctx *c = (border_ctx *)c_; int nr = c->nr; double zt = in[nr], acc = 0;
+  for (int i = 0; i < nr; i++) { out[i] = in[i] - c->hp[i] * zt; acc += c->q[i] * in[i]; }
+  out[nr] = acc + c->xPx * zt;
+}
+static void border_mtv(void *c_, const double *in, double *out) {  /* C' u */
+  border_ctx *c = (border_ctx *)c_; int nr = c->nr; double ut = in[nr], acc = 0;
+  for (int i = 0; i < nr; i++) { out[i] = in[i] + c->q[i] * ut; acc += c->hp[i] * in[i]; }
+  out[nr] = -acc + c->xPx * ut;
+}
+static int vjp_block_precond(const orc_desc *d, bwd_ctx *K, const double *piy, const double *dz, double *r, const orc_settings *st) {
+  int n = d->n, m = d->m, N = n + m + 1, lo = d->z, hi = d->z + d->l;
+  if (!d->P_indptr || d->nq || d->ns || d->ep || d->ed) return -1;
+  int *live = (int *)malloc(sizeof(int) * (m + 1)), nl = 0;
+  for (int i = 0; i < m; i++) if (i < lo || i >= hi || piy[i] > 0) live[nl++] = i;
+  if (nl > n) { free(live); return -1; }
+  int nr = n + nl;
+  double *Lp = (double *)calloc((size_t)n * n + (size_t)nl * n + (size_t)nl * nl + 6 * (size_t)(nr + 1) + 2 * n, sizeof(double));
+  double *W = Lp + (size_t)n * n, *S = W + (size_t)nl * n, *hp = S + (size_t)nl * nl, *q = hp + nr + 1, *rhs = q + nr + 1, *z = rhs + nr + 1,
+         *t1 = z + nr + 1, *t2 = t1 + nr + 1, *tn = t2 + nr + 1;
+  int ok = 1;
+  for (int i = 0; i < n; i++) for (int k = d->P_indptr[i]; k < d->P_indptr[i + 1]; k++) Lp[(size_t)d->P_indices[k] * n + i] += K->Pv[k];  /* lower */
+  if (chol_lower(n, Lp)) ok = 0;
+  if (ok) {
+    for (int l = 0; l < nl; l++) {                       /* W_l = L^{-1} a_l */
+      double *w = W + (size_t)l * n; int i0 = live[l];
+      for (int j = 0; j < n; j++) w[j] = 0;
+      for (int k = d->A_indptr[i0]; k < d->A_indptr[i0 + 1]; k++) w[d->A_indices[k]] = K->Av[k];
+      for (int i = 0; i < n; i++) { double a = w[i]; for (int k = 0; k < i; k++) a -= Lp[(size_t)i * n + k] * w[k]; w[i] = a / Lp[(size_t)i * n + i]; }
+    }
+    for (int a = 0; a < nl; a++) for (int b2 = 0; b2 <= a; b2++) S[(size_t)a * nl + b2] = dot(n, W + (size_t)a * n, W + (size_t)b2 * n);
+    if (nl > 0 && chol_lower(nl, S)) ok = 0;
+  }
+  if (!ok) { free(Lp); free(live); return -1; }
+  /* G^{-1}(f, g) and G^{-T}(f, g); tr = +1 for G, -1 for G' (sign of the A_L coupling) */
+#define GSOLVE(f, g, ox, oL, tr)                                                                          \
+  do {                                                                                                    \
+    for (int i = 0; i < n; i++) { double a = (f)[i]; for (int k = 0; k < i; k++) a -= Lp[(size_t)i * n + k] * tn[k]; tn[i] = a / Lp[(size_t)i * n + i]; } \
+    for (int l = 0; l < nl; l++) (oL)[l] = (tr) * ((g)[l] - (tr) * dot(n, W + (size_t)l * n, tn));      \
+    if (nl > 0) chol_solve(nl, S, (oL));                                                                  \
+    for (int i = 0; i < n; i++) { double a = tn[i]; for (int l = 0; l < nl; l++) a += (tr) * W[(size_t)l * n + i] * (oL)[l]; (ox)[i] = a; } \
+    for (int i = n - 1; i >= 0; i--) { double a = (ox)[i]; for (int k = i + 1; k < n; k++) a -= Lp[(size_t)k * n + i] * (ox)[k]; (ox)[i] = a / Lp[(size_t)i * n + i]; } \
+  } while (0)
+  /* G  : P rx - A_L' rL = f,  A_L rx = g  ->  S rL = g - A_L P^{-1} f,          rx = P^{-1}(f + A_L' rL)
+     G' : P rx + A_L' rL = f, -A_L rx = g  ->  S rL = -(g) ... = -(g + ... ) see tr handling: rL = -(g - (-1) A_L P^{-1} f)... */
+  for (int i = 0; i < n; i++) { hp[i] = K->Px2c[i]; q[i] = K->c[i]; }
+  for (int l = 0; l < nl; l++) { hp[n + l] = K->b[live[l]]; q[n + l] = K->b[live[l]]; }
+  /* q <- G^{-T} g:  P qx + A_L' qL = c ; -A_L qx = b_L */
+  {
+    double *gx = t1, *gL = t1 + n; memcpy(gx, q, sizeof(double) * n); memcpy(gL, q + n, sizeof(double) * nl);
+    /* S qL = -(b_L + A_L P^{-1} c) ... derive: qx = P^{-1}(c - A_L' qL); -A_L P^{-1}(c - A_L' qL) = b_L -> S qL = b_L + A_L P^{-1} c */
+    for (int i = 0; i < n; i++) { double a = gx[i]; for (int k = 0; k < i; k++) a -= Lp[(size_t)i * n + k] * tn[k]; tn[i] = a / Lp[(size_t)i * n + i]; }
+    for (int l = 0; l < nl; l++) q[n + l] = gL[l] + dot(n, W + (size_t)l * n, tn);
+    if (nl > 0) chol_solve(nl, S, q + n);
+    for (int i = 0; i < n; i++) { double a = tn[i]; for (int l = 0; l < nl; l++) a -= W[(size_t)l * n + i] * q[n + l]; q[i] = a; }
+    for (int i = n - 1; i >= 0; i--) { double a = q[i]; for (int k = i + 1; k < n; k++) a -= Lp[(size_t)k * n + i] * q[k]; q[i] = a / Lp[(size_t)i * n + i]; }
+  }
+  for (int i = 0; i < n; i++) rhs[i] = dz[i];
+  for (int l = 0; l < nl; l++) rhs[n + l] = dz[n + live[l]];
+  rhs[nr] = dz[N - 1];
+  border_ctx bc = {nr, hp, q, K->xPx};
+  int its = lsqr_core(nr + 1, nr + 1, border_mv, border_mtv, &bc, rhs, z, st->lsqr_atol, st->lsqr_btol, st->lsqr_conlim, st->lsqr_iter_lim);
+  /* r = blkdiag(G,1)^{-1} z */
+  for (int i = 0; i < N; i++) r[i] = 0;
+  {
+    double *ox = t2, *oL = t2 + n;
+    GSOLVE(z, z + n, ox, oL, 1.0);
+    for (int i = 0; i < n; i++) r[i] = ox[i];
+    for (int l = 0; l < nl; l++) r[n + live[l]] = oL[l];
+  }
+  r[N - 1] = z[nr];
+#undef GSOLVE
+  free(Lp); free(live);
+  return its;
+}
+
 int orc_vjp(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
             const double *x, const double *y, const double *s, const double *dx, const double *dy,
             double *dAv, double *dPv, double *db, double *dc, const orc_settings *st) {
@@ -778,7 +863,10 @@ int orc_vjp(const orc_desc *d, const double *Av, const double *Pv, const double 
   dz[N - 1] = -(dot(n, x, dx) + dot(m, y, dy));
   int its = 0, allz = 1;
   for (int i = 0; i < N; i++) if (fabs(dz[i]) > 1e-8) { allz = 0; break; }
-  if (!allz && st->lsqr_precond) {
+  int done = 0;
+  if (!allz && st->lsqr_precond == 2) { int k2 = vjp_block_precond(d, &K, piy, dz, r, st); if (k2 >= 0) { its = k2; done = 1; } }
+  if (done) { /* solved with the block preconditioner */ }
+  else if (!allz && st->lsqr_precond) {
     lsqr_equilibrate(&K, piy, st->ruiz_passes > 0 ? st->ruiz_passes : 10);
     for (int i = 0; i < N; i++) dz[i] *= K.Ls[i];
     its = lsqr_core(N, N, op_Bs, op_BsT, &K, dz, r, st->lsqr_atol, st->lsqr_btol, st->lsqr_conlim, st->lsqr_iter_lim);

@@ -50,7 +50,7 @@ def test_forward_certificates_and_oracle(name, B, eps, cuda_device):
     assert np.abs(sol.iters.cpu().numpy() - ito).max() <= 50
 
 
-@pytest.mark.parametrize("precond", [1, 0])
+@pytest.mark.parametrize("precond", [2, 1, 0])
 @pytest.mark.parametrize("name,B", CASES)
 def test_backward_matches_oracle(name, B, precond, cuda_device):
     bt = pr.CONFIGS[name](B=B)
@@ -72,7 +72,7 @@ def test_backward_matches_oracle(name, B, precond, cuda_device):
     # north_star tolerance: 1e-4 relative.  The equilibrated LSQR (the engine's default) meets it with
     # margin; plain LSQR (lsqr_precond=0, the reference's exact recurrence) stops at atol=btol=1e-8 on an
     # ill-conditioned system, where two correct implementations only agree to ~1e-3.
-    tol = 1e-4 if (precond == 1 or name in ("C1",)) else 5e-3
+    tol = 1e-4 if (precond >= 1 or name in ("C1",)) else 5e-3
     if name == "C5":
         tol = max(tol, 2e-3)  # rank-deficient SDP optima: min-norm LSQR solutions, looser agreement
     assert rel(db, rb) < tol and rel(dc, rc) < tol and rel(dA, rA) < tol, (rel(dA, rA), rel(db, rb), rel(dc, rc), its, rits)
