@@ -37,7 +37,9 @@ struct Handle {
   DevStruct S{};
   int device = 0, max_batch = 0, num_sms = 0;
   std::vector<void *> allocs;
-  int *counters = nullptr;  // [0] forward, [1] backward work queues
+  static constexpr int RING = 16;  // concurrent calls on different streams each get their own work-queue counters
+  int *counters = nullptr;  // RING x {fwd queue, bwd queue, fail count, fallback queue}
+  int slot = 0;
   int nnz_aug = 0, nb = 0;
   int *d_gather = nullptr, *d_bidx = nullptr;
   int fwd_threads = 0, bwd_threads = 0, fwd_ctas = 0, bwd_ctas = 0;
@@ -47,7 +49,7 @@ struct Handle {
   double *fwd_ws = nullptr, *bwd_ws = nullptr;
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   int block_bwd = 0, blk_threads = 0; size_t blk_smem = 0;   // KKT-block preconditioned backward (lsqr_precond = 2)
-  int *fail_list = nullptr; int fail_cap = 0;
+  int *fail_list[RING] = {nullptr}; int fail_cap[RING] = {0};
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
   std::string err;
@@ -159,7 +161,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     S.Pt_colptr = upload(h, pc); S.Pt_rowidx = upload(h, pr); S.Pt_perm = upload(h, pp);
     S.p_dense = pd ? 1 : 0;
   }
-  if (cudaMalloc((void **)&h->counters, 4 * sizeof(int)) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc counters"); }
+  if (cudaMalloc((void **)&h->counters, Handle::RING * 4 * sizeof(int)) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc counters"); }
   h->allocs.push_back(h->counters);
 
   // --- launch geometry: threads by problem size, shared memory must hold the whole instance ---
@@ -298,9 +300,10 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   FwdArgs a;
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
-  a.counter = h->counters; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
+  int *ctr = h->counters + 4 * (h->slot++ % Handle::RING);
+  a.counter = ctr; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
   a.ws = h->fwd_ws; a.ws_stride = (long long)h->fwd_ws_stride;
-  CK(cudaMemsetAsync(h->counters, 0, sizeof(int), st), "solve counter");
+  CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   const int grid = std::min(B, h->num_sms * h->fwd_ctas);
   CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
   h->launches++;
@@ -319,33 +322,45 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   BwdArgs a;
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.dx = dx; a.dy = dy; a.dA = dA_vals; a.dP = dP_vals; a.db = db; a.dc = dc;
-  a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = h->counters + 1;
+  const int slot = h->slot++ % Handle::RING;
+  int *ctr = h->counters + 4 * slot;
+  a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = ctr + 1;
   a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
   a.ws = h->fast_bwd ? nullptr : h->bwd_ws; a.ws_stride = (long long)h->bwd_ws_stride;
   a.inst_list = nullptr; a.B_dev = nullptr; a.fail_list = nullptr; a.fail_count = nullptr;
   if (h->block_bwd && stg->lsqr_precond == 2) {
     // pass 1: block-preconditioned solve; pass 2: equilibrated LSQR on the instances it rejected
-    if (h->fail_cap < B) {
+    if (h->fail_cap[slot] < B) {
       int *p = nullptr;
       CK(cudaMalloc((void **)&p, (size_t)B * sizeof(int)), "vjp fail list");
-      h->allocs.push_back(p); h->fail_list = p; h->fail_cap = B;
+      h->allocs.push_back(p); h->fail_list[slot] = p; h->fail_cap[slot] = B;
     }
-    CK(cudaMemsetAsync(h->counters + 1, 0, 3 * sizeof(int), st), "vjp counters");
-    a.fail_list = h->fail_list; a.fail_count = h->counters + 2;
+    CK(cudaMemsetAsync(ctr + 1, 0, 3 * sizeof(int), st), "vjp counters");
+    a.fail_list = h->fail_list[slot]; a.fail_count = ctr + 2;
     CK(bc_bwdb_launch(&a, std::min(B, h->num_sms), h->blk_threads, h->blk_smem, st), "vjp launch (block)");
     BwdArgs f = a;
-    f.st.lsqr_precond = 1; f.counter = h->counters + 3; f.inst_list = h->fail_list; f.B_dev = h->counters + 2;
+    f.st.lsqr_precond = 1; f.counter = ctr + 3; f.inst_list = h->fail_list[slot]; f.B_dev = ctr + 2;
     f.fail_list = nullptr; f.fail_count = nullptr;
     CK(bc_bwdf_launch(&f, std::min(B, h->num_sms * h->bwd_ctas), h->bwd_threads, h->bwd_smem, st), "vjp launch (fallback)");
     h->launches += 2;
     return BCONE_OK;
   }
   if (a.st.lsqr_precond == 2) a.st.lsqr_precond = 1;   // block factorisation not available for this structure
-  CK(cudaMemsetAsync(h->counters + 1, 0, sizeof(int), st), "vjp counter");
+  CK(cudaMemsetAsync(ctr + 1, 0, sizeof(int), st), "vjp counter");
   const int grid = std::min(B, h->num_sms * h->bwd_ctas);
   if (h->fast_bwd) CK(bc_bwdf_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch (fast)");
   else CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch");
   h->launches++;
+  return BCONE_OK;
+}
+
+// Strided host<->device copy on the caller's stream (cudaMemcpy2DAsync): lets the reference-facing
+// call move a batch slice of the [rows, B] boundary tensors without a host-side repack.
+extern "C" int bcone_memcpy2d(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t height,
+                              int32_t to_device, void *stream) {
+  cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
+                                    to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_err = std::string("bcone_memcpy2d: ") + cudaGetErrorString(e); return BCONE_ECUDA; }
   return BCONE_OK;
 }
 

@@ -332,6 +332,63 @@ __device__ __forceinline__ void matvec_cols(const double *__restrict__ M, Layout
   }
 }
 
+// ----------------------------------------------------------------------------- wide dense products
+// Dense row-major A (n even, n <= 128) read with 128-bit shared-memory loads: lanes own column
+// pairs.  rows: out_i = sum_j A_ij x_j (4 rows per butterfly); cols: out_j = sum_i A_ij y_i with the
+// rows split in 8 chunks whose partials are combined through `part` (needs 8 n doubles).
+template <bool SQ = false, class Epi>
+__device__ __forceinline__ void dense_rows2(const double *__restrict__ A, int m, int n, const double *x, Epi ep) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool ok0 = 2 * lane < n, ok1 = 2 * lane + 64 < n;
+  const double2 x0 = ok0 ? make_double2(x[2 * lane], x[2 * lane + 1]) : make_double2(0.0, 0.0);
+  const double2 x1 = ok1 ? make_double2(x[2 * lane + 64], x[2 * lane + 65]) : make_double2(0.0, 0.0);
+  for (int i0 = warp * 4; i0 < m; i0 += nw * 4) {
+    double a[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int i = i0 + r;
+      if (i < m) {
+        const double2 *p2 = reinterpret_cast<const double2 *>(A + i * n) + lane;
+        if (ok0) { double2 q = p2[0]; if (SQ) { q.x *= q.x; q.y *= q.y; } a[r] = fma(q.x, x0.x, a[r]); a[r] = fma(q.y, x0.y, a[r]); }
+        if (ok1) { double2 q = p2[32]; if (SQ) { q.x *= q.x; q.y *= q.y; } a[r] = fma(q.x, x1.x, a[r]); a[r] = fma(q.y, x1.y, a[r]); }
+      }
+    }
+    const double tot = butterfly4(a[0], a[1], a[2], a[3], lane);
+    if ((lane & 7) == 0) {
+      const int i = i0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+      if (i < m) ep(i, tot);
+    }
+  }
+}
+template <bool SQ = false, class Epi>
+__device__ __forceinline__ void dense_cols2(const double *__restrict__ A, int m, int n, const double *y, double *part, Epi ep) {
+  const int T = blockDim.x, t = threadIdx.x, npair = n >> 1;
+  const int CH = min(8, T / npair), pr = t % npair, c = t / npair;
+  if (c < CH) {
+    const int lo = (c * m) / CH, hi = ((c + 1) * m) / CH;
+    const double2 *p2 = reinterpret_cast<const double2 *>(A + lo * n) + pr;
+    double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+    int i = lo;
+    for (; i + 1 < hi; i += 2) {
+      double2 q0 = p2[0], q1 = p2[npair];
+      if (SQ) { q0.x *= q0.x; q0.y *= q0.y; q1.x *= q1.x; q1.y *= q1.y; }
+      const double y0 = y[i], y1 = y[i + 1];
+      a0.x = fma(q0.x, y0, a0.x); a0.y = fma(q0.y, y0, a0.y);
+      a1.x = fma(q1.x, y1, a1.x); a1.y = fma(q1.y, y1, a1.y);
+      p2 += 2 * npair;
+    }
+    if (i < hi) { double2 q0 = p2[0]; if (SQ) { q0.x *= q0.x; q0.y *= q0.y; } const double y0 = y[i]; a0.x = fma(q0.x, y0, a0.x); a0.y = fma(q0.y, y0, a0.y); }
+    *reinterpret_cast<double2 *>(part + c * n + 2 * pr) = make_double2(a0.x + a1.x, a0.y + a1.y);
+  }
+  __syncthreads();
+  if (t < n) {
+    double a = 0;
+    for (int cc = 0; cc < CH; cc++) a += part[cc * n + t];
+    ep(t, a);
+  }
+  __syncthreads();
+}
+
 // CSR products for arbitrary patterns (index arrays stay in global memory: they are shared by
 // every CTA of the grid and sit in L1/L2).  Sub-warp groups of G lanes per row.
 template <bool SQ = false, class Epi>
@@ -372,15 +429,19 @@ __device__ __forceinline__ void csr_cols(const double *__restrict__ vals, const 
 }
 
 // A x  and  A' y  for the instance's (scaled) values in shared memory.
+// `wide`: caller guarantees n even, n <= 128, Av 16-byte aligned and (for AT_mul) part >= 8 n doubles.
 template <bool DENSE, bool SQ = false, class Epi>
-__device__ __forceinline__ void A_mul(const DevStruct &S, const double *Av, const double *x, Epi ep) {
-  if (DENSE) matvec_rows<SQ>(Av, DenseLayout{S.n}, S.m, S.n, x, ep);
+__device__ __forceinline__ void A_mul(const DevStruct &S, const double *Av, const double *x, Epi ep, bool wide = false) {
+  if (DENSE && wide) dense_rows2<SQ>(Av, S.m, S.n, x, ep);
+  else if (DENSE) matvec_rows<SQ>(Av, DenseLayout{S.n}, S.m, S.n, x, ep);
   else csr_rows<SQ>(Av, S.A_indptr, S.A_indices, S.m, x, ep);
 }
 // NOTE: ends with a __syncthreads() in the dense case; callers sync themselves in the CSR case.
 template <bool DENSE, bool SQ = false, class Epi>
-__device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, const double *y, double *part, Epi ep, const ColPlan &plA) {
-  if (DENSE) matvec_cols<SQ>(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep, plA);
+__device__ __forceinline__ void AT_mul(const DevStruct &S, const double *Av, const double *y, double *part, Epi ep, const ColPlan &plA,
+                                       bool wide = false) {
+  if (DENSE && wide) dense_cols2<SQ>(Av, S.m, S.n, y, part, ep);
+  else if (DENSE) matvec_cols<SQ>(Av, DenseLayout{S.n}, S.m, S.n, y, part, ep, plA);
   else { csr_cols<SQ>(Av, S.At_colptr, S.At_rowidx, S.At_perm, S.n, y, ep); __syncthreads(); }
 }
 

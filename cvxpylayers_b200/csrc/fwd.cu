@@ -27,9 +27,10 @@ __host__ __device__ inline size_t fwd_vec_doubles(int n, int m, int indirect) {
 }
 // DIRECT: everything on chip.  INDIRECT (instances whose n x n Cholesky does not fit): the CSR values,
 // the reduction scratch and the PSD scratch stay in shared memory, the vectors move to a global slab.
+__host__ __device__ inline size_t fwd_part_doubles(int n, int threads) { return (size_t)(8 * n > threads ? 8 * n : threads); }
 __host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd, int indirect) {
   size_t nA = ((size_t)nnzA + 1) & ~(size_t)1;
-  size_t d = 4 + nA + threads + 8 * 32;
+  size_t d = 4 + nA + fwd_part_doubles(n, threads) + 8 * 32;
   if (!indirect) d += (size_t)n * (n + 1) / 2 + fwd_vec_doubles(n, m, 0);
   if (max_psd > 0) d += (size_t)(threads / 32) * (2 * (size_t)max_psd * max_psd + max_psd);
   return d;
@@ -41,7 +42,7 @@ __device__ __forceinline__ void carve(FwdSmem &M, double *base, double *gws, int
   M.bar = (uint64_t *)q; q += 2;
   M.ibuf = (int *)q; q += 2;
   M.Av = q; q += (nnzA + 1) & ~1;
-  M.part = q; q += threads; M.red = q; q += 8 * 32;
+  M.part = q; q += fwd_part_doubles(n, threads); M.red = q; q += 8 * 32;
   if (!gws) { M.Li = q; q += n * (n + 1) / 2; } else M.Li = nullptr;
   double *v = gws ? gws : q;
   M.w = v; v += N; M.u = v; v += N; M.ut = v; v += N;
@@ -62,10 +63,11 @@ template <bool DENSE>
 __device__ void K_mul(const FwdArgs &a, FwdSmem &M, const double *Pv, double scale, double rho_x, const double *v, double *out,
                       const ColPlan &plA, const ColPlan &plN) {
   const DevStruct &S = a.S;
+  const bool wide = DENSE && (S.n % 2 == 0) && S.n <= 128;
   const int n = S.n, T = blockDim.x, t = threadIdx.x;
-  A_mul<DENSE>(S, M.Av, v, [&](int i, double q) { M.tm[i] = q * inv_ry(S, i, scale); });
+  A_mul<DENSE>(S, M.Av, v, [&](int i, double q) { M.tm[i] = q * inv_ry(S, i, scale); }, wide);
   __syncthreads();
-  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double q) { out[j] = q + rho_x * v[j]; }, plA);
+  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double q) { out[j] = q + rho_x * v[j]; }, plA, wide);
   if (Pv) {
     for (int j = t; j < n; j += T) M.tn3[j] = M.En[j] * v[j];
     __syncthreads();
@@ -117,25 +119,26 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, T = blockDim.x, t = threadIdx.x;
   const int npk = n * (n + 1) / 2;
+  const bool wide = DENSE && (n % 2 == 0) && n <= 128;
   double *K = M.Li;
   if (INDIRECT) {
     // Jacobi preconditioner diag(K), then g = (R_z + M)^{-1} h by CG at tight tolerance
     for (int i = t; i < m; i += T) M.tm[i] = inv_ry(S, i, scale);
     for (int j = t; j < n; j += T) M.tn3[j] = 0.0;
     __syncthreads();
-    AT_mul<DENSE, true>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.kd[j] = rho_x + v; }, plA);
+    AT_mul<DENSE, true>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.kd[j] = rho_x + v; }, plA, wide);
     if (Pv) {
       for (int k = t; k < S.nnzP; k += T) { const int i = __ldg(S.P_rowof + k); if (__ldg(S.P_indices + k) == i) M.kd[i] += Pv[k] * M.En[i] * M.En[i]; }
       __syncthreads();
     }
     for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
     __syncthreads();
-    AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; M.g[j] = 0.0; }, plA);
+    AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; M.g[j] = 0.0; }, plA, wide);
     double nr[1] = {0};
     for (int j = t; j < n; j += T) nr[0] = fma(M.tn[j], M.tn[j], nr[0]);
     block_reduce<1, false>(nr, M.red);
     cg_solve<DENSE>(a, M, Pv, scale, rho_x, M.tn, M.g, 1e-13 * fmax(1.0, sqrt(nr[0])), 10 * n, plA, plN);
-    A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); });
+    A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); }, wide);
     __syncthreads();
     double acc[1] = {0};
     for (int k = t; k < n + m; k += T) {
@@ -146,7 +149,27 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
     gRg = acc[0];
     return true;
   }
-  if (DENSE) {
+  if (DENSE && wide) {
+    // K_jk = scale * sum_i w_i A_ij A_ik (w = 1000 on zero-cone rows): 2x2 register tiles, 128-bit loads
+    const int nb = n >> 1, ntile = (nb * (nb + 1)) >> 1;
+    for (int e = t; e < ntile; e += T) {
+      int J = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while (((J + 1) * (J + 2)) >> 1 <= e) J++;
+      while ((J * (J + 1)) >> 1 > e) J--;
+      const int Kb = e - ((J * (J + 1)) >> 1);
+      const double2 *pj = reinterpret_cast<const double2 *>(M.Av) + J, *pk = reinterpret_cast<const double2 *>(M.Av) + Kb;
+      double z00 = 0, z01 = 0, z10 = 0, z11 = 0, s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+      int i = 0;
+      for (; i < S.z; i++) { const double2 u = pj[i * nb], v = pk[i * nb]; z00 = fma(u.x, v.x, z00); z01 = fma(u.x, v.y, z01); z10 = fma(u.y, v.x, z10); z11 = fma(u.y, v.y, z11); }
+      for (; i < m; i++) { const double2 u = pj[i * nb], v = pk[i * nb]; s00 = fma(u.x, v.x, s00); s01 = fma(u.x, v.y, s01); s10 = fma(u.y, v.x, s10); s11 = fma(u.y, v.y, s11); }
+      const int j0 = 2 * J, k0 = 2 * Kb;
+      K[((j0 * (j0 + 1)) >> 1) + k0] = (z00 * BC_ZERO_CONE_FACTOR + s00) * scale + (j0 == k0 ? rho_x : 0.0);
+      if (k0 + 1 <= j0) K[((j0 * (j0 + 1)) >> 1) + k0 + 1] = (z01 * BC_ZERO_CONE_FACTOR + s01) * scale;
+      K[(((j0 + 1) * (j0 + 2)) >> 1) + k0] = (z10 * BC_ZERO_CONE_FACTOR + s10) * scale;
+      K[(((j0 + 1) * (j0 + 2)) >> 1) + k0 + 1] = (z11 * BC_ZERO_CONE_FACTOR + s11) * scale + (j0 == k0 ? rho_x : 0.0);
+    }
+    __syncthreads();
+  } else if (DENSE) {
     for (int e = t; e < npk; e += T) {
       int j = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
       while ((j + 1) * (j + 2) / 2 <= e) j++;
@@ -186,12 +209,12 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   // ---- g = (R_z + M)^{-1} h, h = (c^, b^) ----
   for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
   __syncthreads();
-  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; }, plA);
+  AT_mul<DENSE>(S, M.Av, M.tm, M.part, [&](int j, double v) { M.tn[j] = M.ch[j] - v; }, plA, wide);
   if (DENSE) { /* AT_mul ended with a sync */ }
   matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
   __syncthreads();
   matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.g[j] = v; }, plN);
-  A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); });
+  A_mul<DENSE>(S, M.Av, M.g, [&](int i, double v) { M.g[n + i] = (M.bh[i] + v) * inv_ry(S, i, scale); }, wide);
   __syncthreads();
   double acc[1] = {0};
   for (int k = t; k < n + m; k += T) {
@@ -215,6 +238,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
   __syncthreads();
   uint32_t tma_phase = 0;
   const ColPlan plA = make_colplan(m, n), plN = make_colplan(n, n);
+  const bool wide = DENSE && (n % 2 == 0) && n <= 128;
   const double rho_x = st.rho_x, alpha = st.alpha, dtau = BC_TAU_FACTOR;
 
   for (;;) {
@@ -246,7 +270,39 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     if (st.normalize) {
       for (int pass = 0; pass < st.ruiz_passes; pass++) {
         // row and column inf-norms of the current A^ (and P^)
-        if (DENSE) {
+        if (DENSE && n <= 128) {
+          // lazily scaled pass: A stays unscaled in shared memory, norms are taken through the running
+          // D, E; one sweep yields row maxima (warp reduce) and column maxima (per-lane, 8 slots)
+          const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+          double er[4], cacc[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; er[k] = c < n ? M.En[c] : 0.0; }
+          for (int i = warp; i < m; i += nw) {
+            const double d = M.Dm[i];
+            const double *row = M.Av + i * n;
+            double r = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int c = lane + 32 * k;
+              if (c < n) { const double v = fabs(row[c]) * er[k]; r = fmax(r, v); cacc[k] = fmax(cacc[k], v * d); }
+            }
+            r = warp_max(r) * d;
+            if (lane == 0) M.tm[i] = r;
+          }
+          const int slot = warp & 7;
+          if (warp < 8) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; if (c < n) M.part[slot * n + c] = cacc[k]; }
+          }
+          __syncthreads();
+          if (warp >= 8) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; if (c < n) M.part[slot * n + c] = fmax(M.part[slot * n + c], cacc[k]); }
+          }
+          __syncthreads();
+          if (t < n) { double r = 0; const int ns = nw < 8 ? nw : 8; for (int q = 0; q < ns; q++) r = fmax(r, M.part[q * n + t]); M.tn[t] = r; }
+          __syncthreads();
+        } else if (DENSE) {
           const int lane = t & 31, warp = t >> 5, nw = T >> 5;
           for (int i = warp; i < m; i += nw) {
             double r = 0;
@@ -254,20 +310,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
             r = warp_max(r);
             if (lane == 0) M.tm[i] = r;
           }
-          const int CH = max(1, T / n);
-          const int j = t % n, c = t / n;
-          if (c < CH && n <= T) {
-            const int lo = (int)(((long long)c * m) / CH), hi = (int)(((long long)(c + 1) * m) / CH);
-            double r = 0;
-            for (int i = lo; i < hi; i++) r = fmax(r, fabs(M.Av[i * n + j]));
-            M.part[t] = r;
-          }
-          __syncthreads();
-          if (n <= T) {
-            if (t < n) { double r = 0; for (int cc = 0; cc < CH; cc++) r = fmax(r, M.part[cc * n + t]); M.tn[t] = r; }
-          } else {
-            for (int jj = t; jj < n; jj += T) { double r = 0; for (int i = 0; i < m; i++) r = fmax(r, fabs(M.Av[i * n + jj])); M.tn[jj] = r; }
-          }
+          for (int jj = t; jj < n; jj += T) { double r = 0; for (int i = 0; i < m; i++) r = fmax(r, fabs(M.Av[i * n + jj])); M.tn[jj] = r; }
           __syncthreads();
         } else {
           for (int i = t; i < m; i += T) {
@@ -313,13 +356,28 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
           }
           __syncthreads();
         }
-        if (DENSE) {
+        if (DENSE && n <= 128) {
+          /* scaling is applied once, after the last pass */
+        } else if (DENSE) {
           for (int k = t; k < S.nnzA; k += T) M.Av[k] *= M.tm[k / n] * M.tn[k % n];
         } else {
           for (int k = t; k < S.nnzA; k += T) M.Av[k] *= M.tm[__ldg(S.A_rowof + k)] * M.tn[__ldg(S.A_indices + k)];
         }
         for (int i = t; i < m; i += T) M.Dm[i] *= M.tm[i];
         for (int j = t; j < n; j += T) M.En[j] *= M.tn[j];
+        __syncthreads();
+      }
+      if (DENSE && n <= 128 && st.ruiz_passes > 0) {   // A^ = D A E in one sweep
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        double er[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; er[k] = c < n ? M.En[c] : 0.0; }
+        for (int i = warp; i < m; i += nw) {
+          const double d = M.Dm[i];
+          double *row = M.Av + i * n;
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; if (c < n) row[c] *= d * er[k]; }
+        }
         __syncthreads();
       }
     }
@@ -349,7 +407,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
 
     for (it = 1; okf && it <= st.max_iters; it++) {
       // ---- affine step ----
-      AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; }, plA);
+      AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; }, plA, wide);
       if (INDIRECT) {
         // warm start from the previous p_x = ut_x + tau~ g_x; tolerance tightens with the iteration count
         double nr[1] = {0};
@@ -364,7 +422,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         __syncthreads();
         matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; }, plN);
       }
-      A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) { M.ut[n + i] = M.w[n + i] + v * inv_ry(S, i, scale); });
+      A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) { M.ut[n + i] = M.w[n + i] + v * inv_ry(S, i, scale); }, wide);
       __syncthreads();
       double d4[4] = {0, 0, 0, 0};  // mu'g, p'Rg, p'Rp, p'mu
       for (int k = t; k < n + m; k += T) {
@@ -398,8 +456,8 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
       if (check) {
         // ---- termination quantities on the un-normalised data ----
         const double tau = M.u[N - 1];
-        A_mul<DENSE>(S, M.Av, M.u, [&](int i, double v) { M.tm[i] = v; });
-        AT_mul<DENSE>(S, M.Av, M.u + n, M.part, [&](int j, double v) { M.tn[j] = v; }, plA);
+        A_mul<DENSE>(S, M.Av, M.u, [&](int i, double v) { M.tm[i] = v; }, wide);
+        AT_mul<DENSE>(S, M.Av, M.u + n, M.part, [&](int j, double v) { M.tn[j] = v; }, plA, wide);
         for (int j = t; j < n; j += T) { M.tn2[j] = 0.0; M.tn3[j] = M.En[j] * M.u[j]; }
         __syncthreads();
         if (Pg) {  // P^ u_x = E (P (E u_x)); no atomics

@@ -126,6 +126,25 @@ class Engine:
         k = ["fwd_threads", "fwd_smem", "fwd_ctas_per_sm", "bwd_threads", "bwd_smem", "bwd_ctas_per_sm"]
         return {a: int(b.value) for a, b in zip(k, v)}
 
+    def alloc_solution(self, B: int) -> Solution:
+        dev, f64, st = self.device, torch.float64, self.structure
+        return Solution(torch.empty((B, st.n), dtype=f64, device=dev), torch.empty((B, st.m), dtype=f64, device=dev),
+                        torch.empty((B, st.m), dtype=f64, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+                        torch.empty(B, dtype=torch.int32, device=dev), torch.empty((B, 3), dtype=f64, device=dev))
+
+    def copy2d(self, dst: torch.Tensor, src: torch.Tensor, lo: int, hi: int, to_device: bool):
+        """Pitched copy of the batch slice [:, lo:hi] between a pinned host tensor [rows, B] and a
+        contiguous device chunk [rows, hi-lo] on the current stream."""
+        host, devt = (src, dst) if to_device else (dst, src)
+        rows, Bfull = host.shape
+        w = (hi - lo) * 8
+        hp = host.data_ptr() + lo * 8
+        args = (devt.data_ptr(), w, hp, Bfull * 8) if to_device else (hp, Bfull * 8, devt.data_ptr(), w)
+        rc = self.lib.bcone_memcpy2d(C.c_void_p(args[0]), C.c_int64(args[1]), C.c_void_p(args[2]), C.c_int64(args[3]),
+                                     C.c_int64(w), C.c_int64(rows), C.c_int32(1 if to_device else 0), self._stream())
+        if rc != 0:
+            raise RuntimeError(f"bcone_memcpy2d failed: {self.lib.bcone_last_error(None).decode()}")
+
     # ------------------------------------------------------------------ boundary re-packing
     def set_boundary(self, gather: np.ndarray, b_idx: np.ndarray):
         gather = np.ascontiguousarray(gather, dtype=np.int32)
@@ -135,8 +154,9 @@ class Engine:
         self._raise(rc, "bcone_set_boundary")
         self._boundary = (gather.size + b_idx.size, b_idx.size)
 
-    def ingest(self, A_eval: torch.Tensor, q_eval: torch.Tensor, P_eval: torch.Tensor | None = None):
-        """[nnz_aug,B] / [n+1,B] boundary tensors -> engine-layout (A_vals, P_vals, b, c)."""
+    def ingest(self, A_eval: torch.Tensor, q_eval: torch.Tensor, P_eval: torch.Tensor | None = None, out=None):
+        """[nnz_aug,B] / [n+1,B] boundary tensors -> engine-layout (A_vals, P_vals, b, c).
+        ``out`` = preallocated (A_vals, P_vals, b, c) views (pipelined callers)."""
         st, dev, f64 = self.structure, self.device, torch.float64
         if self._boundary is None:
             raise RuntimeError("set_boundary() has not been called")
@@ -144,28 +164,34 @@ class Engine:
         _chk(A_eval, (self._boundary[0], B), f64, dev, "A_eval")
         _chk(q_eval, (st.n + 1, B), f64, dev, "q_eval")
         _chk(P_eval, (st.nnzP, B), f64, dev, "P_eval")
-        A_vals = torch.empty((B, st.nnzA), dtype=f64, device=dev)
-        b = torch.empty((B, st.m), dtype=f64, device=dev)
-        c = torch.empty((B, st.n), dtype=f64, device=dev)
-        P_vals = torch.empty((B, st.nnzP), dtype=f64, device=dev) if (P_eval is not None and st.nnzP) else None
+        if out is not None:
+            A_vals, P_vals, b, c = out
+        else:
+            A_vals = torch.empty((B, st.nnzA), dtype=f64, device=dev)
+            b = torch.empty((B, st.m), dtype=f64, device=dev)
+            c = torch.empty((B, st.n), dtype=f64, device=dev)
+            P_vals = torch.empty((B, st.nnzP), dtype=f64, device=dev) if (P_eval is not None and st.nnzP) else None
         rc = self.lib.bcone_ingest(self.h, C.c_int32(B), _ptr(A_eval), _ptr(q_eval), _ptr(P_eval), _ptr(A_vals),
                                    _ptr(P_vals), _ptr(b), _ptr(c), self._stream())
         self._raise(rc, "bcone_ingest")
         return A_vals, P_vals, b, c
 
-    def emit(self, dA_vals, dP_vals, db, dc):
+    def emit(self, dA_vals, dP_vals, db, dc, out=None):
         st, dev, f64 = self.structure, self.device, torch.float64
         B = dA_vals.shape[0]
-        dA_eval = torch.empty((self._boundary[0], B), dtype=f64, device=dev)
-        dq_eval = torch.empty((st.n + 1, B), dtype=f64, device=dev)
-        dP_eval = torch.empty((st.nnzP, B), dtype=f64, device=dev) if (dP_vals is not None and st.nnzP) else None
+        if out is not None:
+            dA_eval, dq_eval, dP_eval = out
+        else:
+            dA_eval = torch.empty((self._boundary[0], B), dtype=f64, device=dev)
+            dq_eval = torch.empty((st.n + 1, B), dtype=f64, device=dev)
+            dP_eval = torch.empty((st.nnzP, B), dtype=f64, device=dev) if (dP_vals is not None and st.nnzP) else None
         rc = self.lib.bcone_emit(self.h, C.c_int32(B), _ptr(dA_vals), _ptr(dP_vals), _ptr(db), _ptr(dc), _ptr(dA_eval),
                                  _ptr(dq_eval), _ptr(dP_eval), self._stream())
         self._raise(rc, "bcone_emit")
         return dA_eval, dq_eval, dP_eval
 
     # ------------------------------------------------------------------ forward / backward
-    def solve(self, A_vals, b, c, P_vals=None, settings: _lib.BconeSettings | None = None) -> Solution:
+    def solve(self, A_vals, b, c, P_vals=None, settings: _lib.BconeSettings | None = None, out: "Solution | None" = None) -> Solution:
         st, dev, f64 = self.structure, self.device, torch.float64
         B = A_vals.shape[0]
         _chk(A_vals, (B, st.nnzA), f64, dev, "A_vals")
@@ -176,12 +202,15 @@ class Engine:
                 raise ValueError("structure has a quadratic term but P_vals is None")
             _chk(P_vals, (B, st.nnzP), f64, dev, "P_vals")
         settings = settings or _lib.default_settings()
-        x = torch.empty((B, st.n), dtype=f64, device=dev)
-        y = torch.empty((B, st.m), dtype=f64, device=dev)
-        s = torch.empty((B, st.m), dtype=f64, device=dev)
-        status = torch.empty(B, dtype=torch.int32, device=dev)
-        iters = torch.empty(B, dtype=torch.int32, device=dev)
-        resid = torch.empty((B, 3), dtype=f64, device=dev)
+        if out is not None:
+            x, y, s, status, iters, resid = out.x, out.y, out.s, out.status, out.iters, out.resid
+        else:
+            x = torch.empty((B, st.n), dtype=f64, device=dev)
+            y = torch.empty((B, st.m), dtype=f64, device=dev)
+            s = torch.empty((B, st.m), dtype=f64, device=dev)
+            status = torch.empty(B, dtype=torch.int32, device=dev)
+            iters = torch.empty(B, dtype=torch.int32, device=dev)
+            resid = torch.empty((B, 3), dtype=f64, device=dev)
         rc = self.lib.bcone_solve(self.h, C.c_int32(B), _ptr(A_vals), _ptr(P_vals if st.nnzP else None), _ptr(b), _ptr(c),
                                   _ptr(x), _ptr(y), _ptr(s), _ptr(status), _ptr(iters), _ptr(resid), C.byref(settings),
                                   self._stream())

@@ -151,6 +151,98 @@ def _to_host_like(t: torch.Tensor | None, device: torch.device, dtype: torch.dty
     return out
 
 
+PIPE_CHUNK = int(os.environ.get("B200_PIPE_CHUNK", "1024"))   # instances per pipeline stage (host-resident inputs)
+
+
+def _chunks(B: int):
+    n = max(1, B // max(PIPE_CHUNK, 1))
+    base, extra = divmod(B, n)
+    lo = 0
+    for k in range(n):
+        hi = lo + base + (1 if k < extra else 0)
+        yield lo, hi
+        lo = hi
+
+
+def _pipe_ok(eng: Engine, B: int, *tensors) -> bool:
+    """Host-resident, pinned, contiguous fp64 inputs and a batch worth splitting: overlap the PCIe copies
+    with the solve by running batch slices on two streams."""
+    if B < 2 * PIPE_CHUNK or PIPE_CHUNK <= 0:
+        return False
+    info = eng.kernel_info()
+    for t in tensors:
+        if t is None:
+            continue
+        if t.device.type != "cpu" or t.dtype != torch.float64 or not t.is_contiguous() or not t.is_pinned():
+            return False
+    return info["fwd_smem"] > 0
+
+
+def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P):
+    st = eng.structure
+    B = A_eval.shape[1]
+    f64 = torch.float64
+    A_vals = torch.empty((B, st.nnzA), dtype=f64, device=dev)
+    b = torch.empty((B, st.m), dtype=f64, device=dev)
+    c = torch.empty((B, st.n), dtype=f64, device=dev)
+    P_vals = torch.empty((B, st.nnzP), dtype=f64, device=dev) if use_P else None
+    sol = eng.alloc_solution(B)
+    primal = torch.empty((B, st.n), dtype=f64, pin_memory=True)
+    dual = torch.empty((B, st.m), dtype=f64, pin_memory=True)
+    cur = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for s_ in streams:
+        s_.wait_stream(cur)
+    for k, (lo, hi) in enumerate(_chunks(B)):
+        with torch.cuda.stream(streams[k % 2]):
+            Bc = hi - lo
+            A_c = torch.empty((A_eval.shape[0], Bc), dtype=f64, device=dev)
+            q_c = torch.empty((q_eval.shape[0], Bc), dtype=f64, device=dev)
+            eng.copy2d(A_c, A_eval, lo, hi, True)
+            eng.copy2d(q_c, q_eval, lo, hi, True)
+            P_c = None
+            if use_P:
+                P_c = torch.empty((P_eval.shape[0], Bc), dtype=f64, device=dev)
+                eng.copy2d(P_c, P_eval, lo, hi, True)
+            eng.ingest(A_c, q_c, P_c, out=(A_vals[lo:hi], P_vals[lo:hi] if use_P else None, b[lo:hi], c[lo:hi]))
+            from .engine import Solution  # noqa: PLC0415
+            eng.solve(A_vals[lo:hi], b[lo:hi], c[lo:hi], P_vals[lo:hi] if use_P else None, settings,
+                      out=Solution(sol.x[lo:hi], sol.y[lo:hi], sol.s[lo:hi], sol.status[lo:hi], sol.iters[lo:hi], sol.resid[lo:hi]))
+            primal[lo:hi].copy_(sol.x[lo:hi], non_blocking=True)
+            dual[lo:hi].copy_(sol.y[lo:hi], non_blocking=True)
+    for s_ in streams:
+        cur.wait_stream(s_)
+    return A_vals, P_vals, b, c, sol, primal, dual
+
+
+def _backward_pipelined(eng: Engine, dev, settings, A_vals, P_vals, b, c, x, y, s, dprimal, ddual, use_P, nnz_aug):
+    st = eng.structure
+    B = A_vals.shape[0]
+    f64 = torch.float64
+    dA_eval = torch.empty((nnz_aug, B), dtype=f64, pin_memory=True)
+    dq_eval = torch.empty((st.n + 1, B), dtype=f64, pin_memory=True)
+    dP_eval = torch.empty((st.nnzP, B), dtype=f64, pin_memory=True) if use_P else None
+    dx = dprimal.detach().to(device=dev, dtype=f64, non_blocking=True).reshape(B, -1).contiguous()
+    dy = ddual.detach().to(device=dev, dtype=f64, non_blocking=True).reshape(B, -1).contiguous()
+    cur = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for s_ in streams:
+        s_.wait_stream(cur)
+    for k, (lo, hi) in enumerate(_chunks(B)):
+        with torch.cuda.stream(streams[k % 2]):
+            gA, gP, gb, gc, _ = eng.vjp(A_vals[lo:hi], b[lo:hi], c[lo:hi], x[lo:hi], y[lo:hi], s[lo:hi], dx[lo:hi], dy[lo:hi],
+                                        P_vals[lo:hi] if P_vals is not None else None, settings)
+            gA_e, gq_e, gP_e = eng.emit(gA, gP if use_P else None, gb, gc)
+            eng.copy2d(dA_eval, gA_e, lo, hi, False)
+            eng.copy2d(dq_eval, gq_e, lo, hi, False)
+            if use_P:
+                eng.copy2d(dP_eval, gP_e, lo, hi, False)
+    for s_ in streams:
+        cur.wait_stream(s_)
+    cur.synchronize()
+    return dA_eval, dq_eval, dP_eval
+
+
 class _CvxpyLayer(torch.autograd.Function):
     """Twin of ``diffcp_if._CvxpyLayer`` (``diffcp_if.py:327-403``)."""
 
@@ -170,10 +262,15 @@ class _CvxpyLayer(torch.autograd.Function):
             merged.update(solver_args)
         settings = make_settings(merged)
         use_P = P_eval is not None and ctx.nnzP > 0
+        piped = _pipe_ok(eng, batch_size, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None)
         with torch.cuda.device(dev):
-            A_vals, P_vals, b, c = eng.ingest(_to_dev(A_eval, dev), _to_dev(q_eval, dev),
-                                              _to_dev(P_eval, dev) if use_P else None)
-            sol = eng.solve(A_vals, b, c, P_vals, settings)
+            if piped:
+                A_vals, P_vals, b, c, sol, primal, dual = _forward_pipelined(
+                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P)
+            else:
+                A_vals, P_vals, b, c = eng.ingest(_to_dev(A_eval, dev), _to_dev(q_eval, dev),
+                                                  _to_dev(P_eval, dev) if use_P else None)
+                sol = eng.solve(A_vals, b, c, P_vals, settings)
             status = sol.status.cpu()  # the one host sync of the forward: per-instance status
         bad = (status != 1) & (status != 2)
         if bool(bad.any()):
@@ -181,12 +278,13 @@ class _CvxpyLayer(torch.autograd.Function):
             raise SolverError(f"instance {i}: solver returned status {STATUS.get(int(status[i]), int(status[i]))}")
         if bool((status == 2).any()):
             warnings.warn("Solved/Inaccurate.", stacklevel=2)
-        with torch.cuda.device(dev):
-            primal = _to_host_like(sol.x, in_device, in_dtype)
-            dual = _to_host_like(sol.y, in_device, in_dtype)
-            if in_device.type == "cpu":
-                torch.cuda.current_stream(dev).synchronize()
-        saved = _Saved(eng, settings, A_vals, P_vals, b, c, sol.x, sol.y, sol.s) if needs_grad else None
+        if not piped:
+            with torch.cuda.device(dev):
+                primal = _to_host_like(sol.x, in_device, in_dtype)
+                dual = _to_host_like(sol.y, in_device, in_dtype)
+                if in_device.type == "cpu":
+                    torch.cuda.current_stream(dev).synchronize()
+        saved = _Saved(eng, settings, A_vals, P_vals, b, c, sol.x, sol.y, sol.s, piped, A_eval.shape[0]) if needs_grad else None
         return primal, dual, saved, (batch_size, originally_unbatched, in_device, in_dtype, use_P)
 
     @staticmethod
@@ -201,9 +299,16 @@ class _CvxpyLayer(torch.autograd.Function):
         batch_size, originally_unbatched, in_device, in_dtype, use_P = ctx.backward_data
         if ctx.saved is None:
             raise RuntimeError("backward called on a forward pass run with needs_grad=False")
-        eng, settings, A_vals, P_vals, b, c, x, y, s = ctx.saved.items
+        eng, settings, A_vals, P_vals, b, c, x, y, s, piped, nnz_aug = ctx.saved.items
         dev = eng.device
         _tb = time.perf_counter() if _TRACE else 0.0
+        if piped and in_dtype == torch.float64:
+            with torch.cuda.device(dev):
+                dA_eval, dq_eval, dP_eval = _backward_pipelined(eng, dev, settings, A_vals, P_vals, b, c, x, y, s, dprimal, ddual,
+                                                                use_P, nnz_aug)
+            if _TRACE:
+                print(f"[b200] backward body (pipelined) {1e3 * (time.perf_counter() - _tb):.1f} ms", file=sys.stderr)
+            return dP_eval, dq_eval, dA_eval, None, None, None, None
         with torch.cuda.device(dev):
             dx = _to_dev(dprimal, dev).reshape(batch_size, -1)
             dy = _to_dev(ddual, dev).reshape(batch_size, -1)

@@ -86,6 +86,11 @@ int bcone_vjp(void *handle, int32_t B, const double *A_vals, const double *P_val
               const double *dy, double *dA_vals, double *dP_vals, double *db, double *dc,
               int32_t *lsqr_iters, const bcone_settings *st, void *cuda_stream);
 
+/* Pitched host<->device copy on the caller's stream (bytes): moves a batch slice [rows, lo:hi] of a
+ * boundary tensor directly between pinned host memory and a contiguous device chunk. */
+int bcone_memcpy2d(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t height,
+                   int32_t to_device, void *cuda_stream);
+
 /* Introspection for benchmarks/tests: kernel launches issued by this handle so far, and the
  * launch geometry chosen for the forward / backward kernels. */
 int64_t bcone_launch_count(void *handle);

@@ -173,3 +173,26 @@ def test_headline_batch_properties(cuda_device):
         assert float((a12 - ref).abs().max() / ref.abs().max()) < 1e-5
     z = run(torch.zeros_like(d1x), torch.zeros_like(d1y))
     assert not z[0].any() and not z[2].any() and not z[3].any() and not z[4].any()
+
+
+def test_pipelined_host_path_equals_plain_path(cuda_device, monkeypatch):
+    """Pinned host inputs with a batch worth splitting run as batch slices on two streams (pitched
+    H2D/D2H copies overlapped with the kernels); results must equal the single-shot path."""
+    import cvxpylayers_b200.interface as itf
+
+    bt = pr.dense_qp(13, 10, 20, 3, seed=9)
+    args = {"eps": 1e-9, "max_iters": 100000, "lsqr_precond": 2}
+    outs = []
+    for chunk in (4, 10**9):
+        monkeypatch.setattr(itf, "PIPE_CHUNK", chunk)
+        ctx, bd, cl = _layer(bt, **args)
+        ctx.device = cuda_device
+        A = torch.tensor(bd.A_eval).pin_memory().requires_grad_(True)
+        q = torch.tensor(bd.q_eval).pin_memory().requires_grad_(True)
+        P = torch.tensor(bd.P_eval).pin_memory().requires_grad_(True)
+        primal, dual, saved, _ = _CvxpyLayer.apply(P, q, A, cl, {}, True, None)
+        assert saved.items[9] == (chunk == 4)   # the pipelined path was / was not taken
+        (primal.sum() + (dual * dual).sum()).backward()
+        outs.append([primal.detach().clone(), dual.detach().clone(), A.grad.clone(), q.grad.clone(), P.grad.clone()])
+    for a_, b_ in zip(*outs):
+        assert a_.device.type == "cpu" and torch.allclose(a_, b_, rtol=1e-9, atol=1e-11)

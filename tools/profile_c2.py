@@ -13,7 +13,7 @@ bt = pr.CONFIGS[name](B=B)
 st = bt.structure
 t = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float64, device=dev)
 eng = Engine(st, dev)
-args = make_settings({"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 1})
+args = make_settings({"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 2})
 A, b, c, P = t(bt.A_vals), t(bt.b), t(bt.c), t(bt.P_vals)
 g = torch.Generator(device="cpu").manual_seed(1)
 dx = torch.randn((B, st.n), dtype=torch.float64, generator=g).to(dev)
