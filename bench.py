@@ -31,10 +31,11 @@ sys.path.insert(0, ROOT)
 METRIC = "QP problems/sec fwd+bwd (batch=4096, n=100, m=200, zero+nonneg cones)"
 UNIT = "problems/s"
 # Solver settings shared by both arms (SCS defaults for the forward; LSQR rules of diffcp).
-SOLVER_ARGS = {"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 2}
-# DRAM bytes per instance measured by ncu --set full on 296-instance launches (profiles/):
-# bwd_fast_kernel 62.17 MB read + 7.17 MB written; fwd_kernel 60.3 MB read + 0.2 MB written.
-NCU_DRAM_BYTES_PER_INSTANCE = {"bwd": (62.166016e6 + 7.173376e6) / 296, "fwd": (60.317696e6 + 0.20608e6) / 296}
+SOLVER_ARGS = {"eps": 1e-4, "max_iters": 10000, "lsqr_precond": 2, "adaptive_check": 1}
+# DRAM bytes per instance measured by ncu --set full on 296-instance launches (profiles/prof_fwd_r1c.txt,
+# prof_bwdblk_r1a.txt): fwd_kernel 60.29 MB read + 0.37 MB written; bwd_block_kernel 34.52 MB read
+# (only the live rows of A are staged) + 6.53 MB written back within the launch (the rest sits in L2).
+NCU_DRAM_BYTES_PER_INSTANCE = {"bwd": (34.524928e6 + 6.534144e6) / 296, "fwd": (60.285184e6 + 0.368384e6) / 296}
 # Algorithmic HBM bytes per instance: fwd reads A,P,b,c + writes x,y,s;
 # bwd re-reads data + x,y,s + dx,dy and writes dA,dP,db,dc.
 def algo_bytes(n, m, nnzA, nnzP):
@@ -257,12 +258,16 @@ def run_ours(a):
         loss_val, gAh, gqh, gPh = step_e2e()   # pool already holds the two generations of result buffers
     sync()
     e0, e1 = ev(), ev()
+    n_e2e = max(1, a.steps)
+    per_step = []
     e0.record()
-    n_e2e = max(1, min(a.steps, 5))
     for _ in range(n_e2e):
+        tw = time.perf_counter()
         loss_val, gAh, gqh, gPh = step_e2e()
+        per_step.append(1e3 * (time.perf_counter() - tw))
     e1.record()
     sync()
+    print("[bench] e2e wall ms per step: " + ", ".join(f"{v:.1f}" for v in per_step), file=sys.stderr)
     ms_e2e = e0.elapsed_time(e1) / n_e2e
     if world > 1:
         tt = torch.tensor([ms_e2e], dtype=f64, device=dev)
@@ -297,7 +302,7 @@ def run_ours(a):
                 "e2e": {"value": Btot / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "fwd_kernel<dense,direct>" if dom == "fwd" else "bwd_block_kernel (+ bwd_fast_kernel fallback)", "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_INSTANCE.get(dom, 0) * B / 1e9 or None,
                              "traffic_unit": "GB per launch (ncu dram__bytes_read+write per instance, profiles/prof_*_r1*.txt, x B)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",

@@ -79,7 +79,7 @@ extern "C" void bcone_default_settings(bcone_settings *st) {
   st->alpha = 1.5; st->rho_x = 1e-6; st->scale = 0.1;
   st->lsqr_atol = 1e-8; st->lsqr_btol = 1e-8; st->lsqr_conlim = 1e8;
   st->max_iters = 100000; st->normalize = 1; st->adaptive_scale = 1; st->check_interval = 25;
-  st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->lsqr_precond = 0; st->reserved1 = 0;
+  st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->lsqr_precond = 0; st->adaptive_check = 0;
 }
 
 extern "C" const char *bcone_last_error(void *handle) {

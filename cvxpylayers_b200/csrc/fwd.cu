@@ -403,10 +403,19 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     __syncthreads();
     double sum_log = 0, rp = nan(""), rd = nan(""), gap = nan("");
     int n_log = 0, last_up = 0;
+    // adaptive check schedule (oracle: cone_oracle.c): log-linear extrapolation of the distance to the tolerance
+    int next_check = st.check_interval < 10 ? st.check_interval : 10, prev_it = 0;
+    double prev_lr = 0;
     if (!okf) status = BCONE_FAILED;
 
     for (it = 1; okf && it <= st.max_iters; it++) {
       // ---- affine step ----
+      const double w_tau = M.w[N - 1];   // read before anything of this iteration can overwrite it
+      double d4[4] = {0, 0, 0, 0};       // mu'g, p'Rg, p'Rp, p'mu  (R-weighted; accumulated in the product epilogues)
+      auto dots = [&](double r, double pk, double wk, double gk) {
+        d4[0] = fma(r * wk, gk, d4[0]); d4[1] = fma(r * pk, gk, d4[1]);
+        d4[2] = fma(r * pk, pk, d4[2]); d4[3] = fma(r * pk, wk, d4[3]);
+      };
       AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; }, plA, wide);
       if (INDIRECT) {
         // warm start from the previous p_x = ut_x + tau~ g_x; tolerance tightens with the iteration count
@@ -415,29 +424,22 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         block_reduce<1, false>(nr, M.red);
         const double tol = fmax(1e-13, fmin(1e-6, 0.1 / pow((double)it, 1.5))) * fmax(1.0, sqrt(nr[0]));
         cg_solve<DENSE>(a, M, Pg, scale, rho_x, M.tn, M.ut, tol, 4 * n, plA, plN);
-        for (int j = t; j < n; j += T) M.cx[j] = M.ut[j];   // keep p_x for the next warm start
+        for (int j = t; j < n; j += T) { const double pk = M.ut[j]; M.cx[j] = pk; dots(rho_x, pk, M.w[j], M.g[j]); }   // keep p_x for the next warm start
         __syncthreads();
       } else {
         matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
         __syncthreads();
-        matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; }, plN);
+        matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; dots(rho_x, v, M.w[j], M.g[j]); }, plN);
       }
-      A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) { M.ut[n + i] = M.w[n + i] + v * inv_ry(S, i, scale); }, wide);
-      __syncthreads();
-      double d4[4] = {0, 0, 0, 0};  // mu'g, p'Rg, p'Rp, p'mu
-      for (int k = t; k < n + m; k += T) {
-        const double r = k < n ? rho_x : 1.0 / inv_ry(S, k - n, scale);
-        const double pk = M.ut[k], wk = M.w[k], gk = M.g[k];
-        d4[0] = fma(r * wk, gk, d4[0]); d4[1] = fma(r * pk, gk, d4[1]);
-        d4[2] = fma(r * pk, pk, d4[2]); d4[3] = fma(r * pk, wk, d4[3]);
-      }
-      block_reduce<4, false>(d4, M.red);
-      const double qa = dtau + gRg, qb = d4[0] - 2.0 * d4[1] - dtau * M.w[N - 1], qc = d4[2] - d4[3];
+      A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) {
+        const double iry = inv_ry(S, i, scale), wk = M.w[n + i], pk = wk + v * iry;
+        M.ut[n + i] = pk; dots(1.0 / iry, pk, wk, M.g[n + i]); }, wide);
+      block_reduce<4, false>(d4, M.red);   // (its barriers also publish ut)
+      const double qa = dtau + gRg, qb = d4[0] - 2.0 * d4[1] - dtau * w_tau, qc = d4[2] - d4[3];
       double disc = qb * qb - 4.0 * qa * qc;
       if (disc < 0) disc = 0;
       const double tau_t = (-qb + sqrt(disc)) / (2.0 * qa);
-      const bool check = (it % st.check_interval == 0) || it == st.max_iters;
-      __syncthreads();  // everyone has read w[N-1] / ut before they are overwritten
+      const bool check = st.adaptive_check ? (it >= next_check || it == st.max_iters) : ((it % st.check_interval == 0) || it == st.max_iters);
       // ---- cone step + relaxation (fused when the cone is polyhedral and no check is due) ----
       const bool nonpoly = S.ncones + S.ep + S.ed > 0;
       const bool fused = !nonpoly && !check;
@@ -495,11 +497,19 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
           const double tp = st.eps_abs + st.eps_rel * np_, td = st.eps_abs + st.eps_rel * nd_;
           const double tg = st.eps_abs + st.eps_rel * fmax(fmax(fabs(xPx), fabs(ctx)), fabs(bty));
           if (rp <= tp && rd <= td && gap <= tg) { status = BCONE_SOLVED; done = true; }
-          else if (st.adaptive_scale) {
+          else if (st.adaptive_check) {
+            const double lr = log(fmax(fmax(rp / tp, rd / td), gap / tg));
+            int step = st.check_interval;
+            if (prev_it > 0 && lr < prev_lr) { const double need = lr * (it - prev_it) / (prev_lr - lr); step = (int)ceil(0.9 * need) + 1; }
+            step = max(3, min(step, st.check_interval));
+            prev_it = it; prev_lr = lr; next_check = it + step;
+          }
+          if (!done && st.adaptive_scale) {
             const double relp = rp / fmax(np_, 1e-18), reld = rd / fmax(nd_, 1e-18);
             if (relp > 0 && reld > 0) { sum_log += log(relp) - log(reld); n_log++; }
           }
         }
+        if (st.adaptive_check && next_check <= it) next_check = it + st.check_interval;
         if (!done) {
           const double bty_c = sm[2] / s2, ctx_c = sm[1] / s2;
           if (bty_c < 0 && mx[6] / (-bty_c) <= st.eps_infeas) { status = BCONE_INFEASIBLE; done = true; }

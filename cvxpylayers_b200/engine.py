@@ -23,7 +23,7 @@ _ARG_MAP = {
     "alpha": "alpha", "rho_x": "rho_x", "scale": "scale", "normalize": "normalize",
     "adaptive_scale": "adaptive_scale", "check_interval": "check_interval", "ruiz_passes": "ruiz_passes",
     "lsqr_atol": "lsqr_atol", "lsqr_btol": "lsqr_btol", "lsqr_conlim": "lsqr_conlim",
-    "lsqr_iter_lim": "lsqr_iter_lim", "lsqr_precond": "lsqr_precond",
+    "lsqr_iter_lim": "lsqr_iter_lim", "lsqr_precond": "lsqr_precond", "adaptive_check": "adaptive_check",
 }
 _IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "acceleration_lookback",
             "acceleration_interval", "warm_starts", "raise_on_error"}

@@ -48,7 +48,8 @@ typedef struct {
   int32_t ruiz_passes, lsqr_iter_lim;  /* lsqr_iter_lim < 0 -> 2N like diffcp                 */
   int32_t lsqr_precond;                /* 0 plain LSQR (reference semantics), 1 diagonally equilibrated,
                                           2 KKT-block preconditioned where applicable (else 1) */
-  int32_t reserved1;
+  int32_t adaptive_check;              /* 0: test termination every check_interval iterations (SCS);
+                                          1: place the checks by log-linear extrapolation (<= check_interval apart) */
 } bcone_settings;
 
 enum { BCONE_SOLVED = 1, BCONE_INACCURATE = 2, BCONE_UNBOUNDED = -1, BCONE_INFEASIBLE = -2, BCONE_FAILED = -4 };

@@ -42,7 +42,7 @@ typedef struct {
   double alpha, rho_x, scale;
   double lsqr_atol, lsqr_btol, lsqr_conlim;
   int32_t max_iters, normalize, adaptive_scale, check_interval;
-  int32_t ruiz_passes, lsqr_iter_lim, lsqr_precond, reserved1;
+  int32_t ruiz_passes, lsqr_iter_lim, lsqr_precond, adaptive_check;
 } orc_settings;
 
 enum { ORC_SOLVED = 1, ORC_INACCURATE = 2, ORC_UNBOUNDED = -1, ORC_INFEASIBLE = -2, ORC_FAILED = -4 };
