@@ -82,10 +82,13 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+CONFIG = "C2"   # BASELINE.json configs[1] is the headline; the others are parity-test cases that can be timed too
+
+
 def make_workload(batch: int, seed: int):
     from cvxpylayers_b200 import problems as pr
 
-    bt = pr.config_c2(B=batch, seed=seed)
+    bt = pr.CONFIGS[CONFIG](B=batch, seed=seed)
     return bt, pr.to_boundary(bt)
 
 
@@ -136,7 +139,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C2 dense QP n={st.n} m={st.m} z={st.cones.z} l={st.cones.l}, planted optimum, seed 0",
+            "config": {"workload": f"{CONFIG} {bt.name}: n={st.n} m={st.m} cones={st.cones.to_dict()}, synthetic, seed 0",
                        "sample_instances": a.cpu_sample, "solver_args": SOLVER_ARGS},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{a.cpu_sample} instances of the C2 batch per step (oracle/cone_oracle.c, OpenMP over instances)"},
@@ -161,12 +164,13 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
     bt, bd = make_workload(B, seed=rank)
     st = bt.structure
-    ctx = B200_ctx((st.P_indices, st.P_indptr, (st.n, st.n)), (bd.con_indices, bd.con_ptr, bd.shape), bd.dims,
-                   options=dict(SOLVER_ARGS))
+    pstruct = (st.P_indices, st.P_indptr, (st.n, st.n)) if st.P_indptr is not None else None
+    ctx = B200_ctx(pstruct, (bd.con_indices, bd.con_ptr, bd.shape), bd.dims, options=dict(SOLVER_ARGS))
     cl_ctx = SimpleNamespace(solver_ctx=ctx)
     eng = ctx.engine(dev)
     settings = make_settings(SOLVER_ARGS)
@@ -174,8 +178,8 @@ def run_ours(a):
     # host (pinned) boundary tensors and their device-resident copies
     hA = torch.from_numpy(bd.A_eval).pin_memory()
     hq = torch.from_numpy(bd.q_eval).pin_memory()
-    hP = torch.from_numpy(bd.P_eval).pin_memory()
-    dA_, dq_, dP_ = hA.to(dev), hq.to(dev), hP.to(dev)
+    hP = torch.from_numpy(bd.P_eval).pin_memory() if bd.P_eval is not None else None
+    dA_, dq_, dP_ = hA.to(dev), hq.to(dev), (hP.to(dev) if hP is not None else None)
     g = torch.Generator(device="cpu").manual_seed(7 + rank)
     dxh = torch.randn((B, st.n), dtype=f64, generator=g)
     dyh = torch.randn((B, st.m), dtype=f64, generator=g)
@@ -204,7 +208,7 @@ def run_ours(a):
     def step_e2e():
         A = hA.detach().requires_grad_(True)
         q = hq.detach().requires_grad_(True)
-        P = hP.detach().requires_grad_(True)
+        P = hP.detach().requires_grad_(True) if hP is not None else None
         t0 = time.perf_counter()
         primal, dual, _, _ = _CvxpyLayer.apply(P, q, A, cl_ctx, {}, True, None)
         t1 = time.perf_counter()
@@ -213,7 +217,7 @@ def run_ours(a):
         t2 = time.perf_counter()
         if os.environ.get("BENCH_E2E_BREAKDOWN"):
             print(f"[e2e] forward {1e3 * (t1 - t0):.1f} ms, loss+backward {1e3 * (t2 - t1):.1f} ms", file=sys.stderr)
-        return float(loss.detach()), A.grad, q.grad, P.grad
+        return float(loss.detach()), A.grad, q.grad, (P.grad if P is not None else None)
 
     def sync():
         if world > 1:
@@ -273,8 +277,9 @@ def run_ours(a):
         tt = torch.tensor([ms_e2e], dtype=f64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e2e = float(tt)
-    h2d = (hA.numel() + hq.numel() + hP.numel() + dxh.numel() + dyh.numel()) * 8
-    d2h = (gAh.numel() + gqh.numel() + gPh.numel() + B * (st.n + st.m)) * 8
+    npel = hP.numel() if hP is not None else 0
+    h2d = (hA.numel() + hq.numel() + npel + dxh.numel() + dyh.numel()) * 8
+    d2h = (gAh.numel() + gqh.numel() + npel + B * (st.n + st.m)) * 8
 
     if rank == 0:
         fwd_b, bwd_b = algo_bytes(st.n, st.m, st.nnzA, st.nnzP)
@@ -296,14 +301,14 @@ def run_ours(a):
         line = {"metric": METRIC, "value": Btot / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C2 dense QP n={st.n} m={st.m} z={st.cones.z} l={st.cones.l}, planted optimum, seed=rank",
+                "config": {"workload": f"{CONFIG} {bt.name}: n={st.n} m={st.m} cones={st.cones.to_dict()}, synthetic, seed=rank",
                            "batch_per_gpu": B, "global_batch": Btot, "parallelism": f"batch-shard x{world}",
-                           "l2": "inputs (0.8 GB/step) larger than L2", "solver_args": SOLVER_ARGS},
+                           "l2": f"inputs ({(hA.numel() + npel) * 8 / 1e9:.2f} GB/step) vs 126 MB L2" + ("" if (hA.numel() + npel) * 8 > 130e6 else "; NOT larger than L2 (secondary config, no flush)"), "solver_args": SOLVER_ARGS},
                 "e2e": {"value": Btot / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "fwd_kernel<dense,direct>" if dom == "fwd" else "bwd_block_kernel (+ bwd_fast_kernel fallback)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_INSTANCE.get(dom, 0) * B / 1e9 or None,
+                             "frac": ach / peak, "traffic": (NCU_DRAM_BYTES_PER_INSTANCE.get(dom, 0) * B / 1e9 or None) if CONFIG == "C2" else None,
                              "traffic_unit": "GB per launch (ncu dram__bytes_read+write per instance, profiles/prof_*_r1*.txt, x B)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                              "note": "on-chip iterative solve: HBM is touched once in/out per instance, the loop runs in shared memory"},
@@ -327,7 +332,14 @@ def main():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     p.add_argument("--cpu-sample", type=int, default=512, help="instances per CPU-baseline pass")
+    p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C5", "EXP"],
+                   help="workload (default: the headline C2; others are secondary measurements)")
     a = p.parse_args()
+    global CONFIG, METRIC
+    CONFIG = a.config
+    if CONFIG != "C2":
+        METRIC = f"problems/sec fwd+bwd, BASELINE config {CONFIG} (secondary measurement)"
+        a.cpu_sample = min(a.cpu_sample, a.batch)
     if a.impl == "reference":
         run_reference(a)
     else:
