@@ -16,7 +16,7 @@ _f64p = C.POINTER(C.c_double)
 
 EXPORTS = [
     "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary",
-    "bcone_ingest", "bcone_emit", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_memcpy2d",
+    "bcone_ingest", "bcone_emit", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
 
@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.bcone_vjp.restype = C.c_int
     lib.bcone_memcpy2d.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, vp]
     lib.bcone_memcpy2d.restype = C.c_int
+    lib.bcone_set_profile.argtypes = [vp, C.c_int32, C.POINTER(C.c_uint64)]
+    lib.bcone_set_profile.restype = C.c_int
     lib.bcone_launch_count.argtypes = [vp]
     lib.bcone_launch_count.restype = C.c_int64
     lib.bcone_kernel_info.argtypes = [vp] + [_i32p] * 6

@@ -52,6 +52,7 @@ struct Handle {
   int *fail_list[RING] = {nullptr}; int fail_cap[RING] = {0};
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
+  unsigned long long *prof = nullptr;   // device [16] phase cycle counters (bcone_set_profile)
   std::string err;
 };
 thread_local std::string g_create_err;
@@ -194,7 +195,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
       if (sm <= smem_cap) { h->fast_bwd = 1; h->bwd_threads = tt; h->bwd_smem = sm; h->p_in_smem = S.nnzP > 0; break; }
     }
   }
-  if (h->fast_bwd && S.nnzP > 0) {   // block-preconditioned variant for strongly convex QPs
+  if (h->fast_bwd && S.nnzP > 0 && 6 * (n + m + 1) >= 8 * n + 72) {   // block-preconditioned variant for strongly convex QPs
     for (int tt = threads; tt >= 128; tt /= 2) {
       size_t sm = bc_bwdb_smem_bytes(n, m, tt);
       if (sm <= smem_cap) { h->block_bwd = 1; h->blk_threads = tt; h->blk_smem = sm; break; }
@@ -302,7 +303,7 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
   int *ctr = h->counters + 4 * (h->slot++ % Handle::RING);
   a.counter = ctr; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
-  a.ws = h->fwd_ws; a.ws_stride = (long long)h->fwd_ws_stride;
+  a.ws = h->fwd_ws; a.ws_stride = (long long)h->fwd_ws_stride; a.prof = h->prof;
   CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   const int grid = std::min(B, h->num_sms * h->fwd_ctas);
   CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
@@ -327,7 +328,7 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = ctr + 1;
   a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
   a.ws = h->fast_bwd ? nullptr : h->bwd_ws; a.ws_stride = (long long)h->bwd_ws_stride;
-  a.inst_list = nullptr; a.B_dev = nullptr; a.fail_list = nullptr; a.fail_count = nullptr;
+  a.inst_list = nullptr; a.B_dev = nullptr; a.fail_list = nullptr; a.fail_count = nullptr; a.prof = h->prof;
   if (h->block_bwd && stg->lsqr_precond == 2) {
     // pass 1: block-preconditioned solve; pass 2: equilibrated LSQR on the instances it rejected
     if (h->fail_cap[slot] < B) {
@@ -361,6 +362,19 @@ extern "C" int bcone_memcpy2d(void *dst, int64_t dpitch, const void *src, int64_
   cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
                                     to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e != cudaSuccess) { g_create_err = std::string("bcone_memcpy2d: ") + cudaGetErrorString(e); return BCONE_ECUDA; }
+  return BCONE_OK;
+}
+
+// Debug: enable (on != 0) or read-and-reset the per-phase cycle counters of the forward / block-backward
+// kernels.  out (HOST, 16 x uint64) may be NULL.  Phases: 0 load, 1 equilibration, 2 factorisation + g,
+// 3 iterations, 4 checks | 8 load, 9 P factor, 10 W, 11 S, 12 S factor, 13 q + LSQR, 14 solve + write.
+extern "C" int bcone_set_profile(void *handle, int32_t on, uint64_t *out) {
+  Handle *h = (Handle *)handle;
+  if (!h) return BCONE_EINVAL;
+  cudaSetDevice(h->device);
+  if (out && h->prof) { cudaDeviceSynchronize(); cudaMemcpy(out, h->prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost); cudaMemset(h->prof, 0, 16 * sizeof(uint64_t)); }
+  if (on && !h->prof) { if (cudaMalloc((void **)&h->prof, 16 * sizeof(uint64_t)) != cudaSuccess) return BCONE_ENOMEM; h->allocs.push_back(h->prof); cudaMemset(h->prof, 0, 16 * sizeof(uint64_t)); }
+  if (!on) h->prof = nullptr;
   return BCONE_OK;
 }
 

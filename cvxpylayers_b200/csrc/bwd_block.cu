@@ -36,7 +36,8 @@ __device__ __forceinline__ void carve_blk(BlkSmem &M, double *base, int n, int m
   M.Ab = q; q += (m * n + 1) & ~1;
   M.x = q; q += n; M.c = q; q += n; M.px2c = q; q += n;
   M.piy = q; q += m; M.ry = q; q += m;
-  M.hp = q; q += N; M.q = q; q += N; M.rhs = q; q += N; M.z = q; q += N; M.U = q; q += N; M.V = q; q += N; M.W = q; q += N;
+  M.rhs = q; q += N;
+  M.hp = q; q += N; M.q = q; q += N; M.z = q; q += N; M.U = q; q += N; M.V = q; q += N; M.W = q; q += N;   // 6 N contiguous: factorisation scratch
   M.tn = q; q += n; M.t2 = q; q += n; M.tL = q; q += m;
   M.part = q; q += threads; M.red = q; q += 4 * 32;
   M.live = (int *)q;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
     const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
     const double *Pg = a.P_vals + (size_t)inst * S.nnzP;
     const double *dxg = a.dx + (size_t)inst * n, *dyg = a.dy + (size_t)inst * m;
+    PhaseTimer pt; pt.start(a.prof);
     // ---- vectors, pi_y, dz ----
     double d2[2] = {0, 0};
     for (int j = t; j < n; j += T) {
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
     if (applicable && !a.use_tma) {
       for (int e = t; e < nl * n; e += T) { const int l = e / n, j = e - l * n; M.Ab[e] = Ag[(size_t)M.live[l] * n + j]; }
     }
+    pt.stamp(8);   // load vectors, live list, P scatter
     // ---- 2Px + c and x'Px from the packed lower P (before it is overwritten by its factor) ----
     double xPx = 0;
     if (applicable) {
@@ -122,11 +125,12 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
       for (int j = t; j < n; j += T) { const double px = M.px2c[j]; s1[0] = fma(M.x[j], px, s1[0]); M.px2c[j] = 2.0 * px + M.c[j]; }
       block_reduce<1, false>(s1, M.red);
       xPx = s1[0];
-      applicable = chol_inv_packed(M.Pb, n, M.tn);   // Pb <- L^{-1}
+      applicable = chol_inv_packed(M.Pb, n, M.hp, a.prof);   // Pb <- L^{-1}   (scratch: hp..W are free here, 6 N >= 8 n + 72 checked on the host)
     }
     if (applicable && a.use_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }
     if (!applicable && nl <= n && a.use_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }  // drain the copies already issued
     __syncthreads();
+    pt.stamp(9);   // Px + Cholesky/inverse of P (+ wait for the row copies)
     double *Ws = M.Ab, *Sb = M.Ab + nl * n;
     if (applicable && nl > 0) {
       // ---- W = L^{-1} A_L' in place: one warp per staged row, a_l held in registers ----
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
         }
       }
       __syncthreads();
+      pt.stamp(10);  // W = L^{-1} A_L'
       // ---- S = W W' (nl x nl, packed lower) : 2x2 register tiles ----
       const int nb = (nl + 1) >> 1, ntile = (nb * (nb + 1)) >> 1;
       for (int e = t; e < ntile; e += T) {
@@ -178,7 +183,9 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
         }
       }
       __syncthreads();
-      applicable = chol_inv_packed(Sb, nl, M.W);   // Sb <- L_S^{-1}  (W is free scratch here)
+      pt.stamp(11);  // S = W W'
+      applicable = chol_inv_packed(Sb, nl, M.hp);   // Sb <- L_S^{-1}  (scratch: hp..W)
+      pt.stamp(12);  // Cholesky/inverse of S
     }
     if (!applicable) {   // hand the instance to the fallback pass (block-uniform branch)
       if (t == 0) { const int k = atomicAdd(a.fail_count, 1); a.fail_list[k] = inst; }
@@ -300,6 +307,7 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
       }
     }
     __syncthreads();
+    pt.stamp(13);  // q, LSQR
     // ---- r = blkdiag(G,1)^{-1} z :  S rL = zL - A_L P^{-1} zx,  rx = P^{-1}(zx + A_L' rL) ----
     const double rt = M.z[nr];
     matvec_rows(M.Pb, PackedLowerLayout{}, n, n, M.z, [&](int i, double v) { M.tn[i] = v; });              // tn = L^{-1} zx
@@ -332,6 +340,7 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
       if (t == 0 && a.lsqr_iters) a.lsqr_iters[inst] = itn;
     }
     __syncthreads();
+    pt.stamp(14);  // final solve + gradient write
   }
 }
 

@@ -51,6 +51,7 @@ struct FwdArgs {
   int use_tma;
   double *ws;            // INDIRECT mode: per-CTA slab of global memory holding the iterate vectors
   long long ws_stride;   // doubles per CTA
+  unsigned long long *prof;  // optional: [16] phase cycle counters (debug, bcone_set_profile)
 };
 
 struct BwdArgs {
@@ -67,8 +68,18 @@ struct BwdArgs {
   const int *inst_list;  // optional: work item k is instance inst_list[k] (fallback pass of the block solver)
   const int *B_dev;      // optional: number of work items read from device memory
   int *fail_list, *fail_count;  // block solver: instances it could not handle, for the fallback pass
+  unsigned long long *prof;     // optional: [16] phase cycle counters (debug, bcone_set_profile)
   double *ws;            // large instances: LSQR vectors live in a per-CTA slab of global memory (L2)
   long long ws_stride;
+};
+
+// Phase timing (debug): thread 0 of every CTA adds the cycles since the previous stamp to prof[phase].
+struct PhaseTimer {
+  unsigned long long *p; long long t0;
+  __device__ __forceinline__ void start(unsigned long long *prof) { p = prof; if (p && threadIdx.x == 0) t0 = clock64(); }
+  __device__ __forceinline__ void stamp(int phase) {
+    if (p && threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(p + phase, (unsigned long long)(t1 - t0)); t0 = t1; }
+  }
 };
 
 // ----------------------------------------------------------------------------- PTX helpers
@@ -481,46 +492,155 @@ __device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, cons
 
 // ----------------------------------------------------------------------------- packed Cholesky + inverse
 // In-place Cholesky K = L L' of a packed-lower SPD matrix (row i at i(i+1)/2) followed by the
-// in-place inverse L^{-1}: the factor is applied afterwards as two triangular products, which keeps
-// every solve free of sequential substitution.  tmp: n doubles.  Block-uniform result (false: not PD).
-__device__ inline bool chol_inv_packed(double *K, int n, double *tmp) {
+// in-place inverse X = L^{-1}: the factor is applied afterwards as two triangular products, which keeps
+// every solve free of sequential substitution.  Both sweeps advance FOUR columns / rows per step:
+// the 4x4 diagonal block is factored and inverted redundantly by every thread in registers (rsqrt +
+// multiplies, no divisions, no single-warp section), so a step is: panel (one row per thread) | barrier |
+// rank-4 trailing update (warp per row) | barrier.  n/4 steps instead of n, measured 3-4x faster than
+// the column-at-a-time version (profiles/README.md).  tmp is unused scratch kept for the callers'
+// signature.  Block-uniform result (false: not positive definite).
+struct Tri4 { double l00, l10, l11, l20, l21, l22, l30, l31, l32, l33, m00, m10, m11, m20, m21, m22, m30, m31, m32, m33; bool pd; };
+// Cholesky factor (l) and its inverse (m) of the jb x jb (jb <= 4) diagonal block at (r0, r0); when
+// `factored` the block already holds L.  Missing rows / columns are padded with the identity.
+__device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool factored) {
+  Tri4 q;
+  const double *R0 = K + ((r0 * (r0 + 1)) >> 1) + r0;
+  const double *R1 = K + (((r0 + 1) * (r0 + 2)) >> 1) + r0, *R2 = K + (((r0 + 2) * (r0 + 3)) >> 1) + r0, *R3 = K + (((r0 + 3) * (r0 + 4)) >> 1) + r0;
+  const double d00 = R0[0];
+  const double d10 = jb > 1 ? R1[0] : 0.0, d11 = jb > 1 ? R1[1] : 1.0;
+  const double d20 = jb > 2 ? R2[0] : 0.0, d21 = jb > 2 ? R2[1] : 0.0, d22 = jb > 2 ? R2[2] : 1.0;
+  const double d30 = jb > 3 ? R3[0] : 0.0, d31 = jb > 3 ? R3[1] : 0.0, d32 = jb > 3 ? R3[2] : 0.0, d33 = jb > 3 ? R3[3] : 1.0;
+  double r0_, r1_, r2_, r3_;
+  if (factored) {
+    q.l00 = d00; q.l10 = d10; q.l11 = d11; q.l20 = d20; q.l21 = d21; q.l22 = d22; q.l30 = d30; q.l31 = d31; q.l32 = d32; q.l33 = d33;
+    r0_ = 1.0 / d00; r1_ = 1.0 / d11; r2_ = 1.0 / d22; r3_ = 1.0 / d33; q.pd = true;
+  } else {
+    const double p0 = d00; r0_ = rsqrt(p0);
+    q.l00 = p0 * r0_; q.l10 = d10 * r0_; q.l20 = d20 * r0_; q.l30 = d30 * r0_;
+    const double p1 = fma(-q.l10, q.l10, d11); r1_ = rsqrt(p1);
+    q.l11 = p1 * r1_; q.l21 = fma(-q.l20, q.l10, d21) * r1_; q.l31 = fma(-q.l30, q.l10, d31) * r1_;
+    const double p2 = fma(-q.l21, q.l21, fma(-q.l20, q.l20, d22)); r2_ = rsqrt(p2);
+    q.l22 = p2 * r2_; q.l32 = fma(-q.l31, q.l21, fma(-q.l30, q.l20, d32)) * r2_;
+    const double p3 = fma(-q.l32, q.l32, fma(-q.l31, q.l31, fma(-q.l30, q.l30, d33))); r3_ = rsqrt(p3);
+    q.l33 = p3 * r3_;
+    q.pd = (p0 > 0) && (p1 > 0) && (p2 > 0) && (p3 > 0);
+  }
+  q.m00 = r0_; q.m11 = r1_; q.m22 = r2_; q.m33 = r3_;
+  q.m10 = -q.l10 * q.m00 * r1_;
+  q.m20 = -fma(q.l21, q.m10, q.l20 * q.m00) * r2_; q.m21 = -q.l21 * q.m11 * r2_;
+  q.m30 = -fma(q.l32, q.m20, fma(q.l31, q.m10, q.l30 * q.m00)) * r3_;
+  q.m31 = -fma(q.l32, q.m21, q.l31 * q.m11) * r3_; q.m32 = -q.l32 * q.m22 * r3_;
+  return q;
+}
+__device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned long long *prof = nullptr) {
+  (void)tmp;
   const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
-  bool ok = true;
-  for (int k = 0; k < n; k++) {
-    const int kk = (k * (k + 1)) >> 1;
-    const double dkk = K[kk + k];
-    if (!(dkk > 0)) { ok = false; break; }   // every thread reads the same word
-    const double ilkk = 1.0 / sqrt(dkk);
+  long long tA = 0, tB = 0, t0 = 0;
+  if (prof && t == 0) t0 = clock64();
+  // ---------------- Cholesky, four columns per step ----------------
+  for (int J0 = 0; J0 < n; J0 += 4) {
+    const int jb = min(4, n - J0), R0 = J0 + jb;
+    const Tri4 q = tri4_block(K, J0, jb, false);
+    if (!q.pd) return false;   // block-uniform: every thread factors the same block
+    // panel: row i >= R0, l_i = a_i L_D^{-T}; one row per thread, in place
+    for (int i = R0 + t; i < n; i += T) {
+      double *row = K + ((i * (i + 1)) >> 1) + J0;
+      const double a0 = row[0], a1 = jb > 1 ? row[1] : 0.0, a2 = jb > 2 ? row[2] : 0.0, a3 = jb > 3 ? row[3] : 0.0;
+      row[0] = a0 * q.m00;
+      if (jb > 1) row[1] = fma(a1, q.m11, a0 * q.m10);
+      if (jb > 2) row[2] = fma(a2, q.m22, fma(a1, q.m21, a0 * q.m20));
+      if (jb > 3) row[3] = fma(a3, q.m33, fma(a2, q.m32, fma(a1, q.m31, a0 * q.m30)));
+    }
     __syncthreads();
-    if (t == 0) K[kk + k] = dkk * ilkk;
-    for (int i = k + 1 + t; i < n; i += T) K[((i * (i + 1)) >> 1) + k] *= ilkk;
-    __syncthreads();
-    // trailing update: warp per row i, lanes across columns j in (k, i]
-    for (int i = k + 1 + warp; i < n; i += nw) {
-      const int ri = (i * (i + 1)) >> 1;
-      const double lik = K[ri + k];
-      for (int j = k + 1 + lane; j <= i; j += 32) K[ri + j] = fma(-lik, K[((j * (j + 1)) >> 1) + k], K[ri + j]);
+    if (t == 0) {   // the diagonal block itself (nobody reads it during the trailing update)
+      double *D0 = K + ((J0 * (J0 + 1)) >> 1) + J0;
+      D0[0] = q.l00;
+      if (jb > 1) { double *D1 = K + (((J0 + 1) * (J0 + 2)) >> 1) + J0; D1[0] = q.l10; D1[1] = q.l11; }
+      if (jb > 2) { double *D2 = K + (((J0 + 2) * (J0 + 3)) >> 1) + J0; D2[0] = q.l20; D2[1] = q.l21; D2[2] = q.l22; }
+      if (jb > 3) { double *D3 = K + (((J0 + 3) * (J0 + 4)) >> 1) + J0; D3[0] = q.l30; D3[1] = q.l31; D3[2] = q.l32; D3[3] = q.l33; }
+    }
+    // rank-4 trailing update: K[i][j] -= sum_c L[i][J0+c] L[j][J0+c]; warp per row i, lanes across j in [R0, i].
+    // A lane's columns are the same for every row, so their panel entries are loaded once per step.
+    if (R0 < n) {
+      constexpr int QC = 4;
+      double b0[QC], b1[QC], b2[QC], b3[QC];
+#pragma unroll
+      for (int u = 0; u < QC; u++) {
+        const int jc = R0 + lane + 32 * u;
+        b0[u] = b1[u] = b2[u] = b3[u] = 0.0;
+        if (jc < n) {
+          const double *pj = K + ((jc * (jc + 1)) >> 1) + J0;
+          b0[u] = pj[0];
+          if (jb > 1) b1[u] = pj[1];
+          if (jb > 2) b2[u] = pj[2];
+          if (jb > 3) b3[u] = pj[3];
+        }
+      }
+      for (int i = R0 + warp; i < n; i += nw) {
+        double *pi = K + ((i * (i + 1)) >> 1);
+        const double a0 = -pi[J0], a1 = jb > 1 ? -pi[J0 + 1] : 0.0, a2 = jb > 2 ? -pi[J0 + 2] : 0.0, a3 = jb > 3 ? -pi[J0 + 3] : 0.0;
+#pragma unroll
+        for (int u = 0; u < QC; u++) {
+          const int jc = R0 + lane + 32 * u;
+          if (jc <= i) pi[jc] = fma(a3, b3[u], fma(a2, b2[u], fma(a1, b1[u], fma(a0, b0[u], pi[jc]))));
+        }
+        for (int jc = R0 + lane + 32 * QC; jc <= i; jc += 32) {   // orders beyond R0 + 128
+          const double *pj = K + ((jc * (jc + 1)) >> 1) + J0;
+          double v = fma(a0, pj[0], pi[jc]);
+          if (jb > 1) v = fma(a1, pj[1], v);
+          if (jb > 2) v = fma(a2, pj[2], v);
+          if (jb > 3) v = fma(a3, pj[3], v);
+          pi[jc] = v;
+        }
+      }
     }
     __syncthreads();
   }
-  if (!ok) return false;
-  // X = L^{-1}, row by row: X[i][j] = -(1/l_ii) sum_{k=j}^{i-1} L[i][k] X[k][j]; four lanes per output
-  for (int i = 0; i < n; i++) {
-    const int ro = (i * (i + 1)) >> 1;
-    for (int k = t; k <= i; k += T) tmp[k] = K[ro + k];
-    __syncthreads();
-    const double il = 1.0 / tmp[i];
-    const int g = t & 3;
-    for (int base = 0; base <= i; base += T >> 2) {   // block-uniform trip count (full-mask shuffles)
-      const int j = base + (t >> 2);
-      double acc = 0;
-      if (j < i) for (int k = j + g; k < i; k += 4) acc = fma(tmp[k], K[((k * (k + 1)) >> 1) + j], acc);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (g == 0 && j <= i) K[ro + j] = (j == i) ? il : -acc * il;
+  if (prof && t == 0) { const long long t1 = clock64(); tA = t1 - t0; t0 = t1; }
+  // ---------------- X = L^{-1}, four rows per step ----------------
+  // X_II = L_II^{-1};  X_Ij = -X_II * (sum_{i=j}^{I0-1} L_Ii X_ij)  for j < I0;  four lanes per output column
+  const int g = t & 3, q4 = t >> 2, nq = T >> 2;
+  for (int I0 = 0; I0 < n; I0 += 4) {
+    const int ib = min(4, n - I0);
+    const Tri4 q = tri4_block(K, I0, ib, true);
+    const double *L0 = K + ((I0 * (I0 + 1)) >> 1), *L1 = K + (((I0 + 1) * (I0 + 2)) >> 1), *L2 = K + (((I0 + 2) * (I0 + 3)) >> 1),
+                 *L3 = K + (((I0 + 3) * (I0 + 4)) >> 1);
+    int jg = 0;
+    do {   // groups of blockDim/4 output columns, ascending: a group only reads columns >= its own
+      const int j = jg + q4;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      if (j < I0) {
+        for (int i = j + g; i < I0; i += 4) {
+          const double x = K[((i * (i + 1)) >> 1) + j];
+          s0 = fma(L0[i], x, s0);
+          if (ib > 1) s1 = fma(L1[i], x, s1);
+          if (ib > 2) s2 = fma(L2[i], x, s2);
+          if (ib > 3) s3 = fma(L3[i], x, s3);
+        }
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s3 += __shfl_xor_sync(0xffffffffu, s3, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 2); s3 += __shfl_xor_sync(0xffffffffu, s3, 2);
+      __syncthreads();   // every read of block row I at this group's columns is done
+      if (g == 0 && j < I0) {
+        K[((I0 * (I0 + 1)) >> 1) + j] = -(q.m00 * s0);
+        if (ib > 1) K[(((I0 + 1) * (I0 + 2)) >> 1) + j] = -fma(q.m11, s1, q.m10 * s0);
+        if (ib > 2) K[(((I0 + 2) * (I0 + 3)) >> 1) + j] = -fma(q.m22, s2, fma(q.m21, s1, q.m20 * s0));
+        if (ib > 3) K[(((I0 + 3) * (I0 + 4)) >> 1) + j] = -fma(q.m33, s3, fma(q.m32, s2, fma(q.m31, s1, q.m30 * s0)));
+      }
+      jg += nq;
+    } while (jg < I0);
+    if (t == 0) {
+      double *D0 = K + ((I0 * (I0 + 1)) >> 1) + I0;
+      D0[0] = q.m00;
+      if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = q.m10; D1[1] = q.m11; }
+      if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = q.m20; D2[1] = q.m21; D2[2] = q.m22; }
+      if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = q.m30; D3[1] = q.m31; D3[2] = q.m32; D3[3] = q.m33; }
     }
     __syncthreads();
   }
+  if (prof && t == 0) { const long long t1 = clock64(); tB = t1 - t0; atomicAdd(prof + 5, (unsigned long long)tA); atomicAdd(prof + 6, (unsigned long long)tB); }
   return true;
 }
 

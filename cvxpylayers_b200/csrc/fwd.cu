@@ -205,7 +205,7 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
     }
     __syncthreads();
   }
-  if (!chol_inv_packed(K, n, M.tn)) return false;
+  if (!chol_inv_packed(K, n, M.part)) return false;   // scratch: part (8 n) + red (256) are contiguous
   // ---- g = (R_z + M)^{-1} h, h = (c^, b^) ----
   for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
   __syncthreads();
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
     const double *Pg = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
     const double *bg = a.b + (size_t)inst * m, *cg = a.c + (size_t)inst * n;
+    PhaseTimer pt; pt.start(a.prof);
 
     // ---- stage the instance: one TMA bulk copy for the CSR values, plain loads for b, c ----
     if (a.use_tma) {
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     if (a.use_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }
     __syncthreads();
 
+    pt.stamp(0);   // load
     // ---- Ruiz equilibration: A^ = D A E, P^ = E P E ----
     if (st.normalize) {
       for (int pass = 0; pass < st.ruiz_passes; pass++) {
@@ -395,12 +397,14 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
       __syncthreads();
     }
 
+    pt.stamp(1);   // equilibration + sigma
     double scale = st.scale, gRg = 0;
     int status = BCONE_INACCURATE, it = 0;
     bool okf = factor_and_g<DENSE, INDIRECT>(a, M, Pg, scale, rho_x, gRg, plA, plN);
     for (int k = t; k < N; k += T) { M.w[k] = (k == N - 1) ? 1.0 : 0.0; M.u[k] = 0; M.ut[k] = 0; }
     if (INDIRECT) for (int j = t; j < n; j += T) M.cx[j] = 0.0;
     __syncthreads();
+    pt.stamp(2);   // K formation + Cholesky + inverse + g
     double sum_log = 0, rp = nan(""), rd = nan(""), gap = nan("");
     int n_log = 0, last_up = 0;
     // adaptive check schedule (oracle: cone_oracle.c): log-linear extrapolation of the distance to the tolerance
@@ -455,6 +459,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
       __syncthreads();
       if (nonpoly) { project_cones(S, M.u + n, M.psd); __syncthreads(); }
 
+      pt.stamp(3);   // iteration body
       if (check) {
         // ---- termination quantities on the un-normalised data ----
         const double tau = M.u[N - 1];
@@ -536,13 +541,14 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
           }
         }
       }
+      if (check) pt.stamp(4);   // termination check (+ rescale)
       if (!fused && it < st.max_iters) {  // (the last iterate keeps w so that s = R(u - t) is recoverable)
         for (int k = t; k < N; k += T) M.w[k] += alpha * (M.u[k] - M.ut[k]);
         __syncthreads();
       }
     }
     if (it > st.max_iters) it = st.max_iters;
-
+    pt.stamp(4);
     // ---- write back ----
     {
       double *xo = a.x + (size_t)inst * n, *yo = a.y + (size_t)inst * m, *so = a.s + (size_t)inst * m;

@@ -92,6 +92,9 @@ int bcone_vjp(void *handle, int32_t B, const double *A_vals, const double *P_val
 int bcone_memcpy2d(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t height,
                    int32_t to_device, void *cuda_stream);
 
+/* Debug: per-phase cycle counters of the forward / block-backward kernels (see csrc/api.cu). */
+int bcone_set_profile(void *handle, int32_t on, uint64_t *out16);
+
 /* Introspection for benchmarks/tests: kernel launches issued by this handle so far, and the
  * launch geometry chosen for the forward / backward kernels. */
 int64_t bcone_launch_count(void *handle);

@@ -1,6 +1,4 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 5 --warmup 3 > gpurun_out/bench_r1_n4.json 2> gpurun_out/bench_r1_n4.err; grep "bench\]" gpurun_out/bench_r1_n4.err | head -2; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1_n4.json')); print('C2 x4', d['value'], d['ms_per_step'], d['e2e']['value'])"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 5 --warmup 3 --config C3 --batch 512 > gpurun_out/bench_r1_c3_n4.json 2> gpurun_out/bench_r1_c3_n4.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1_c3_n4.json')); print('C3 x4 (2048 total)', d['value'], d['ms_per_step'], d['e2e']['value'], d['kernel_ms'])"
-python bench.py --steps 5 --warmup 3 --config C3 --batch 2048 --cpu-sample 2048 > gpurun_out/bench_r1_c3_n1.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1_c3_n1.json')); print('C3 x1', d['value'], d['ms_per_step'], d['e2e']['value'], d['kernel_ms'], d['cpu_baseline']['value'])"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests.log
+timeout 300 python tools/phase_profile.py 592 2>&1 | tee gpurun_out/phase.log
+timeout 600 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
