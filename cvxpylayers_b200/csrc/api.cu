@@ -52,7 +52,7 @@ struct Handle {
   int *fail_list[RING] = {nullptr}; int fail_cap[RING] = {0};
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
-  unsigned long long *prof = nullptr;   // device [16] phase cycle counters (bcone_set_profile)
+  unsigned long long *prof = nullptr;   // device [32] phase cycle counters (bcone_set_profile)
   std::string err;
 };
 thread_local std::string g_create_err;
@@ -372,8 +372,8 @@ extern "C" int bcone_set_profile(void *handle, int32_t on, uint64_t *out) {
   Handle *h = (Handle *)handle;
   if (!h) return BCONE_EINVAL;
   cudaSetDevice(h->device);
-  if (out && h->prof) { cudaDeviceSynchronize(); cudaMemcpy(out, h->prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost); cudaMemset(h->prof, 0, 16 * sizeof(uint64_t)); }
-  if (on && !h->prof) { if (cudaMalloc((void **)&h->prof, 16 * sizeof(uint64_t)) != cudaSuccess) return BCONE_ENOMEM; h->allocs.push_back(h->prof); cudaMemset(h->prof, 0, 16 * sizeof(uint64_t)); }
+  if (out && h->prof) { cudaDeviceSynchronize(); cudaMemcpy(out, h->prof, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost); cudaMemset(h->prof, 0, 32 * sizeof(uint64_t)); }
+  if (on && !h->prof) { if (cudaMalloc((void **)&h->prof, 32 * sizeof(uint64_t)) != cudaSuccess) return BCONE_ENOMEM; h->allocs.push_back(h->prof); cudaMemset(h->prof, 0, 32 * sizeof(uint64_t)); }
   if (!on) h->prof = nullptr;
   return BCONE_OK;
 }

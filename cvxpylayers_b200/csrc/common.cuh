@@ -80,6 +80,7 @@ struct PhaseTimer {
   __device__ __forceinline__ void stamp(int phase) {
     if (p && threadIdx.x == 0) { const long long t1 = clock64(); atomicAdd(p + phase, (unsigned long long)(t1 - t0)); t0 = t1; }
   }
+  __device__ __forceinline__ void skip() { if (p && threadIdx.x == 0) t0 = clock64(); }   // restart without charging
 };
 
 // ----------------------------------------------------------------------------- PTX helpers

@@ -178,6 +178,16 @@ def _pipe_ok(eng: Engine, B: int, *tensors) -> bool:
     return info["fwd_smem"] > 0
 
 
+def _side_streams(eng: Engine, dev):
+    """The two pipeline streams of an engine, created once: torch's device allocator keeps one block pool per
+    stream, so fresh streams per call would cudaMalloc every chunk buffer again (tens of ms per step)."""
+    ss = getattr(eng, "_pipe_streams", None)
+    if ss is None:
+        ss = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        eng._pipe_streams = ss
+    return ss
+
+
 def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P):
     st = eng.structure
     B = A_eval.shape[1]
@@ -190,7 +200,7 @@ def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P
     primal = torch.empty((B, st.n), dtype=f64, pin_memory=True)
     dual = torch.empty((B, st.m), dtype=f64, pin_memory=True)
     cur = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = _side_streams(eng, dev)
     for s_ in streams:
         s_.wait_stream(cur)
     for k, (lo, hi) in enumerate(_chunks(B)):
@@ -219,27 +229,43 @@ def _backward_pipelined(eng: Engine, dev, settings, A_vals, P_vals, b, c, x, y, 
     st = eng.structure
     B = A_vals.shape[0]
     f64 = torch.float64
+    _t0 = time.perf_counter()
     dA_eval = torch.empty((nnz_aug, B), dtype=f64, pin_memory=True)
     dq_eval = torch.empty((st.n + 1, B), dtype=f64, pin_memory=True)
     dP_eval = torch.empty((st.nnzP, B), dtype=f64, pin_memory=True) if use_P else None
+    _t1 = time.perf_counter()
+    _evs = []
     dx = dprimal.detach().to(device=dev, dtype=f64, non_blocking=True).reshape(B, -1).contiguous()
     dy = ddual.detach().to(device=dev, dtype=f64, non_blocking=True).reshape(B, -1).contiguous()
     cur = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    streams = _side_streams(eng, dev)
     for s_ in streams:
         s_.wait_stream(cur)
     for k, (lo, hi) in enumerate(_chunks(B)):
         with torch.cuda.stream(streams[k % 2]):
+            if _TRACE:
+                _e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                _e[0].record()
             gA, gP, gb, gc, _ = eng.vjp(A_vals[lo:hi], b[lo:hi], c[lo:hi], x[lo:hi], y[lo:hi], s[lo:hi], dx[lo:hi], dy[lo:hi],
                                         P_vals[lo:hi] if P_vals is not None else None, settings)
             gA_e, gq_e, gP_e = eng.emit(gA, gP if use_P else None, gb, gc)
+            if _TRACE:
+                _e[1].record()
             eng.copy2d(dA_eval, gA_e, lo, hi, False)
             eng.copy2d(dq_eval, gq_e, lo, hi, False)
             if use_P:
                 eng.copy2d(dP_eval, gP_e, lo, hi, False)
+            if _TRACE:
+                _e[2].record()
+                _evs.append(_e)
     for s_ in streams:
         cur.wait_stream(s_)
+    _t2 = time.perf_counter()
     cur.synchronize()
+    if _TRACE:
+        _t3 = time.perf_counter()
+        print(f"[b200] bwd: pinned alloc {1e3 * (_t1 - _t0):.1f} ms, enqueue {1e3 * (_t2 - _t1):.1f} ms, drain {1e3 * (_t3 - _t2):.1f} ms; chunks (compute, d2h) "
+              + ", ".join(f"({e[0].elapsed_time(e[1]):.1f}, {e[1].elapsed_time(e[2]):.1f})" for e in _evs), file=sys.stderr)
     return dA_eval, dq_eval, dP_eval
 
 

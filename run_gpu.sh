@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests.log
-timeout 300 python tools/phase_profile.py 592 2>&1 | tee gpurun_out/phase.log
-timeout 600 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
+./tools/microbench 2>&1 | tee gpurun_out/micro.log
