@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-SOURCES = ["api.cu", "fwd.cu", "bwd.cu", "bwd_fast.cu", "bwd_block.cu", "pack.cu"]
+SOURCES = ["api.cu", "fwd.cu", "fwd_fast.cu", "bwd.cu", "bwd_fast.cu", "bwd_block.cu", "pack.cu"]
 HEADERS = [CSRC / "common.cuh", PKG.parent / "include" / "bcone.h"]
 LIB = PKG / "libbcone.so"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <cstdlib>
 #include "common.cuh"
 
 // ---- kernels / launchers implemented in fwd.cu, bwd.cu, pack.cu ----
@@ -16,6 +17,12 @@ size_t bc_fwd_ws_doubles(int n, int m);
 cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem);
 cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas);
 cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t st);
+size_t bc_fwdf_smem_bytes(int n, int m);
+int bc_fwdf_threads(void);
+int bc_fwdf_eligible(int n, int m);
+cudaError_t bc_fwdf_configure(size_t smem);
+cudaError_t bc_fwdf_occupancy(size_t smem, int *ctas);
+cudaError_t bc_fwdf_launch(const FwdArgs *a, int grid, size_t smem, cudaStream_t st);
 size_t bc_bwd_ws_doubles(int n, int m, int npoly);
 size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp, int vec_global);
 cudaError_t bc_bwd_configure(int dense, size_t smem);
@@ -50,6 +57,7 @@ struct Handle {
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   int block_bwd = 0, blk_threads = 0; size_t blk_smem = 0;   // KKT-block preconditioned backward (lsqr_precond = 2)
   int *fail_list[RING] = {nullptr}; int fail_cap[RING] = {0};
+  int fast_fwd = 0;  // dense A, polyhedral cones, direct mode: register-tiled forward (fwd_fast.cu)
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
   unsigned long long *prof = nullptr;   // device [32] phase cycle counters (bcone_set_profile)
@@ -209,14 +217,22 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     return fail(nullptr, BCONE_EUNSUPPORTED, buf);
   }
   cudaError_t e;
-  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fwd_smem)) != cudaSuccess ||
+  // register-tiled forward (fwd_fast.cu) when the structure allows it; BCONE_NO_FAST_FWD=1 keeps the generic kernel
+  if (S.dense && S.ncones == 0 && d->ep + d->ed == 0 && !h->fwd_indirect && bc_fwdf_eligible(n, m) &&
+      bc_fwdf_smem_bytes(n, m) <= smem_cap && !(getenv("BCONE_NO_FAST_FWD") && atoi(getenv("BCONE_NO_FAST_FWD")))) {
+    if (bc_fwdf_configure(bc_fwdf_smem_bytes(n, m)) == cudaSuccess) {
+      h->fast_fwd = 1; h->fwd_threads = bc_fwdf_threads(); h->fwd_smem = bc_fwdf_smem_bytes(n, m);
+    }
+  }
+  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect) : h->fwd_smem)) != cudaSuccess ||
       (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
   if (h->block_bwd && (e = bc_bwdb_configure(h->blk_smem)) != cudaSuccess) h->block_bwd = 0;
-  bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
+  if (h->fast_fwd) bc_fwdf_occupancy(h->fwd_smem, &h->fwd_ctas);
+  else bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
   if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
@@ -306,7 +322,8 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   a.ws = h->fwd_ws; a.ws_stride = (long long)h->fwd_ws_stride; a.prof = h->prof;
   CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   const int grid = std::min(B, h->num_sms * h->fwd_ctas);
-  CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
+  if (h->fast_fwd) CK(bc_fwdf_launch(&a, grid, h->fwd_smem, st), "solve launch (fast)");
+  else CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
   h->launches++;
   return BCONE_OK;
 }
