@@ -20,8 +20,8 @@ cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads,
 size_t bc_fwdf_smem_bytes(int n, int m);
 int bc_fwdf_threads(void);
 int bc_fwdf_eligible(int n, int m);
-cudaError_t bc_fwdf_configure(size_t smem);
-cudaError_t bc_fwdf_occupancy(size_t smem, int *ctas);
+cudaError_t bc_fwdf_configure(int n, int m, size_t smem);
+cudaError_t bc_fwdf_occupancy(int n, int m, size_t smem, int *ctas);
 cudaError_t bc_fwdf_launch(const FwdArgs *a, int grid, size_t smem, cudaStream_t st);
 size_t bc_bwd_ws_doubles(int n, int m, int npoly);
 size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp, int vec_global);
@@ -220,7 +220,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   // register-tiled forward (fwd_fast.cu) when the structure allows it; BCONE_NO_FAST_FWD=1 keeps the generic kernel
   if (S.dense && S.ncones == 0 && d->ep + d->ed == 0 && !h->fwd_indirect && bc_fwdf_eligible(n, m) &&
       bc_fwdf_smem_bytes(n, m) <= smem_cap && !(getenv("BCONE_NO_FAST_FWD") && atoi(getenv("BCONE_NO_FAST_FWD")))) {
-    if (bc_fwdf_configure(bc_fwdf_smem_bytes(n, m)) == cudaSuccess) {
+    if (bc_fwdf_configure(n, m, bc_fwdf_smem_bytes(n, m)) == cudaSuccess) {
       h->fast_fwd = 1; h->fwd_threads = bc_fwdf_threads(); h->fwd_smem = bc_fwdf_smem_bytes(n, m);
     }
   }
@@ -231,7 +231,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
     return fail(nullptr, BCONE_ECUDA, msg);
   }
   if (h->block_bwd && (e = bc_bwdb_configure(h->blk_smem)) != cudaSuccess) h->block_bwd = 0;
-  if (h->fast_fwd) bc_fwdf_occupancy(h->fwd_smem, &h->fwd_ctas);
+  if (h->fast_fwd) bc_fwdf_occupancy(n, m, h->fwd_smem, &h->fwd_ctas);
   else bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
   if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);

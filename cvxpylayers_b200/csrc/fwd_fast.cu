@@ -18,57 +18,60 @@
 // on-chip re-factorisation, write-back) is the algorithm of fwd.cu verbatim.
 #include "common.cuh"
 
+// Sub-phase cycle counters (tools/phase_profile.py) cost registers in the hot loop: compiled in only with -DBC_SUBPROF.
+#ifdef BC_SUBPROF
+#define SUB_DECL(name) PhaseTimer name; name.start(a.prof)
+#define SUB_SKIP(name) name.skip()
+#define SUB_STAMP(name, k) name.stamp(k)
+#else
+#define SUB_DECL(name)
+#define SUB_SKIP(name)
+#define SUB_STAMP(name, k)
+#endif
+
 namespace {
 
 constexpr int FT = 512;          // threads per CTA
-constexpr int TR = 4, TC = 10;   // register tile of A
+constexpr int TR = 4, TC = 10;   // tile of A per thread: columns [0, TCR) in registers, [TCR, TC) in a private shared-memory slot
+constexpr int TCR = 8;
 
-struct FastGeom { int CT, RTu, npad, mpad, KR, npk, XD; };
-
-__host__ __device__ inline bool fwdf_geom(int n, int m, FastGeom &g) {
-  g.CT = (n + TC - 1) / TC; g.RTu = (m + TR - 1) / TR; g.npad = g.CT * TC; g.mpad = g.RTu * TR;
-  if ((long long)g.CT * g.RTu > FT || n > FT || m > FT) return false;
-  g.KR = (((n + 1) / 2) * g.CT <= FT) ? 2 : 4;
-  if (((n + g.KR - 1) / g.KR) * g.CT > FT) return false;
-  g.npk = (n * (n + 1) / 2 + 1) & ~1;
-  const int rowsR = g.mpad > n + 3 ? g.mpad : n + 3;
-  const long long iter = (long long)n * g.npad + (long long)g.RTu * g.npad + (long long)rowsR * g.CT;   // Kinv | column partials | row partials
-  const long long stage = (long long)m * n + 2;                                                          // A as delivered by TMA / staged for K
-  long long xd = iter > stage ? iter : stage;
-  if (xd < FT) xd = FT;                                                                                  // P_mul scratch
-  g.XD = (int)((xd + 1) & ~1LL);
-  return true;
-}
-__host__ __device__ inline size_t fwdf_smem_doubles(int n, int m) {
-  FastGeom g;
-  if (!fwdf_geom(n, m, g)) return (size_t)1 << 40;
-  return 4 + (size_t)g.XD + g.npk + 9 * (size_t)g.npad + 7 * (size_t)g.mpad + 8 * 32;
-}
-
-struct FSmem {   // few base pointers, the vectors are addressed as base + k * stride (registers are for the A tile)
-  uint64_t *bar; int *ibuf;
-  double *X, *Li, *vx, *vy, *red;
-  int npad, mpad, oXC, oXR;
-  __device__ __forceinline__ double *wx() const { return vx; }
-  __device__ __forceinline__ double *ux() const { return vx + npad; }
-  __device__ __forceinline__ double *utx() const { return vx + 2 * npad; }
-  __device__ __forceinline__ double *gx() const { return vx + 3 * npad; }
-  __device__ __forceinline__ double *ch() const { return vx + 4 * npad; }
-  __device__ __forceinline__ double *En() const { return vx + 5 * npad; }
-  __device__ __forceinline__ double *tn() const { return vx + 6 * npad; }
-  __device__ __forceinline__ double *tn2() const { return vx + 7 * npad; }
-  __device__ __forceinline__ double *tn3() const { return vx + 8 * npad; }
-  __device__ __forceinline__ double *wy() const { return vy; }
-  __device__ __forceinline__ double *uy() const { return vy + mpad; }
-  __device__ __forceinline__ double *uty() const { return vy + 2 * mpad; }
-  __device__ __forceinline__ double *gy() const { return vy + 3 * mpad; }
-  __device__ __forceinline__ double *bh() const { return vy + 4 * mpad; }
-  __device__ __forceinline__ double *Dm() const { return vy + 5 * mpad; }
-  __device__ __forceinline__ double *tm() const { return vy + 6 * mpad; }
-  __device__ __forceinline__ double *Kinv() const { return X; }    // views into X during the iterations
-  __device__ __forceinline__ double *XC() const { return X + oXC; }
-  __device__ __forceinline__ double *XR() const { return X + oXR; }
+// Tile geometry.  CT column tiles x RTu row tiles; with non-zero template arguments every shared-memory offset
+// below is a compile-time constant (addresses fold into instruction immediates, reduction loops unroll), which
+// is what keeps the iteration loop inside 128 registers next to the 80 of the tile; <0, 0> is the runtime
+// fallback for other shapes.
+template <int CT_, int RTU_>
+struct Geo {
+  int ct, rtu;
+  __host__ __device__ Geo(int n, int m) : ct((n + TC - 1) / TC), rtu((m + TR - 1) / TR) {}
+  __host__ __device__ __forceinline__ int CT() const { return CT_ ? CT_ : ct; }
+  __host__ __device__ __forceinline__ int RTu() const { return RTU_ ? RTU_ : rtu; }
+  __host__ __device__ __forceinline__ int npad() const { return CT() * TC; }
+  __host__ __device__ __forceinline__ int mpad() const { return RTu() * TR; }
+  __host__ __device__ __forceinline__ int KR() const { return (npad() / 2) * CT() <= FT ? 2 : 4; }
+  __host__ __device__ __forceinline__ int npk() const { return (npad() * (npad() + 1) / 2 + 1) & ~1; }
+  __host__ __device__ __forceinline__ int rowsR() const { return mpad() > npad() ? mpad() : npad(); }
+  // X region during the iterations: [Kinv npad x npad | partial sums (column partials RTu x npad and row partials
+  // rowsR x CT take turns) | private tile slots TR x FT double2]; it also stages A (m x n) for the K formation,
+  // and during the Ruiz passes (no Kinv yet) the row partials sit at its start.
+  __host__ __device__ __forceinline__ int oXC() const { return npad() * npad(); }
+  __host__ __device__ __forceinline__ int szPart() const { const int a = RTu() * npad(), b = rowsR() * CT(); return ((a > b ? a : b) + 1) & ~1; }
+  __host__ __device__ __forceinline__ int oPS() const { return oXC() + szPart(); }
+  __host__ __device__ __forceinline__ int XD() const { const int it = oPS() + TR * FT * (TC - TCR), stg = mpad() * npad(); return ((it > stg ? it : stg) + 1) & ~1; }
+  // whole block (doubles): [bar, ibuf (4) | X | Li | 9 x-vectors | 7 y-vectors | red (8 x 32) | scalars (64)]
+  __host__ __device__ __forceinline__ int oX() const { return 4; }
+  __host__ __device__ __forceinline__ int oLi() const { return oX() + XD(); }
+  __host__ __device__ __forceinline__ int oVx() const { return oLi() + npk(); }
+  __host__ __device__ __forceinline__ int oVy() const { return oVx() + 9 * npad(); }
+  __host__ __device__ __forceinline__ int oRed() const { return oVy() + 7 * mpad(); }
+  __host__ __device__ __forceinline__ int total() const { return oRed() + 256 + 64; }
+  __host__ __device__ __forceinline__ bool ok(int n, int m) const {
+    return n <= FT && m <= FT && CT() * RTu() <= FT && ((npad() + KR() - 1) / KR()) * CT() <= FT;
+  }
 };
+
+// Vector slots (x-space: k * npad from oVx; y-space: k * mpad from oVy)
+enum { VX_W = 0, VX_U, VX_UT, VX_G, VX_CH, VX_EN, VX_TN, VX_TN2, VX_TN3 };
+enum { VY_W = 0, VY_U, VY_UT, VY_G, VY_BH, VY_DM, VY_TM };
 
 __device__ __forceinline__ double inv_ry_f(int z, int i, double scale) { return i < z ? BC_ZERO_CONE_FACTOR * scale : scale; }
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
@@ -76,14 +79,19 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 // ---------------------------------------------------------------- register-tile products
 // out_j = sum_i A_ij y_i.  Every active thread folds its 4 rows into 10 column partials, thread j < n adds
 // the RTu partials of its column.  ep(j, value) runs on thread j.  One barrier inside, none at the end.
-template <class Epi>
-__device__ __forceinline__ void rt_cols(const double (&ar)[TR][TC], const FastGeom &g, bool act, int R, int C, const double *y,
+template <class G, class Epi>
+__device__ __forceinline__ void rt_cols(const double (&ar)[TR][TCR], const double2 *ps, const G &g, bool act, int R, int C, const double *y,
                                         double *XC, int n, Epi ep) {
   if (act) {
     const double2 y01 = *reinterpret_cast<const double2 *>(y + TR * R), y23 = *reinterpret_cast<const double2 *>(y + TR * R + 2);
-    double2 *dst = reinterpret_cast<double2 *>(XC + R * g.npad + TC * C);
+    double2 *dst = reinterpret_cast<double2 *>(XC + R * g.npad() + TC * C);
+    {   // the slot columns first: their loads overlap the register part
+      const double2 s0 = ps[0], s1 = ps[FT], s2 = ps[2 * FT], s3 = ps[3 * FT];
+      dst[TCR >> 1] = make_double2(fma(s3.x, y23.y, fma(s2.x, y23.x, fma(s1.x, y01.y, s0.x * y01.x))),
+                                   fma(s3.y, y23.y, fma(s2.y, y23.x, fma(s1.y, y01.y, s0.y * y01.x))));
+    }
 #pragma unroll
-    for (int c = 0; c < TC; c += 2) {
+    for (int c = 0; c < TCR; c += 2) {
       const double q0 = fma(ar[3][c], y23.y, fma(ar[2][c], y23.x, fma(ar[1][c], y01.y, ar[0][c] * y01.x)));
       const double q1 = fma(ar[3][c + 1], y23.y, fma(ar[2][c + 1], y23.x, fma(ar[1][c + 1], y01.y, ar[0][c + 1] * y01.x)));
       dst[c >> 1] = make_double2(q0, q1);
@@ -95,74 +103,82 @@ __device__ __forceinline__ void rt_cols(const double (&ar)[TR][TC], const FastGe
     const double *p = XC + t;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int Rr = 0;
-    for (; Rr + 3 < g.RTu; Rr += 4) {
-      s0 += p[Rr * g.npad]; s1 += p[(Rr + 1) * g.npad]; s2 += p[(Rr + 2) * g.npad]; s3 += p[(Rr + 3) * g.npad];
+#pragma unroll 4
+    for (; Rr + 3 < g.RTu(); Rr += 4) {
+      s0 += p[Rr * g.npad()]; s1 += p[(Rr + 1) * g.npad()]; s2 += p[(Rr + 2) * g.npad()]; s3 += p[(Rr + 3) * g.npad()];
     }
-    for (; Rr < g.RTu; Rr++) s0 += p[Rr * g.npad];
+    for (; Rr < g.RTu(); Rr++) s0 += p[Rr * g.npad()];
     ep(t, (s0 + s1) + (s2 + s3));
   }
 }
 // out_i = sum_j A_ij x_j.  ep(i, value) runs on thread i < m.  One barrier inside, none at the end.
-template <class Epi>
-__device__ __forceinline__ void rt_rows(const double (&ar)[TR][TC], const FastGeom &g, bool act, int R, int C, const double *x,
+template <class G, class Epi>
+__device__ __forceinline__ void rt_rows(const double (&ar)[TR][TCR], const double2 *ps, const G &g, bool act, int R, int C, const double *x,
                                         double *XR, int m, Epi ep) {
   if (act) {
-    double xv[TC];
+    double s[TR];
+    {
+      const double2 v = *reinterpret_cast<const double2 *>(x + TC * C + TCR);
 #pragma unroll
-    for (int c = 0; c < TC; c += 2) { const double2 v = *reinterpret_cast<const double2 *>(x + TC * C + c); xv[c] = v.x; xv[c + 1] = v.y; }
-#pragma unroll
-    for (int r = 0; r < TR; r++) {
-      double s0 = 0, s1 = 0;
-#pragma unroll
-      for (int c = 0; c < TC; c += 2) { s0 = fma(ar[r][c], xv[c], s0); s1 = fma(ar[r][c + 1], xv[c + 1], s1); }
-      XR[(TR * R + r) * g.CT + C] = s0 + s1;
+      for (int r = 0; r < TR; r++) { const double2 q = ps[r * FT]; s[r] = fma(q.y, v.y, q.x * v.x); }
     }
+#pragma unroll
+    for (int c = 0; c < TCR; c += 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(x + TC * C + c);
+#pragma unroll
+      for (int r = 0; r < TR; r++) s[r] = fma(ar[r][c + 1], v.y, fma(ar[r][c], v.x, s[r]));
+    }
+#pragma unroll
+    for (int r = 0; r < TR; r++) XR[(TR * R + r) * g.CT() + C] = s[r];
   }
   __syncthreads();
   const int t = threadIdx.x;
   if (t < m) {
-    const double *p = XR + t * g.CT;
+    const double *p = XR + t * g.CT();
     double s0 = 0, s1 = 0;
     int c = 0;
-    for (; c + 1 < g.CT; c += 2) { s0 += p[c]; s1 += p[c + 1]; }
-    if (c < g.CT) s0 += p[c];
+#pragma unroll
+    for (; c + 1 < g.CT(); c += 2) { s0 += p[c]; s1 += p[c + 1]; }
+    if (c < g.CT()) s0 += p[c];
     ep(t, s0 + s1);
   }
 }
-// out_i = sum_j Kinv_ij x_j for the symmetric n x n inverse stored with row stride npad (KR x 10 tiles read from
+// out_i = sum_j Kinv_ij x_j for the symmetric inverse stored with row stride npad (KR x 10 tiles read from
 // shared memory).  ep(i, value) runs on thread i < n.  One barrier inside, none at the end.
-template <int KR, class Epi>
-__device__ __forceinline__ void kinv_rows(const double *Kinv, const FastGeom &g, int n, const double *x, double *XR, Epi ep) {
-  const int t = threadIdx.x, R = t / g.CT, C = t - R * g.CT;
+template <int KR, class G, class Epi>
+__device__ __forceinline__ void kinv_rows(const double *Kinv, const G &g, int n, int R, int C, const double *x, double *XR, Epi ep) {
+  const int t = threadIdx.x;
   if (KR * R < n) {
-    double xv[TC];
+    double s[KR];
 #pragma unroll
-    for (int c = 0; c < TC; c += 2) { const double2 v = *reinterpret_cast<const double2 *>(x + TC * C + c); xv[c] = v.x; xv[c + 1] = v.y; }
+    for (int r = 0; r < KR; r++) s[r] = 0.0;
+    const double2 *row = reinterpret_cast<const double2 *>(Kinv + (KR * R) * g.npad() + TC * C);
+    const int rs = g.npad() >> 1;   // row stride in double2
 #pragma unroll
-    for (int r = 0; r < KR; r++) {
-      const int i = KR * R + r;
-      if (i < n) {
-        const double2 *row = reinterpret_cast<const double2 *>(Kinv + i * g.npad + TC * C);
-        double s0 = 0, s1 = 0;
+    for (int c = 0; c < TC; c += 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(x + TC * C + c);
 #pragma unroll
-        for (int c = 0; c < TC; c += 2) { const double2 q = row[c >> 1]; s0 = fma(q.x, xv[c], s0); s1 = fma(q.y, xv[c + 1], s1); }
-        XR[i * g.CT + C] = s0 + s1;
+      for (int r = 0; r < KR; r++) {
+        if (KR * R + r < n) { const double2 q = row[r * rs + (c >> 1)]; s[r] = fma(q.y, v.y, fma(q.x, v.x, s[r])); }
       }
     }
+#pragma unroll
+    for (int r = 0; r < KR; r++) if (KR * R + r < n) XR[(KR * R + r) * g.CT() + C] = s[r];
   }
   __syncthreads();
   if (t < n) {
-    const double *p = XR + t * g.CT;
+    const double *p = XR + t * g.CT();
     double s0 = 0, s1 = 0;
     int c = 0;
-    for (; c + 1 < g.CT; c += 2) { s0 += p[c]; s1 += p[c + 1]; }
-    if (c < g.CT) s0 += p[c];
+#pragma unroll
+    for (; c + 1 < g.CT(); c += 2) { s0 += p[c]; s1 += p[c + 1]; }
+    if (c < g.CT()) s0 += p[c];
     ep(t, s0 + s1);
   }
 }
-template <class Epi>
-__device__ __forceinline__ void kinv_mul(const double *Kinv, const FastGeom &g, int n, const double *x, double *XR, Epi ep) {
-  if (g.KR == 2) kinv_rows<2>(Kinv, g, n, x, XR, ep); else kinv_rows<4>(Kinv, g, n, x, XR, ep);
+template <class G, class Epi>
+__device__ __forceinline__ void kinv_mul(const double *Kinv, const G &g, int n, int R, int C, const double *x, double *XR, Epi ep) {
+  if (g.KR() == 2) kinv_rows<2>(Kinv, g, n, R, C, x, XR, ep); else kinv_rows<4>(Kinv, g, n, R, C, x, XR, ep);
 }
 
 // Sum of four per-thread values over the block when only the first `nwc` warps hold non-zero terms.
@@ -189,7 +205,7 @@ __device__ __forceinline__ void reduce4_lead(double (&v)[4], double *red, int nw
 
 // K = rho_x I + scale * sum_i w_i a_i a_i' (+ P^ already sitting in K as unscaled packed P when Psm) for the
 // staged, equilibrated A (row-major m x n in shared memory), packed lower.
-__device__ void form_K(const double *Av, int m, int n, int z, double scale, double rho_x, double *K, bool haveP, const double *En) {
+__device__ __noinline__ void form_K(const double *Av, int m, int n, int z, double scale, double rho_x, double *K, bool haveP, const double *En) {
   const int T = blockDim.x, t = threadIdx.x;
   if ((n & 1) == 0) {
     const int nb = n >> 1, ntile = (nb * (nb + 1)) >> 1;
@@ -241,7 +257,7 @@ __device__ void form_K(const double *Av, int m, int n, int z, double scale, doub
 
 // Kinv = X' X for the packed lower-triangular X = L^{-1}: full symmetric n x n with row stride npad.
 // 2 x 2 tiles of the lower triangle; both triangles are written.
-__device__ void form_Kinv(const double *Xp, int n, int npad, double *Kinv) {
+__device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, double *Kinv) {
   const int T = blockDim.x, t = threadIdx.x;
   const int nb = (n + 1) >> 1, ntile = (nb * (nb + 1)) >> 1;
   for (int e = t; e < ntile; e += T) {
@@ -272,103 +288,250 @@ __device__ void form_Kinv(const double *Xp, int n, int npad, double *Kinv) {
   __syncthreads();
 }
 
-__device__ __forceinline__ void carve_fast(FSmem &M, double *base, const FastGeom &g, int n) {
-  double *q = base;
-  M.bar = (uint64_t *)q; q += 2;
-  M.ibuf = (int *)q; q += 2;
-  M.X = q; q += g.XD;
-  M.Li = q; q += g.npk;
-  M.vx = q; q += 9 * g.npad;
-  M.vy = q; q += 7 * g.mpad;
-  M.red = q;
-  M.npad = g.npad; M.mpad = g.mpad;
-  M.oXC = n * g.npad; M.oXR = M.oXC + g.RTu * g.npad;
+__device__ __noinline__ bool chol_cold(double *K, int n, double *tmp) { return chol_inv_packed(K, n, tmp); }
+
+// Slots of the shared scalar block sc[] (= red + 256): values every thread agrees on but only the cold paths
+// need, kept out of the register file.
+enum { SC_SIGMA = 0, SC_NB0, SC_NC0, SC_SUMLOG, SC_PREVLR, SC_RP, SC_RD, SC_GAP, SC_UTAU, SC_NLOG, SC_LASTUP, SC_PREVIT,
+       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT };
+
+// Everything of a termination check after the two products with A (A u_x in tm, A' u_y in tn): P^ u_x, the
+// residual norms on the un-normalised data, termination and certificates, the adaptive
+// check schedule and the adaptive-scale decision (including the w_y correction that keeps R (w + u - 2 u~)
+// invariant).  A handful of calls per solve and deliberately NOT inlined: the register allocation of the
+// iteration loop belongs to the tiles.  Results travel through sc[]; ends with a barrier.
+__device__ __noinline__ void check_tail(const FwdArgs &a, double *vx, double *vy, double *red, double *scratch, const double *Pv,
+                                        int npad, int mpad, int it, double scale, double tau) {
+  const DevStruct &S = a.S;
+  const bcone_settings &st = a.st;
+  const int n = S.n, m = S.m, t = threadIdx.x, z = S.z;
+  double *sc = red + 256;
+  const double *ux = vx + npad, *ch = vx + 4 * npad, *En = vx + 5 * npad, *tn = vx + 6 * npad;
+  double *tn2 = vx + 7 * npad, *tn3 = vx + 8 * npad;
+  double *wy = vy;
+  const double *uy = vy + mpad, *uty = vy + 2 * mpad, *bh = vy + 4 * mpad, *Dm = vy + 5 * mpad, *tm = vy + 6 * mpad;
+  const double sigma = sc[SC_SIGMA], nb0 = sc[SC_NB0], nc0 = sc[SC_NC0];
+  double sum_log = sc[SC_SUMLOG], prev_lr = sc[SC_PREVLR];
+  int n_log = (int)sc[SC_NLOG], last_up = (int)sc[SC_LASTUP], prev_it = (int)sc[SC_PREVIT], next_check = (int)sc[SC_NEXT];
+  int status = BCONE_INACCURATE;
+  double rp = sc[SC_RP], rd = sc[SC_RD], gap = sc[SC_GAP], new_scale = 0.0;
+  double pxu = 0;
+  if (t < n) { tn2[t] = 0.0; tn3[t] = En[t] * ux[t]; }
+  __syncthreads();
+  if (Pv) {  // P^ u_x = E (P (E u_x))
+    const ColPlan plN = make_colplan(n, n);
+    P_mul(S, Pv, tn3, scratch, [&](int j, double v) { tn2[j] += v; }, plN);
+    if (t < n) pxu = tn2[t] * En[t];
+  }
+  double sm[3] = {0, 0, 0};   // xPx_u, ctx_u, bty_u
+  double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // rp, nAx, nS, nAxs, rd, nPx, nATy
+  if (t < m) {
+    const double ax = tm[t];
+    const double rsk = (uy[t] - (2.0 * uty[t] - wy[t])) / inv_ry_f(z, t, scale);
+    const double sc_ = 1.0 / (Dm[t] * sigma);
+    mx[0] = fabs(ax + rsk - bh[t] * tau) * sc_;
+    mx[1] = fabs(ax) * sc_; mx[2] = fabs(rsk) * sc_;
+    mx[3] = fabs(ax + rsk) * sc_;
+    sm[2] = bh[t] * uy[t];
+  }
+  if (t < n) {
+    const double aty = tn[t];
+    const double sc_ = 1.0 / (En[t] * sigma);
+    mx[4] = fabs(pxu + aty + ch[t] * tau) * sc_;
+    mx[5] = fabs(pxu) * sc_; mx[6] = fabs(aty) * sc_;
+    sm[0] = ux[t] * pxu; sm[1] = ch[t] * ux[t];
+  }
+  block_reduce<3, false>(sm, red);
+  block_reduce<7, true>(mx, red);
+  const double s2 = sigma * sigma;
+  bool done = false;
+  if (tau > 1e-12) {
+    const double itau = 1.0 / tau;
+    const double xPx = sm[0] * itau * itau / s2, ctx = sm[1] * itau / s2, bty = sm[2] * itau / s2;
+    rp = mx[0] * itau; rd = mx[4] * itau; gap = fabs(xPx + ctx + bty);
+    const double np_ = fmax(fmax(mx[1] * itau, mx[2] * itau), nb0);
+    const double nd_ = fmax(fmax(mx[5] * itau, mx[6] * itau), nc0);
+    const double tp = st.eps_abs + st.eps_rel * np_, td = st.eps_abs + st.eps_rel * nd_;
+    const double tg = st.eps_abs + st.eps_rel * fmax(fmax(fabs(xPx), fabs(ctx)), fabs(bty));
+    if (rp <= tp && rd <= td && gap <= tg) { status = BCONE_SOLVED; done = true; }
+    else if (st.adaptive_check) {
+      const double lr = log(fmax(fmax(rp / tp, rd / td), gap / tg));
+      int step = st.check_interval;
+      if (prev_it > 0 && lr < prev_lr) { const double need = lr * (it - prev_it) / (prev_lr - lr); step = (int)ceil(0.9 * need) + 1; }
+      step = max(3, min(step, st.check_interval));
+      prev_it = it; prev_lr = lr; next_check = it + step;
+    }
+    if (!done && st.adaptive_scale) {
+      const double relp = rp / fmax(np_, 1e-18), reld = rd / fmax(nd_, 1e-18);
+      if (relp > 0 && reld > 0) { sum_log += log(relp) - log(reld); n_log++; }
+    }
+  }
+  if (st.adaptive_check && next_check <= it) next_check = it + st.check_interval;
+  if (!done) {
+    const double bty_c = sm[2] / s2, ctx_c = sm[1] / s2;
+    if (bty_c < 0 && mx[6] / (-bty_c) <= st.eps_infeas) { status = BCONE_INFEASIBLE; done = true; }
+    else if (ctx_c < 0 && fmax(mx[5], mx[3]) / (-ctx_c) <= st.eps_infeas) { status = BCONE_UNBOUNDED; done = true; }
+  }
+  if (!done && st.adaptive_scale && n_log > 0 && it - last_up >= BC_RESCALE_MIN_ITERS) {
+    const double fac = sqrt(exp(sum_log / n_log));
+    if (fac > 3.1622776601683795 || fac < 0.31622776601683794) {
+      const double ns = fmin(fmax(scale * fac, BC_MIN_SCALE), BC_MAX_SCALE);
+      if (ns != scale) {
+        const double ratio = ns / scale;  // r_old / r_new
+        if (t < m) wy[t] = ratio * (wy[t] + uy[t] - 2.0 * uty[t]) + 2.0 * uty[t] - uy[t];
+        new_scale = ns;
+        sum_log = 0; n_log = 0; last_up = it;
+      }
+    }
+  }
+  if (t == 0) {
+    sc[SC_SUMLOG] = sum_log; sc[SC_PREVLR] = prev_lr; sc[SC_RP] = rp; sc[SC_RD] = rd; sc[SC_GAP] = gap; sc[SC_UTAU] = tau;
+    sc[SC_NLOG] = n_log; sc[SC_LASTUP] = last_up; sc[SC_PREVIT] = prev_it; sc[SC_NEXT] = next_check;
+    sc[SC_STATUS] = status; sc[SC_DONE] = done ? 1.0 : 0.0; sc[SC_NEWSCALE] = new_scale;
+  }
+  __syncthreads();
+}
+
+// Column maxima of |P^| for one Ruiz pass: four lanes per index over the packed symmetric matrix, folded into tn.
+__device__ __noinline__ void ruiz_P_part(const double *Pl, const double *En, double *tn, int n) {
+  const int t = threadIdx.x, j = t >> 2, q = t & 3;
+  double mx = 0;
+  if (j < n) {
+    const double ej = En[j];
+    for (int i = q; i < n; i += 4) {
+      const int lo = min(i, j), hi = max(i, j);
+      const double p = Pl[((hi * (hi + 1)) >> 1) + lo];
+      const double elo = i < j ? En[i] : ej, ehi = i < j ? ej : En[i];
+      mx = dmax(mx, fabs(p * elo * ehi));
+    }
+  }
+  mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  if (q == 0 && j < n) tn[j] = dmax(tn[j], mx);
+  __syncthreads();
+}
+
+// P as a packed symmetric matrix (lower, row j at j(j+1)/2) in the factor's buffer; ends with a barrier.
+__device__ __noinline__ void scatter_P(const DevStruct &S, const double *Pg, double *Pl, int npk) {
+  const int t = threadIdx.x, T = blockDim.x;
+  if (!S.p_dense) { for (int e = t; e < npk; e += T) Pl[e] = 0.0; __syncthreads(); }
+  for (int k = t; k < S.nnzP; k += T) {
+    const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);   // j >= i
+    Pl[((j * (j + 1)) >> 1) + i] = Pg[k];
+  }
+  __syncthreads();
 }
 
 }  // namespace
 
+template <int CT_, int RTU_>
 __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__ FwdArgs a) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(16) double sm[];
   const DevStruct &S = a.S;
-  const int n = S.n, m = S.m, t = threadIdx.x, z = S.z, zl = S.z + S.l;
+  const int n = S.n, m = S.m, t = threadIdx.x, z = S.z;
   const bcone_settings &st = a.st;
-  FastGeom g;
-  fwdf_geom(n, m, g);
-  FSmem M;
-  carve_fast(M, smem, g, n);
-  if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
+  const Geo<CT_, RTU_> g(n, m);
+  uint64_t *bar = (uint64_t *)sm;
+  int *ibuf = (int *)(sm + 2);
+  double *const X = sm + g.oX(), *const Li = sm + g.oLi(), *const red = sm + g.oRed(), *const sc = red + 256;
+  auto vx = [&](int k) { return sm + g.oVx() + k * g.npad(); };
+  auto vy = [&](int k) { return sm + g.oVy() + k * g.mpad(); };
+  double *const Kinv = X, *const XC = X + g.oXC(), *const XR = XC;   // column / row partials take turns in one buffer
+  double2 *const ps = reinterpret_cast<double2 *>(X + g.oPS()) + t;   // private slot r: ps[r * FT] = tile columns 8, 9 of row r
+  if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   // vectors: the padding entries are read by the tile products (against zero matrix entries) and must stay finite
-  for (int k = t; k < 9 * g.npad + 7 * g.mpad; k += FT) M.vx[k] = 0.0;
+  for (int k = t; k < 9 * g.npad() + 7 * g.mpad(); k += FT) sm[g.oVx() + k] = 0.0;
   __syncthreads();
   uint32_t tma_phase = 0;
-  const ColPlan plN = make_colplan(n, n);
-  const double rho_x = st.rho_x, alpha = st.alpha, dtau = BC_TAU_FACTOR;
-  const int R = t / g.CT, C = t - R * g.CT;
-  const bool act = R < g.RTu;
+  const int R = t / g.CT(), C = t - R * g.CT();
+  const bool act = R < g.RTu();
   const int nwc = (max(m, n) + 31) >> 5;   // warps owning an output of the products
   const bool p_tma = (S.nnzP % 2 == 0) && (((uintptr_t)a.P_vals & 15) == 0) && ((size_t)S.nnzP * 8 < (1u << 20));
-  double ar[TR][TC];
+  double ar[TR][TCR];
 
   for (;;) {
-    if (t == 0) M.ibuf[0] = atomicAdd(a.counter, 1);
+    if (t == 0) ibuf[0] = atomicAdd(a.counter, 1);
     __syncthreads();
-    const int inst = M.ibuf[0];
+    const int inst = ibuf[0];
     if (inst >= a.B) break;
-    const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
     const double *Pg = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
-    const double *bg = a.b + (size_t)inst * m, *cg = a.c + (size_t)inst * n;
-    PhaseTimer pt; pt.start(a.prof);
-    PhaseTimer pi; pi.start(a.prof);
+    long long *pt_t0 = reinterpret_cast<long long *>(sc + SC_COUNT);
+    if (a.prof && t == 0) *pt_t0 = clock64();
+    auto pt_stamp = [&](int k) { if (a.prof && t == 0) { const long long now = clock64(); atomicAdd(a.prof + k, (unsigned long long)(now - *pt_t0)); *pt_t0 = now; } };
+    SUB_DECL(pi);
 
     // ---- stage the instance ----
-    if (a.use_tma) {
-      if (t == 0) {
-        fence_proxy_async();
-        mbar_expect_tx(M.bar, (uint32_t)(S.nnzA * sizeof(double)));
-        tma_bulk_g2s(M.X, Ag, (uint32_t)(S.nnzA * sizeof(double)), M.bar);
+    {
+      const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
+      if (a.use_tma) {
+        if (t == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(bar, (uint32_t)(S.nnzA * sizeof(double)));
+          tma_bulk_g2s(X, Ag, (uint32_t)(S.nnzA * sizeof(double)), bar);
+        }
+      } else {
+        for (int k = t; k < S.nnzA; k += FT) X[k] = Ag[k];
       }
-    } else {
-      for (int k = t; k < S.nnzA; k += FT) M.X[k] = Ag[k];
     }
-    double nb0 = 0, nc0 = 0;
-    if (t < m) { const double v = bg[t]; M.bh()[t] = v; M.Dm()[t] = 1.0; nb0 = fabs(v); }
-    if (t < n) { const double v = cg[t]; M.ch()[t] = v; M.En()[t] = 1.0; nc0 = fabs(v); }
-    // P as a packed symmetric matrix (lower, row j at j(j+1)/2) in the factor's buffer
-    auto scatter_P = [&]() {
-      if (!Pg) return;
-      if (!S.p_dense) { for (int e = t; e < g.npk; e += FT) M.Li[e] = 0.0; __syncthreads(); }
-      for (int k = t; k < S.nnzP; k += FT) {
-        const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);   // j >= i
-        M.Li[((j * (j + 1)) >> 1) + i] = Pg[k];
+    {
+      const double *bg = a.b + (size_t)inst * m, *cg = a.c + (size_t)inst * n;
+      double v4[2] = {0, 0};
+      if (t < m) { const double v = bg[t]; vy(VY_BH)[t] = v; vy(VY_DM)[t] = 1.0; v4[0] = fabs(v); }
+      if (t < n) { const double v = cg[t]; vx(VX_CH)[t] = v; vx(VX_EN)[t] = 1.0; v4[1] = fabs(v); }
+      block_reduce<2, true>(v4, red);
+      if (t == 0) {
+        sc[SC_NB0] = v4[0]; sc[SC_NC0] = v4[1];
+        sc[SC_SUMLOG] = 0; sc[SC_PREVLR] = 0; sc[SC_NLOG] = 0; sc[SC_LASTUP] = 0; sc[SC_PREVIT] = 0;
+        sc[SC_RP] = nan(""); sc[SC_RD] = nan(""); sc[SC_GAP] = nan(""); sc[SC_UTAU] = 0; sc[SC_STATUS] = BCONE_INACCURATE;
       }
-    };
-    scatter_P();
-    if (a.use_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }
+    }
+    if (Pg) scatter_P(S, Pg, Li, g.npk());
+    if (a.use_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }
     __syncthreads();
     // ---- register tiles ----
+    auto load_tile = [&]() {   // registers + slots from the staged m x n copy in X (ends with a barrier)
+      double2 sl[TR];
 #pragma unroll
-    for (int r = 0; r < TR; r++)
+      for (int r = 0; r < TR; r++) {
+        const int i = TR * R + r;
 #pragma unroll
-      for (int c = 0; c < TC; c++) {
-        const int i = TR * R + r, j = TC * C + c;
-        ar[r][c] = (act && i < m && j < n) ? M.X[i * n + j] : 0.0;
+        for (int c = 0; c < TCR; c++) { const int j = TC * C + c; ar[r][c] = (act && i < m && j < n) ? X[i * n + j] : 0.0; }
+        const int j8 = TC * C + TCR;
+        sl[r].x = (act && i < m && j8 < n) ? X[i * n + j8] : 0.0;
+        sl[r].y = (act && i < m && j8 + 1 < n) ? X[i * n + j8 + 1] : 0.0;
       }
-    __syncthreads();   // X is free: partial buffers of the Ruiz passes
-    pt.stamp(0);
+      __syncthreads();   // every read of the staged copy is done: X is free (partial buffers, slots, later Kinv)
+#pragma unroll
+      for (int r = 0; r < TR; r++) ps[r * FT] = sl[r];
+    };
+    load_tile();
+    double *const XRz = X;   // row partials of the Ruiz passes (the Kinv area is still unused)
+    pt_stamp(0);
 
     // ---- Ruiz equilibration: A^ = D A E, P^ = E P E ----
     if (st.normalize) {
       for (int pass = 0; pass < st.ruiz_passes; pass++) {
-        pi.skip();
+        SUB_SKIP(pi);
         if (act) {
-          double e[TC], d[TR], rowp[TR] = {0, 0, 0, 0};
+          double e[TC], d[TR], rowp[TR];
 #pragma unroll
-          for (int c = 0; c < TC; c += 2) { const double2 v = *reinterpret_cast<const double2 *>(M.En() + TC * C + c); e[c] = v.x; e[c + 1] = v.y; }
+          for (int c = 0; c < TC; c += 2) { const double2 v = *reinterpret_cast<const double2 *>(vx(VX_EN) + TC * C + c); e[c] = v.x; e[c + 1] = v.y; }
 #pragma unroll
-          for (int r = 0; r < TR; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(M.Dm() + TR * R + r); d[r] = v.x; d[r + 1] = v.y; }
-          double2 *dst = reinterpret_cast<double2 *>(M.XC() + R * g.npad + TC * C);
+          for (int r = 0; r < TR; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(vy(VY_DM) + TR * R + r); d[r] = v.x; d[r + 1] = v.y; }
+          double2 *dst = reinterpret_cast<double2 *>(XC + R * g.npad() + TC * C);
+          {
+            double c0 = 0, c1 = 0;
 #pragma unroll
-          for (int c = 0; c < TC; c += 2) {
+            for (int r = 0; r < TR; r++) {
+              const double2 q = ps[r * FT];
+              const double v0 = fabs(q.x) * e[TCR] * d[r], v1 = fabs(q.y) * e[TCR + 1] * d[r];
+              c0 = dmax(c0, v0); c1 = dmax(c1, v1);
+              rowp[r] = dmax(v0, v1);
+            }
+            dst[TCR >> 1] = make_double2(c0, c1);
+          }
+#pragma unroll
+          for (int c = 0; c < TCR; c += 2) {
             double c0 = 0, c1 = 0;
 #pragma unroll
             for (int r = 0; r < TR; r++) {
@@ -379,140 +542,136 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
             dst[c >> 1] = make_double2(c0, c1);
           }
 #pragma unroll
-          for (int r = 0; r < TR; r++) M.XR()[(TR * R + r) * g.CT + C] = rowp[r];
+          for (int r = 0; r < TR; r++) XRz[(TR * R + r) * g.CT() + C] = rowp[r];
         }
         __syncthreads();
-        if (t < m) { const double *p = M.XR() + t * g.CT; double r = 0; for (int c = 0; c < g.CT; c++) r = dmax(r, p[c]); M.tm()[t] = r; }
+        if (t < m) {
+          const double *p = XRz + t * g.CT(); double r = 0;
+#pragma unroll
+          for (int c = 0; c < g.CT(); c++) r = dmax(r, p[c]);
+          vy(VY_TM)[t] = r;
+        }
         {
-          const int j = t - (FT - 128);   // the upper warps take the column maxima
-          if (j >= 0 && j < n) { const double *p = M.XC() + j; double r = 0; for (int Rr = 0; Rr < g.RTu; Rr++) r = dmax(r, p[Rr * g.npad]); M.tn()[j] = r; }
-          if (n > 128 && t < n && t >= 128) { const double *p = M.XC() + t; double r = 0; for (int Rr = 0; Rr < g.RTu; Rr++) r = dmax(r, p[Rr * g.npad]); M.tn()[t] = r; }
-        }
-        __syncthreads();
-        pi.stamp(16);
-        if (Pg) {   // column maxima of |P^|: four lanes per index over the packed symmetric matrix
-          const int j = t >> 2, q = t & 3;
-          double mx = 0;
-          if (j < n) {
-            const double ej = M.En()[j];
-            for (int i = q; i < n; i += 4) {
-              const int lo = min(i, j), hi = max(i, j);
-              const double p = M.Li[((hi * (hi + 1)) >> 1) + lo];
-              const double elo = i < j ? M.En()[i] : ej, ehi = i < j ? ej : M.En()[i];
-              mx = dmax(mx, fabs(p * elo * ehi));
-            }
+          const int j = (n <= 128) ? t - (FT - 128) : t;   // the upper warps take the column maxima when they suffice
+          if (j >= 0 && j < n) {
+            const double *p = XC + j; double r0 = 0, r1 = 0;
+            int Rr = 0;
+#pragma unroll 4
+            for (; Rr + 1 < g.RTu(); Rr += 2) { r0 = dmax(r0, p[Rr * g.npad()]); r1 = dmax(r1, p[(Rr + 1) * g.npad()]); }
+            if (Rr < g.RTu()) r0 = dmax(r0, p[Rr * g.npad()]);
+            vx(VX_TN)[j] = dmax(r0, r1);
           }
-          mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-          if (q == 0 && j < n) M.tn()[j] = dmax(M.tn()[j], mx);
-          __syncthreads();
         }
-        pi.stamp(17);
-        if (t < m) { const double r = M.tm()[t]; M.Dm()[t] *= fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
-        if (t < n) { const double r = M.tn()[t]; M.En()[t] *= fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
         __syncthreads();
-        pi.stamp(18);
+        SUB_STAMP(pi, 16);
+        if (Pg) ruiz_P_part(Li, vx(VX_EN), vx(VX_TN), n);
+        SUB_STAMP(pi, 17);
+        if (t < m) { const double r = vy(VY_TM)[t]; vy(VY_DM)[t] *= fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
+        if (t < n) { const double r = vx(VX_TN)[t]; vx(VX_EN)[t] *= fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
+        __syncthreads();
+        SUB_STAMP(pi, 18);
       }
       if (st.ruiz_passes > 0 && act) {   // A^ = D A E on the tiles
         double e[TC], d[TR];
 #pragma unroll
-        for (int c = 0; c < TC; c += 2) { const double2 v = *reinterpret_cast<const double2 *>(M.En() + TC * C + c); e[c] = v.x; e[c + 1] = v.y; }
+        for (int c = 0; c < TC; c += 2) { const double2 v = *reinterpret_cast<const double2 *>(vx(VX_EN) + TC * C + c); e[c] = v.x; e[c + 1] = v.y; }
 #pragma unroll
-        for (int r = 0; r < TR; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(M.Dm() + TR * R + r); d[r] = v.x; d[r + 1] = v.y; }
+        for (int r = 0; r < TR; r += 2) { const double2 v = *reinterpret_cast<const double2 *>(vy(VY_DM) + TR * R + r); d[r] = v.x; d[r + 1] = v.y; }
 #pragma unroll
-        for (int r = 0; r < TR; r++)
+        for (int r = 0; r < TR; r++) {
 #pragma unroll
-          for (int c = 0; c < TC; c++) ar[r][c] *= d[r] * e[c];
+          for (int c = 0; c < TCR; c++) ar[r][c] *= d[r] * e[c];
+          double2 q = ps[r * FT];
+          q.x *= d[r] * e[TCR]; q.y *= d[r] * e[TCR + 1];
+          ps[r * FT] = q;
+        }
       }
     }
-    double sigma;
     {
-      double v[4] = {nb0, nc0, 0, 0};
-      if (t < m) { const double q = M.Dm()[t] * M.bh()[t]; M.bh()[t] = q; v[2] = fabs(q); }
-      if (t < n) { const double q = M.En()[t] * M.ch()[t]; M.ch()[t] = q; v[3] = fabs(q); }
-      block_reduce<4, true>(v, M.red);
-      nb0 = v[0]; nc0 = v[1];
-      sigma = fmax(v[2], v[3]);
+      double v[2] = {0, 0};
+      if (t < m) { const double q = vy(VY_DM)[t] * vy(VY_BH)[t]; vy(VY_BH)[t] = q; v[0] = fabs(q); }
+      if (t < n) { const double q = vx(VX_EN)[t] * vx(VX_CH)[t]; vx(VX_CH)[t] = q; v[1] = fabs(q); }
+      block_reduce<2, true>(v, red);
+      double sigma = fmax(v[0], v[1]);
       sigma = (!st.normalize || sigma < 1e-6) ? 1.0 : 1.0 / sigma;
-      if (t < m) M.bh()[t] *= sigma;
-      if (t < n) M.ch()[t] *= sigma;
+      if (t < m) vy(VY_BH)[t] *= sigma;
+      if (t < n) vx(VX_CH)[t] *= sigma;
+      if (t == 0) sc[SC_SIGMA] = sigma;
       __syncthreads();
     }
-    pt.stamp(1);
+    pt_stamp(1);
 
-    double scale = st.scale, gRg = 0, ry_z = 0, ry_l = 0;
-    int status = BCONE_INACCURATE, it = 0;
-    if (t < n) { M.wx()[t] = 0; M.ux()[t] = 0; M.utx()[t] = 0; }
-    if (t < m) { M.wy()[t] = 0; M.uy()[t] = 0; M.uty()[t] = 0; }
-    double w_tau = 1.0, u_tau = 0.0, ut_tau = 0.0;
-    double sum_log = 0, rp = nan(""), rd = nan(""), gap = nan("");
-    int n_log = 0, last_up = 0;
-    int next_check = st.check_interval < 10 ? st.check_interval : 10, prev_it = 0;
-    double prev_lr = 0;
+    double scale = st.scale, w_tau = 1.0;
+    int it = 0, next_check = st.check_interval < 10 ? st.check_interval : 10;
+    if (t < n) { vx(VX_W)[t] = 0; vx(VX_U)[t] = 0; vx(VX_UT)[t] = 0; }
+    if (t < m) { vy(VY_W)[t] = 0; vy(VY_U)[t] = 0; vy(VY_UT)[t] = 0; }
     bool refactor = true, first = true;
 
     for (it = 1; it <= st.max_iters; it++) {
       if (refactor) {
         // Factorisation at the current scale (the one place it is written, so the tiles stay in registers):
         // stage A^ from the tiles -> K -> Cholesky -> Linv -> Kinv; then g = (R_z + M)^{-1} h and g'Rg.
-        PhaseTimer pf; pf.start(a.prof);
-        if (!first) { scatter_P(); }   // the factor's buffer held P in CSR order for the checks
-        if (act) {
+        SUB_DECL(pf);
+        if (!first && Pg) scatter_P(S, Pg, Li, g.npk());   // the factor's buffer held P in CSR order for the checks
+        {
+          double2 sl[TR];
 #pragma unroll
-          for (int r = 0; r < TR; r++) {
-            const int i = TR * R + r;
-            if (i < m) {
+          for (int r = 0; r < TR; r++) sl[r] = ps[r * FT];
+          __syncthreads();   // the staged copy overwrites the slots (and Kinv, partials)
+          if (act) {
 #pragma unroll
-              for (int c = 0; c < TC; c++) { const int j = TC * C + c; if (j < n) M.X[i * n + j] = ar[r][c]; }
+            for (int r = 0; r < TR; r++) {
+              const int i = TR * R + r;
+              if (i < m) {
+#pragma unroll
+                for (int c = 0; c < TCR; c++) { const int j = TC * C + c; if (j < n) X[i * n + j] = ar[r][c]; }
+                const int j8 = TC * C + TCR;
+                if (j8 < n) X[i * n + j8] = sl[r].x;
+                if (j8 + 1 < n) X[i * n + j8 + 1] = sl[r].y;
+              }
             }
           }
         }
         __syncthreads();
-        form_K(M.X, m, n, z, scale, rho_x, M.Li, Pg != nullptr, M.En());
-        pf.stamp(19);
-        const bool okf = chol_inv_packed(M.Li, n, M.red);
-        if (!okf) { status = BCONE_FAILED; if (first) it = 0; break; }
-        pf.stamp(21);
+        form_K(X, m, n, z, scale, st.rho_x, Li, Pg != nullptr, vx(VX_EN));
+        SUB_STAMP(pf, 19);
+        const bool okf = chol_cold(Li, n, red);
+        if (!okf) { if (t == 0) sc[SC_STATUS] = BCONE_FAILED; if (first) it = 0; break; }
+        SUB_STAMP(pf, 21);
         // the tiles come back from the staged copy: nothing has to stay live across the factorisation
-#pragma unroll
-        for (int r = 0; r < TR; r++)
-#pragma unroll
-          for (int c = 0; c < TC; c++) {
-            const int i = TR * R + r, j = TC * C + c;
-            ar[r][c] = (act && i < m && j < n) ? M.X[i * n + j] : 0.0;
-          }
+        load_tile();
         __syncthreads();
-        form_Kinv(M.Li, n, g.npad, M.Kinv());
+        form_Kinv(Li, n, g.npad(), Kinv);
         if (Pg) {   // the factor's buffer now carries P (CSR order) for the termination checks
           if (p_tma) {
             if (t == 0) {
               fence_proxy_async();
-              mbar_expect_tx(M.bar, (uint32_t)(S.nnzP * sizeof(double)));
-              tma_bulk_g2s(M.Li, Pg, (uint32_t)(S.nnzP * sizeof(double)), M.bar);
+              mbar_expect_tx(bar, (uint32_t)(S.nnzP * sizeof(double)));
+              tma_bulk_g2s(Li, Pg, (uint32_t)(S.nnzP * sizeof(double)), bar);
             }
           } else {
-            for (int k = t; k < S.nnzP; k += FT) M.Li[k] = Pg[k];
+            for (int k = t; k < S.nnzP; k += FT) Li[k] = Pg[k];
           }
         }
-        pf.stamp(20);
-        ry_z = 1.0 / (BC_ZERO_CONE_FACTOR * scale); ry_l = 1.0 / scale;
-        if (t < m) M.tm()[t] = M.bh()[t] * inv_ry_f(z, t, scale);
+        SUB_STAMP(pf, 20);
+        if (t == 0) { sc[SC_RYZ] = 1.0 / (BC_ZERO_CONE_FACTOR * scale); sc[SC_RYL] = 1.0 / scale; }
+        if (t < m) vy(VY_TM)[t] = vy(VY_BH)[t] * inv_ry_f(z, t, scale);
         __syncthreads();
-        rt_cols(ar, g, act, R, C, M.tm(), M.XC(), n, [&](int j, double v) { M.tn()[j] = M.ch()[j] - v; });
+        rt_cols(ar, ps, g, act, R, C, vy(VY_TM), XC, n, [&](int j, double v) { vx(VX_TN)[j] = vx(VX_CH)[j] - v; });
         __syncthreads();
-        kinv_mul(M.Kinv(), g, n, M.tn(), M.XR(), [&](int j, double v) { M.gx()[j] = v; });
+        kinv_mul(Kinv, g, n, R, C, vx(VX_TN), XR, [&](int j, double v) { vx(VX_G)[j] = v; });
         __syncthreads();
         double acc[1] = {0};
-        rt_rows(ar, g, act, R, C, M.gx(), M.XR(), m, [&](int i, double v) {
-          const double iry = inv_ry_f(z, i, scale), gi = (M.bh()[i] + v) * iry;
-          M.gy()[i] = gi; acc[0] = fma((1.0 / iry) * gi, gi, acc[0]); });
-        if (t < n) acc[0] = fma(rho_x * M.gx()[t], M.gx()[t], acc[0]);
-        block_reduce<1, false>(acc, M.red);
-        gRg = acc[0];
-        if (Pg && p_tma) { mbar_wait(M.bar, tma_phase); tma_phase ^= 1; }
+        rt_rows(ar, ps, g, act, R, C, vx(VX_G), XR, m, [&](int i, double v) {
+          const double iry = inv_ry_f(z, i, scale), gi = (vy(VY_BH)[i] + v) * iry;
+          vy(VY_G)[i] = gi; acc[0] = fma((1.0 / iry) * gi, gi, acc[0]); });
+        if (t < n) acc[0] = fma(st.rho_x * vx(VX_G)[t], vx(VX_G)[t], acc[0]);
+        block_reduce<1, false>(acc, red);
+        if (t == 0) sc[SC_GRG] = acc[0];
+        if (Pg && p_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }
         __syncthreads();
-        pf.stamp(22);
-        pt.stamp(2);
+        SUB_STAMP(pf, 22);
+        pt_stamp(2);
         refactor = false; first = false;
       }
       double d4[4] = {0, 0, 0, 0};   // mu'g, p'Rg, p'Rp, p'mu (R-weighted)
@@ -520,142 +679,81 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         d4[0] = fma(r * wk, gk, d4[0]); d4[1] = fma(r * pk, gk, d4[1]);
         d4[2] = fma(r * pk, pk, d4[2]); d4[3] = fma(r * pk, wk, d4[3]);
       };
-      pi.skip();
-      rt_cols(ar, g, act, R, C, M.wy(), M.XC(), n, [&](int j, double v) { M.tn()[j] = rho_x * M.wx()[j] - v; });
+      SUB_SKIP(pi);
+      rt_cols(ar, ps, g, act, R, C, vy(VY_W), XC, n, [&](int j, double v) { vx(VX_TN)[j] = st.rho_x * vx(VX_W)[j] - v; });
       __syncthreads();
-      pi.stamp(23);
+      SUB_STAMP(pi, 23);
       double px = 0, py = 0;
-      kinv_mul(M.Kinv(), g, n, M.tn(), M.XR(), [&](int j, double v) { px = v; M.utx()[j] = v; dots(rho_x, v, M.wx()[j], M.gx()[j]); });
+      kinv_mul(Kinv, g, n, R, C, vx(VX_TN), XR, [&](int j, double v) { px = v; vx(VX_UT)[j] = v; dots(st.rho_x, v, vx(VX_W)[j], vx(VX_G)[j]); });
       __syncthreads();
-      pi.stamp(24);
-      rt_rows(ar, g, act, R, C, M.utx(), M.XR(), m, [&](int i, double v) {
+      SUB_STAMP(pi, 24);
+      rt_rows(ar, ps, g, act, R, C, vx(VX_UT), XR, m, [&](int i, double v) {
         const bool zr = i < z;
-        const double iry = zr ? BC_ZERO_CONE_FACTOR * scale : scale, wk = M.wy()[i];
+        const double iry = zr ? BC_ZERO_CONE_FACTOR * scale : scale, wk = vy(VY_W)[i];
         py = wk + v * iry;
-        dots(zr ? ry_z : ry_l, py, wk, M.gy()[i]); });
-      pi.stamp(26);
-      reduce4_lead(d4, M.red, nwc);
-      pi.stamp(27);
-      const double qa = dtau + gRg, qb = d4[0] - 2.0 * d4[1] - dtau * w_tau, qc = d4[2] - d4[3];
+        dots(sc[zr ? SC_RYZ : SC_RYL], py, wk, vy(VY_G)[i]); });
+      SUB_STAMP(pi, 26);
+      reduce4_lead(d4, red, nwc);
+      SUB_STAMP(pi, 27);
+      const double qa = BC_TAU_FACTOR + sc[SC_GRG], qb = d4[0] - 2.0 * d4[1] - BC_TAU_FACTOR * w_tau, qc = d4[2] - d4[3];
       double disc = qb * qb - 4.0 * qa * qc;
       if (disc < 0) disc = 0;
       const double tau_t = (-qb + sqrt(disc)) / (2.0 * qa);
       const bool check = st.adaptive_check ? (it >= next_check || it == st.max_iters) : ((it % st.check_interval == 0) || it == st.max_iters);
-      const bool fused = !check;
+      // cone step + relaxation (the relaxation is fused here unless a check needs the plain iterate)
       if (t < n) {
-        const double utk = px - tau_t * M.gx()[t], wk = M.wx()[t], uk = 2.0 * utk - wk;
-        M.utx()[t] = utk; M.ux()[t] = uk;
-        if (fused) M.wx()[t] = wk + alpha * (uk - utk);
+        const double utk = px - tau_t * vx(VX_G)[t], wk = vx(VX_W)[t], uk = 2.0 * utk - wk;
+        vx(VX_UT)[t] = utk; vx(VX_U)[t] = uk;
+        if (!check) vx(VX_W)[t] = wk + st.alpha * (uk - utk);
       }
       if (t < m) {
-        const double utk = py - tau_t * M.gy()[t], wk = M.wy()[t];
+        const double utk = py - tau_t * vy(VY_G)[t], wk = vy(VY_W)[t];
         double uk = 2.0 * utk - wk;
-        if (t >= z && t < zl) uk = fmax(uk, 0.0);
-        M.uty()[t] = utk; M.uy()[t] = uk;
-        if (fused) M.wy()[t] = wk + alpha * (uk - utk);
+        if (t >= z && t < z + S.l) uk = fmax(uk, 0.0);
+        vy(VY_UT)[t] = utk; vy(VY_U)[t] = uk;
+        if (!check) vy(VY_W)[t] = wk + st.alpha * (uk - utk);
       }
-      ut_tau = tau_t; u_tau = fmax(2.0 * tau_t - w_tau, 0.0);
-      if (fused) w_tau += alpha * (u_tau - ut_tau);
+      const double u_tau = fmax(2.0 * tau_t - w_tau, 0.0);
+      if (!check) w_tau += st.alpha * (u_tau - tau_t);
       __syncthreads();
-      pi.stamp(28);
-      pt.stamp(3);
+      SUB_STAMP(pi, 28);
       if (check) {
-        // ---- termination quantities on the un-normalised data ----
-        const double tau = u_tau;
-        double ax = 0, aty = 0, pxu = 0;
-        rt_rows(ar, g, act, R, C, M.ux(), M.XR(), m, [&](int i, double v) { ax = v; });
-        rt_cols(ar, g, act, R, C, M.uy(), M.XC(), n, [&](int j, double v) { aty = v; });
-        if (t < n) { M.tn2()[t] = 0.0; M.tn3()[t] = M.En()[t] * M.ux()[t]; }
+        pt_stamp(3);
+        rt_rows(ar, ps, g, act, R, C, vx(VX_U), XR, m, [&](int i, double v) { vy(VY_TM)[i] = v; });
+        __syncthreads();   // row and column partials share one buffer
+        rt_cols(ar, ps, g, act, R, C, vy(VY_U), XC, n, [&](int j, double v) { vx(VX_TN)[j] = v; });
         __syncthreads();
-        if (Pg) {  // P^ u_x = E (P (E u_x)); scratch: the column-partial buffer
-          P_mul(S, M.Li, M.tn3(), M.XC(), [&](int j, double v) { M.tn2()[j] += v; }, plN);
-          if (t < n) pxu = M.tn2()[t] * M.En()[t];
-        }
-        double sm[3] = {0, 0, 0};   // xPx_u, ctx_u, bty_u
-        double mx[7] = {0, 0, 0, 0, 0, 0, 0};  // rp, nAx, nS, nAxs, rd, nPx, nATy
-        if (t < m) {
-          const double rsk = (M.uy()[t] - (2.0 * M.uty()[t] - M.wy()[t])) / inv_ry_f(z, t, scale);
-          const double sc = 1.0 / (M.Dm()[t] * sigma);
-          mx[0] = fabs(ax + rsk - M.bh()[t] * tau) * sc;
-          mx[1] = fabs(ax) * sc; mx[2] = fabs(rsk) * sc;
-          mx[3] = fabs(ax + rsk) * sc;
-          sm[2] = M.bh()[t] * M.uy()[t];
-        }
-        if (t < n) {
-          const double sc = 1.0 / (M.En()[t] * sigma);
-          mx[4] = fabs(pxu + aty + M.ch()[t] * tau) * sc;
-          mx[5] = fabs(pxu) * sc; mx[6] = fabs(aty) * sc;
-          sm[0] = M.ux()[t] * pxu; sm[1] = M.ch()[t] * M.ux()[t];
-        }
-        block_reduce<3, false>(sm, M.red);
-        block_reduce<7, true>(mx, M.red);
-        const double s2 = sigma * sigma;
-        bool done = false;
-        if (tau > 1e-12) {
-          const double itau = 1.0 / tau;
-          const double xPx = sm[0] * itau * itau / s2, ctx = sm[1] * itau / s2, bty = sm[2] * itau / s2;
-          rp = mx[0] * itau; rd = mx[4] * itau; gap = fabs(xPx + ctx + bty);
-          const double np_ = fmax(fmax(mx[1] * itau, mx[2] * itau), nb0);
-          const double nd_ = fmax(fmax(mx[5] * itau, mx[6] * itau), nc0);
-          const double tp = st.eps_abs + st.eps_rel * np_, td = st.eps_abs + st.eps_rel * nd_;
-          const double tg = st.eps_abs + st.eps_rel * fmax(fmax(fabs(xPx), fabs(ctx)), fabs(bty));
-          if (rp <= tp && rd <= td && gap <= tg) { status = BCONE_SOLVED; done = true; }
-          else if (st.adaptive_check) {
-            const double lr = log(fmax(fmax(rp / tp, rd / td), gap / tg));
-            int step = st.check_interval;
-            if (prev_it > 0 && lr < prev_lr) { const double need = lr * (it - prev_it) / (prev_lr - lr); step = (int)ceil(0.9 * need) + 1; }
-            step = max(3, min(step, st.check_interval));
-            prev_it = it; prev_lr = lr; next_check = it + step;
-          }
-          if (!done && st.adaptive_scale) {
-            const double relp = rp / fmax(np_, 1e-18), reld = rd / fmax(nd_, 1e-18);
-            if (relp > 0 && reld > 0) { sum_log += log(relp) - log(reld); n_log++; }
-          }
-        }
-        if (st.adaptive_check && next_check <= it) next_check = it + st.check_interval;
-        if (!done) {
-          const double bty_c = sm[2] / s2, ctx_c = sm[1] / s2;
-          if (bty_c < 0 && mx[6] / (-bty_c) <= st.eps_infeas) { status = BCONE_INFEASIBLE; done = true; }
-          else if (ctx_c < 0 && fmax(mx[5], mx[3]) / (-ctx_c) <= st.eps_infeas) { status = BCONE_UNBOUNDED; done = true; }
-        }
+        check_tail(a, vx(0), vy(0), red, XC, Pg ? Li : nullptr, g.npad(), g.mpad(), it, scale, u_tau);
+        next_check = (int)sc[SC_NEXT];
+        const bool done = sc[SC_DONE] != 0.0;
+        const double ns = sc[SC_NEWSCALE];
+        pt_stamp(4);
         if (done) break;
-        if (st.adaptive_scale && n_log > 0 && it - last_up >= BC_RESCALE_MIN_ITERS) {
-          const double fac = sqrt(exp(sum_log / n_log));
-          if (fac > 3.1622776601683795 || fac < 0.31622776601683794) {
-            const double ns = fmin(fmax(scale * fac, BC_MIN_SCALE), BC_MAX_SCALE);
-            if (ns != scale) {
-              // keep R (w + u - 2 u~) invariant across the metric change (y block only)
-              const double ratio = ns / scale;  // r_old / r_new
-              if (t < m) M.wy()[t] = ratio * (M.wy()[t] + M.uy()[t] - 2.0 * M.uty()[t]) + 2.0 * M.uty()[t] - M.uy()[t];
-              scale = ns;
-              refactor = true;
-              sum_log = 0; n_log = 0; last_up = it;
-            }
-          }
-        }
-        pt.stamp(4);
+        if (ns != 0.0) { scale = ns; refactor = true; }
         if (it < st.max_iters) {  // (the last iterate keeps w so that s = R(u - t) is recoverable)
-          if (t < n) M.wx()[t] += alpha * (M.ux()[t] - M.utx()[t]);
-          if (t < m) M.wy()[t] += alpha * (M.uy()[t] - M.uty()[t]);
-          w_tau += alpha * (u_tau - ut_tau);
+          if (t < n) vx(VX_W)[t] += st.alpha * (vx(VX_U)[t] - vx(VX_UT)[t]);
+          if (t < m) vy(VY_W)[t] += st.alpha * (vy(VY_U)[t] - vy(VY_UT)[t]);
+          w_tau += st.alpha * (u_tau - tau_t);
           __syncthreads();
         }
       }
     }
     if (it > st.max_iters) it = st.max_iters;
-    pt.stamp(4);
+    __syncthreads();
+    pt_stamp(4);
     // ---- write back ----
     {
+      const int status = (int)sc[SC_STATUS];
       double *xo = a.x + (size_t)inst * n, *yo = a.y + (size_t)inst * m, *so = a.s + (size_t)inst * m;
       if (status == BCONE_SOLVED || status == BCONE_INACCURATE) {
-        double tau = u_tau;
+        double tau = sc[SC_UTAU];
         if (!(tau > 1e-12)) tau = 1e-12;
-        const double k0 = 1.0 / (sigma * tau);
-        if (t < n) xo[t] = M.En()[t] * M.ux()[t] * k0;
+        const double k0 = 1.0 / (sc[SC_SIGMA] * tau);
+        if (t < n) xo[t] = vx(VX_EN)[t] * vx(VX_U)[t] * k0;
         if (t < m) {
-          const double rsk = (M.uy()[t] - (2.0 * M.uty()[t] - M.wy()[t])) / inv_ry_f(z, t, scale);
-          yo[t] = M.Dm()[t] * M.uy()[t] * k0;
-          so[t] = rsk * k0 / M.Dm()[t];
+          const double rsk = (vy(VY_U)[t] - (2.0 * vy(VY_UT)[t] - vy(VY_W)[t])) / inv_ry_f(z, t, scale);
+          yo[t] = vy(VY_DM)[t] * vy(VY_U)[t] * k0;
+          so[t] = rsk * k0 / vy(VY_DM)[t];
         }
       } else {
         const double qn = nan("");
@@ -664,7 +762,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
       }
       if (t == 0) {
         a.status[inst] = status; a.iters[inst] = it;
-        if (a.resid) { a.resid[inst * 3 + 0] = rp; a.resid[inst * 3 + 1] = rd; a.resid[inst * 3 + 2] = gap; }
+        if (a.resid) { a.resid[inst * 3 + 0] = sc[SC_RP]; a.resid[inst * 3 + 1] = sc[SC_RD]; a.resid[inst * 3 + 2] = sc[SC_GAP]; }
       }
     }
     __syncthreads();
@@ -672,22 +770,37 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
 }
 
 // ----------------------------------------------------------------------------- host launcher
-extern "C" size_t bc_fwdf_smem_bytes(int n, int m) { return fwdf_smem_doubles(n, m) * sizeof(double); }
+// Specialised geometries (compile-time offsets); anything else runs the <0, 0> instantiation.
+#define FWDF_DISPATCH(n, m, EXPR)                                                      \
+  do {                                                                                 \
+    const Geo<0, 0> g0(n, m);                                                          \
+    if (g0.CT() == 10 && g0.RTu() == 50) { auto k = fwd_fast_kernel<10, 50>; EXPR; }   \
+    else { auto k = fwd_fast_kernel<0, 0>; EXPR; }                                     \
+  } while (0)
+
+extern "C" size_t bc_fwdf_smem_bytes(int n, int m) {
+  const Geo<0, 0> g(n, m);
+  if (!g.ok(n, m)) return (size_t)1 << 40;
+  return (size_t)g.total() * sizeof(double);
+}
 extern "C" int bc_fwdf_threads(void) { return FT; }
 // Eligibility beyond "dense A, polyhedral cones, direct mode" (checked by the caller): the tile grid has to
 // cover the matrix with at least half of the threads busy.
 extern "C" int bc_fwdf_eligible(int n, int m) {
-  FastGeom g;
-  if (!fwdf_geom(n, m, g)) return 0;
-  return g.CT * g.RTu >= FT / 2;
+  const Geo<0, 0> g(n, m);
+  return g.ok(n, m) && g.CT() * g.RTu() >= FT / 2;
 }
-extern "C" cudaError_t bc_fwdf_configure(size_t smem) {
-  return cudaFuncSetAttribute(fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+extern "C" cudaError_t bc_fwdf_configure(int n, int m, size_t smem) {
+  cudaError_t e = cudaSuccess;
+  FWDF_DISPATCH(n, m, e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return e;
 }
-extern "C" cudaError_t bc_fwdf_occupancy(size_t smem, int *ctas_per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fwd_fast_kernel, FT, smem);
+extern "C" cudaError_t bc_fwdf_occupancy(int n, int m, size_t smem, int *ctas_per_sm) {
+  cudaError_t e = cudaSuccess;
+  FWDF_DISPATCH(n, m, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k, FT, smem));
+  return e;
 }
 extern "C" cudaError_t bc_fwdf_launch(const FwdArgs *a, int grid, size_t smem, cudaStream_t stream) {
-  fwd_fast_kernel<<<grid, FT, smem, stream>>>(*a);
+  FWDF_DISPATCH(a->S.n, a->S.m, (k<<<grid, FT, smem, stream>>>(*a)));
   return cudaGetLastError();
 }

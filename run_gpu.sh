@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fwd_fast_kernel -s 1 -c 1 -o gpurun_out/fwdf_r1 -f python tools/profile_c2.py 296 2 > gpurun_out/ncu_fwdf.log 2>&1; tail -3 gpurun_out/ncu_fwdf.log
-ls -la gpurun_out/*.ncu-rep
+./tools/microbench 2>&1 | tee gpurun_out/micro.log
+timeout 300 python tools/compare_fwd.py 2>&1 | tee gpurun_out/compare.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/tests.log
+timeout 300 python tools/phase_profile.py 592 2>&1 | grep -v "^  \[" | tee gpurun_out/phase.log
+timeout 600 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json

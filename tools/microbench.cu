@@ -5,6 +5,10 @@
 #include "../cvxpylayers_b200/csrc/common.cuh"
 
 constexpr int NT = 16;
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 struct Args { double *A; double *out; unsigned long long *cyc; int m, n, reps; };
 
 template <class F>
@@ -194,6 +198,91 @@ __global__ void __launch_bounds__(512, 1) mb_kernel(Args a) {
       __syncthreads();
     });
   }
+  // 12: DMMA m8n8k4 throughput: 8 independent accumulator pairs x 16 per rep
+  {
+    double acc[8][2];
+    for (int k = 0; k < 8; k++) { acc[k][0] = x[(t + k) % n]; acc[k][1] = 0; }
+    const double fa = y[t % m], fb = x[t % n];
+    timed(a.cyc, 12, reps, [&](int) {
+#pragma unroll
+      for (int q = 0; q < 16; q++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) dmma(acc[k][0], acc[k][1], fa, fb);
+    });
+    double s = 0; for (int k = 0; k < 8; k++) s += acc[k][0] + acc[k][1];
+    if (s == 1.2345) a.out[t] = s;
+  }
+  // 13: K = A' W A (lower, 8x8 tiles, 13 x 13 blocks) with DMMA: warp per 16 x 32 macro tile strip
+  {
+    const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+    const int nb = (n + 7) >> 3;                 // 13
+    double *Kout = Li;                           // packed lower n(n+1)/2
+    timed(a.cyc, 13, 20, [&](int) {
+      // macro tiles: block-row pair JP (rows 16 JP .. 16 JP + 15), block-col quad KQ (cols 32 KQ ..): only those touching the lower triangle
+      const int nJP = (nb + 1) >> 1, nKQ = (nb + 3) >> 2;
+      int cnt = 0;
+      for (int JP = 0; JP < nJP; JP++)
+        for (int KQ = 0; KQ < nKQ; KQ++) {
+          if (4 * KQ > 2 * JP + 1) continue;     // entirely above the diagonal
+          if ((cnt++ % nw) != warp) continue;
+          double acc[2][4][2];
+#pragma unroll
+          for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[u][v][0] = acc[u][v][1] = 0.0;
+          const int jr = 16 * JP + (lane >> 2), kc = 32 * KQ + (lane >> 2);
+          for (int i = 0; i < m; i += 4) {
+            const double *row = Av + (i + (lane & 3)) * n;
+            const double w = (i + (lane & 3)) < 50 ? 1000.0 : 1.0;
+            double fa[2], fb[4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) { const int j = jr + 8 * u; fa[u] = j < n ? row[j] * w : 0.0; }
+#pragma unroll
+            for (int v = 0; v < 4; v++) { const int k = kc + 8 * v; fb[v] = k < n ? row[k] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+#pragma unroll
+              for (int v = 0; v < 4; v++) dmma(acc[u][v][0], acc[u][v][1], fa[u], fb[v]);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; u++)
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+              const int j = 16 * JP + 8 * u + (lane >> 2), k = 32 * KQ + 8 * v + 2 * (lane & 3);
+              if (j < n && k <= j) Kout[((j * (j + 1)) >> 1) + k] = acc[u][v][0];
+              if (j < n && k + 1 <= j) Kout[((j * (j + 1)) >> 1) + k + 1] = acc[u][v][1];
+            }
+        }
+      __syncthreads();
+    });
+    if (t == 0) a.out[2000] = Kout[(57 * 58 >> 1) + 13];
+    __syncthreads();
+  }
+  // 14: the same K by 2 x 2 register tiles (the current form_K)
+  {
+    double *Kout = Li;
+    timed(a.cyc, 14, 20, [&](int) {
+      const int nb2 = n >> 1, ntile = (nb2 * (nb2 + 1)) >> 1;
+      for (int e = t; e < ntile; e += T) {
+        int J = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while (((J + 1) * (J + 2)) >> 1 <= e) J++;
+        while ((J * (J + 1)) >> 1 > e) J--;
+        const int Kb = e - ((J * (J + 1)) >> 1);
+        const double2 *pj = reinterpret_cast<const double2 *>(Av) + J, *pk = reinterpret_cast<const double2 *>(Av) + Kb;
+        double z00 = 0, z01 = 0, z10 = 0, z11 = 0, s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+        int i = 0;
+        for (; i < 50; i++) { const double2 u = pj[i * nb2], v = pk[i * nb2]; z00 = fma(u.x, v.x, z00); z01 = fma(u.x, v.y, z01); z10 = fma(u.y, v.x, z10); z11 = fma(u.y, v.y, z11); }
+        for (; i < m; i++) { const double2 u = pj[i * nb2], v = pk[i * nb2]; s00 = fma(u.x, v.x, s00); s01 = fma(u.x, v.y, s01); s10 = fma(u.y, v.x, s10); s11 = fma(u.y, v.y, s11); }
+        const int j0 = 2 * J, k0 = 2 * Kb;
+        Kout[((j0 * (j0 + 1)) >> 1) + k0] = z00 * 1000.0 + s00;
+        if (k0 + 1 <= j0) Kout[((j0 * (j0 + 1)) >> 1) + k0 + 1] = z01 * 1000.0 + s01;
+        Kout[(((j0 + 1) * (j0 + 2)) >> 1) + k0] = z10 * 1000.0 + s10;
+        Kout[(((j0 + 1) * (j0 + 2)) >> 1) + k0 + 1] = z11 * 1000.0 + s11;
+      }
+      __syncthreads();
+    });
+    if (t == 0) a.out[2001] = Kout[(57 * 58 >> 1) + 13];
+  }
   if (t < n) a.out[512 + t] = o2[t];
   if (t < m) a.out[1024 + t] = o1[t];
 }
@@ -216,9 +305,9 @@ int main() {
   unsigned long long h[NT]; cudaMemcpy(h, a.cyc, sizeof(h), cudaMemcpyDeviceToHost);
   std::vector<double> ho(4096); cudaMemcpy(ho.data(), a.out, sizeof(double) * 4096, cudaMemcpyDeviceToHost);
   const char *names[NT] = {"barrier", "DFMA x256/thread", "LDS.128 x16/thread", "dense_rows2 + barrier", "dense_cols2", "packed rows + barrier", "packed cols",
-                           "block_reduce<4>", "regtile rows", "regtile cols (100x50)", "regtile cols (quad)", "ruiz A sweep", "", "", "", ""};
+                           "block_reduce<4>", "regtile rows", "regtile cols (100x50)", "regtile cols (quad)", "ruiz A sweep", "DMMA x128/thread", "K formation DMMA (x20)", "K formation 2x2 (x20)", ""};
   printf("smem %zu B\n", smem);
-  for (int k = 0; k < 12; k++) printf("%-26s %10.1f cycles/call\n", names[k], (double)h[k] / grid / reps);
-  printf("check o2[3]=%g o1[5]=%g\n", ho[512 + 3], ho[1024 + 5]);
+  for (int k = 0; k < 15; k++) printf("%-26s %10.1f cycles/call\n", names[k], (double)h[k] / grid / (k >= 13 ? 20 : reps));
+  printf("check o2[3]=%g o1[5]=%g  K[57][13] dmma=%.12g 2x2=%.12g\n", ho[512 + 3], ho[1024 + 5], ho[2000], ho[2001]);
   return 0;
 }
