@@ -133,53 +133,58 @@ __global__ void __launch_bounds__(512, 1) bwd_block_kernel(const __grid_constant
     pt.stamp(9);   // Px + Cholesky/inverse of P (+ wait for the row copies)
     double *Ws = M.Ab, *Sb = M.Ab + nl * n;
     if (applicable && nl > 0) {
-      // ---- W = L^{-1} A_L' in place: one warp per staged row, a_l held in registers ----
-      for (int l = warp; l < nl; l += nw) {
-        double *row = Ws + l * n;
-        double ar[4];
+      // ---- W = A_L Linv' in place on the tensor cores (DMMA 8x8x4): one warp per 8 staged rows, whose A fragments
+      //      (8 x n, n <= 128) are held in registers for every k-step, so the rows can be overwritten tile by tile ----
+      {
+        constexpr int KSMAX = 32;                 // k-steps of 4 columns: n <= 128
+        const int fr = lane >> 2, fc = lane & 3;
+        const int ntl = (nl + 7) >> 3, nti = (n + 7) >> 3;
+        for (int lt = warp; lt < ntl; lt += nw) {
+          const int l = 8 * lt + fr;
+          double af[KSMAX];
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; ar[k] = c < n ? row[c] : 0.0; }
-        __syncwarp();
-        for (int i0 = 0; i0 < n; i0 += 4) {
-          double acc[4] = {0, 0, 0, 0};
+          for (int ks = 0; ks < KSMAX; ks++) { const int cidx = 4 * ks + fc; af[ks] = (l < nl && cidx < n) ? Ws[l * n + cidx] : 0.0; }
+          __syncwarp();
+          for (int it = 0; it < nti; it++) {
+            const int i = 8 * it + fr;            // row of Linv feeding output column i
+            const double *Lrow = M.Pb + ((i * (i + 1)) >> 1);
+            const int klim = 8 * it + 8;          // Linv[i][c] = 0 for c > i
+            double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-          for (int r = 0; r < 4; r++) {
-            const int i = i0 + r;
-            if (i < n) {
-              const double *Li = M.Pb + ((i * (i + 1)) >> 1);
-#pragma unroll
-              for (int k = 0; k < 4; k++) { const int c = lane + 32 * k; if (c <= i) acc[r] = fma(Li[c], ar[k], acc[r]); }
+            for (int ks = 0; ks < KSMAX; ks++) {
+              if (4 * ks < klim) {                // warp-uniform
+                const int cidx = 4 * ks + fc;
+                const double fb = (i < n && cidx <= i) ? Lrow[cidx] : 0.0;
+                dmma884(c0, c1, af[ks], fb);
+              }
             }
+            const int col = 8 * it + 2 * fc;
+            if (l < nl && col < n) *reinterpret_cast<double2 *>(Ws + l * n + col) = make_double2(c0, c1);   // n is even
           }
-          const double tot = butterfly4(acc[0], acc[1], acc[2], acc[3], lane);
-          if ((lane & 7) == 0) { const int i = i0 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1); if (i < n) row[i] = tot; }
         }
       }
       __syncthreads();
       pt.stamp(10);  // W = L^{-1} A_L'
-      // ---- S = W W' (nl x nl, packed lower) : 2x2 register tiles ----
-      const int nb = (nl + 1) >> 1, ntile = (nb * (nb + 1)) >> 1;
-      for (int e = t; e < ntile; e += T) {
-        int A_ = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-        while (((A_ + 1) * (A_ + 2)) >> 1 <= e) A_++;
-        while ((A_ * (A_ + 1)) >> 1 > e) A_--;
-        const int B_ = e - ((A_ * (A_ + 1)) >> 1);
-        const int a0 = 2 * A_, a1 = min(a0 + 1, nl - 1), b0 = 2 * B_, b1 = min(b0 + 1, nl - 1);
-        const double2 *pa0 = reinterpret_cast<const double2 *>(Ws + a0 * n), *pa1 = reinterpret_cast<const double2 *>(Ws + a1 * n);
-        const double2 *pb0 = reinterpret_cast<const double2 *>(Ws + b0 * n), *pb1 = reinterpret_cast<const double2 *>(Ws + b1 * n);
-        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-        for (int k = 0; k < (n >> 1); k++) {
-          const double2 u0 = pa0[k], u1 = pa1[k], v0 = pb0[k], v1 = pb1[k];
-          s00 = fma(u0.x, v0.x, s00); s00 = fma(u0.y, v0.y, s00);
-          s01 = fma(u0.x, v1.x, s01); s01 = fma(u0.y, v1.y, s01);
-          s10 = fma(u1.x, v0.x, s10); s10 = fma(u1.y, v0.y, s10);
-          s11 = fma(u1.x, v1.x, s11); s11 = fma(u1.y, v1.y, s11);
-        }
-        Sb[((a0 * (a0 + 1)) >> 1) + b0] = s00;
-        if (b0 + 1 <= a0 && b0 + 1 < nl) Sb[((a0 * (a0 + 1)) >> 1) + b0 + 1] = s01;
-        if (a0 + 1 < nl) {
-          Sb[(((a0 + 1) * (a0 + 2)) >> 1) + b0] = s10;
-          if (b0 + 1 < nl && b0 + 1 <= a0 + 1) Sb[(((a0 + 1) * (a0 + 2)) >> 1) + b0 + 1] = s11;
+      // ---- S = W W' (nl x nl, packed lower): 8 x 8 tiles of the lower triangle, one DMMA per 4 columns of W ----
+      {
+        const int fr = lane >> 2, fc = lane & 3;
+        const int ntl = (nl + 7) >> 3, ntile = (ntl * (ntl + 1)) >> 1, nks = (n + 3) >> 2;
+        for (int e = warp; e < ntile; e += nw) {
+          int ta = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+          while (((ta + 1) * (ta + 2)) >> 1 <= e) ta++;
+          while ((ta * (ta + 1)) >> 1 > e) ta--;
+          const int tb = e - ((ta * (ta + 1)) >> 1);
+          const int la = 8 * ta + fr, lb = 8 * tb + fr;
+          const double *pa = Ws + min(la, nl - 1) * n, *pb = Ws + min(lb, nl - 1) * n;
+          double c0 = 0.0, c1 = 0.0;
+          for (int ks = 0; ks < nks; ks++) {
+            const int cidx = 4 * ks + fc;
+            const double fa = (la < nl && cidx < n) ? pa[cidx] : 0.0, fb = (lb < nl && cidx < n) ? pb[cidx] : 0.0;
+            dmma884(c0, c1, fa, fb);
+          }
+          const int r = 8 * ta + fr, q = 8 * tb + 2 * fc;
+          if (r < nl && q <= r) Sb[((r * (r + 1)) >> 1) + q] = c0;
+          if (r < nl && q + 1 <= r) Sb[((r * (r + 1)) >> 1) + q + 1] = c1;
         }
       }
       __syncthreads();

@@ -213,6 +213,14 @@ __device__ __forceinline__ double butterfly4(double a0, double a1, double a2, do
   return k;
 }
 
+// FP64 tensor-core tile product D(8x8) += A(8x4) * B(4x8), one warp (SASS: DMMA.8x8x4).  Fragment layout
+// (PTX mma.m8n8k4.f64): lane holds A[lane >> 2][lane & 3], B[lane & 3][lane >> 2] and the two accumulator
+// entries D[lane >> 2][2 (lane & 3) + {0, 1}].  There is no tcgen05 kind for f64; this is the tensor path the
+// dense fp64 set-up phases (K formation, Cholesky trailing update, W = L^{-1} A', S = W W') run on.
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // out_i = sum_j M[i][j] * x[j]: one warp per row, lanes across columns (conflict-free for any
 // row stride), x held in registers (ncols <= 128), four rows reduced together.
 // ep(i, value) is called by exactly one lane.
@@ -560,39 +568,26 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
       if (jb > 2) { double *D2 = K + (((J0 + 2) * (J0 + 3)) >> 1) + J0; D2[0] = q.l20; D2[1] = q.l21; D2[2] = q.l22; }
       if (jb > 3) { double *D3 = K + (((J0 + 3) * (J0 + 4)) >> 1) + J0; D3[0] = q.l30; D3[1] = q.l31; D3[2] = q.l32; D3[3] = q.l33; }
     }
-    // rank-4 trailing update: K[i][j] -= sum_c L[i][J0+c] L[j][J0+c]; warp per row i, lanes across j in [R0, i].
-    // A lane's columns are the same for every row, so their panel entries are loaded once per step.
+    // rank-4 trailing update K[i][j] -= sum_c L[i][J0+c] L[j][J0+c] on the tensor cores: one DMMA (k = 4 is exactly
+    // the block width) per 8 x 8 tile of the trailing lower triangle, tiles dealt round-robin to the warps.
     if (R0 < n) {
-      constexpr int QC = 4;
-      double b0[QC], b1[QC], b2[QC], b3[QC];
-#pragma unroll
-      for (int u = 0; u < QC; u++) {
-        const int jc = R0 + lane + 32 * u;
-        b0[u] = b1[u] = b2[u] = b3[u] = 0.0;
-        if (jc < n) {
-          const double *pj = K + ((jc * (jc + 1)) >> 1) + J0;
-          b0[u] = pj[0];
-          if (jb > 1) b1[u] = pj[1];
-          if (jb > 2) b2[u] = pj[2];
-          if (jb > 3) b3[u] = pj[3];
-        }
-      }
-      for (int i = R0 + warp; i < n; i += nw) {
-        double *pi = K + ((i * (i + 1)) >> 1);
-        const double a0 = -pi[J0], a1 = jb > 1 ? -pi[J0 + 1] : 0.0, a2 = jb > 2 ? -pi[J0 + 2] : 0.0, a3 = jb > 3 ? -pi[J0 + 3] : 0.0;
-#pragma unroll
-        for (int u = 0; u < QC; u++) {
-          const int jc = R0 + lane + 32 * u;
-          if (jc <= i) pi[jc] = fma(a3, b3[u], fma(a2, b2[u], fma(a1, b1[u], fma(a0, b0[u], pi[jc]))));
-        }
-        for (int jc = R0 + lane + 32 * QC; jc <= i; jc += 32) {   // orders beyond R0 + 128
-          const double *pj = K + ((jc * (jc + 1)) >> 1) + J0;
-          double v = fma(a0, pj[0], pi[jc]);
-          if (jb > 1) v = fma(a1, pj[1], v);
-          if (jb > 2) v = fma(a2, pj[2], v);
-          if (jb > 3) v = fma(a3, pj[3], v);
-          pi[jc] = v;
-        }
+      const int ntl = (n - R0 + 7) >> 3, ntile = (ntl * (ntl + 1)) >> 1;
+      const int fr = lane >> 2, fc = lane & 3;
+      for (int e = warp; e < ntile; e += nw) {
+        int ta = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while (((ta + 1) * (ta + 2)) >> 1 <= e) ta++;
+        while ((ta * (ta + 1)) >> 1 > e) ta--;
+        const int tb = e - ((ta * (ta + 1)) >> 1);
+        const int ra = R0 + 8 * ta + fr, rb = R0 + 8 * tb + fr;
+        const double fa = (ra < n && fc < jb) ? -K[((ra * (ra + 1)) >> 1) + J0 + fc] : 0.0;
+        const double fb = (rb < n && fc < jb) ? K[((rb * (rb + 1)) >> 1) + J0 + fc] : 0.0;
+        double *pc = K + ((ra * (ra + 1)) >> 1) + R0 + 8 * tb + 2 * fc;   // C entries (ra, cc), (ra, cc + 1)
+        const int cc = R0 + 8 * tb + 2 * fc;
+        const bool ok0 = ra < n && cc <= ra, ok1 = ra < n && cc + 1 <= ra;
+        double c0 = ok0 ? pc[0] : 0.0, c1 = ok1 ? pc[1] : 0.0;
+        dmma884(c0, c1, fa, fb);
+        if (ok0) pc[0] = c0;
+        if (ok1) pc[1] = c1;
       }
     }
     __syncthreads();

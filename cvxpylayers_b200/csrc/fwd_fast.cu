@@ -203,55 +203,71 @@ __device__ __forceinline__ void reduce4_lead(double (&v)[4], double *red, int nw
   __syncthreads();   // red may be rewritten by the next reduction
 }
 
-// K = rho_x I + scale * sum_i w_i a_i a_i' (+ P^ already sitting in K as unscaled packed P when Psm) for the
-// staged, equilibrated A (row-major m x n in shared memory), packed lower.
+// K = rho_x I + sum_i r_i a_i a_i' (r_i = scale, x 1000 on zero-cone rows) (+ P^ when haveP: K then holds the
+// unscaled packed P on entry) for the staged, equilibrated A (row-major m x n in shared memory), packed lower.
+// Tensor-core SYRK: a warp owns a 16 x 32 strip of 8 x 8 tiles (two A fragments feed four B fragments per
+// k-step of 4 rows), strips touching the lower triangle are dealt round-robin; tiles above the diagonal are
+// skipped.  Fragments of the next k-step are loaded while the current DMMAs issue.
 __device__ __noinline__ void form_K(const double *Av, int m, int n, int z, double scale, double rho_x, double *K, bool haveP, const double *En) {
-  const int T = blockDim.x, t = threadIdx.x;
-  if ((n & 1) == 0) {
-    const int nb = n >> 1, ntile = (nb * (nb + 1)) >> 1;
-    for (int e = t; e < ntile; e += T) {
-      int J = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-      while (((J + 1) * (J + 2)) >> 1 <= e) J++;
-      while ((J * (J + 1)) >> 1 > e) J--;
-      const int Kb = e - ((J * (J + 1)) >> 1);
-      const double2 *pj = reinterpret_cast<const double2 *>(Av) + J, *pk = reinterpret_cast<const double2 *>(Av) + Kb;
-      double z00 = 0, z01 = 0, z10 = 0, z11 = 0, s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-      int i = 0;
-      for (; i < z; i++) { const double2 u = pj[i * nb], v = pk[i * nb]; z00 = fma(u.x, v.x, z00); z01 = fma(u.x, v.y, z01); z10 = fma(u.y, v.x, z10); z11 = fma(u.y, v.y, z11); }
-      for (; i < m; i++) { const double2 u = pj[i * nb], v = pk[i * nb]; s00 = fma(u.x, v.x, s00); s01 = fma(u.x, v.y, s01); s10 = fma(u.y, v.x, s10); s11 = fma(u.y, v.y, s11); }
-      const int j0 = 2 * J, k0 = 2 * Kb;
-      const int e00 = ((j0 * (j0 + 1)) >> 1) + k0, e10 = (((j0 + 1) * (j0 + 2)) >> 1) + k0;
-      double v00 = (z00 * BC_ZERO_CONE_FACTOR + s00) * scale + (j0 == k0 ? rho_x : 0.0);
-      double v01 = (z01 * BC_ZERO_CONE_FACTOR + s01) * scale;
-      double v10 = (z10 * BC_ZERO_CONE_FACTOR + s10) * scale;
-      double v11 = (z11 * BC_ZERO_CONE_FACTOR + s11) * scale + (j0 == k0 ? rho_x : 0.0);
-      if (haveP) {
-        v00 += K[e00] * En[k0] * En[j0];
-        if (k0 + 1 <= j0) v01 += K[e00 + 1] * En[k0 + 1] * En[j0];
-        v10 += K[e10] * En[k0] * En[j0 + 1];
-        v11 += K[e10 + 1] * En[k0 + 1] * En[j0 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int nb = (n + 7) >> 3, nJP = (nb + 1) >> 1, nKQ = (nb + 3) >> 2;
+  const double wz = BC_ZERO_CONE_FACTOR * scale, wl = scale;
+  int cnt = 0;
+  for (int JP = 0; JP < nJP; JP++)
+    for (int KQ = 0; KQ < nKQ; KQ++) {
+      if (4 * KQ > 2 * JP + 1) continue;        // strip entirely above the diagonal
+      if ((cnt++ % nw) != warp) continue;
+      double acc[2][4][2];
+      bool need[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) { acc[u][v][0] = acc[u][v][1] = 0.0; need[u][v] = (4 * KQ + v <= 2 * JP + u) && (2 * JP + u < nb); }
+      const int jr = 16 * JP + fr, kc = 32 * KQ + fr;
+      double fa[2], fb[4], ga[2], gb[4];
+      auto load = [&](int i, double (&xa)[2], double (&xb)[4]) {
+        const int ii = i + fc;
+        const bool valid = ii < m;
+        const double *row = Av + ii * n;
+        const double w = ii < z ? wz : wl;
+#pragma unroll
+        for (int u = 0; u < 2; u++) { const int j = jr + 8 * u; xa[u] = (valid && j < n) ? row[j] * w : 0.0; }
+#pragma unroll
+        for (int v = 0; v < 4; v++) { const int k = kc + 8 * v; xb[v] = (valid && k < n) ? row[k] : 0.0; }
+      };
+      load(0, fa, fb);
+      for (int i = 0; i < m; i += 8) {
+        load(i + 4, ga, gb);                      // rows past m load zeros
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+          for (int v = 0; v < 4; v++) if (need[u][v]) dmma884(acc[u][v][0], acc[u][v][1], fa[u], fb[v]);
+        load(i + 8, fa, fb);
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+          for (int v = 0; v < 4; v++) if (need[u][v]) dmma884(acc[u][v][0], acc[u][v][1], ga[u], gb[v]);
       }
-      K[e00] = v00;
-      if (k0 + 1 <= j0) K[e00 + 1] = v01;
-      K[e10] = v10; K[e10 + 1] = v11;
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          if (!need[u][v]) continue;
+          const int j = 16 * JP + 8 * u + fr, k = 32 * KQ + 8 * v + 2 * fc;
+          if (j < n && k <= j) {
+            const int e0 = ((j * (j + 1)) >> 1) + k;
+            double v0 = acc[u][v][0] + (j == k ? rho_x : 0.0);
+            if (haveP) v0 += K[e0] * En[k] * En[j];
+            K[e0] = v0;
+            if (k + 1 <= j) {
+              double v1 = acc[u][v][1] + (j == k + 1 ? rho_x : 0.0);
+              if (haveP) v1 += K[e0 + 1] * En[k + 1] * En[j];
+              K[e0 + 1] = v1;
+            }
+          }
+        }
     }
-  } else {
-    const int npk = n * (n + 1) / 2;
-    for (int e = t; e < npk; e += T) {
-      int j = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-      while ((j + 1) * (j + 2) / 2 <= e) j++;
-      while (j * (j + 1) / 2 > e) j--;
-      const int k = e - j * (j + 1) / 2;
-      double acc0 = 0, acc1 = 0;
-      const double *cj = Av + j, *ck = Av + k;
-      int i = 0;
-      for (; i < z; i++) acc0 = fma(cj[i * n], ck[i * n], acc0);
-      for (; i < m; i++) acc1 = fma(cj[i * n], ck[i * n], acc1);
-      double v = (acc0 * BC_ZERO_CONE_FACTOR + acc1) * scale + (j == k ? rho_x : 0.0);
-      if (haveP) v += K[e] * En[k] * En[j];
-      K[e] = v;
-    }
-  }
   __syncthreads();
 }
 
