@@ -511,7 +511,7 @@ __device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, cons
 struct Tri4 { double l00, l10, l11, l20, l21, l22, l30, l31, l32, l33, m00, m10, m11, m20, m21, m22, m30, m31, m32, m33; bool pd; };
 // Cholesky factor (l) and its inverse (m) of the jb x jb (jb <= 4) diagonal block at (r0, r0); when
 // `factored` the block already holds L.  Missing rows / columns are padded with the identity.
-__device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool factored) {
+__device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool factored, const double *isd = nullptr) {
   Tri4 q;
   const double *R0 = K + ((r0 * (r0 + 1)) >> 1) + r0;
   const double *R1 = K + (((r0 + 1) * (r0 + 2)) >> 1) + r0, *R2 = K + (((r0 + 2) * (r0 + 3)) >> 1) + r0, *R3 = K + (((r0 + 3) * (r0 + 4)) >> 1) + r0;
@@ -522,7 +522,8 @@ __device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool
   double r0_, r1_, r2_, r3_;
   if (factored) {
     q.l00 = d00; q.l10 = d10; q.l11 = d11; q.l20 = d20; q.l21 = d21; q.l22 = d22; q.l30 = d30; q.l31 = d31; q.l32 = d32; q.l33 = d33;
-    r0_ = 1.0 / d00; r1_ = 1.0 / d11; r2_ = 1.0 / d22; r3_ = 1.0 / d33; q.pd = true;
+    // reciprocal diagonal: kept by the factorisation sweep (isd[k] = 1 / L_kk), no divisions here
+    r0_ = isd[0]; r1_ = jb > 1 ? isd[1] : 1.0; r2_ = jb > 2 ? isd[2] : 1.0; r3_ = jb > 3 ? isd[3] : 1.0; q.pd = true;
   } else {
     const double p0 = d00; r0_ = rsqrt(p0);
     q.l00 = p0 * r0_; q.l10 = d10 * r0_; q.l20 = d20 * r0_; q.l30 = d30 * r0_;
@@ -541,16 +542,24 @@ __device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool
   q.m31 = -fma(q.l32, q.m21, q.l31 * q.m11) * r3_; q.m32 = -q.l32 * q.m22 * r3_;
   return q;
 }
+#ifdef BC_CHOLPROF   // sub-phase cycle counters for tools/microbench.cu (thread 0, slots 16..24 of prof)
+#define CP_STAMP(k) if (prof && t == 0) { const long long now_ = clock64(); atomicAdd(prof + (k), (unsigned long long)(now_ - tt)); tt = now_; }
+#else
+#define CP_STAMP(k)
+#endif
 __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned long long *prof = nullptr) {
-  (void)tmp;
   const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
   long long tA = 0, tB = 0, t0 = 0;
   if (prof && t == 0) t0 = clock64();
+#ifdef BC_CHOLPROF
+  long long tt = t0;
+#endif
   // ---------------- Cholesky, four columns per step ----------------
   for (int J0 = 0; J0 < n; J0 += 4) {
     const int jb = min(4, n - J0), R0 = J0 + jb;
     const Tri4 q = tri4_block(K, J0, jb, false);
     if (!q.pd) return false;   // block-uniform: every thread factors the same block
+    CP_STAMP(16);
     // panel: row i >= R0, l_i = a_i L_D^{-T}; one row per thread, in place
     for (int i = R0 + t; i < n; i += T) {
       double *row = K + ((i * (i + 1)) >> 1) + J0;
@@ -560,13 +569,15 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
       if (jb > 2) row[2] = fma(a2, q.m22, fma(a1, q.m21, a0 * q.m20));
       if (jb > 3) row[3] = fma(a3, q.m33, fma(a2, q.m32, fma(a1, q.m31, a0 * q.m30)));
     }
+    CP_STAMP(17);
     __syncthreads();
+    CP_STAMP(18);
     if (t == 0) {   // the diagonal block itself (nobody reads it during the trailing update)
       double *D0 = K + ((J0 * (J0 + 1)) >> 1) + J0;
-      D0[0] = q.l00;
-      if (jb > 1) { double *D1 = K + (((J0 + 1) * (J0 + 2)) >> 1) + J0; D1[0] = q.l10; D1[1] = q.l11; }
-      if (jb > 2) { double *D2 = K + (((J0 + 2) * (J0 + 3)) >> 1) + J0; D2[0] = q.l20; D2[1] = q.l21; D2[2] = q.l22; }
-      if (jb > 3) { double *D3 = K + (((J0 + 3) * (J0 + 4)) >> 1) + J0; D3[0] = q.l30; D3[1] = q.l31; D3[2] = q.l32; D3[3] = q.l33; }
+      D0[0] = q.l00; tmp[J0] = q.m00;
+      if (jb > 1) { double *D1 = K + (((J0 + 1) * (J0 + 2)) >> 1) + J0; D1[0] = q.l10; D1[1] = q.l11; tmp[J0 + 1] = q.m11; }
+      if (jb > 2) { double *D2 = K + (((J0 + 2) * (J0 + 3)) >> 1) + J0; D2[0] = q.l20; D2[1] = q.l21; D2[2] = q.l22; tmp[J0 + 2] = q.m22; }
+      if (jb > 3) { double *D3 = K + (((J0 + 3) * (J0 + 4)) >> 1) + J0; D3[0] = q.l30; D3[1] = q.l31; D3[2] = q.l32; D3[3] = q.l33; tmp[J0 + 3] = q.m33; }
     }
     // rank-4 trailing update K[i][j] -= sum_c L[i][J0+c] L[j][J0+c] on the tensor cores: one DMMA (k = 4 is exactly
     // the block width) per 8 x 8 tile of the trailing lower triangle, tiles dealt round-robin to the warps.
@@ -590,7 +601,9 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
         if (ok1) pc[1] = c1;
       }
     }
+    CP_STAMP(19);
     __syncthreads();
+    CP_STAMP(20);
   }
   if (prof && t == 0) { const long long t1 = clock64(); tA = t1 - t0; t0 = t1; }
   // ---------------- X = L^{-1}, four rows per step ----------------
@@ -598,7 +611,8 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
   const int g = t & 3, q4 = t >> 2, nq = T >> 2;
   for (int I0 = 0; I0 < n; I0 += 4) {
     const int ib = min(4, n - I0);
-    const Tri4 q = tri4_block(K, I0, ib, true);
+    const Tri4 q = tri4_block(K, I0, ib, true, tmp + I0);
+    CP_STAMP(21);
     const double *L0 = K + ((I0 * (I0 + 1)) >> 1), *L1 = K + (((I0 + 1) * (I0 + 2)) >> 1), *L2 = K + (((I0 + 2) * (I0 + 3)) >> 1),
                  *L3 = K + (((I0 + 3) * (I0 + 4)) >> 1);
     int jg = 0;
@@ -618,7 +632,9 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
       s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s3 += __shfl_xor_sync(0xffffffffu, s3, 1);
       s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       s2 += __shfl_xor_sync(0xffffffffu, s2, 2); s3 += __shfl_xor_sync(0xffffffffu, s3, 2);
+      CP_STAMP(22);
       __syncthreads();   // every read of block row I at this group's columns is done
+      CP_STAMP(23);
       if (g == 0 && j < I0) {
         K[((I0 * (I0 + 1)) >> 1) + j] = -(q.m00 * s0);
         if (ib > 1) K[(((I0 + 1) * (I0 + 2)) >> 1) + j] = -fma(q.m11, s1, q.m10 * s0);
@@ -635,6 +651,7 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
       if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = q.m30; D3[1] = q.m31; D3[2] = q.m32; D3[3] = q.m33; }
     }
     __syncthreads();
+    CP_STAMP(24);
   }
   if (prof && t == 0) { const long long t1 = clock64(); tB = t1 - t0; atomicAdd(prof + 5, (unsigned long long)tA); atomicAdd(prof + 6, (unsigned long long)tB); }
   return true;

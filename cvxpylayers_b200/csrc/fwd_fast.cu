@@ -81,7 +81,7 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 // the RTu partials of its column.  ep(j, value) runs on thread j.  One barrier inside, none at the end.
 template <class G, class Epi>
 __device__ __forceinline__ void rt_cols(const double (&ar)[TR][TCR], const double2 *ps, const G &g, bool act, int R, int C, const double *y,
-                                        double *XC, int n, Epi ep) {
+                                        double *XC, int n, Epi ep, int t = threadIdx.x) {
   if (act) {
     const double2 y01 = *reinterpret_cast<const double2 *>(y + TR * R), y23 = *reinterpret_cast<const double2 *>(y + TR * R + 2);
     double2 *dst = reinterpret_cast<double2 *>(XC + R * g.npad() + TC * C);
@@ -98,7 +98,6 @@ __device__ __forceinline__ void rt_cols(const double (&ar)[TR][TCR], const doubl
     }
   }
   __syncthreads();
-  const int t = threadIdx.x;
   if (t < n) {
     const double *p = XC + t;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -114,7 +113,7 @@ __device__ __forceinline__ void rt_cols(const double (&ar)[TR][TCR], const doubl
 // out_i = sum_j A_ij x_j.  ep(i, value) runs on thread i < m.  One barrier inside, none at the end.
 template <class G, class Epi>
 __device__ __forceinline__ void rt_rows(const double (&ar)[TR][TCR], const double2 *ps, const G &g, bool act, int R, int C, const double *x,
-                                        double *XR, int m, Epi ep) {
+                                        double *XR, int m, Epi ep, int t = threadIdx.x) {
   if (act) {
     double s[TR];
     {
@@ -132,7 +131,6 @@ __device__ __forceinline__ void rt_rows(const double (&ar)[TR][TCR], const doubl
     for (int r = 0; r < TR; r++) XR[(TR * R + r) * g.CT() + C] = s[r];
   }
   __syncthreads();
-  const int t = threadIdx.x;
   if (t < m) {
     const double *p = XR + t * g.CT();
     double s0 = 0, s1 = 0;
@@ -146,8 +144,7 @@ __device__ __forceinline__ void rt_rows(const double (&ar)[TR][TCR], const doubl
 // out_i = sum_j Kinv_ij x_j for the symmetric inverse stored with row stride npad (KR x 10 tiles read from
 // shared memory).  ep(i, value) runs on thread i < n.  One barrier inside, none at the end.
 template <int KR, class G, class Epi>
-__device__ __forceinline__ void kinv_rows(const double *Kinv, const G &g, int n, int R, int C, const double *x, double *XR, Epi ep) {
-  const int t = threadIdx.x;
+__device__ __forceinline__ void kinv_rows(const double *Kinv, const G &g, int n, int R, int C, const double *x, double *XR, Epi ep, int t) {
   if (KR * R < n) {
     double s[KR];
 #pragma unroll
@@ -177,8 +174,8 @@ __device__ __forceinline__ void kinv_rows(const double *Kinv, const G &g, int n,
   }
 }
 template <class G, class Epi>
-__device__ __forceinline__ void kinv_mul(const double *Kinv, const G &g, int n, int R, int C, const double *x, double *XR, Epi ep) {
-  if (g.KR() == 2) kinv_rows<2>(Kinv, g, n, R, C, x, XR, ep); else kinv_rows<4>(Kinv, g, n, R, C, x, XR, ep);
+__device__ __forceinline__ void kinv_mul(const double *Kinv, const G &g, int n, int R, int C, const double *x, double *XR, Epi ep, int t = threadIdx.x) {
+  if (g.KR() == 2) kinv_rows<2>(Kinv, g, n, R, C, x, XR, ep, t); else kinv_rows<4>(Kinv, g, n, R, C, x, XR, ep, t);
 }
 
 // Sum of four per-thread values over the block when only the first `nwc` warps hold non-zero terms.
@@ -497,7 +494,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
       block_reduce<2, true>(v4, red);
       if (t == 0) {
         sc[SC_NB0] = v4[0]; sc[SC_NC0] = v4[1];
-        sc[SC_SUMLOG] = 0; sc[SC_PREVLR] = 0; sc[SC_NLOG] = 0; sc[SC_LASTUP] = 0; sc[SC_PREVIT] = 0;
+        sc[SC_SUMLOG] = 0; sc[SC_PREVLR] = 0; sc[SC_NLOG] = 0; sc[SC_LASTUP] = 0; sc[SC_PREVIT] = 0; sc[SC_NEXT] = 0;
         sc[SC_RP] = nan(""); sc[SC_RD] = nan(""); sc[SC_GAP] = nan(""); sc[SC_UTAU] = 0; sc[SC_STATUS] = BCONE_INACCURATE;
       }
     }
@@ -618,7 +615,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     pt_stamp(1);
 
     double scale = st.scale, w_tau = 1.0;
-    int it = 0, next_check = st.check_interval < 10 ? st.check_interval : 10;
+    int it = 0, next_check = st.adaptive_check ? (st.check_interval < 10 ? st.check_interval : 10) : st.check_interval;
     if (t < n) { vx(VX_W)[t] = 0; vx(VX_U)[t] = 0; vx(VX_UT)[t] = 0; }
     if (t < m) { vy(VY_W)[t] = 0; vy(VY_U)[t] = 0; vy(VY_UT)[t] = 0; }
     bool refactor = true, first = true;
@@ -651,7 +648,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         __syncthreads();
         form_K(X, m, n, z, scale, st.rho_x, Li, Pg != nullptr, vx(VX_EN));
         SUB_STAMP(pf, 19);
-        const bool okf = chol_cold(Li, n, red);
+        const bool okf = chol_cold(Li, n, vx(VX_TN3));   // scratch: n reciprocal pivots
         if (!okf) { if (t == 0) sc[SC_STATUS] = BCONE_FAILED; if (first) it = 0; break; }
         SUB_STAMP(pf, 21);
         // the tiles come back from the staged copy: nothing has to stay live across the factorisation
@@ -690,24 +687,31 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         pt_stamp(2);
         refactor = false; first = false;
       }
+      SUB_SKIP(pi);
+      // thread-dependent addresses are re-derived every iteration instead of being kept (and spilled) as loop invariants
+      int Ri = R, Ci = C, ti = t;
+      asm volatile("" : "+r"(Ri), "+r"(Ci), "+r"(ti));
+      const double2 *psi = reinterpret_cast<const double2 *>(X + g.oPS()) + ti;
+      rt_cols(ar, psi, g, act, Ri, Ci, vy(VY_W), XC, n, [&](int j, double v) { vx(VX_TN)[j] = st.rho_x * vx(VX_W)[j] - v; }, ti);
+      __syncthreads();
+      SUB_STAMP(pi, 23);
+      // (p_x, p_y go through shared memory and the dot products are taken after the last product: nothing but the
+      //  tiles is live across the three products)
+      kinv_mul(Kinv, g, n, Ri, Ci, vx(VX_TN), XR, [&](int j, double v) { vx(VX_UT)[j] = v; }, ti);
+      __syncthreads();
+      SUB_STAMP(pi, 24);
       double d4[4] = {0, 0, 0, 0};   // mu'g, p'Rg, p'Rp, p'mu (R-weighted)
       auto dots = [&](double r, double pk, double wk, double gk) {
         d4[0] = fma(r * wk, gk, d4[0]); d4[1] = fma(r * pk, gk, d4[1]);
         d4[2] = fma(r * pk, pk, d4[2]); d4[3] = fma(r * pk, wk, d4[3]);
       };
-      SUB_SKIP(pi);
-      rt_cols(ar, ps, g, act, R, C, vy(VY_W), XC, n, [&](int j, double v) { vx(VX_TN)[j] = st.rho_x * vx(VX_W)[j] - v; });
-      __syncthreads();
-      SUB_STAMP(pi, 23);
-      double px = 0, py = 0;
-      kinv_mul(Kinv, g, n, R, C, vx(VX_TN), XR, [&](int j, double v) { px = v; vx(VX_UT)[j] = v; dots(st.rho_x, v, vx(VX_W)[j], vx(VX_G)[j]); });
-      __syncthreads();
-      SUB_STAMP(pi, 24);
-      rt_rows(ar, ps, g, act, R, C, vx(VX_UT), XR, m, [&](int i, double v) {
+      rt_rows(ar, psi, g, act, Ri, Ci, vx(VX_UT), XR, m, [&](int i, double v) {
         const bool zr = i < z;
         const double iry = zr ? BC_ZERO_CONE_FACTOR * scale : scale, wk = vy(VY_W)[i];
-        py = wk + v * iry;
-        dots(sc[zr ? SC_RYZ : SC_RYL], py, wk, vy(VY_G)[i]); });
+        const double py = wk + v * iry;
+        vy(VY_UT)[i] = py;
+        dots(sc[zr ? SC_RYZ : SC_RYL], py, wk, vy(VY_G)[i]); }, ti);
+      if (ti < n) dots(st.rho_x, vx(VX_UT)[ti], vx(VX_W)[ti], vx(VX_G)[ti]);
       SUB_STAMP(pi, 26);
       reduce4_lead(d4, red, nwc);
       SUB_STAMP(pi, 27);
@@ -715,19 +719,19 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
       double disc = qb * qb - 4.0 * qa * qc;
       if (disc < 0) disc = 0;
       const double tau_t = (-qb + sqrt(disc)) / (2.0 * qa);
-      const bool check = st.adaptive_check ? (it >= next_check || it == st.max_iters) : ((it % st.check_interval == 0) || it == st.max_iters);
+      const bool check = it >= next_check || it == st.max_iters;
       // cone step + relaxation (the relaxation is fused here unless a check needs the plain iterate)
-      if (t < n) {
-        const double utk = px - tau_t * vx(VX_G)[t], wk = vx(VX_W)[t], uk = 2.0 * utk - wk;
-        vx(VX_UT)[t] = utk; vx(VX_U)[t] = uk;
-        if (!check) vx(VX_W)[t] = wk + st.alpha * (uk - utk);
+      if (ti < n) {
+        const double utk = vx(VX_UT)[ti] - tau_t * vx(VX_G)[ti], wk = vx(VX_W)[ti], uk = 2.0 * utk - wk;
+        vx(VX_UT)[ti] = utk; vx(VX_U)[ti] = uk;
+        if (!check) vx(VX_W)[ti] = wk + st.alpha * (uk - utk);
       }
-      if (t < m) {
-        const double utk = py - tau_t * vy(VY_G)[t], wk = vy(VY_W)[t];
+      if (ti < m) {
+        const double utk = vy(VY_UT)[ti] - tau_t * vy(VY_G)[ti], wk = vy(VY_W)[ti];
         double uk = 2.0 * utk - wk;
-        if (t >= z && t < z + S.l) uk = fmax(uk, 0.0);
-        vy(VY_UT)[t] = utk; vy(VY_U)[t] = uk;
-        if (!check) vy(VY_W)[t] = wk + st.alpha * (uk - utk);
+        if (ti >= z && ti < z + S.l) uk = fmax(uk, 0.0);
+        vy(VY_UT)[ti] = utk; vy(VY_U)[ti] = uk;
+        if (!check) vy(VY_W)[ti] = wk + st.alpha * (uk - utk);
       }
       const double u_tau = fmax(2.0 * tau_t - w_tau, 0.0);
       if (!check) w_tau += st.alpha * (u_tau - tau_t);
@@ -740,7 +744,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         rt_cols(ar, ps, g, act, R, C, vy(VY_U), XC, n, [&](int j, double v) { vx(VX_TN)[j] = v; });
         __syncthreads();
         check_tail(a, vx(0), vy(0), red, XC, Pg ? Li : nullptr, g.npad(), g.mpad(), it, scale, u_tau);
-        next_check = (int)sc[SC_NEXT];
+        next_check = st.adaptive_check ? (int)sc[SC_NEXT] : it + st.check_interval;
         const bool done = sc[SC_DONE] != 0.0;
         const double ns = sc[SC_NEWSCALE];
         pt_stamp(4);

@@ -114,3 +114,70 @@ def test_large_sparse_qp_indirect_forward_and_l2_backward(cuda_device):
     rA, rP, rb, rc, rits = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, xo, yo, so, dx, dy, bt.P_vals, lsqr_iter_lim=lim, lsqr_precond=1)
     rel = lambda a, b_: np.abs(a.cpu().numpy() - b_).max() / max(np.abs(b_).max(), 1e-30)  # noqa: E731
     assert rel(db, rb) < 1e-4 and rel(dc, rc) < 1e-4 and rel(dA, rA) < 1e-4 and rel(dP, rP) < 1e-4, (rel(dA, rA), rel(db, rb), rel(dc, rc), its, rits)
+
+
+# ----------------------------------------------------------------------------- register-tiled forward (fwd_fast.cu)
+def _two_engines(st, dev, monkeypatch):
+    monkeypatch.delenv("BCONE_NO_FAST_FWD", raising=False)
+    fast = Engine(st, dev)
+    monkeypatch.setenv("BCONE_NO_FAST_FWD", "1")
+    generic = Engine(st, dev)
+    monkeypatch.delenv("BCONE_NO_FAST_FWD", raising=False)
+    return fast, generic
+
+
+@pytest.mark.parametrize("shape", [(100, 200, 50, True), (80, 200, 30, True), (75, 190, 20, True), (90, 170, 0, False)])
+@pytest.mark.parametrize("eps", [1e-4, 1e-9])
+def test_tiled_forward_equals_generic_forward(shape, eps, cuda_device, monkeypatch):
+    """The register-tiled kernel is the same algorithm as fwd.cu: identical iteration counts and solutions that
+    differ only by summation order, on the compile-time geometry (100 x 200), on runtime geometries with column /
+    row padding (80 x 200, 75 x 190) and on an LP without a quadratic term; both against the oracle's certificate."""
+    n, m, z, with_P = shape
+    bt = pr.dense_qp(B=12, n=n, m=m, z=z, seed=11, with_P=with_P)
+    st, dev = bt.structure, cuda_device
+    fast, generic = _two_engines(st, dev, monkeypatch)
+    assert fast.kernel_info()["fwd_smem"] != generic.kernel_info()["fwd_smem"]   # two different kernels were picked
+    args = make_settings({"eps": eps, "max_iters": 50000, "adaptive_check": 1})
+    A, b, c, P = _t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev), _t(bt.P_vals, dev)
+    s1, s2 = fast.solve(A, b, c, P, args), generic.solve(A, b, c, P, args)
+    torch.cuda.synchronize()
+    assert (s1.status == s2.status).all(), (s1.status, s2.status)
+    # same checks at the same iterations; at the tight tolerance a residual that sits within rounding of its
+    # threshold may cross it one check later in one of the two summation orders
+    di = (s1.iters - s2.iters).abs()
+    assert int(di.max()) <= (0 if eps > 1e-6 else 25) and int((di > 0).sum()) <= bt.B // 4, (s1.iters, s2.iters)
+    solved = (s1.status.cpu().numpy() == 1)
+    assert solved.all() or not with_P   # (plain operator splitting may need more than 50000 iterations on an LP)
+    scale = max(1.0, float(s2.x.abs().max()))
+    tol = max(1e-7, 20 * eps)
+    assert float((s1.x - s2.x).abs().max()) <= tol * scale
+    assert float((s1.y - s2.y).abs().max()) <= 10 * tol * max(1.0, float(s2.y.abs().max()))
+    assert float((s1.s - s2.s).abs().max()) <= tol * max(1.0, float(s2.s.abs().max()))
+    x, y, s = s1.x.cpu().numpy(), s1.y.cpu().numpy(), s1.s.cpu().numpy()
+    for i in np.nonzero(solved)[0]:
+        Pd = bt.P_dense(i) if bt.P_vals is not None else None
+        r = np_ref.kkt_residuals(bt.A_dense(i), Pd, bt.b[i], bt.c[i], x[i], y[i], s[i])
+        assert np_ref.is_converged(r, eps, eps, 1.001), (i, r)
+
+
+def test_tiled_forward_certificates(cuda_device):
+    """Infeasible and unbounded instances inside one batch of the tiled kernel are reported per instance
+    (reference behaviour: tests/test_torch.py:299-316 raises on them) and agree with the oracle."""
+    n, m = 100, 200
+    bt = pr.dense_qp(B=6, n=n, m=m, z=0, seed=4, with_P=True)
+    A, b, c, P = bt.A_vals.copy(), bt.b.copy(), bt.c.copy(), bt.P_vals.copy()
+    Ad = A.reshape(6, m, n)
+    # instance 1: rows 0 / 1 state x_0 <= -1 and -x_0 <= -1 (infeasible)
+    Ad[1, 0, :] = 0; Ad[1, 0, 0] = 1.0; b[1, 0] = -1.0
+    Ad[1, 1, :] = 0; Ad[1, 1, 0] = -1.0; b[1, 1] = -1.0
+    # instance 4: linear objective, no constraint touches x_0 and c pushes it to -infinity (unbounded)
+    P[4, :] = 0.0; Ad[4, :, 0] = 0.0; c[4, :] = 0.0; c[4, 0] = 1.0
+    eng = Engine(bt.structure, cuda_device)
+    assert eng.kernel_info()["fwd_threads"] == 512
+    dev = cuda_device
+    sol = eng.solve(_t(Ad.reshape(6, -1), dev), _t(b, dev), _t(c, dev), _t(P, dev), make_settings({"eps": 1e-6, "max_iters": 50000}))
+    st_ = sol.status.cpu().numpy()
+    assert st_[1] == -2 and st_[4] == -1, st_
+    assert (st_[[0, 2, 3, 5]] == 1).all(), st_
+    xo, yo, so, sto, _ = orc.solve_batch(bt.structure, Ad.reshape(6, -1), b, c, P, eps=1e-6, max_iters=50000)
+    assert (sto == st_).all(), (sto, st_)

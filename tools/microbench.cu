@@ -2,9 +2,10 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
 #include <cstdio>
 #include <vector>
+#define BC_CHOLPROF 1
 #include "../cvxpylayers_b200/csrc/common.cuh"
 
-constexpr int NT = 16;
+constexpr int NT = 32;
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
@@ -283,6 +284,44 @@ __global__ void __launch_bounds__(512, 1) mb_kernel(Args a) {
     });
     if (t == 0) a.out[2001] = Kout[(57 * 58 >> 1) + 13];
   }
+  // 25: DMMA latency: one dependent chain of 64 per rep (all warps), 26: the same on warp 0 only; 27: DFMA dependent chain of 64
+  {
+    double c0 = x[t % n], c1 = 0;
+    const double fa = 1e-3 * y[t % m], fb = x[t % n];
+    timed(a.cyc, 25, reps, [&](int) {
+#pragma unroll
+      for (int q = 0; q < 64; q++) dmma(c0, c1, fa, fb);
+    });
+    timed(a.cyc, 26, reps, [&](int) {
+      if (t < 32) {
+#pragma unroll
+        for (int q = 0; q < 64; q++) dmma(c0, c1, fa, fb);
+      }
+    });
+    double f0 = c0;
+    timed(a.cyc, 27, reps, [&](int) {
+      if (t < 32) {
+#pragma unroll
+        for (int q = 0; q < 64; q++) f0 = fma(f0, fa, fb);
+      }
+    });
+    if (c0 + c1 + f0 == 1.2345) a.out[t] = c0;
+  }
+  // 15 (+ sub-phases 16..24): packed Cholesky + inverse of a 100 x 100 SPD matrix
+  {
+    for (int e = t; e < n * (n + 1) / 2; e += T) {
+      int j = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while ((j + 1) * (j + 2) / 2 <= e) j++;
+      while (j * (j + 1) / 2 > e) j--;
+      const int k = e - j * (j + 1) / 2;
+      Li[e] = (j == k) ? 3.0 + 0.01 * j : 0.5 * sin(0.37 * j + 0.11 * k) / (1.0 + abs(j - k));
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    const bool ok = chol_inv_packed(Li, n, part, a.cyc);
+    __syncthreads();
+    if (t == 0) { atomicAdd(a.cyc + 15, (unsigned long long)(clock64() - t0)); a.out[2002] = ok ? Li[(57 * 58 >> 1) + 13] : -1.0; }
+  }
   if (t < n) a.out[512 + t] = o2[t];
   if (t < m) a.out[1024 + t] = o1[t];
 }
@@ -308,6 +347,11 @@ int main() {
                            "block_reduce<4>", "regtile rows", "regtile cols (100x50)", "regtile cols (quad)", "ruiz A sweep", "DMMA x128/thread", "K formation DMMA (x20)", "K formation 2x2 (x20)", ""};
   printf("smem %zu B\n", smem);
   for (int k = 0; k < 15; k++) printf("%-26s %10.1f cycles/call\n", names[k], (double)h[k] / grid / (k >= 13 ? 20 : reps));
+  const char *cn[10] = {"chol+inv total", "  F tri4 (factor)", "  F panel", "  F barrier 1", "  F trailing (DMMA)", "  F barrier 2", "  I tri4 (inverse)", "  I dot loop + shuffles",
+                        "  I barrier 1", "  I write + barrier 2"};
+  for (int k = 15; k < 25; k++) printf("%-26s %10.1f cycles/call\n", cn[k - 15], (double)h[k] / grid);
+  printf("DMMA chain x64 (16 warps) %.1f, (1 warp) %.1f, DFMA chain x64 (1 warp) %.1f cycles/call\n", (double)h[25] / grid / reps, (double)h[26] / grid / reps, (double)h[27] / grid / reps);
+  printf("chol check Linv[57][13]=%.12g  factor %.1f inverse %.1f\n", ho[2002], (double)h[5] / grid, (double)h[6] / grid);
   printf("check o2[3]=%g o1[5]=%g  K[57][13] dmma=%.12g 2x2=%.12g\n", ho[512 + 3], ho[1024 + 5], ho[2000], ho[2001]);
   return 0;
 }
