@@ -500,18 +500,22 @@ __device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, cons
 }
 
 // ----------------------------------------------------------------------------- packed Cholesky + inverse
-// In-place Cholesky K = L L' of a packed-lower SPD matrix (row i at i(i+1)/2) followed by the
-// in-place inverse X = L^{-1}: the factor is applied afterwards as two triangular products, which keeps
-// every solve free of sequential substitution.  Both sweeps advance FOUR columns / rows per step:
-// the 4x4 diagonal block is factored and inverted redundantly by every thread in registers (rsqrt +
-// multiplies, no divisions, no single-warp section), so a step is: panel (one row per thread) | barrier |
-// rank-4 trailing update (warp per row) | barrier.  n/4 steps instead of n, measured 3-4x faster than
-// the column-at-a-time version (profiles/README.md).  tmp is unused scratch kept for the callers'
-// signature.  Block-uniform result (false: not positive definite).
+// In-place Cholesky K = L L' of a packed-lower SPD matrix (row i at i(i+1)/2) followed by the in-place
+// inverse X = L^{-1}: the factor is applied afterwards as triangular / dense products, which keeps every
+// solve free of sequential substitution.  Both sweeps advance FOUR columns / rows per step and are
+// instruction-issue bound with 16 warps (tools/microbench.cu), so the design minimises warp-instructions:
+//   * factor step = panel (one row per thread) | barrier | rank-4 trailing update on the tensor cores (one
+//     DMMA per 8 x 8 tile, k = 4 is exactly the block width) | barrier;
+//   * the 4 x 4 diagonal block (Cholesky + inverse: 4 dependent rsqrt) is done by WARP 0 ONLY, one step ahead:
+//     it owns the trailing tile that contains the next diagonal block, factors it right after updating it and
+//     publishes the inverse through `tmp`, while the other warps finish the trailing update;
+//   * the inverse sweep reuses those 4 x 4 inverses (no divisions, no second factorisation pass).
+// tmp: scratch of chol_scratch_doubles(n) doubles.  Block-uniform result (false: not positive definite).
+__host__ __device__ __forceinline__ int chol_scratch_doubles(int n) { return 10 * ((n + 3) >> 2) + 2; }
 struct Tri4 { double l00, l10, l11, l20, l21, l22, l30, l31, l32, l33, m00, m10, m11, m20, m21, m22, m30, m31, m32, m33; bool pd; };
-// Cholesky factor (l) and its inverse (m) of the jb x jb (jb <= 4) diagonal block at (r0, r0); when
-// `factored` the block already holds L.  Missing rows / columns are padded with the identity.
-__device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool factored, const double *isd = nullptr) {
+// Cholesky factor (l) and its inverse (m) of the jb x jb (jb <= 4) diagonal block at (r0, r0).
+// Missing rows / columns are padded with the identity.
+__device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb) {
   Tri4 q;
   const double *R0 = K + ((r0 * (r0 + 1)) >> 1) + r0;
   const double *R1 = K + (((r0 + 1) * (r0 + 2)) >> 1) + r0, *R2 = K + (((r0 + 2) * (r0 + 3)) >> 1) + r0, *R3 = K + (((r0 + 3) * (r0 + 4)) >> 1) + r0;
@@ -519,22 +523,15 @@ __device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool
   const double d10 = jb > 1 ? R1[0] : 0.0, d11 = jb > 1 ? R1[1] : 1.0;
   const double d20 = jb > 2 ? R2[0] : 0.0, d21 = jb > 2 ? R2[1] : 0.0, d22 = jb > 2 ? R2[2] : 1.0;
   const double d30 = jb > 3 ? R3[0] : 0.0, d31 = jb > 3 ? R3[1] : 0.0, d32 = jb > 3 ? R3[2] : 0.0, d33 = jb > 3 ? R3[3] : 1.0;
-  double r0_, r1_, r2_, r3_;
-  if (factored) {
-    q.l00 = d00; q.l10 = d10; q.l11 = d11; q.l20 = d20; q.l21 = d21; q.l22 = d22; q.l30 = d30; q.l31 = d31; q.l32 = d32; q.l33 = d33;
-    // reciprocal diagonal: kept by the factorisation sweep (isd[k] = 1 / L_kk), no divisions here
-    r0_ = isd[0]; r1_ = jb > 1 ? isd[1] : 1.0; r2_ = jb > 2 ? isd[2] : 1.0; r3_ = jb > 3 ? isd[3] : 1.0; q.pd = true;
-  } else {
-    const double p0 = d00; r0_ = rsqrt(p0);
-    q.l00 = p0 * r0_; q.l10 = d10 * r0_; q.l20 = d20 * r0_; q.l30 = d30 * r0_;
-    const double p1 = fma(-q.l10, q.l10, d11); r1_ = rsqrt(p1);
-    q.l11 = p1 * r1_; q.l21 = fma(-q.l20, q.l10, d21) * r1_; q.l31 = fma(-q.l30, q.l10, d31) * r1_;
-    const double p2 = fma(-q.l21, q.l21, fma(-q.l20, q.l20, d22)); r2_ = rsqrt(p2);
-    q.l22 = p2 * r2_; q.l32 = fma(-q.l31, q.l21, fma(-q.l30, q.l20, d32)) * r2_;
-    const double p3 = fma(-q.l32, q.l32, fma(-q.l31, q.l31, fma(-q.l30, q.l30, d33))); r3_ = rsqrt(p3);
-    q.l33 = p3 * r3_;
-    q.pd = (p0 > 0) && (p1 > 0) && (p2 > 0) && (p3 > 0);
-  }
+  const double p0 = d00, r0_ = rsqrt(p0);
+  q.l00 = p0 * r0_; q.l10 = d10 * r0_; q.l20 = d20 * r0_; q.l30 = d30 * r0_;
+  const double p1 = fma(-q.l10, q.l10, d11), r1_ = rsqrt(p1);
+  q.l11 = p1 * r1_; q.l21 = fma(-q.l20, q.l10, d21) * r1_; q.l31 = fma(-q.l30, q.l10, d31) * r1_;
+  const double p2 = fma(-q.l21, q.l21, fma(-q.l20, q.l20, d22)), r2_ = rsqrt(p2);
+  q.l22 = p2 * r2_; q.l32 = fma(-q.l31, q.l21, fma(-q.l30, q.l20, d32)) * r2_;
+  const double p3 = fma(-q.l32, q.l32, fma(-q.l31, q.l31, fma(-q.l30, q.l30, d33))), r3_ = rsqrt(p3);
+  q.l33 = p3 * r3_;
+  q.pd = (p0 > 0) && (p1 > 0) && (p2 > 0) && (p3 > 0);
   q.m00 = r0_; q.m11 = r1_; q.m22 = r2_; q.m33 = r3_;
   q.m10 = -q.l10 * q.m00 * r1_;
   q.m20 = -fma(q.l21, q.m10, q.l20 * q.m00) * r2_; q.m21 = -q.l21 * q.m11 * r2_;
@@ -549,56 +546,91 @@ __device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb, bool
 #endif
 __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned long long *prof = nullptr) {
   const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
+  const int nblk = (n + 3) >> 2;
+  double *isd = tmp, *moff = tmp + 4 * nblk, *flag = tmp + 10 * nblk;   // 1 / L_kk | off-diagonal inverse entries per block | pd flag
   long long tA = 0, tB = 0, t0 = 0;
   if (prof && t == 0) t0 = clock64();
 #ifdef BC_CHOLPROF
   long long tt = t0;
 #endif
+  // Diagonal block at J0 (warp 0, every lane computes, lane 0 publishes): L_D in place, its inverse in tmp.
+  auto diag_block = [&](int J0) {
+    const int jb = min(4, n - J0);
+    const Tri4 q = tri4_block(K, J0, jb);
+    __syncwarp();   // every lane has read the block
+    if (lane == 0) {
+      double *D0 = K + ((J0 * (J0 + 1)) >> 1) + J0;
+      D0[0] = q.l00;
+      if (jb > 1) { double *D1 = K + (((J0 + 1) * (J0 + 2)) >> 1) + J0; D1[0] = q.l10; D1[1] = q.l11; }
+      if (jb > 2) { double *D2 = K + (((J0 + 2) * (J0 + 3)) >> 1) + J0; D2[0] = q.l20; D2[1] = q.l21; D2[2] = q.l22; }
+      if (jb > 3) { double *D3 = K + (((J0 + 3) * (J0 + 4)) >> 1) + J0; D3[0] = q.l30; D3[1] = q.l31; D3[2] = q.l32; D3[3] = q.l33; }
+      isd[J0] = q.m00; isd[J0 + 1] = q.m11; isd[J0 + 2] = q.m22; isd[J0 + 3] = q.m33;
+      double *mo = moff + 6 * (J0 >> 2);
+      mo[0] = q.m10; mo[1] = q.m20; mo[2] = q.m21; mo[3] = q.m30; mo[4] = q.m31; mo[5] = q.m32;
+      if (!q.pd) *flag = 0.0;
+    }
+  };
+  // One 8 x 8 tile (ta, tb), tb <= ta, of the trailing update K[i][j] -= sum_c L[i][J0+c] L[j][J0+c], i, j >= R0.
+  auto trail_tile = [&](int ta, int tb, int J0, int jb, int R0) {
+    const int fr = lane >> 2, fc = lane & 3;
+    const int ra = R0 + 8 * ta + fr, rb = R0 + 8 * tb + fr;
+    const double fa = (ra < n && fc < jb) ? -K[((ra * (ra + 1)) >> 1) + J0 + fc] : 0.0;
+    const double fb = (rb < n && fc < jb) ? K[((rb * (rb + 1)) >> 1) + J0 + fc] : 0.0;
+    const int cc = R0 + 8 * tb + 2 * fc;
+    double *pc = K + ((ra * (ra + 1)) >> 1) + cc;   // C entries (ra, cc), (ra, cc + 1)
+    const bool ok0 = ra < n && cc <= ra, ok1 = ra < n && cc + 1 <= ra;
+    double c0 = ok0 ? pc[0] : 0.0, c1 = ok1 ? pc[1] : 0.0;
+    dmma884(c0, c1, fa, fb);
+    if (ok0) pc[0] = c0;
+    if (ok1) pc[1] = c1;
+  };
+  if (warp == 0) {
+    if (lane == 0) *flag = 1.0;
+    __syncwarp();
+    diag_block(0);
+  }
+  __syncthreads();
   // ---------------- Cholesky, four columns per step ----------------
   for (int J0 = 0; J0 < n; J0 += 4) {
     const int jb = min(4, n - J0), R0 = J0 + jb;
-    const Tri4 q = tri4_block(K, J0, jb, false);
-    if (!q.pd) return false;   // block-uniform: every thread factors the same block
+    if (*flag == 0.0) return false;   // block-uniform: written before the last barrier
     CP_STAMP(16);
     // panel: row i >= R0, l_i = a_i L_D^{-T}; one row per thread, in place
-    for (int i = R0 + t; i < n; i += T) {
-      double *row = K + ((i * (i + 1)) >> 1) + J0;
-      const double a0 = row[0], a1 = jb > 1 ? row[1] : 0.0, a2 = jb > 2 ? row[2] : 0.0, a3 = jb > 3 ? row[3] : 0.0;
-      row[0] = a0 * q.m00;
-      if (jb > 1) row[1] = fma(a1, q.m11, a0 * q.m10);
-      if (jb > 2) row[2] = fma(a2, q.m22, fma(a1, q.m21, a0 * q.m20));
-      if (jb > 3) row[3] = fma(a3, q.m33, fma(a2, q.m32, fma(a1, q.m31, a0 * q.m30)));
+    if (R0 + t < n) {
+      const double *mo = moff + 6 * (J0 >> 2);
+      const double m00 = isd[J0], m11 = isd[J0 + 1], m22 = isd[J0 + 2], m33 = isd[J0 + 3];
+      const double m10 = mo[0], m20 = mo[1], m21 = mo[2], m30 = mo[3], m31 = mo[4], m32 = mo[5];
+      for (int i = R0 + t; i < n; i += T) {
+        double *row = K + ((i * (i + 1)) >> 1) + J0;
+        const double a0 = row[0], a1 = jb > 1 ? row[1] : 0.0, a2 = jb > 2 ? row[2] : 0.0, a3 = jb > 3 ? row[3] : 0.0;
+        row[0] = a0 * m00;
+        if (jb > 1) row[1] = fma(a1, m11, a0 * m10);
+        if (jb > 2) row[2] = fma(a2, m22, fma(a1, m21, a0 * m20));
+        if (jb > 3) row[3] = fma(a3, m33, fma(a2, m32, fma(a1, m31, a0 * m30)));
+      }
     }
     CP_STAMP(17);
     __syncthreads();
     CP_STAMP(18);
-    if (t == 0) {   // the diagonal block itself (nobody reads it during the trailing update)
-      double *D0 = K + ((J0 * (J0 + 1)) >> 1) + J0;
-      D0[0] = q.l00; tmp[J0] = q.m00;
-      if (jb > 1) { double *D1 = K + (((J0 + 1) * (J0 + 2)) >> 1) + J0; D1[0] = q.l10; D1[1] = q.l11; tmp[J0 + 1] = q.m11; }
-      if (jb > 2) { double *D2 = K + (((J0 + 2) * (J0 + 3)) >> 1) + J0; D2[0] = q.l20; D2[1] = q.l21; D2[2] = q.l22; tmp[J0 + 2] = q.m22; }
-      if (jb > 3) { double *D3 = K + (((J0 + 3) * (J0 + 4)) >> 1) + J0; D3[0] = q.l30; D3[1] = q.l31; D3[2] = q.l32; D3[3] = q.l33; tmp[J0 + 3] = q.m33; }
-    }
-    // rank-4 trailing update K[i][j] -= sum_c L[i][J0+c] L[j][J0+c] on the tensor cores: one DMMA (k = 4 is exactly
-    // the block width) per 8 x 8 tile of the trailing lower triangle, tiles dealt round-robin to the warps.
+    // rank-4 trailing update on the tensor cores; warp 0 takes the tile holding the next diagonal block and
+    // factors that block as soon as it is up to date, the other warps share the remaining tiles
     if (R0 < n) {
       const int ntl = (n - R0 + 7) >> 3, ntile = (ntl * (ntl + 1)) >> 1;
-      const int fr = lane >> 2, fc = lane & 3;
-      for (int e = warp; e < ntile; e += nw) {
-        int ta = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-        while (((ta + 1) * (ta + 2)) >> 1 <= e) ta++;
-        while ((ta * (ta + 1)) >> 1 > e) ta--;
-        const int tb = e - ((ta * (ta + 1)) >> 1);
-        const int ra = R0 + 8 * ta + fr, rb = R0 + 8 * tb + fr;
-        const double fa = (ra < n && fc < jb) ? -K[((ra * (ra + 1)) >> 1) + J0 + fc] : 0.0;
-        const double fb = (rb < n && fc < jb) ? K[((rb * (rb + 1)) >> 1) + J0 + fc] : 0.0;
-        double *pc = K + ((ra * (ra + 1)) >> 1) + R0 + 8 * tb + 2 * fc;   // C entries (ra, cc), (ra, cc + 1)
-        const int cc = R0 + 8 * tb + 2 * fc;
-        const bool ok0 = ra < n && cc <= ra, ok1 = ra < n && cc + 1 <= ra;
-        double c0 = ok0 ? pc[0] : 0.0, c1 = ok1 ? pc[1] : 0.0;
-        dmma884(c0, c1, fa, fb);
-        if (ok0) pc[0] = c0;
-        if (ok1) pc[1] = c1;
+      if (warp == 0) {
+        trail_tile(0, 0, J0, jb, R0);
+        if (nw == 1) {
+          for (int e = 1, ta = 1, tb = 0; e < ntile; e++) { trail_tile(ta, tb, J0, jb, R0); if (++tb > ta) { tb = 0; ta++; } }
+        }
+        __syncwarp();
+        diag_block(R0);
+      } else {
+        int ta = 0, tb = warp;                       // tile e = warp, then e += nw - 1 (tile 0 belongs to warp 0)
+        while (tb > ta) { tb -= ta + 1; ta++; }
+        for (int e = warp; e < ntile; e += nw - 1) {
+          trail_tile(ta, tb, J0, jb, R0);
+          tb += nw - 1;
+          while (tb > ta) { tb -= ta + 1; ta++; }
+        }
       }
     }
     CP_STAMP(19);
@@ -607,11 +639,13 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
   }
   if (prof && t == 0) { const long long t1 = clock64(); tA = t1 - t0; t0 = t1; }
   // ---------------- X = L^{-1}, four rows per step ----------------
-  // X_II = L_II^{-1};  X_Ij = -X_II * (sum_{i=j}^{I0-1} L_Ii X_ij)  for j < I0;  four lanes per output column
+  // X_II = L_II^{-1} (kept from the factorisation);  X_Ij = -X_II * (sum_{i=j}^{I0-1} L_Ii X_ij)  for j < I0;  four lanes per output column
   const int g = t & 3, q4 = t >> 2, nq = T >> 2;
   for (int I0 = 0; I0 < n; I0 += 4) {
     const int ib = min(4, n - I0);
-    const Tri4 q = tri4_block(K, I0, ib, true, tmp + I0);
+    const double *mo = moff + 6 * (I0 >> 2);
+    const double m00 = isd[I0], m11 = isd[I0 + 1], m22 = isd[I0 + 2], m33 = isd[I0 + 3];
+    const double m10 = mo[0], m20 = mo[1], m21 = mo[2], m30 = mo[3], m31 = mo[4], m32 = mo[5];
     CP_STAMP(21);
     const double *L0 = K + ((I0 * (I0 + 1)) >> 1), *L1 = K + (((I0 + 1) * (I0 + 2)) >> 1), *L2 = K + (((I0 + 2) * (I0 + 3)) >> 1),
                  *L3 = K + (((I0 + 3) * (I0 + 4)) >> 1);
@@ -636,19 +670,19 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
       __syncthreads();   // every read of block row I at this group's columns is done
       CP_STAMP(23);
       if (g == 0 && j < I0) {
-        K[((I0 * (I0 + 1)) >> 1) + j] = -(q.m00 * s0);
-        if (ib > 1) K[(((I0 + 1) * (I0 + 2)) >> 1) + j] = -fma(q.m11, s1, q.m10 * s0);
-        if (ib > 2) K[(((I0 + 2) * (I0 + 3)) >> 1) + j] = -fma(q.m22, s2, fma(q.m21, s1, q.m20 * s0));
-        if (ib > 3) K[(((I0 + 3) * (I0 + 4)) >> 1) + j] = -fma(q.m33, s3, fma(q.m32, s2, fma(q.m31, s1, q.m30 * s0)));
+        K[((I0 * (I0 + 1)) >> 1) + j] = -(m00 * s0);
+        if (ib > 1) K[(((I0 + 1) * (I0 + 2)) >> 1) + j] = -fma(m11, s1, m10 * s0);
+        if (ib > 2) K[(((I0 + 2) * (I0 + 3)) >> 1) + j] = -fma(m22, s2, fma(m21, s1, m20 * s0));
+        if (ib > 3) K[(((I0 + 3) * (I0 + 4)) >> 1) + j] = -fma(m33, s3, fma(m32, s2, fma(m31, s1, m30 * s0)));
       }
       jg += nq;
     } while (jg < I0);
     if (t == 0) {
       double *D0 = K + ((I0 * (I0 + 1)) >> 1) + I0;
-      D0[0] = q.m00;
-      if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = q.m10; D1[1] = q.m11; }
-      if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = q.m20; D2[1] = q.m21; D2[2] = q.m22; }
-      if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = q.m30; D3[1] = q.m31; D3[2] = q.m32; D3[3] = q.m33; }
+      D0[0] = m00;
+      if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = m10; D1[1] = m11; }
+      if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = m20; D2[1] = m21; D2[2] = m22; }
+      if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = m30; D3[1] = m31; D3[2] = m32; D3[3] = m33; }
     }
     __syncthreads();
     CP_STAMP(24);

@@ -57,13 +57,14 @@ struct Geo {
   __host__ __device__ __forceinline__ int szPart() const { const int a = RTu() * npad(), b = rowsR() * CT(); return ((a > b ? a : b) + 1) & ~1; }
   __host__ __device__ __forceinline__ int oPS() const { return oXC() + szPart(); }
   __host__ __device__ __forceinline__ int XD() const { const int it = oPS() + TR * FT * (TC - TCR), stg = mpad() * npad(); return ((it > stg ? it : stg) + 1) & ~1; }
-  // whole block (doubles): [bar, ibuf (4) | X | Li | 9 x-vectors | 7 y-vectors | red (8 x 32) | scalars (64)]
+  // whole block (doubles): [bar, ibuf (4) | X | Li | 9 x-vectors | 7 y-vectors | red (8 x 32) | scalars (64) | Cholesky scratch]
   __host__ __device__ __forceinline__ int oX() const { return 4; }
   __host__ __device__ __forceinline__ int oLi() const { return oX() + XD(); }
   __host__ __device__ __forceinline__ int oVx() const { return oLi() + npk(); }
   __host__ __device__ __forceinline__ int oVy() const { return oVx() + 9 * npad(); }
   __host__ __device__ __forceinline__ int oRed() const { return oVy() + 7 * mpad(); }
-  __host__ __device__ __forceinline__ int total() const { return oRed() + 256 + 64; }
+  __host__ __device__ __forceinline__ int oCh() const { return oRed() + 256 + 64; }   // Cholesky scratch (4 x 4 block inverses)
+  __host__ __device__ __forceinline__ int total() const { return oCh() + ((chol_scratch_doubles(npad()) + 1) & ~1); }
   __host__ __device__ __forceinline__ bool ok(int n, int m) const {
     return n <= FT && m <= FT && CT() * RTu() <= FT && ((npad() + KR() - 1) / KR()) * CT() <= FT;
   }
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         __syncthreads();
         form_K(X, m, n, z, scale, st.rho_x, Li, Pg != nullptr, vx(VX_EN));
         SUB_STAMP(pf, 19);
-        const bool okf = chol_cold(Li, n, vx(VX_TN3));   // scratch: n reciprocal pivots
+        const bool okf = chol_cold(Li, n, sm + g.oCh());
         if (!okf) { if (t == 0) sc[SC_STATUS] = BCONE_FAILED; if (first) it = 0; break; }
         SUB_STAMP(pf, 21);
         // the tiles come back from the staged copy: nothing has to stay live across the factorisation
