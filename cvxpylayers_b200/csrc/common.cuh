@@ -512,6 +512,16 @@ __device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, cons
 //   * the inverse sweep reuses those 4 x 4 inverses (no divisions, no second factorisation pass).
 // tmp: scratch of chol_scratch_doubles(n) doubles.  Block-uniform result (false: not positive definite).
 __host__ __device__ __forceinline__ int chol_scratch_doubles(int n) { return 10 * ((n + 3) >> 2) + 2; }
+// 1 / sqrt(x) for the Cholesky pivots: hardware approximation (2^-23) + two Newton steps (full double precision up to
+// a couple of ulp); roughly half the dependent latency of the library rsqrt, and four of them are chained per block.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
 struct Tri4 { double l00, l10, l11, l20, l21, l22, l30, l31, l32, l33, m00, m10, m11, m20, m21, m22, m30, m31, m32, m33; bool pd; };
 // Cholesky factor (l) and its inverse (m) of the jb x jb (jb <= 4) diagonal block at (r0, r0).
 // Missing rows / columns are padded with the identity.
@@ -523,13 +533,13 @@ __device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb) {
   const double d10 = jb > 1 ? R1[0] : 0.0, d11 = jb > 1 ? R1[1] : 1.0;
   const double d20 = jb > 2 ? R2[0] : 0.0, d21 = jb > 2 ? R2[1] : 0.0, d22 = jb > 2 ? R2[2] : 1.0;
   const double d30 = jb > 3 ? R3[0] : 0.0, d31 = jb > 3 ? R3[1] : 0.0, d32 = jb > 3 ? R3[2] : 0.0, d33 = jb > 3 ? R3[3] : 1.0;
-  const double p0 = d00, r0_ = rsqrt(p0);
+  const double p0 = d00, r0_ = rsqrt_nr(p0);
   q.l00 = p0 * r0_; q.l10 = d10 * r0_; q.l20 = d20 * r0_; q.l30 = d30 * r0_;
-  const double p1 = fma(-q.l10, q.l10, d11), r1_ = rsqrt(p1);
+  const double p1 = fma(-q.l10, q.l10, d11), r1_ = rsqrt_nr(p1);
   q.l11 = p1 * r1_; q.l21 = fma(-q.l20, q.l10, d21) * r1_; q.l31 = fma(-q.l30, q.l10, d31) * r1_;
-  const double p2 = fma(-q.l21, q.l21, fma(-q.l20, q.l20, d22)), r2_ = rsqrt(p2);
+  const double p2 = fma(-q.l21, q.l21, fma(-q.l20, q.l20, d22)), r2_ = rsqrt_nr(p2);
   q.l22 = p2 * r2_; q.l32 = fma(-q.l31, q.l21, fma(-q.l30, q.l20, d32)) * r2_;
-  const double p3 = fma(-q.l32, q.l32, fma(-q.l31, q.l31, fma(-q.l30, q.l30, d33))), r3_ = rsqrt(p3);
+  const double p3 = fma(-q.l32, q.l32, fma(-q.l31, q.l31, fma(-q.l30, q.l30, d33))), r3_ = rsqrt_nr(p3);
   q.l33 = p3 * r3_;
   q.pd = (p0 > 0) && (p1 > 0) && (p2 > 0) && (p3 > 0);
   q.m00 = r0_; q.m11 = r1_; q.m22 = r2_; q.m33 = r3_;
@@ -639,53 +649,74 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
   }
   if (prof && t == 0) { const long long t1 = clock64(); tA = t1 - t0; t0 = t1; }
   // ---------------- X = L^{-1}, four rows per step ----------------
-  // X_II = L_II^{-1} (kept from the factorisation);  X_Ij = -X_II * (sum_{i=j}^{I0-1} L_Ii X_ij)  for j < I0;  four lanes per output column
-  const int g = t & 3, q4 = t >> 2, nq = T >> 2;
-  for (int I0 = 0; I0 < n; I0 += 4) {
-    const int ib = min(4, n - I0);
-    const double *mo = moff + 6 * (I0 >> 2);
-    const double m00 = isd[I0], m11 = isd[I0 + 1], m22 = isd[I0 + 2], m33 = isd[I0 + 3];
-    const double m10 = mo[0], m20 = mo[1], m21 = mo[2], m30 = mo[3], m31 = mo[4], m32 = mo[5];
-    CP_STAMP(21);
-    const double *L0 = K + ((I0 * (I0 + 1)) >> 1), *L1 = K + (((I0 + 1) * (I0 + 2)) >> 1), *L2 = K + (((I0 + 2) * (I0 + 3)) >> 1),
-                 *L3 = K + (((I0 + 3) * (I0 + 4)) >> 1);
-    int jg = 0;
-    do {   // groups of blockDim/4 output columns, ascending: a group only reads columns >= its own
-      const int j = jg + q4;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-      if (j < I0) {
-        for (int i = j + g; i < I0; i += 4) {
-          const double x = K[((i * (i + 1)) >> 1) + j];
-          s0 = fma(L0[i], x, s0);
-          if (ib > 1) s1 = fma(L1[i], x, s1);
-          if (ib > 2) s2 = fma(L2[i], x, s2);
-          if (ib > 3) s3 = fma(L3[i], x, s3);
-        }
+  // X_II = L_II^{-1} =: M (kept from the factorisation);  X_Ij = Z X_{<I, j} with Z = -M L_{I,<I} (4 x I0).
+  // Step: Z in place (one column per thread) | barrier | tensor-core product, one warp per 8 output columns, the k range
+  // [8 jt, I0) of the triangular X in steps of 4 on two independent accumulators | barrier | store | barrier.
+  {
+    const int fr = lane >> 2, fc = lane & 3;
+    for (int I0 = 0; I0 < n; I0 += 4) {
+      const int ib = min(4, n - I0);
+      const double *mo = moff + 6 * (I0 >> 2);
+      const double m00 = isd[I0], m11 = isd[I0 + 1], m22 = isd[I0 + 2], m33 = isd[I0 + 3];
+      const double m10 = mo[0], m20 = mo[1], m21 = mo[2], m30 = mo[3], m31 = mo[4], m32 = mo[5];
+      double *L0 = K + ((I0 * (I0 + 1)) >> 1), *L1 = K + (((I0 + 1) * (I0 + 2)) >> 1), *L2 = K + (((I0 + 2) * (I0 + 3)) >> 1),
+             *L3 = K + (((I0 + 3) * (I0 + 4)) >> 1);
+      for (int i = t; i < I0; i += T) {
+        const double a0 = L0[i], a1 = ib > 1 ? L1[i] : 0.0, a2 = ib > 2 ? L2[i] : 0.0, a3 = ib > 3 ? L3[i] : 0.0;
+        L0[i] = -(m00 * a0);
+        if (ib > 1) L1[i] = -fma(m11, a1, m10 * a0);
+        if (ib > 2) L2[i] = -fma(m22, a2, fma(m21, a1, m20 * a0));
+        if (ib > 3) L3[i] = -fma(m33, a3, fma(m32, a2, fma(m31, a1, m30 * a0)));
       }
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s3 += __shfl_xor_sync(0xffffffffu, s3, 1);
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, 2); s3 += __shfl_xor_sync(0xffffffffu, s3, 2);
+      CP_STAMP(21);
+      __syncthreads();
       CP_STAMP(22);
-      __syncthreads();   // every read of block row I at this group's columns is done
-      CP_STAMP(23);
-      if (g == 0 && j < I0) {
-        K[((I0 * (I0 + 1)) >> 1) + j] = -(m00 * s0);
-        if (ib > 1) K[(((I0 + 1) * (I0 + 2)) >> 1) + j] = -fma(m11, s1, m10 * s0);
-        if (ib > 2) K[(((I0 + 2) * (I0 + 3)) >> 1) + j] = -fma(m22, s2, fma(m21, s1, m20 * s0));
-        if (ib > 3) K[(((I0 + 3) * (I0 + 4)) >> 1) + j] = -fma(m33, s3, fma(m32, s2, fma(m31, s1, m30 * s0)));
+      const int ntj = (I0 + 7) >> 3;
+      double c0 = 0.0, c1 = 0.0;            // (one tile per warp per step: n <= 8 * warps, else the tiles are looped with a barrier each)
+      for (int jb0 = 0; jb0 < ntj; jb0 += nw) {
+        const int jt = jb0 + warp;
+        c0 = 0.0; c1 = 0.0;
+        if (jt < ntj) {
+          double d0 = 0.0, d1 = 0.0;
+          const double *zrow = K + (((I0 + fr) * (I0 + fr + 1)) >> 1);
+          const int jcol = 8 * jt + fr;
+          int k = 8 * jt;
+          for (; k + 4 < I0; k += 8) {
+            const int k0 = k + fc, k1 = k + 4 + fc;
+            const double a0 = (fr < ib && k0 < I0) ? zrow[k0] : 0.0, a1 = (fr < ib && k1 < I0) ? zrow[k1] : 0.0;
+            const double b0 = (k0 < I0 && jcol <= k0) ? K[((k0 * (k0 + 1)) >> 1) + jcol] : 0.0;
+            const double b1 = (k1 < I0 && jcol <= k1) ? K[((k1 * (k1 + 1)) >> 1) + jcol] : 0.0;
+            dmma884(c0, c1, a0, b0);
+            dmma884(d0, d1, a1, b1);
+          }
+          if (k < I0) {
+            const int k0 = k + fc;
+            const double a0 = (fr < ib && k0 < I0) ? zrow[k0] : 0.0;
+            const double b0 = (k0 < I0 && jcol <= k0) ? K[((k0 * (k0 + 1)) >> 1) + jcol] : 0.0;
+            dmma884(c0, c1, a0, b0);
+          }
+          c0 += d0; c1 += d1;
+        }
+        __syncthreads();   // every read of Z (rows I0..I0+3) by every warp is done
+        if (jt < ntj && fr < ib) {
+          const int col = 8 * jt + 2 * fc;
+          double *xr = K + (((I0 + fr) * (I0 + fr + 1)) >> 1);
+          if (col < I0) xr[col] = c0;
+          if (col + 1 < I0) xr[col + 1] = c1;
+        }
+        if (jb0 + nw < ntj) __syncthreads();   // next group of tiles reads Z columns not yet overwritten? (no: it reads columns >= its own) -- but keep the stores ordered
       }
-      jg += nq;
-    } while (jg < I0);
-    if (t == 0) {
-      double *D0 = K + ((I0 * (I0 + 1)) >> 1) + I0;
-      D0[0] = m00;
-      if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = m10; D1[1] = m11; }
-      if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = m20; D2[1] = m21; D2[2] = m22; }
-      if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = m30; D3[1] = m31; D3[2] = m32; D3[3] = m33; }
+      CP_STAMP(23);
+      if (t == 0) {
+        double *D0 = K + ((I0 * (I0 + 1)) >> 1) + I0;
+        D0[0] = m00;
+        if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = m10; D1[1] = m11; }
+        if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = m20; D2[1] = m21; D2[2] = m22; }
+        if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = m30; D3[1] = m31; D3[2] = m32; D3[3] = m33; }
+      }
+      __syncthreads();
+      CP_STAMP(24);
     }
-    __syncthreads();
-    CP_STAMP(24);
   }
   if (prof && t == 0) { const long long t1 = clock64(); tB = t1 - t0; atomicAdd(prof + 5, (unsigned long long)tA); atomicAdd(prof + 6, (unsigned long long)tB); }
   return true;
