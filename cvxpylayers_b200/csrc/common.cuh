@@ -500,18 +500,21 @@ __device__ __forceinline__ void P_mul(const DevStruct &S, const double *Pv, cons
 }
 
 // ----------------------------------------------------------------------------- packed Cholesky + inverse
-// In-place Cholesky K = L L' of a packed-lower SPD matrix (row i at i(i+1)/2) followed by the in-place
-// inverse X = L^{-1}: the factor is applied afterwards as triangular / dense products, which keeps every
-// solve free of sequential substitution.  Both sweeps advance FOUR columns / rows per step and are
-// instruction-issue bound with 16 warps (tools/microbench.cu), so the design minimises warp-instructions:
-//   * factor step = panel (one row per thread) | barrier | rank-4 trailing update on the tensor cores (one
-//     DMMA per 8 x 8 tile, k = 4 is exactly the block width) | barrier;
-//   * the 4 x 4 diagonal block (Cholesky + inverse: 4 dependent rsqrt) is done by WARP 0 ONLY, one step ahead:
-//     it owns the trailing tile that contains the next diagonal block, factors it right after updating it and
-//     publishes the inverse through `tmp`, while the other warps finish the trailing update;
-//   * the inverse sweep reuses those 4 x 4 inverses (no divisions, no second factorisation pass).
+// In-place Cholesky K = L L' of a packed-lower SPD matrix (row i at i(i+1)/2) and in-place inverse X = L^{-1}:
+// the factor is applied afterwards as triangular / dense products, which keeps every solve free of sequential
+// substitution.  Everything advances FOUR columns / rows per step and is instruction-issue / latency bound with
+// 16 warps (tools/microbench.cu), so the design minimises warp-instructions and overlaps the serial chain:
+//   * ONE sweep does both jobs.  Block row s of L is final (left of its diagonal) once panel s-1 is done, so its
+//     inverse step X_s = -M_s L_s X_{<s} runs inside factor step s: two barriers per step for both.
+//   * Phase A (thread-parallel): store X_{s-1} from the staging rows | panel s (one row per thread) |
+//     Z_s = -M_s L_s in place (one column per thread).
+//   * Phase B (warp-parallel, tensor cores): warp 0 updates the trailing tile that holds the next diagonal block
+//     and factors + inverts that 4 x 4 block right away (4 dependent rsqrt: the serial chain of the algorithm, one
+//     step ahead of everybody else); the other warps share the rank-4 trailing update (one DMMA per 8 x 8 tile,
+//     k = 4 is exactly the block width) and the inverse step (Z_s X_{<s}, one warp per 8 output columns, results to
+//     the staging rows).  The trailing work shrinks with s while the inverse work grows.
 // tmp: scratch of chol_scratch_doubles(n) doubles.  Block-uniform result (false: not positive definite).
-__host__ __device__ __forceinline__ int chol_scratch_doubles(int n) { return 10 * ((n + 3) >> 2) + 2; }
+__host__ __device__ __forceinline__ int chol_scratch_doubles(int n) { return 26 * ((n + 3) >> 2) + 2; }
 // 1 / sqrt(x) for the Cholesky pivots: hardware approximation (2^-23) + two Newton steps (full double precision up to
 // a couple of ulp); roughly half the dependent latency of the library rsqrt, and four of them are chained per block.
 __device__ __forceinline__ double rsqrt_nr(double x) {
@@ -556,13 +559,15 @@ __device__ __forceinline__ Tri4 tri4_block(const double *K, int r0, int jb) {
 #endif
 __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned long long *prof = nullptr) {
   const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
-  const int nblk = (n + 3) >> 2;
-  double *isd = tmp, *moff = tmp + 4 * nblk, *flag = tmp + 10 * nblk;   // 1 / L_kk | off-diagonal inverse entries per block | pd flag
-  long long tA = 0, tB = 0, t0 = 0;
+  const int nblk = (n + 3) >> 2, ld = 4 * nblk;
+  // scratch: 1 / L_kk | off-diagonal entries of the 4 x 4 inverses | staging rows of the inverse step | pd flag
+  double *isd = tmp, *moff = tmp + 4 * nblk, *Tst = tmp + 10 * nblk, *flag = tmp + 26 * nblk;
+  long long t0 = 0;
   if (prof && t == 0) t0 = clock64();
 #ifdef BC_CHOLPROF
   long long tt = t0;
 #endif
+  const int fr = lane >> 2, fc = lane & 3;
   // Diagonal block at J0 (warp 0, every lane computes, lane 0 publishes): L_D in place, its inverse in tmp.
   auto diag_block = [&](int J0) {
     const int jb = min(4, n - J0);
@@ -582,7 +587,6 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
   };
   // One 8 x 8 tile (ta, tb), tb <= ta, of the trailing update K[i][j] -= sum_c L[i][J0+c] L[j][J0+c], i, j >= R0.
   auto trail_tile = [&](int ta, int tb, int J0, int jb, int R0) {
-    const int fr = lane >> 2, fc = lane & 3;
     const int ra = R0 + 8 * ta + fr, rb = R0 + 8 * tb + fr;
     const double fa = (ra < n && fc < jb) ? -K[((ra * (ra + 1)) >> 1) + J0 + fc] : 0.0;
     const double fb = (rb < n && fc < jb) ? K[((rb * (rb + 1)) >> 1) + J0 + fc] : 0.0;
@@ -594,23 +598,74 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
     if (ok0) pc[0] = c0;
     if (ok1) pc[1] = c1;
   };
+  // Inverse step of block row I0 (ib rows), output columns [8 jt, 8 jt + 8): (Z X_{<I0})[:, cols] into the staging rows.
+  auto inv_tile = [&](int jt, int I0, int ib) {
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    const bool zr = fr < ib;
+    const double *zrow = K + (((I0 + (zr ? fr : 0)) * (I0 + (zr ? fr : 0) + 1)) >> 1);
+    const int jcol = 8 * jt + fr;
+    int k = 8 * jt;
+    // rows [8 jt, 8 jt + 8) of X meet the diagonal: triangular guard
+    for (int q = 0; q < 2 && k < I0; q++, k += 4) {
+      const int k0 = k + fc;
+      const double a0 = zr ? zrow[k0] : 0.0;
+      const double b0 = jcol <= k0 ? K[((k0 * (k0 + 1)) >> 1) + jcol] : 0.0;
+      if (q == 0) dmma884(c0, c1, a0, b0); else dmma884(d0, d1, a0, b0);
+    }
+    // full rows below: no guards, packed row offsets advanced incrementally, two accumulators in flight
+    int k0 = k + fc, o0 = ((k0 * (k0 + 1)) >> 1) + jcol;
+    for (; k + 8 <= I0; k += 8) {
+      const int o1 = o0 + 4 * k0 + 10;                 // row k0 + 4
+      const double a0 = zr ? zrow[k0] : 0.0, a1 = zr ? zrow[k0 + 4] : 0.0;
+      const double b0 = K[o0], b1 = K[o1];
+      dmma884(c0, c1, a0, b0);
+      dmma884(d0, d1, a1, b1);
+      o0 += 8 * k0 + 36; k0 += 8;                      // row k0 + 8
+    }
+    if (k < I0) {                                      // one k-step left (I0 is a multiple of 4)
+      const double a0 = zr ? zrow[k0] : 0.0;
+      dmma884(c0, c1, a0, K[o0]);
+    }
+    if (fr < 4) {
+      const int col = 8 * jt + 2 * fc;
+      Tst[fr * ld + col] = c0 + d0; Tst[fr * ld + col + 1] = c1 + d1;   // col + 1 <= 8 jt + 7 < ld
+    }
+  };
+  // X rows of block row I0 from the staging rows, and its diagonal block M
+  auto store_X = [&](int I0) {
+    const int ib = min(4, n - I0);
+    for (int j = (t + (T >> 1)) % T; j < I0; j += T) {   // (phase A runs three jobs: each starts on its own warps)
+      K[((I0 * (I0 + 1)) >> 1) + j] = Tst[j];
+      if (ib > 1) K[(((I0 + 1) * (I0 + 2)) >> 1) + j] = Tst[ld + j];
+      if (ib > 2) K[(((I0 + 2) * (I0 + 3)) >> 1) + j] = Tst[2 * ld + j];
+      if (ib > 3) K[(((I0 + 3) * (I0 + 4)) >> 1) + j] = Tst[3 * ld + j];
+    }
+    if (t == T - 1) {
+      const double *mo = moff + 6 * (I0 >> 2);
+      double *D0 = K + ((I0 * (I0 + 1)) >> 1) + I0;
+      D0[0] = isd[I0];
+      if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = mo[0]; D1[1] = isd[I0 + 1]; }
+      if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = mo[1]; D2[1] = mo[2]; D2[2] = isd[I0 + 2]; }
+      if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = mo[3]; D3[1] = mo[4]; D3[2] = mo[5]; D3[3] = isd[I0 + 3]; }
+    }
+  };
   if (warp == 0) {
     if (lane == 0) *flag = 1.0;
     __syncwarp();
     diag_block(0);
   }
   __syncthreads();
-  // ---------------- Cholesky, four columns per step ----------------
   for (int J0 = 0; J0 < n; J0 += 4) {
     const int jb = min(4, n - J0), R0 = J0 + jb;
     if (*flag == 0.0) return false;   // block-uniform: written before the last barrier
-    CP_STAMP(16);
-    // panel: row i >= R0, l_i = a_i L_D^{-T}; one row per thread, in place
-    if (R0 + t < n) {
+    // ---- phase A: X of the previous block row | panel | Z of this block row ----
+    if (J0 > 0) store_X(J0 - 4);
+    const int tz = (t + T - (T >> 2)) % T;   // Z starts at thread T / 4, the panel at thread 0, the X store at T / 2
+    if (R0 + t < n || tz < J0) {
       const double *mo = moff + 6 * (J0 >> 2);
       const double m00 = isd[J0], m11 = isd[J0 + 1], m22 = isd[J0 + 2], m33 = isd[J0 + 3];
       const double m10 = mo[0], m20 = mo[1], m21 = mo[2], m30 = mo[3], m31 = mo[4], m32 = mo[5];
-      for (int i = R0 + t; i < n; i += T) {
+      for (int i = R0 + t; i < n; i += T) {   // panel: l_i = a_i L_D^{-T}
         double *row = K + ((i * (i + 1)) >> 1) + J0;
         const double a0 = row[0], a1 = jb > 1 ? row[1] : 0.0, a2 = jb > 2 ? row[2] : 0.0, a3 = jb > 3 ? row[3] : 0.0;
         row[0] = a0 * m00;
@@ -618,28 +673,40 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
         if (jb > 2) row[2] = fma(a2, m22, fma(a1, m21, a0 * m20));
         if (jb > 3) row[3] = fma(a3, m33, fma(a2, m32, fma(a1, m31, a0 * m30)));
       }
+      double *L0 = K + ((J0 * (J0 + 1)) >> 1), *L1 = K + (((J0 + 1) * (J0 + 2)) >> 1), *L2 = K + (((J0 + 2) * (J0 + 3)) >> 1),
+             *L3 = K + (((J0 + 3) * (J0 + 4)) >> 1);
+      for (int i = tz; i < J0; i += T) {      // Z = -M L on block row J0
+        const double a0 = L0[i], a1 = jb > 1 ? L1[i] : 0.0, a2 = jb > 2 ? L2[i] : 0.0, a3 = jb > 3 ? L3[i] : 0.0;
+        L0[i] = -(m00 * a0);
+        if (jb > 1) L1[i] = -fma(m11, a1, m10 * a0);
+        if (jb > 2) L2[i] = -fma(m22, a2, fma(m21, a1, m20 * a0));
+        if (jb > 3) L3[i] = -fma(m33, a3, fma(m32, a2, fma(m31, a1, m30 * a0)));
+      }
     }
     CP_STAMP(17);
     __syncthreads();
     CP_STAMP(18);
-    // rank-4 trailing update on the tensor cores; warp 0 takes the tile holding the next diagonal block and
-    // factors that block as soon as it is up to date, the other warps share the remaining tiles
-    if (R0 < n) {
-      const int ntl = (n - R0 + 7) >> 3, ntile = (ntl * (ntl + 1)) >> 1;
-      if (warp == 0) {
+    // ---- phase B: trailing update + next diagonal block | inverse step of this block row ----
+    {
+      const int ntl = R0 < n ? (n - R0 + 7) >> 3 : 0, ntile = (ntl * (ntl + 1)) >> 1;
+      const int ntj = (J0 + 7) >> 3;                   // inverse tiles (output columns < J0)
+      if (warp == 0 && ntile > 0) {
         trail_tile(0, 0, J0, jb, R0);
-        if (nw == 1) {
-          for (int e = 1, ta = 1, tb = 0; e < ntile; e++) { trail_tile(ta, tb, J0, jb, R0); if (++tb > ta) { tb = 0; ta++; } }
-        }
         __syncwarp();
         diag_block(R0);
-      } else {
-        int ta = 0, tb = warp;                       // tile e = warp, then e += nw - 1 (tile 0 belongs to warp 0)
-        while (tb > ta) { tb -= ta + 1; ta++; }
-        for (int e = warp; e < ntile; e += nw - 1) {
-          trail_tile(ta, tb, J0, jb, R0);
-          tb += nw - 1;
-          while (tb > ta) { tb -= ta + 1; ta++; }
+      }
+      if (warp > 0 || nw == 1) {
+        const int W = nw > 1 ? nw - 1 : 1, w0 = nw > 1 ? warp - 1 : 0;
+        const int nwork = ntj + (ntile > 0 ? ntile - 1 : 0);   // inverse tiles first (longest first), then trailing tiles 1..
+        int ta = 0, tb = 0, e_cur = 0;
+        for (int u = w0; u < nwork; u += W) {
+          if (u < ntj) inv_tile(u, J0, jb);
+          else {
+            const int e = u - ntj + 1;
+            tb += e - e_cur; e_cur = e;
+            while (tb > ta) { tb -= ta + 1; ta++; }
+            trail_tile(ta, tb, J0, jb, R0);
+          }
         }
       }
     }
@@ -647,78 +714,10 @@ __device__ inline bool chol_inv_packed(double *K, int n, double *tmp, unsigned l
     __syncthreads();
     CP_STAMP(20);
   }
-  if (prof && t == 0) { const long long t1 = clock64(); tA = t1 - t0; t0 = t1; }
-  // ---------------- X = L^{-1}, four rows per step ----------------
-  // X_II = L_II^{-1} =: M (kept from the factorisation);  X_Ij = Z X_{<I, j} with Z = -M L_{I,<I} (4 x I0).
-  // Step: Z in place (one column per thread) | barrier | tensor-core product, one warp per 8 output columns, the k range
-  // [8 jt, I0) of the triangular X in steps of 4 on two independent accumulators | barrier | store | barrier.
-  {
-    const int fr = lane >> 2, fc = lane & 3;
-    for (int I0 = 0; I0 < n; I0 += 4) {
-      const int ib = min(4, n - I0);
-      const double *mo = moff + 6 * (I0 >> 2);
-      const double m00 = isd[I0], m11 = isd[I0 + 1], m22 = isd[I0 + 2], m33 = isd[I0 + 3];
-      const double m10 = mo[0], m20 = mo[1], m21 = mo[2], m30 = mo[3], m31 = mo[4], m32 = mo[5];
-      double *L0 = K + ((I0 * (I0 + 1)) >> 1), *L1 = K + (((I0 + 1) * (I0 + 2)) >> 1), *L2 = K + (((I0 + 2) * (I0 + 3)) >> 1),
-             *L3 = K + (((I0 + 3) * (I0 + 4)) >> 1);
-      for (int i = t; i < I0; i += T) {
-        const double a0 = L0[i], a1 = ib > 1 ? L1[i] : 0.0, a2 = ib > 2 ? L2[i] : 0.0, a3 = ib > 3 ? L3[i] : 0.0;
-        L0[i] = -(m00 * a0);
-        if (ib > 1) L1[i] = -fma(m11, a1, m10 * a0);
-        if (ib > 2) L2[i] = -fma(m22, a2, fma(m21, a1, m20 * a0));
-        if (ib > 3) L3[i] = -fma(m33, a3, fma(m32, a2, fma(m31, a1, m30 * a0)));
-      }
-      CP_STAMP(21);
-      __syncthreads();
-      CP_STAMP(22);
-      const int ntj = (I0 + 7) >> 3;
-      double c0 = 0.0, c1 = 0.0;            // (one tile per warp per step: n <= 8 * warps, else the tiles are looped with a barrier each)
-      for (int jb0 = 0; jb0 < ntj; jb0 += nw) {
-        const int jt = jb0 + warp;
-        c0 = 0.0; c1 = 0.0;
-        if (jt < ntj) {
-          double d0 = 0.0, d1 = 0.0;
-          const double *zrow = K + (((I0 + fr) * (I0 + fr + 1)) >> 1);
-          const int jcol = 8 * jt + fr;
-          int k = 8 * jt;
-          for (; k + 4 < I0; k += 8) {
-            const int k0 = k + fc, k1 = k + 4 + fc;
-            const double a0 = (fr < ib && k0 < I0) ? zrow[k0] : 0.0, a1 = (fr < ib && k1 < I0) ? zrow[k1] : 0.0;
-            const double b0 = (k0 < I0 && jcol <= k0) ? K[((k0 * (k0 + 1)) >> 1) + jcol] : 0.0;
-            const double b1 = (k1 < I0 && jcol <= k1) ? K[((k1 * (k1 + 1)) >> 1) + jcol] : 0.0;
-            dmma884(c0, c1, a0, b0);
-            dmma884(d0, d1, a1, b1);
-          }
-          if (k < I0) {
-            const int k0 = k + fc;
-            const double a0 = (fr < ib && k0 < I0) ? zrow[k0] : 0.0;
-            const double b0 = (k0 < I0 && jcol <= k0) ? K[((k0 * (k0 + 1)) >> 1) + jcol] : 0.0;
-            dmma884(c0, c1, a0, b0);
-          }
-          c0 += d0; c1 += d1;
-        }
-        __syncthreads();   // every read of Z (rows I0..I0+3) by every warp is done
-        if (jt < ntj && fr < ib) {
-          const int col = 8 * jt + 2 * fc;
-          double *xr = K + (((I0 + fr) * (I0 + fr + 1)) >> 1);
-          if (col < I0) xr[col] = c0;
-          if (col + 1 < I0) xr[col + 1] = c1;
-        }
-        if (jb0 + nw < ntj) __syncthreads();   // next group of tiles reads Z columns not yet overwritten? (no: it reads columns >= its own) -- but keep the stores ordered
-      }
-      CP_STAMP(23);
-      if (t == 0) {
-        double *D0 = K + ((I0 * (I0 + 1)) >> 1) + I0;
-        D0[0] = m00;
-        if (ib > 1) { double *D1 = K + (((I0 + 1) * (I0 + 2)) >> 1) + I0; D1[0] = m10; D1[1] = m11; }
-        if (ib > 2) { double *D2 = K + (((I0 + 2) * (I0 + 3)) >> 1) + I0; D2[0] = m20; D2[1] = m21; D2[2] = m22; }
-        if (ib > 3) { double *D3 = K + (((I0 + 3) * (I0 + 4)) >> 1) + I0; D3[0] = m30; D3[1] = m31; D3[2] = m32; D3[3] = m33; }
-      }
-      __syncthreads();
-      CP_STAMP(24);
-    }
-  }
-  if (prof && t == 0) { const long long t1 = clock64(); tB = t1 - t0; atomicAdd(prof + 5, (unsigned long long)tA); atomicAdd(prof + 6, (unsigned long long)tB); }
+  if (*flag == 0.0) return false;
+  store_X(((n - 1) >> 2) << 2);
+  __syncthreads();
+  if (prof && t == 0) { const long long t1 = clock64(); atomicAdd(prof + 5, (unsigned long long)(t1 - t0)); }
   return true;
 }
 
