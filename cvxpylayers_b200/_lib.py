@@ -16,7 +16,7 @@ _f64p = C.POINTER(C.c_double)
 
 EXPORTS = [
     "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary",
-    "bcone_ingest", "bcone_emit", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_memcpy2d", "bcone_set_profile",
+    "bcone_ingest", "bcone_emit", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
 
@@ -83,6 +83,8 @@ def load() -> C.CDLL:
     lib.bcone_launch_count.restype = C.c_int64
     lib.bcone_kernel_info.argtypes = [vp] + [_i32p] * 6
     lib.bcone_kernel_info.restype = C.c_int
+    lib.bcone_path_info.argtypes = [vp, _i32p, _i32p]
+    lib.bcone_path_info.restype = C.c_int
     _lib = lib
     return lib
 

@@ -397,6 +397,14 @@ extern "C" int bcone_set_profile(void *handle, int32_t on, uint64_t *out) {
 
 extern "C" int64_t bcone_launch_count(void *handle) { return handle ? ((Handle *)handle)->launches : 0; }
 
+extern "C" int bcone_path_info(void *handle, int32_t *fwd_path, int32_t *bwd_path) {
+  Handle *h = (Handle *)handle;
+  if (!h) return BCONE_EINVAL;
+  if (fwd_path) *fwd_path = h->fast_fwd ? 2 : (h->fwd_indirect ? 1 : 0);
+  if (bwd_path) *bwd_path = h->block_bwd ? 2 : (h->fast_bwd ? 1 : 0);
+  return BCONE_OK;
+}
+
 extern "C" int bcone_kernel_info(void *handle, int32_t *ft, int32_t *fs, int32_t *fc, int32_t *bt, int32_t *bs, int32_t *bcx) {
   Handle *h = (Handle *)handle;
   if (!h) return BCONE_EINVAL;

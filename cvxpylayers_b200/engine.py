@@ -126,6 +126,14 @@ class Engine:
         k = ["fwd_threads", "fwd_smem", "fwd_ctas_per_sm", "bwd_threads", "bwd_smem", "bwd_ctas_per_sm"]
         return {a: int(b.value) for a, b in zip(k, v)}
 
+    FWD_PATHS = ("fwd_kernel (on-chip Cholesky)", "fwd_kernel (indirect, CG)", "fwd_fast_kernel (register-tiled)")
+    BWD_PATHS = ("bwd_kernel (generic LSQR)", "bwd_fast_kernel (fused single-pass LSQR)", "bwd_block_kernel (KKT-block preconditioned, bwd_fast_kernel fallback)")
+
+    def path_info(self) -> dict:
+        f, b = C.c_int32(), C.c_int32()
+        self.lib.bcone_path_info(self.h, C.byref(f), C.byref(b))
+        return {"fwd": self.FWD_PATHS[f.value], "bwd": self.BWD_PATHS[b.value]}
+
     def alloc_solution(self, B: int) -> Solution:
         dev, f64, st = self.device, torch.float64, self.structure
         return Solution(torch.empty((B, st.n), dtype=f64, device=dev), torch.empty((B, st.m), dtype=f64, device=dev),

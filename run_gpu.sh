@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-./tools/microbench 2>&1 | tail -14 | tee gpurun_out/micro.log
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/tests.log
-timeout 300 python tools/phase_profile.py 592 2>&1 | grep -v "^  \[" | tee gpurun_out/phase.log
-timeout 600 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench.err | tee gpurun_out/bench.json
+B200_TRACE=1 BENCH_E2E_BREAKDOWN=1 timeout 600 python bench.py --steps 20 --warmup 3 --cpu-sample 0 2>gpurun_out/bench_trace.err > gpurun_out/bench_trace.json
+grep -c "b200\] bwd" gpurun_out/bench_trace.err
+grep "b200\] bwd\|\[e2e\]" gpurun_out/bench_trace.err | paste - - | awk '{print}' | cut -c1-230 | tail -24
+tail -1 gpurun_out/bench_trace.err
