@@ -164,7 +164,6 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
     bt, bd = make_workload(B, seed=rank)
@@ -347,10 +346,18 @@ def main():
     if CONFIG != "C2":
         METRIC = f"problems/sec fwd+bwd, BASELINE config {CONFIG} (secondary measurement)"
         a.cpu_sample = min(a.cpu_sample, a.batch)
+    # The contract is ONE JSON line on stdout.  Libraries write there behind Python's back (NCCL prints its version
+    # banner on fd 1 when NCCL_DEBUG is set), so fd 1 points at stderr while the run is in progress and the
+    # result line is written to the saved descriptor by the print() calls below via sys.stdout.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-B200_TRACE=1 BENCH_E2E_BREAKDOWN=1 timeout 600 python bench.py --steps 20 --warmup 3 --cpu-sample 0 2>gpurun_out/bench_trace.err > gpurun_out/bench_trace.json
-grep -c "b200\] bwd" gpurun_out/bench_trace.err
-grep "b200\] bwd\|\[e2e\]" gpurun_out/bench_trace.err | paste - - | awk '{print}' | cut -c1-230 | tail -24
-tail -1 gpurun_out/bench_trace.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 2>gpurun_out/bench_n2.err > gpurun_out/bench_n2.json
+echo "stdout lines: $(wc -l < gpurun_out/bench_n2.json)"; python -c "
+import json;d=json.loads(open('gpurun_out/bench_n2.json').read());print(d['n_gpus'],d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e']['ms_per_step'],d['kernel_ms'])"
+grep -c "NCCL version" gpurun_out/bench_n2.err
