@@ -14,6 +14,18 @@
 // infeasibility certificates, adaptive scale (re-factorisation on chip).
 #include "common.cuh"
 
+// Sub-phase cycle counters (tools/phase_profile.py, slots 16..28) cost registers and issue slots in the iteration
+// loop: compiled in only with -DBC_SUBPROF.  The five coarse phases (slots 0..4) are always available.
+#ifdef BC_SUBPROF
+#define SUB_DECL(name) PhaseTimer name; name.start(a.prof)
+#define SUB_SKIP(name) name.skip()
+#define SUB_STAMP(name, k) name.stamp(k)
+#else
+#define SUB_DECL(name)
+#define SUB_SKIP(name)
+#define SUB_STAMP(name, k)
+#endif
+
 struct FwdSmem {
   double *Av, *Li, *w, *u, *ut, *g, *bh, *ch, *Dm, *En, *tn, *tn2, *tn3, *tm, *part, *red, *psd, *cr, *cp, *cq, *kd, *cx;
   uint64_t *bar;
@@ -121,7 +133,7 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   const int npk = n * (n + 1) / 2;
   const bool wide = DENSE && (n % 2 == 0) && n <= 128;
   double *K = M.Li;
-  PhaseTimer pf; pf.start(a.prof);
+  SUB_DECL(pf);
   if (INDIRECT) {
     // Jacobi preconditioner diag(K), then g = (R_z + M)^{-1} h by CG at tight tolerance
     for (int i = t; i < m; i += T) M.tm[i] = inv_ry(S, i, scale);
@@ -199,7 +211,7 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
     }
     __syncthreads();
   }
-  pf.stamp(19);
+  SUB_STAMP(pf, 19);
   if (Pv) {
     for (int k = t; k < S.nnzP; k += T) {
       const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);  // j >= i
@@ -207,9 +219,9 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
     }
     __syncthreads();
   }
-  pf.stamp(20);
+  SUB_STAMP(pf, 20);
   if (!chol_inv_packed(K, n, M.part)) return false;   // scratch: part (8 n) + red (256) are contiguous
-  pf.stamp(21);
+  SUB_STAMP(pf, 21);
   // ---- g = (R_z + M)^{-1} h, h = (c^, b^) ----
   for (int i = t; i < m; i += T) M.tm[i] = M.bh[i] * inv_ry(S, i, scale);
   __syncthreads();
@@ -227,7 +239,7 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   }
   block_reduce<1, false>(acc, M.red);
   gRg = acc[0];
-  pf.stamp(22);
+  SUB_STAMP(pf, 22);
   return true;
 }
 
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     const double *Pg = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
     const double *bg = a.b + (size_t)inst * m, *cg = a.c + (size_t)inst * n;
     PhaseTimer pt; pt.start(a.prof);
-    PhaseTimer pi; pi.start(a.prof);
+    SUB_DECL(pi);
 
     // ---- stage the instance: one TMA bulk copy for the CSR values, plain loads for b, c ----
     if (a.use_tma) {
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     // ---- Ruiz equilibration: A^ = D A E, P^ = E P E ----
     if (st.normalize) {
       for (int pass = 0; pass < st.ruiz_passes; pass++) {
-        pi.skip();
+        SUB_SKIP(pi);
         // row and column inf-norms of the current A^ (and P^)
         if (DENSE && n <= 128) {
           // lazily scaled pass: A stays unscaled in shared memory, norms are taken through the running
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
           }
           __syncthreads();
         }
-        pi.stamp(16);
+        SUB_STAMP(pi, 16);
         if (Pg) {
           for (int k = t; k < S.nnzP; k += T) {
             const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
           }
           __syncthreads();
         }
-        pi.stamp(17);
+        SUB_STAMP(pi, 17);
         for (int i = t; i < m; i += T) { const double r = M.tm[i]; M.tm[i] = fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
         for (int j = t; j < n; j += T) { const double r = M.tn[j]; M.tn[j] = fmin(fmax(r < 1e-8 ? 1.0 : rsqrt(r), BC_EQ_MIN), BC_EQ_MAX); }
         __syncthreads();
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         for (int i = t; i < m; i += T) M.Dm[i] *= M.tm[i];
         for (int j = t; j < n; j += T) M.En[j] *= M.tn[j];
         __syncthreads();
-        pi.stamp(18);
+        SUB_STAMP(pi, 18);
       }
       if (DENSE && n <= 128 && st.ruiz_passes > 0) {   // A^ = D A E in one sweep
         const int lane = t & 31, warp = t >> 5, nw = T >> 5;
@@ -430,9 +442,9 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         d4[0] = fma(r * wk, gk, d4[0]); d4[1] = fma(r * pk, gk, d4[1]);
         d4[2] = fma(r * pk, pk, d4[2]); d4[3] = fma(r * pk, wk, d4[3]);
       };
-      pi.skip();
+      SUB_SKIP(pi);
       AT_mul<DENSE>(S, M.Av, M.w + n, M.part, [&](int j, double v) { M.tn[j] = rho_x * M.w[j] - v; }, plA, wide);
-      pi.stamp(23);
+      SUB_STAMP(pi, 23);
       if (INDIRECT) {
         // warm start from the previous p_x = ut_x + tau~ g_x; tolerance tightens with the iteration count
         double nr[1] = {0};
@@ -445,16 +457,16 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
       } else {
         matvec_rows(M.Li, PackedLowerLayout{}, n, n, M.tn, [&](int i, double v) { M.tn2[i] = v; });
         __syncthreads();
-        pi.stamp(24);
+        SUB_STAMP(pi, 24);
         matvec_cols(M.Li, PackedLowerLayout{}, n, n, M.tn2, M.part, [&](int j, double v) { M.ut[j] = v; dots(rho_x, v, M.w[j], M.g[j]); }, plN);
-        pi.stamp(25);
+        SUB_STAMP(pi, 25);
       }
       A_mul<DENSE>(S, M.Av, M.ut, [&](int i, double v) {
         const double iry = inv_ry(S, i, scale), wk = M.w[n + i], pk = wk + v * iry;
         M.ut[n + i] = pk; dots(1.0 / iry, pk, wk, M.g[n + i]); }, wide);
-      pi.stamp(26);
+      SUB_STAMP(pi, 26);
       block_reduce<4, false>(d4, M.red);   // (its barriers also publish ut)
-      pi.stamp(27);
+      SUB_STAMP(pi, 27);
       const double qa = dtau + gRg, qb = d4[0] - 2.0 * d4[1] - dtau * w_tau, qc = d4[2] - d4[3];
       double disc = qb * qb - 4.0 * qa * qc;
       if (disc < 0) disc = 0;
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
       __syncthreads();
       if (nonpoly) { project_cones(S, M.u + n, M.psd); __syncthreads(); }
 
-      pi.stamp(28);
+      SUB_STAMP(pi, 28);
       pt.stamp(3);   // iteration body
       if (check) {
         // ---- termination quantities on the un-normalised data ----

@@ -1,4 +1,5 @@
-"""Per-phase cycle shares of the forward and block-backward kernels (clock64 stamps by thread 0)."""
+"""Per-phase cycle shares of the forward and block-backward kernels (clock64 stamps by thread 0).
+The indented sub-phase rows ([eq], [K], [it]) are only filled by a library built with -DBC_SUBPROF."""
 import ctypes as C, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
