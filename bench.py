@@ -338,11 +338,16 @@ def main():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=4096, help="instances per GPU")
     p.add_argument("--cpu-sample", type=int, default=512, help="instances per CPU-baseline pass")
-    p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C5", "EXP"],
+    p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "C5S", "EXP"],
                    help="workload (default: the headline C2; others are secondary measurements)")
+    p.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
+                   help="override a solver argument for both arms, e.g. --set acceleration_lookback=0")
     a = p.parse_args()
     global CONFIG, METRIC
     CONFIG = a.config
+    for kv in a.set:
+        k, v = kv.split("=", 1)
+        SOLVER_ARGS[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
     if CONFIG != "C2":
         METRIC = f"problems/sec fwd+bwd, BASELINE config {CONFIG} (secondary measurement)"
         a.cpu_sample = min(a.cpu_sample, a.batch)

@@ -53,8 +53,11 @@ struct Handle {
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
   int fwd_indirect = 0, bwd_vec_global = 0;   // large instances: CG instead of Cholesky, vectors in a global slab
-  double *fwd_ws = nullptr, *bwd_ws = nullptr;
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
+  // Per-stream scratch slabs (one per CTA of the grid): launches on different streams may overlap, launches on one
+  // stream cannot, so the stream is the unit of ownership.  Allocated on first use.
+  struct StreamWs { cudaStream_t s; double *fwd = nullptr, *bwd = nullptr, *aa = nullptr; size_t aa_cap = 0; };
+  std::vector<StreamWs> sws;
   int block_bwd = 0, blk_threads = 0; size_t blk_smem = 0;   // KKT-block preconditioned backward (lsqr_precond = 2)
   int *fail_list[RING] = {nullptr}; int fail_cap[RING] = {0};
   int fast_fwd = 0;  // dense A, polyhedral cones, direct mode: register-tiled forward (fwd_fast.cu)
@@ -81,6 +84,22 @@ int fail(Handle *h, int code, const std::string &msg) {
 int cuda_fail(Handle *h, cudaError_t e, const char *where) {
   return fail(h, BCONE_ECUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
+Handle::StreamWs *stream_ws(Handle *h, cudaStream_t s) {
+  for (auto &w : h->sws) if (w.s == s) return &w;
+  Handle::StreamWs w; w.s = s;
+  h->sws.push_back(w);
+  return &h->sws.back();
+}
+// slab of `doubles` per CTA for `ctas` CTAs; *cap tracks the current size in doubles (0: fixed-size slab)
+bool ensure_slab(Handle *h, double **p, size_t *cap, size_t doubles) {
+  if (*p && (!cap || *cap >= doubles)) return true;
+  double *q = nullptr;
+  if (cudaMalloc((void **)&q, doubles * sizeof(double)) != cudaSuccess) return false;
+  h->allocs.push_back(q);   // (an outgrown slab stays alive until destroy: a kernel in flight may still use it)
+  *p = q;
+  if (cap) *cap = doubles;
+  return true;
+}
 }  // namespace
 
 extern "C" void bcone_default_settings(bcone_settings *st) {
@@ -89,6 +108,7 @@ extern "C" void bcone_default_settings(bcone_settings *st) {
   st->lsqr_atol = 1e-8; st->lsqr_btol = 1e-8; st->lsqr_conlim = 1e8;
   st->max_iters = 100000; st->normalize = 1; st->adaptive_scale = 1; st->check_interval = 25;
   st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->lsqr_precond = 0; st->adaptive_check = 0;
+  st->acceleration_lookback = 10; st->acceleration_interval = 10;   // SCS defaults
 }
 
 extern "C" const char *bcone_last_error(void *handle) {
@@ -237,16 +257,8 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;
-  if (h->fwd_indirect) {
-    h->fwd_ws_stride = bc_fwd_ws_doubles(n, m);
-    if (cudaMalloc((void **)&h->fwd_ws, h->fwd_ws_stride * sizeof(double) * h->num_sms * h->fwd_ctas) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc forward workspace"); }
-    h->allocs.push_back(h->fwd_ws);
-  }
-  if (h->bwd_vec_global && !h->fast_bwd) {
-    h->bwd_ws_stride = bc_bwd_ws_doubles(n, m, npoly);
-    if (cudaMalloc((void **)&h->bwd_ws, h->bwd_ws_stride * sizeof(double) * h->num_sms * h->bwd_ctas) != cudaSuccess) { bcone_destroy(h); return fail(nullptr, BCONE_ENOMEM, "cudaMalloc backward workspace"); }
-    h->allocs.push_back(h->bwd_ws);
-  }
+  if (h->fwd_indirect) h->fwd_ws_stride = bc_fwd_ws_doubles(n, m);
+  if (h->bwd_vec_global && !h->fast_bwd) h->bwd_ws_stride = bc_bwd_ws_doubles(n, m, npoly);
   h->tma_ok = (d->nnzA > 0 && (d->nnzA % 2) == 0 && (size_t)d->nnzA * 8 < (1u << 20)) ? 1 : 0;
   *out = h;
   return BCONE_OK;
@@ -313,15 +325,31 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   if (!h || B <= 0 || !A_vals || !b || !c || !x || !y || !s || !status || !iters || !stg) return fail(h, BCONE_EINVAL, "solve: null argument");
   if (h->S.nnzP > 0 && !P_vals) return fail(h, BCONE_EINVAL, "solve: structure has P but P_vals is NULL");
   if (stg->check_interval <= 0 || stg->max_iters <= 0) return fail(h, BCONE_EINVAL, "solve: check_interval and max_iters must be positive");
+  if (stg->acceleration_lookback > BC_AA_MAXMEM || stg->acceleration_lookback < -BC_AA_MAXMEM)
+    return fail(h, BCONE_EINVAL, "solve: |acceleration_lookback| must be <= 16");
   cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device), "solve set device");
   FwdArgs a;
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
   int *ctr = h->counters + 4 * (h->slot++ % Handle::RING);
   a.counter = ctr; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
-  a.ws = h->fwd_ws; a.ws_stride = (long long)h->fwd_ws_stride; a.prof = h->prof;
-  CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   const int grid = std::min(B, h->num_sms * h->fwd_ctas);
+  const size_t max_grid = (size_t)h->num_sms * h->fwd_ctas;
+  Handle::StreamWs *sw = stream_ws(h, st);
+  a.ws = nullptr; a.ws_stride = (long long)h->fwd_ws_stride; a.prof = h->prof;
+  if (h->fwd_indirect) {
+    if (!ensure_slab(h, &sw->fwd, nullptr, h->fwd_ws_stride * max_grid)) return fail(h, BCONE_ENOMEM, "cudaMalloc forward workspace");
+    a.ws = sw->fwd;
+  }
+  a.aa_ws = nullptr; a.aa_stride = 0;
+  if (stg->acceleration_lookback != 0 && stg->max_iters > 1) {
+    const int mem = std::abs(stg->acceleration_lookback);
+    a.aa_stride = (long long)((aa_ws_doubles(h->S.n + h->S.m + 1, mem) + 1) & ~(size_t)1);
+    if (!ensure_slab(h, &sw->aa, &sw->aa_cap, (size_t)a.aa_stride * max_grid)) return fail(h, BCONE_ENOMEM, "cudaMalloc acceleration workspace");
+    a.aa_ws = sw->aa;
+  }
+  CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   if (h->fast_fwd) CK(bc_fwdf_launch(&a, grid, h->fwd_smem, st), "solve launch (fast)");
   else CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
   h->launches++;
@@ -344,7 +372,13 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   int *ctr = h->counters + 4 * slot;
   a.lsqr_iters = lsqr_iters; a.st = *stg; a.counter = ctr + 1;
   a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0); a.psd_total = h->psd_total; a.p_in_smem = h->p_in_smem;
-  a.ws = h->fast_bwd ? nullptr : h->bwd_ws; a.ws_stride = (long long)h->bwd_ws_stride;
+  CK(cudaSetDevice(h->device), "vjp set device");
+  a.ws = nullptr; a.ws_stride = (long long)h->bwd_ws_stride;
+  if (h->bwd_vec_global && !h->fast_bwd) {
+    Handle::StreamWs *sw = stream_ws(h, st);
+    if (!ensure_slab(h, &sw->bwd, nullptr, h->bwd_ws_stride * (size_t)h->num_sms * h->bwd_ctas)) return fail(h, BCONE_ENOMEM, "cudaMalloc backward workspace");
+    a.ws = sw->bwd;
+  }
   a.inst_list = nullptr; a.B_dev = nullptr; a.fail_list = nullptr; a.fail_count = nullptr; a.prof = h->prof;
   if (h->block_bwd && stg->lsqr_precond == 2) {
     // pass 1: block-preconditioned solve; pass 2: equilibrated LSQR on the instances it rejected

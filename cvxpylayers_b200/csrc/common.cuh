@@ -52,6 +52,8 @@ struct FwdArgs {
   double *ws;            // INDIRECT mode: per-CTA slab of global memory holding the iterate vectors
   long long ws_stride;   // doubles per CTA
   unsigned long long *prof;  // optional: [16] phase cycle counters (debug, bcone_set_profile)
+  double *aa_ws;         // Anderson acceleration: per-CTA slab of global memory (L2-resident), or NULL when off
+  long long aa_stride;   // doubles per CTA
 };
 
 struct BwdArgs {
@@ -147,6 +149,182 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], double *red) {
     const double a = lane < nw ? red[k * 32 + lane] : 0.0;
     v[k] = MAX ? warp_max(a) : warp_sum(a);
   }
+}
+
+// ----------------------------------------------------------------------------- Anderson acceleration
+// Safeguarded Anderson acceleration of the iterate w = (w_x, w_y, w_tau), the device twin of the oracle's
+// aa_apply / aa_safeguard (oracle/cone_oracle.c; SCS 3 defaults: acceleration_lookback 10 = type-I,
+// negative = type-II, acceleration_interval 10; the reference's tests switch it off with
+// {"acceleration_lookback": 0}, tests/test_torch.py:401-405, i.e. it is on by default on that path).
+// The window (three mem x N difference matrices + four N-vectors) does not fit next to the instance in shared
+// memory, so it lives in a per-CTA slab of global memory that stays in L2 (85 KB per CTA for N = 301); it is
+// touched once every `interval` iterations.  The mem x mem normal matrix is kept incrementally (only the row
+// and column of the replaced difference pair are recomputed: 3 mem dot products per call instead of mem^2),
+// the small solve runs on one warp with one matrix row per lane (partial pivoting through shuffles).
+#define BC_AA_MAXMEM 16
+#define BC_AA_HDR (8 + BC_AA_MAXMEM * BC_AA_MAXMEM + 3 * BC_AA_MAXMEM)
+#define BC_AA_MAX_WEIGHT_NORM 1e10
+#define BC_AA_SAFEGUARD_FACTOR 1.0
+__host__ __device__ inline size_t aa_ws_doubles(int N, int mem) {
+  const size_t Np = ((size_t)N + 1) & ~(size_t)1;
+  return BC_AA_HDR + (4 + 3 * (size_t)mem) * Np;
+}
+struct AaIter {   // where the kernel keeps the iterate
+  double *wx; int n; double *wy; int m; double *wtau;
+  __device__ __forceinline__ double &at(int e) const { return e < n ? wx[e] : (e < n + m ? wy[e - n] : *wtau); }
+};
+__device__ __forceinline__ void aa_reset_dev(double *ws) { if (threadIdx.x == 0) { ws[0] = 0.0; ws[1] = 0.0; } }
+// w_prev <- w (tau passed by value: the register-tiled kernel keeps it in a register)
+static __device__ __noinline__ void aa_store_prev(double *ws, int mem, const AaIter w, double tau) {
+  const int N = w.n + w.m + 1, Np = (N + 1) & ~1;
+  double *wprev = ws + BC_AA_HDR + 3 * Np;
+  for (int e = threadIdx.x; e < N; e += blockDim.x) wprev[e] = e == N - 1 ? tau : w.at(e);
+}
+// w (the newest iterate, reached by one step from w_prev) is overwritten with the accelerated point when a
+// step is taken.  Block-uniform return value: ||gamma|| (0 nothing done, < 0 step dropped).  Starts and ends
+// with a barrier; *w.wtau must have been written before the call (any thread).
+static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, const AaIter w, double *sscr, double *red) {
+  const int T = blockDim.x, t = threadIdx.x, N = w.n + w.m + 1, Np = (N + 1) & ~1;
+  const int mem = lookback > 0 ? lookback : -lookback;
+  const bool type1 = lookback > 0;
+  double *hdr = ws, *Mm = ws + 8, *yn = Mm + BC_AA_MAXMEM * BC_AA_MAXMEM, *sn = yn + BC_AA_MAXMEM, *work = sn + BC_AA_MAXMEM;
+  double *ax = ws + BC_AA_HDR, *af = ax + Np, *gp = af + Np, *wprev = gp + Np, *Y = wprev + Np, *Sm = Y + (size_t)mem * Np, *D = Sm + (size_t)mem * Np;
+  __syncthreads();
+  const int iter = (int)hdr[0];
+  __syncthreads();   // everybody has read the header before thread 0 rewrites it
+  if (iter == 0) {
+    for (int e = t; e < N; e += T) { const double xe = wprev[e], fe = w.at(e); ax[e] = xe; af[e] = fe; gp[e] = xe - fe; }
+    if (t == 0) { hdr[0] = 1.0; hdr[1] = 0.0; }
+    __syncthreads();
+    return 0.0;
+  }
+  const int len = iter < mem ? iter : mem, idx = (iter - 1) % mem;
+  double ng[1] = {0.0};
+  {
+    double *Yc = Y + (size_t)idx * Np, *Sc = Sm + (size_t)idx * Np, *Dc = D + (size_t)idx * Np;
+    for (int e = t; e < N; e += T) {
+      const double xe = wprev[e], fe = w.at(e), g = xe - fe;
+      Sc[e] = xe - ax[e]; Dc[e] = fe - af[e]; Yc[e] = g - gp[e];
+      gp[e] = g; ax[e] = xe; af[e] = fe;
+      ng[0] = fma(g, g, ng[0]);
+    }
+  }
+  if (iter < mem) {   // SCS fills the memory before the first solve
+    if (t == 0) { hdr[0] = iter + 1; hdr[1] = 0.0; }
+    __syncthreads();
+    return 0.0;
+  }
+  block_reduce<1, false>(ng, red);   // (its barriers publish the new columns)
+  const double norm_g = sqrt(ng[0]);
+  {   // Gram entries: everything at the first solve, afterwards only what the new pair touches
+    const bool full = iter == mem;
+    const double *Lm = type1 ? Sm : Y;
+    const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+    const int njobs = full ? len * len + 3 * len : 3 * len + 1;
+    for (int job = warp; job < njobs; job += nw) {
+      const double *pa, *pb; double *dst;
+      if (full) {
+        if (job < len * len) { const int i = job / len, j = job - i * len; pa = Lm + (size_t)i * Np; pb = Y + (size_t)j * Np; dst = Mm + i * BC_AA_MAXMEM + j; }
+        else if (job < len * len + len) { const int c = job - len * len; pa = pb = Y + (size_t)c * Np; dst = yn + c; }
+        else if (job < len * len + 2 * len) { const int c = job - len * len - len; pa = pb = Sm + (size_t)c * Np; dst = sn + c; }
+        else { const int i = job - len * len - 2 * len; pa = Lm + (size_t)i * Np; pb = gp; dst = work + i; }
+      } else {
+        if (job < len) { pa = Lm + (size_t)job * Np; pb = Y + (size_t)idx * Np; dst = Mm + job * BC_AA_MAXMEM + idx; }
+        else if (job < 2 * len - 1) { int j = job - len; if (j >= idx) j++; pa = Lm + (size_t)idx * Np; pb = Y + (size_t)j * Np; dst = Mm + idx * BC_AA_MAXMEM + j; }
+        else if (job == 2 * len - 1) { pa = pb = Y + (size_t)idx * Np; dst = yn + idx; }
+        else if (job == 2 * len) { pa = pb = Sm + (size_t)idx * Np; dst = sn + idx; }
+        else { const int i = job - 2 * len - 1; pa = Lm + (size_t)i * Np; pb = gp; dst = work + i; }
+      }
+      double acc = 0.0;
+      for (int e = lane; e < N; e += 32) acc = fma(pa[e], pb[e], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) *dst = acc;
+    }
+  }
+  __syncthreads();
+  if (t < 32) {   // (M + r I) gamma = work: one row per lane, Gaussian elimination with partial pivoting
+    const int lane = t;
+    double nys = 0.0;
+    for (int c = 0; c < len; c++) nys += yn[c] + sn[c];
+    const double r = (type1 ? 1e-6 : 1e-10) * nys;
+    double a[BC_AA_MAXMEM], rhs = lane < len ? work[lane] : 0.0;
+#pragma unroll
+    for (int k = 0; k < BC_AA_MAXMEM; k++) a[k] = (lane < len && k < len) ? Mm[lane * BC_AA_MAXMEM + k] + (k == lane ? r : 0.0) : 0.0;
+    int myc = -1;
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < BC_AA_MAXMEM; c++) {
+      if (c < len) {
+        const double v = (lane < len && myc < 0) ? fabs(a[c]) : -1.0;
+        const double best = warp_max(v);
+        const int p = __ffs(__ballot_sync(0xffffffffu, v == best)) - 1;
+        if (!(best > 0.0)) ok = false;
+        const double pc = __shfl_sync(0xffffffffu, a[c], p);
+        const double f = (lane < len && myc < 0 && lane != p && ok) ? a[c] / pc : 0.0;
+#pragma unroll
+        for (int k = 0; k < BC_AA_MAXMEM; k++) { const double pk = __shfl_sync(0xffffffffu, a[k], p); if (k >= c) a[k] = fma(-f, pk, a[k]); }
+        rhs = fma(-f, __shfl_sync(0xffffffffu, rhs, p), rhs);
+        if (lane == p) myc = c;
+      }
+    }
+    double xs[BC_AA_MAXMEM], nrm = 0.0;
+#pragma unroll
+    for (int c = BC_AA_MAXMEM - 1; c >= 0; c--) {
+      xs[c] = 0.0;
+      if (c < len) {
+        double acc = rhs;
+#pragma unroll
+        for (int k = c + 1; k < BC_AA_MAXMEM; k++) if (k < len) acc = fma(-a[k], xs[k], acc);
+        const double xv = acc / a[c];
+        const int p = __ffs(__ballot_sync(0xffffffffu, myc == c)) - 1;
+        xs[c] = __shfl_sync(0xffffffffu, xv, p < 0 ? 0 : p);
+        nrm = fma(xs[c], xs[c], nrm);
+      }
+    }
+    nrm = sqrt(nrm);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < BC_AA_MAXMEM; c++) sscr[c] = xs[c];
+      sscr[BC_AA_MAXMEM] = (ok && nrm < BC_AA_MAX_WEIGHT_NORM) ? nrm : -1.0;
+    }
+  }
+  __syncthreads();
+  const double aa_norm = sscr[BC_AA_MAXMEM];
+  if (!(aa_norm >= 0.0)) {
+    if (t == 0) { hdr[0] = 0.0; hdr[1] = 0.0; }
+    __syncthreads();
+    return -1.0;
+  }
+  for (int e = t; e < N; e += T) {
+    double v = w.at(e);
+    for (int c = 0; c < len; c++) v = fma(-sscr[c], D[(size_t)c * Np + e], v);
+    w.at(e) = v;
+  }
+  if (t == 0) { hdr[0] = iter + 1; hdr[1] = 1.0; hdr[2] = norm_g; }
+  __syncthreads();
+  return aa_norm;
+}
+// After one plain step from the accelerated point (w_prev = that point, w = the step's result): reject the
+// acceleration if the fixed-point residual grew.  Returns true when w and w_prev were restored.  Barriers inside.
+static __device__ __noinline__ bool aa_safeguard_dev(double *ws, int lookback, const AaIter w, double *red) {
+  const int T = blockDim.x, t = threadIdx.x, N = w.n + w.m + 1, Np = (N + 1) & ~1;
+  double *hdr = ws, *ax = ws + BC_AA_HDR, *af = ax + Np, *wprev = af + 2 * Np;
+  __syncthreads();
+  const bool success = hdr[1] != 0.0;
+  const double norm_g = hdr[2];
+  __syncthreads();
+  if (!success) return false;
+  double nd[1] = {0.0};
+  for (int e = t; e < N; e += T) { const double q = wprev[e] - w.at(e); nd[0] = fma(q, q, nd[0]); }
+  block_reduce<1, false>(nd, red);
+  if (t == 0) hdr[1] = 0.0;
+  const bool reject = sqrt(nd[0]) > BC_AA_SAFEGUARD_FACTOR * norm_g;
+  if (reject) {
+    for (int e = t; e < N; e += T) { w.at(e) = af[e]; wprev[e] = ax[e]; }
+    if (t == 0) hdr[0] = 0.0;
+  }
+  __syncthreads();
+  return reject;
 }
 
 // ----------------------------------------------------------------------------- matrix layouts

@@ -433,8 +433,16 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     int next_check = st.check_interval < 10 ? st.check_interval : 10, prev_it = 0;
     double prev_lr = 0;
     if (!okf) status = BCONE_FAILED;
+    // Anderson acceleration of w (common.cuh; oracle: aa_apply / aa_safeguard in cone_oracle.c)
+    const int aa_lb = a.aa_ws ? st.acceleration_lookback : 0, aa_iv = st.acceleration_interval > 0 ? st.acceleration_interval : 1;
+    double *const aaw = aa_lb ? a.aa_ws + (size_t)blockIdx.x * a.aa_stride : nullptr;
+    const AaIter aait{M.w, n, M.w + n, m, M.w + N - 1};
+    if (aa_lb) aa_reset_dev(aaw);
 
     for (it = 1; okf && it <= st.max_iters; it++) {
+      const bool aa_now = aa_lb && it > 1 && (it - 1) % aa_iv == 0;
+      if (aa_now) aa_apply_dev(aaw, aa_lb, aait, M.red + 128, M.red);
+      if (aa_lb && (aa_now || it % aa_iv == 0)) { aa_store_prev(aaw, aa_lb, aait, M.w[N - 1]); __syncthreads(); }
       // ---- affine step ----
       const double w_tau = M.w[N - 1];   // read before anything of this iteration can overwrite it
       double d4[4] = {0, 0, 0, 0};       // mu'g, p'Rg, p'Rp, p'mu  (R-weighted; accumulated in the product epilogues)
@@ -566,6 +574,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
               okf = factor_and_g<DENSE, INDIRECT>(a, M, Pg, scale, rho_x, gRg, plA, plN);
               if (!okf) { status = BCONE_FAILED; break; }
               sum_log = 0; n_log = 0; last_up = it;
+              if (aa_lb) aa_reset_dev(aaw);   // the fixed-point map changed
             }
           }
         }
@@ -575,6 +584,8 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         for (int k = t; k < N; k += T) M.w[k] += alpha * (M.u[k] - M.ut[k]);
         __syncthreads();
       }
+      // safeguard after the convergence check: it acts on w, convergence is judged on u
+      if (aa_now && it < st.max_iters) aa_safeguard_dev(aaw, aa_lb, aait, M.red);
     }
     if (it > st.max_iters) it = st.max_iters;
     pt.stamp(4);

@@ -307,7 +307,7 @@ __device__ __noinline__ bool chol_cold(double *K, int n, double *tmp) { return c
 // Slots of the shared scalar block sc[] (= red + 256): values every thread agrees on but only the cold paths
 // need, kept out of the register file.
 enum { SC_SIGMA = 0, SC_NB0, SC_NC0, SC_SUMLOG, SC_PREVLR, SC_RP, SC_RD, SC_GAP, SC_UTAU, SC_NLOG, SC_LASTUP, SC_PREVIT,
-       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT };
+       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AASCR };   // SC_AASCR: 17 slots
 
 // Everything of a termination check after the two products with A (A u_x in tm, A' u_y in tn): P^ u_x, the
 // residual norms on the un-normalised data, termination and certificates, the adaptive
@@ -619,9 +619,24 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     int it = 0, next_check = st.adaptive_check ? (st.check_interval < 10 ? st.check_interval : 10) : st.check_interval;
     if (t < n) { vx(VX_W)[t] = 0; vx(VX_U)[t] = 0; vx(VX_UT)[t] = 0; }
     if (t < m) { vy(VY_W)[t] = 0; vy(VY_U)[t] = 0; vy(VY_UT)[t] = 0; }
+    __syncthreads();
     bool refactor = true, first = true;
+    // Anderson acceleration of w (common.cuh): state and window in a global slab, touched every aa_iv iterations
+    const int aa_lb = a.aa_ws ? st.acceleration_lookback : 0, aa_iv = st.acceleration_interval > 0 ? st.acceleration_interval : 1;
+    double *const aaw = aa_lb ? a.aa_ws + (size_t)blockIdx.x * a.aa_stride : nullptr;
+    if (aa_lb) aa_reset_dev(aaw);
 
     for (it = 1; it <= st.max_iters; it++) {
+      if (aa_lb && (it % aa_iv == 0 || (it > 1 && (it - 1) % aa_iv == 0))) {
+        const AaIter aait{vx(VX_W), n, vy(VY_W), m, sc + SC_AATAU};
+        if (it > 1 && (it - 1) % aa_iv == 0) {
+          if (t == 0) sc[SC_AATAU] = w_tau;
+          aa_apply_dev(aaw, aa_lb, aait, sc + SC_AASCR, red);
+          w_tau = sc[SC_AATAU];
+        }
+        aa_store_prev(aaw, aa_lb, aait, w_tau);
+        __syncthreads();
+      }
       if (refactor) {
         // Factorisation at the current scale (the one place it is written, so the tiles stay in registers):
         // stage A^ from the tiles -> K -> Cholesky -> Linv -> Kinv; then g = (R_z + M)^{-1} h and g'Rg.
@@ -750,13 +765,18 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         const double ns = sc[SC_NEWSCALE];
         pt_stamp(4);
         if (done) break;
-        if (ns != 0.0) { scale = ns; refactor = true; }
+        if (ns != 0.0) { scale = ns; refactor = true; if (aa_lb) aa_reset_dev(aaw); }
         if (it < st.max_iters) {  // (the last iterate keeps w so that s = R(u - t) is recoverable)
           if (t < n) vx(VX_W)[t] += st.alpha * (vx(VX_U)[t] - vx(VX_UT)[t]);
           if (t < m) vy(VY_W)[t] += st.alpha * (vy(VY_U)[t] - vy(VY_UT)[t]);
           w_tau += st.alpha * (u_tau - tau_t);
           __syncthreads();
         }
+      }
+      if (aa_lb && it > 1 && (it - 1) % aa_iv == 0 && it < st.max_iters) {   // safeguard after the convergence check
+        const AaIter aait{vx(VX_W), n, vy(VY_W), m, sc + SC_AATAU};
+        if (t == 0) sc[SC_AATAU] = w_tau;
+        if (aa_safeguard_dev(aaw, aa_lb, aait, red)) w_tau = sc[SC_AATAU];
       }
     }
     if (it > st.max_iters) it = st.max_iters;

@@ -24,9 +24,9 @@ _ARG_MAP = {
     "adaptive_scale": "adaptive_scale", "check_interval": "check_interval", "ruiz_passes": "ruiz_passes",
     "lsqr_atol": "lsqr_atol", "lsqr_btol": "lsqr_btol", "lsqr_conlim": "lsqr_conlim",
     "lsqr_iter_lim": "lsqr_iter_lim", "lsqr_precond": "lsqr_precond", "adaptive_check": "adaptive_check",
+    "acceleration_lookback": "acceleration_lookback", "acceleration_interval": "acceleration_interval",
 }
-_IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "acceleration_lookback",
-            "acceleration_interval", "warm_starts", "raise_on_error"}
+_IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "warm_starts", "raise_on_error"}
 
 
 def make_settings(args: dict | None) -> _lib.BconeSettings:

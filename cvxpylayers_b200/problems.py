@@ -273,8 +273,14 @@ def sparse_qp(B: int = 8, n: int = 300, m: int = 600, density: float = 0.03, see
     return plant(st, A_vals, P_vals, rng, name=f"sparse_qp_n{n}_m{m}", active_frac=0.2)
 
 
-def sdp(B: int = 256, k: int = 10, n_eq: int = 10, seed: int = 0) -> Batch:
-    """C5: min <C,X> s.t. <A_i,X> = b_i, X >= 0 with x = svec(X); planted optimum."""
+def sdp(B: int = 256, k: int = 10, n_eq: int = 10, seed: int = 0, rank: int | None = None) -> Batch:
+    """C5: min <C,X> s.t. <A_i,X> = b_i, X >= 0 with x = svec(X); planted optimum.
+
+    ``rank=None`` plants z ~ N(0,1) as SURVEY.md 8d says: the primal optimum then has a random rank r around k/2
+    and, with only ``n_eq = 10`` equalities, is NOT unique (the optimal face has r(r+1)/2 > n_eq dimensions), so
+    the solution map has no derivative and two correct adjoints only agree up to the choice of a min-norm solution.
+    ``rank=r`` plants exactly r positive eigenvalues in the primal slack; with r(r+1)/2 <= n_eq <=
+    k(k+1)/2 - (k-r)(k-r+1)/2 the optimum is generically unique, strictly complementary and nondegenerate."""
     rng = np.random.default_rng(seed)
     n = k * (k + 1) // 2
     m = n_eq + n
@@ -286,7 +292,21 @@ def sdp(B: int = 256, k: int = 10, n_eq: int = 10, seed: int = 0) -> Batch:
     G = rng.standard_normal((B, n_eq, k, k))
     Asym = 0.5 * (G + np.swapaxes(G, 2, 3))
     A_vals = np.concatenate([mat_to_svec(Asym).reshape(B, n_eq * n), -np.ones((B, n))], axis=1)
-    return plant(st, A_vals, None, rng, name=f"sdp_k{k}_eq{n_eq}")
+    if rank is None:
+        return plant(st, A_vals, None, rng, name=f"sdp_k{k}_eq{n_eq}")
+    # planted pair with prescribed inertia: v = y - s, y = Pi(v) has k - rank positive eigenvalues, s = y - v has `rank`
+    x = rng.standard_normal((B, n))
+    z = rng.standard_normal((B, m))
+    Q = np.linalg.qr(rng.standard_normal((B, k, k)))[0]
+    lam = np.abs(rng.standard_normal((B, k))) + 0.2
+    lam[:, :rank] *= -1.0   # negative eigenvalues of v = positive eigenvalues of the primal slack s
+    V = (Q * lam[:, None, :]) @ np.swapaxes(Q, 1, 2)
+    z[:, n_eq:] = mat_to_svec(V)
+    y = proj_dual_cone(z, st.cones)
+    s = y - z
+    b = _apply_A(st, A_vals, x) + s
+    c = -_apply_AT(st, A_vals, y)
+    return Batch(st, np.ascontiguousarray(A_vals), b, c, None, x, y, s, f"sdp_k{k}_eq{n_eq}_rank{rank}")
 
 
 def exp_sum(B: int = 64, p: int = 6, k: int = 12, lam: float = 1.0, seed: int = 0) -> Batch:
@@ -329,7 +349,10 @@ CONFIGS = {
     "C2": lambda B=4096, seed=0: dense_qp(B, 100, 200, 50, seed),
     "C3": lambda B=2048, seed=0: socp_portfolio(B, seed=seed),
     "C4": lambda B=512, seed=0: sparse_lp(B, seed=seed),
-    "C5": lambda B=256, seed=0: sdp(B, seed=seed),
+    # C5: 20 equalities and a rank-5 planted optimum (unique, differentiable); C5S is SURVEY.md 8d's literal default
+    # (10 equalities, random rank: the optimum is not unique and the solution map has no derivative)
+    "C5": lambda B=256, seed=0: sdp(B, n_eq=20, seed=seed, rank=5),
+    "C5S": lambda B=256, seed=0: sdp(B, seed=seed),
     "EXP": lambda B=64, seed=0: exp_sum(B, seed=seed),
 }
 

@@ -50,6 +50,9 @@ typedef struct {
                                           2 KKT-block preconditioned where applicable (else 1) */
   int32_t adaptive_check;              /* 0: test termination every check_interval iterations (SCS);
                                           1: place the checks by log-linear extrapolation (<= check_interval apart) */
+  int32_t acceleration_lookback;       /* SCS: Anderson acceleration window; 10 (type-I), < 0 type-II, 0 off
+                                          (what the reference's tests pass, tests/test_torch.py:401-405); |.| <= 16 */
+  int32_t acceleration_interval;       /* SCS: accelerate every this many iterations (10)                    */
 } bcone_settings;
 
 enum { BCONE_SOLVED = 1, BCONE_INACCURATE = 2, BCONE_UNBOUNDED = -1, BCONE_INFEASIBLE = -2, BCONE_FAILED = -4 };

@@ -41,6 +41,7 @@ void orc_default_settings(orc_settings *st) {
   st->lsqr_atol = 1e-8; st->lsqr_btol = 1e-8; st->lsqr_conlim = 1e8;
   st->max_iters = 100000; st->normalize = 1; st->adaptive_scale = 1; st->check_interval = 25;
   st->ruiz_passes = 10; st->lsqr_iter_lim = -1; st->lsqr_precond = 0; st->adaptive_check = 0;
+  st->acceleration_lookback = 10; st->acceleration_interval = 10;
 }
 
 int orc_max_threads(void) {
@@ -348,6 +349,114 @@ static void symu_mv(int n, const int32_t *ip, const int32_t *ix, const double *v
 static double dot(int n, const double *a, const double *b) { double s = 0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; }
 static double nrm2(int n, const double *a) { return sqrt(dot(n, a, a)); }
 
+/* ------------------------------------------------------ Anderson acceleration
+ * Restatement of the safeguarded Anderson acceleration SCS 3 applies to its iterate v (our w) -- SCS default
+ * acceleration_lookback = 10 (type-I; a negative lookback selects type-II), acceleration_interval = 10; the
+ * reference's tests switch it off explicitly with {"acceleration_lookback": 0} (tests/test_torch.py:401-405), so it
+ * is ON on the reference's default path.  Algorithm: Zhang, O'Donoghue, Boyd, "Globally convergent type-I Anderson
+ * acceleration for non-smooth fixed-point iterations" (2020) in the simplified form of SCS's aa.c [recalled, not
+ * vendored: UPSTREAM, unverified constants]: every `interval` iterations the pair (x = iterate before the last step,
+ * f = iterate after it) is pushed into a window of `mem` difference columns
+ *     s = x - x_prev,  d = f - f_prev,  y = (x - f) - (x_prev - f_prev),
+ * and once the window is full (SCS fills the memory before the first solve) the iterate is replaced by
+ *     f - D gamma,   (S'Y + r I) gamma = S'g   [type-I]   or   (Y'Y + r I) gamma = Y'g   [type-II],
+ * r = reg * (||Y||_F^2 + ||S||_F^2), reg = 1e-6 (type-I) / 1e-10 (type-II).  A step with ||gamma|| >= 1e10 (or a
+ * singular system) is dropped and the window reset.  Safeguard: after the next plain step from the accelerated
+ * point, if its fixed-point residual exceeds the residual of the pair that produced it (factor 1.0), the
+ * accelerated point is rejected, the un-accelerated f restored and the window reset. */
+typedef struct {
+  int type1, mem, dim, iter, success;
+  double reg, norm_g;
+  double *x, *f, *g_prev, *g, *Y, *S, *D, *M, *work;
+} aa_work;
+#define AA_SAFEGUARD_FACTOR 1.0
+#define AA_MAX_WEIGHT_NORM 1e10
+static aa_work *aa_init(int dim, int lookback) {
+  if (lookback == 0) return NULL;
+  aa_work *a = (aa_work *)calloc(1, sizeof(aa_work));
+  a->type1 = lookback > 0; a->mem = abs(lookback); a->dim = dim; a->iter = 0; a->success = 0;
+  a->reg = a->type1 ? 1e-6 : 1e-10;
+  size_t l = (size_t)dim, M = (size_t)a->mem;
+  a->x = (double *)calloc(4 * l + 3 * l * M + M * M + M, sizeof(double));
+  a->f = a->x + l; a->g_prev = a->f + l; a->g = a->g_prev + l; a->Y = a->g + l; a->S = a->Y + l * M; a->D = a->S + l * M;
+  a->M = a->D + l * M; a->work = a->M + M * M;
+  return a;
+}
+static void aa_free(aa_work *a) { if (a) { free(a->x); free(a); } }
+static void aa_reset(aa_work *a) { if (a) { a->iter = 0; a->success = 0; } }
+/* dense solve by Gaussian elimination with partial pivoting (len <= mem); returns 0 if singular */
+static int aa_gesv(int len, double *Mx, double *rhs) {
+  for (int c = 0; c < len; c++) {
+    int pv = c; double best = fabs(Mx[c * len + c]);
+    for (int r = c + 1; r < len; r++) if (fabs(Mx[r * len + c]) > best) { best = fabs(Mx[r * len + c]); pv = r; }
+    if (!(best > 0)) return 0;
+    if (pv != c) { for (int k = 0; k < len; k++) { double t = Mx[c * len + k]; Mx[c * len + k] = Mx[pv * len + k]; Mx[pv * len + k] = t; }
+                   double t = rhs[c]; rhs[c] = rhs[pv]; rhs[pv] = t; }
+    for (int r = c + 1; r < len; r++) {
+      double f = Mx[r * len + c] / Mx[c * len + c];
+      if (f == 0) continue;
+      for (int k = c; k < len; k++) Mx[r * len + k] -= f * Mx[c * len + k];
+      rhs[r] -= f * rhs[c];
+    }
+  }
+  for (int r = len - 1; r >= 0; r--) {
+    double acc = rhs[r];
+    for (int k = r + 1; k < len; k++) acc -= Mx[r * len + k] * rhs[k];
+    rhs[r] = acc / Mx[r * len + r];
+  }
+  return 1;
+}
+/* f (the newest iterate) is overwritten with the accelerated point when a step is taken; x is the iterate the last
+ * step started from.  Returns ||gamma|| (0: nothing done, < 0: step rejected). */
+static double aa_apply(aa_work *a, double *f, const double *x) {
+  if (!a) return 0.0;
+  const int l = a->dim;
+  if (a->iter == 0) {
+    for (int i = 0; i < l; i++) { a->x[i] = x[i]; a->f[i] = f[i]; a->g_prev[i] = x[i] - f[i]; }
+    a->iter++;
+    return 0.0;
+  }
+  const int len = a->iter < a->mem ? a->iter : a->mem, idx = (a->iter - 1) % a->mem;
+  double *Yc = a->Y + (size_t)idx * l, *Sc = a->S + (size_t)idx * l, *Dc = a->D + (size_t)idx * l;
+  for (int i = 0; i < l; i++) {
+    const double g = x[i] - f[i];
+    Sc[i] = x[i] - a->x[i]; Dc[i] = f[i] - a->f[i]; Yc[i] = g - a->g_prev[i];
+    a->g[i] = g; a->g_prev[i] = g; a->x[i] = x[i]; a->f[i] = f[i];
+  }
+  a->norm_g = nrm2(l, a->g);
+  double aa_norm = 0.0;
+  if (a->iter >= a->mem) {   /* the memory is filled before the first solve */
+    double ny = 0, ns = 0;
+    for (int c = 0; c < len; c++) { ny += dot(l, a->Y + (size_t)c * l, a->Y + (size_t)c * l); ns += dot(l, a->S + (size_t)c * l, a->S + (size_t)c * l); }
+    const double r = a->reg * (ny + ns);
+    const double *Lm = a->type1 ? a->S : a->Y;
+    for (int i = 0; i < len; i++) {
+      for (int j = 0; j < len; j++) a->M[i * len + j] = dot(l, Lm + (size_t)i * l, a->Y + (size_t)j * l) + (i == j ? r : 0.0);
+      a->work[i] = dot(l, Lm + (size_t)i * l, a->g);
+    }
+    const int ok = aa_gesv(len, a->M, a->work);
+    aa_norm = ok ? nrm2(len, a->work) : INFINITY;
+    if (!ok || !(aa_norm < AA_MAX_WEIGHT_NORM)) { aa_reset(a); return -1.0; }
+    for (int c = 0; c < len; c++) { const double gc = a->work[c]; const double *Dk = a->D + (size_t)c * l; for (int i = 0; i < l; i++) f[i] -= gc * Dk[i]; }
+    a->success = 1;
+  }
+  a->iter++;
+  return aa_norm;
+}
+/* x_new: the accelerated point, f_new: one plain step from it.  Returns 1 if the step was rejected (both restored). */
+static int aa_safeguard(aa_work *a, double *f_new, double *x_new) {
+  if (!a || !a->success) return 0;
+  a->success = 0;
+  double nd = 0;
+  for (int i = 0; i < a->dim; i++) { const double q = x_new[i] - f_new[i]; nd += q * q; }
+  if (sqrt(nd) > AA_SAFEGUARD_FACTOR * a->norm_g) {
+    memcpy(f_new, a->f, sizeof(double) * a->dim); memcpy(x_new, a->x, sizeof(double) * a->dim);
+    aa_reset(a);
+    return 1;
+  }
+  return 0;
+}
+
 /* ----------------------------------------------------------- forward solve */
 typedef struct {
   int n, m;
@@ -423,6 +532,7 @@ int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const doubl
   double *w = q; q += N; double *u = q; q += N; double *ut = q; q += N; double *p = q; q += N; double *t = q; q += N;
   double *rsk = q; q += N; double *Axv = q; q += m; double *ATy = q; q += n; double *Pxv = q; q += n; double *tm2 = q; q += m;
   cblock *CB; int ncb = cone_blocks(d, &CB);
+  aa_work *aa = NULL; double *wprev = NULL;
 
   memcpy(W.Ah, Av, sizeof(double) * nnzA);
   if (nnzP) memcpy(W.Ph, Pv, sizeof(double) * nnzP);
@@ -467,15 +577,24 @@ int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const doubl
   double scale = st->scale, dtau = TAU_FACTOR, alpha = st->alpha;
   set_ry(&W, scale);
   int status = ORC_INACCURATE, it = 0;
+  double rp = NAN, rd = NAN, gap = NAN;
   if (factor(&W)) { status = ORC_FAILED; goto done; }
   w[N - 1] = 1.0;
+  aa = aa_init(N, st->acceleration_lookback);
+  if (aa) wprev = (double *)calloc(N, sizeof(double));
+  const int aa_iv = st->acceleration_interval > 0 ? st->acceleration_interval : 1;
   double sum_log = 0; int n_log = 0, last_up = 0;
   /* adaptive check schedule: the distance to the tolerance is extrapolated log-linearly from the last
    * two checks and the next check is placed where convergence is predicted (same criteria, fewer
    * wasted iterations than a fixed stride) */
   int next_check = st->check_interval < 10 ? st->check_interval : 10, prev_it = 0; double prev_lr = 0;
-  double rp = NAN, rd = NAN, gap = NAN;
   for (it = 1; it <= st->max_iters; it++) {
+    /* Anderson acceleration of the iterate w (SCS: "accelerate here so that the last step is always a
+     * projection onto the cone"): i = it - 1 is SCS's 0-based iteration counter. */
+    const int aa_now = aa && it > 1 && (it - 1) % aa_iv == 0;
+    double aa_nrm = 0.0;
+    if (aa_now) aa_nrm = aa_apply(aa, w, wprev);
+    if (aa) memcpy(wprev, w, sizeof(double) * N);
     /* affine step: ut = (R + Q)^{-1} R w    */
     csr_mtv(m, n, d->A_indptr, d->A_indices, W.Ah, w + n, W.tn);
     for (int j = 0; j < n; j++) p[j] = W.rho_x * w[j] - W.tn[j];
@@ -556,11 +675,15 @@ int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const doubl
             /* keep R(w + u - 2 ut) invariant across the metric change */
             for (int i = 0; i < m; i++) { int k = n + i; w[k] = (tm2[i] / W.ry[i]) * (w[k] + u[k] - 2.0 * ut[k]) + 2.0 * ut[k] - u[k]; }
             sum_log = 0; n_log = 0; last_up = it;
+            aa_reset(aa);   /* the fixed-point map changed */
+            aa_nrm = 0.0;
           }
         }
       }
     }
     for (int k = 0; k < N; k++) w[k] += alpha * (u[k] - ut[k]);
+    /* safeguard after the convergence check (it acts on w, convergence is judged on u) */
+    if (aa_now && aa_nrm > 0) aa_safeguard(aa, w, wprev);
   }
   if (it > st->max_iters) it = st->max_iters;
   {
@@ -578,6 +701,7 @@ int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const doubl
 done:
   if (iters) *iters = it;
   if (resid) { resid[0] = rp; resid[1] = rd; resid[2] = gap; }
+  aa_free(aa); free(wprev);
   free(CB); free(buf);
   return status;
 }

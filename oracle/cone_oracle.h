@@ -43,6 +43,8 @@ typedef struct {
   double lsqr_atol, lsqr_btol, lsqr_conlim;
   int32_t max_iters, normalize, adaptive_scale, check_interval;
   int32_t ruiz_passes, lsqr_iter_lim, lsqr_precond, adaptive_check;
+  int32_t acceleration_lookback;  /* SCS: Anderson acceleration window, 10 (type-I); < 0 type-II; 0 off */
+  int32_t acceleration_interval;  /* SCS: accelerate every this many iterations, 10 */
 } orc_settings;
 
 enum { ORC_SOLVED = 1, ORC_INACCURATE = 2, ORC_UNBOUNDED = -1, ORC_INFEASIBLE = -2, ORC_FAILED = -4 };

@@ -28,7 +28,8 @@ CASES = {
     "socp": lambda: pr.socp_portfolio(3, n_assets=8, n_soc=2, k=3, seed=14),
     "sdp": lambda: pr.sdp(2, k=4, n_eq=3, seed=15),
 }
-ARGS = dict(eps=1e-9, max_iters=200000)
+# (the fixtures were generated before Anderson acceleration existed in the oracle: plain operator splitting)
+ARGS = dict(eps=1e-9, max_iters=200000, acceleration_lookback=0)
 
 
 def main():

@@ -15,11 +15,11 @@ from cvxpylayers_b200 import problems as pr
 from cvxpylayers_b200.structure import ConeSpec, Structure
 from oracle import np_ref
 from oracle import oracle as orc
-from tests.util import GOLDEN_CASES, load_golden, rel_err
+from tests.util import GOLDEN_CASES, load_golden, ref_sdp_batch, ref_soc_batch, rel_err
 
 
 # ----------------------------------------------------------------------------- forward
-@pytest.mark.parametrize("name,B", [("C1", 4), ("C2", 3), ("C3", 4), ("C5", 3)])
+@pytest.mark.parametrize("name,B", [("C1", 4), ("C2", 3), ("C3", 4), ("C5", 3), ("C5S", 3)])
 @pytest.mark.parametrize("eps", [1e-4, 1e-8])
 def test_forward_kkt_certificate(name, B, eps):
     """Every returned point satisfies SCS's own termination criteria on the original data."""
@@ -31,7 +31,7 @@ def test_forward_kkt_certificate(name, B, eps):
         r = np_ref.kkt_residuals(bt.A_dense(i), P, bt.b[i], bt.c[i], x[i], y[i], s[i])
         assert np_ref.is_converged(r, eps, eps, 1.0001)
         assert abs(s[i] @ y[i]) <= 1e-9 * max(1.0, np.abs(s[i]).max() * np.abs(y[i]).max() * bt.structure.m)  # exact complementarity
-    if bt.x_star is not None and name != "C5":
+    if bt.x_star is not None and name != "C5S":   # (C5S: SURVEY's literal SDP, non-unique optimum)
         assert np.abs(x - bt.x_star).max() < 200 * eps  # planted optimum recovered
 
 
@@ -107,6 +107,48 @@ def test_max_iters_degrades_answer():
     x2, _, _, st2, _ = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-8)
     assert st1[0] == 2 and it1[0] == 1 and st2[0] == 1
     assert np.abs(x1 - bt.x_star).max() > 100 * np.abs(x2 - bt.x_star).max()
+
+
+# ----------------------------------------------------------------------------- Anderson acceleration
+@pytest.mark.parametrize("name,B", [("C2", 6), ("C3", 6), ("C5", 4), ("C5S", 4)])
+def test_anderson_acceleration_same_solution_fewer_iterations(name, B):
+    """SCS accelerates its iterate by default (lookback 10, every 10 iterations, memory filled first); the reference's
+    tests switch it off with {"acceleration_lookback": 0} (tests/test_torch.py:401-405).  Off / type-I / type-II must
+    reach the same certified optimum; at a tight tolerance the accelerated runs need fewer iterations; within the first
+    100 iterations (window not full yet) the accelerated and the plain run are the same run."""
+    bt = pr.CONFIGS[name](B=B)
+    st = bt.structure
+    runs = {}
+    for lb in (0, 10, -10):
+        x, y, s, status, iters = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=100000, acceleration_lookback=lb)
+        assert (status == 1).all(), (lb, status)
+        for i in range(B):
+            P = bt.P_dense(i) if bt.P_vals is not None else None
+            assert np_ref.is_converged(np_ref.kkt_residuals(bt.A_dense(i), P, bt.b[i], bt.c[i], x[i], y[i], s[i]), 1e-9, 1e-9, 1.0001)
+        runs[lb] = (x, iters)
+    for lb in (10, -10):
+        if name == "C5S":   # the planted SDP optimum is not unique in x: compare the objective value
+            assert np.abs((runs[lb][0] * bt.c).sum(1) - (runs[0][0] * bt.c).sum(1)).max() < 1e-6 * max(1.0, np.abs((runs[0][0] * bt.c).sum(1)).max())
+        else:
+            assert np.abs(runs[lb][0] - runs[0][0]).max() < 1e-6 * max(1.0, np.abs(runs[0][0]).max())
+        if runs[0][1].mean() > 300:   # long runs: acceleration pays clearly; short ones have at most a few accelerated steps
+            assert runs[lb][1].mean() < 0.9 * runs[0][1].mean(), (lb, runs[lb][1], runs[0][1])
+        else:
+            assert runs[lb][1].mean() <= 1.15 * runs[0][1].mean(), (lb, runs[lb][1], runs[0][1])
+    short = {lb: orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=100, acceleration_lookback=lb) for lb in (0, 10)}
+    assert np.array_equal(short[0][0], short[10][0]) and np.array_equal(short[0][2], short[10][2])
+
+
+def test_anderson_acceleration_safeguard_keeps_lps_convergent():
+    """LP vertices are where unsafeguarded acceleration misbehaves; with the safeguard every variant still terminates
+    with the certificate (and the every-iteration variant, acceleration_interval=1, too)."""
+    bt = pr.dense_lp(4, 8, 20, seed=4)
+    for lb, iv in ((10, 10), (-10, 10), (5, 1)):
+        x, y, s, status, iters = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, eps=1e-6, max_iters=400000,
+                                                 acceleration_lookback=lb, acceleration_interval=iv)
+        assert (status == 1).all(), (lb, iv, status, iters)
+        for i in range(bt.B):
+            assert np_ref.is_converged(np_ref.kkt_residuals(bt.A_dense(i), None, bt.b[i], bt.c[i], x[i], y[i], s[i]), 1e-6, 1e-6, 1.0001)
 
 
 # ----------------------------------------------------------------------------- cones
@@ -191,14 +233,85 @@ def test_vjp_matches_finite_differences():
             assert abs(fd - grad[0, k]) <= 1e-4 + 1e-3 * abs(fd), (which, k, fd, grad[0, k])
 
 
+def _fd_check(make, params, which, args, dx, dy, grads, atol=1e-4, rtol=1e-3, h=1e-6):
+    """Central differences of loss = <x, dx> + <y, dy> in every entry of `params` (a flat vector the builder `make`
+    turns into a one-instance batch) against the adjoint's gradient wrt that entry -- the reference's gradcheck
+    tolerances (atol 1e-4, rtol 1e-3)."""
+    for k in range(params.size):
+        vals = []
+        for sgn in (+1, -1):
+            p = params.copy(); p[k] += sgn * h
+            bt = make(p)
+            x, y, _, stt, _ = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+            assert stt[0] == 1
+            vals.append(float(x[0] @ dx + y[0] @ dy))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(fd - grads[k]) <= atol + rtol * abs(fd), (which, k, fd, grads[k])
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_psd_adjoint_matches_finite_differences(precond):
+    """The reference's PSD gradcheck (tests/test_torch.py:233-248: min tr(CX), tr X = 1, X >> 0 at a well-conditioned
+    C, atol 1e-4 / rtol 1e-3) restated on the oracle: this pins the PSD projection Jacobian *inside* the adjoint
+    independently of any other implementation."""
+    C0 = np.array([[2.0, 0.5, 0.1], [0.5, 3.0, 0.2], [0.1, 0.2, 1.5]])
+    iu = np.triu_indices(3)
+
+    def make(p):   # p = the 6 free entries of the symmetric parameter
+        C = np.zeros((3, 3)); C[iu] = p; C = C + C.T - np.diag(np.diag(C))
+        return ref_sdp_batch([C])
+
+    p0 = C0[iu].copy()
+    bt = make(p0)
+    st = bt.structure
+    args = dict(eps=1e-12, max_iters=400000)
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, **args)
+    assert status[0] == 1
+    lam, V = np.linalg.eigh(C0)
+    assert np.abs(pr.svec_to_mat(x[0], 3) - np.outer(V[:, 0], V[:, 0])).max() < 1e-8   # analytic optimum: projector on the min eigenvector
+    rng = np.random.default_rng(4)
+    dx, dy = rng.standard_normal(st.n), rng.standard_normal(st.m)
+    dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, x, y, s, dx[None], dy[None], lsqr_precond=precond, lsqr_iter_lim=20000,
+                                      lsqr_atol=1e-12, lsqr_btol=1e-12)
+    # chain rule svec(C) -> free entries of C: diagonal entries map 1:1, an off-diagonal C_ij feeds sqrt2 * C_ij
+    svec_pos = {(0, 0): 0, (1, 0): 1, (2, 0): 2, (1, 1): 3, (2, 1): 4, (2, 2): 5}
+    grads = np.array([dc[0, svec_pos[(max(i, j), min(i, j))]] * (1.0 if i == j else np.sqrt(2.0)) for i, j in zip(*iu)])
+    _fd_check(make, p0, "C", args, dx, dy, grads)
+    # and the data the reference never perturbs (b: the trace level)
+    def make_b(p):
+        bt2 = make(p0); bt2.b[0, 0] = p[0]; return bt2
+    _fd_check(make_b, np.array([1.0]), "b", args, dx, dy, np.array([db[0, 0]]))
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_soc_adjoint_matches_finite_differences(precond):
+    """The reference's SOC gradcheck (tests/test_dual_variables.py:346-369: min c'x + 0.1||x||^2, ||x|| <= t, output =
+    sum of the SOC dual, parameters c and t, atol 1e-4 / rtol 1e-3) restated on the oracle."""
+    p0 = np.array([0.5, 0.3, -0.2, 2.0])
+    make = lambda p: ref_soc_batch([p[:3]], [p[3]])  # noqa: E731
+    bt = make(p0)
+    st = bt.structure
+    args = dict(eps=1e-12, max_iters=400000)
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+    assert status[0] == 1
+    assert abs(np.linalg.norm(x[0]) - 2.0) < 1e-8 and np.abs(x[0] / np.linalg.norm(x[0]) + p0[:3] / np.linalg.norm(p0[:3])).max() < 1e-8
+    for dx, dy in ((np.zeros(3), np.ones(4)), (np.array([1.0, -2.0, 0.5]), np.array([0.3, -1.0, 2.0, 0.7]))):
+        dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, x, y, s, dx[None], dy[None], bt.P_vals, lsqr_precond=precond,
+                                          lsqr_iter_lim=20000, lsqr_atol=1e-12, lsqr_btol=1e-12)
+        _fd_check(make, p0, "c,t", args, dx, dy, np.concatenate([dc[0], db[0, :1]]))
+
+
 # ----------------------------------------------------------------------------- golden fixtures
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_oracle_reproduces_golden_fixtures(name):
     bt, g = load_golden(name)
     st = bt.structure
-    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=200000)
+    x, y, s, status, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=200000, acceleration_lookback=0)
     assert (status == 1).all()
     assert np.abs(x - g["x"]).max() < 1e-9 and np.abs(y - g["y"]).max() < 1e-9 and np.abs(s - g["s"]).max() < 1e-9
+    # Anderson acceleration (SCS default) changes the path, not the destination
+    x2, y2, s2, status2, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-9, max_iters=200000)
+    assert (status2 == 1).all() and np.abs(x2 - g["x"]).max() < 2e-6 * max(1.0, np.abs(g["x"]).max())
     dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, g["x"], g["y"], g["s"], g["dx"], g["dy"], bt.P_vals,
                                       lsqr_precond=1, lsqr_iter_lim=100000)
     assert rel_err(dA, g["dA"]) < 1e-9 and rel_err(db, g["db"]) < 1e-9 and rel_err(dc, g["dc"]) < 1e-9
