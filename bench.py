@@ -336,7 +336,7 @@ def main():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    p.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the BASELINE.json batch of the config)")
     p.add_argument("--cpu-sample", type=int, default=512, help="instances per CPU-baseline pass")
     p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "C5S", "EXP"],
                    help="workload (default: the headline C2; others are secondary measurements)")
@@ -348,9 +348,13 @@ def main():
     for kv in a.set:
         k, v = kv.split("=", 1)
         SOLVER_ARGS[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
+    if a.batch <= 0:
+        a.batch = {"C1": 4096, "C2": 4096, "C3": 2048, "C4": 512, "C5": 256, "C5S": 256, "EXP": 1024}[CONFIG]
     if CONFIG != "C2":
         METRIC = f"problems/sec fwd+bwd, BASELINE config {CONFIG} (secondary measurement)"
         a.cpu_sample = min(a.cpu_sample, a.batch)
+        if CONFIG == "C4":   # LP: no quadratic term for the block factorisation; thousands of iterations per instance
+            SOLVER_ARGS.update({"lsqr_precond": 1, "max_iters": 100000})
     # The contract is ONE JSON line on stdout.  Libraries write there behind Python's back (NCCL prints its version
     # banner on fd 1 when NCCL_DEBUG is set), so fd 1 points at stderr while the run is in progress and the
     # result line is written to the saved descriptor by the print() calls below via sys.stdout.

@@ -12,7 +12,7 @@
 
 // ---- kernels / launchers implemented in fwd.cu, bwd.cu, pack.cu ----
 extern "C" {
-size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect);
+size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect, int ns, int nexp);
 size_t bc_fwd_ws_doubles(int n, int m);
 cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem);
 cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas);
@@ -201,7 +201,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   auto pick_fwd = [&]() -> bool {   // DIRECT (Cholesky on chip) if the instance fits, else INDIRECT (CG, vectors in L2)
     for (int ind = 0; ind <= 1; ind++)
       for (int tt = threads; tt >= 64; tt /= 2) {
-        size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd, ind);
+        size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd, ind, d->ns, d->ep + d->ed);
         if (sm <= smem_cap) { h->fwd_threads = tt; h->fwd_smem = sm; h->fwd_indirect = ind; return true; }
       }
     return false;
@@ -232,7 +232,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   if (!pick_fwd() || (!h->fast_bwd && !pick_bwd())) {
     char buf[256];
     snprintf(buf, sizeof buf, "instance does not fit the shared-memory-resident engine (fwd %zu B / bwd %zu B needed, %zu B per CTA available)",
-             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, 1), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total, d->ep + d->ed, 1), smem_cap);
+             bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, 1, d->ns, d->ep + d->ed), bc_bwd_smem_bytes(n, m, npoly, d->nnzA, 0, 64, max_psd, psd_total, d->ep + d->ed, 1), smem_cap);
     bcone_destroy(h);
     return fail(nullptr, BCONE_EUNSUPPORTED, buf);
   }
@@ -244,7 +244,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
       h->fast_fwd = 1; h->fwd_threads = bc_fwdf_threads(); h->fwd_smem = bc_fwdf_smem_bytes(n, m);
     }
   }
-  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect) : h->fwd_smem)) != cudaSuccess ||
+  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect, d->ns, d->ep + d->ed) : h->fwd_smem)) != cudaSuccess ||
       (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
@@ -346,6 +346,7 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   if (stg->acceleration_lookback != 0 && stg->max_iters > 1) {
     const int mem = std::abs(stg->acceleration_lookback);
     a.aa_stride = (long long)((aa_ws_doubles(h->S.n + h->S.m + 1, mem) + 1) & ~(size_t)1);
+    if (h->fast_fwd) a.aa_stride += 32 * 512;   // the register-tiled kernel parks its tile here during an acceleration event
     if (!ensure_slab(h, &sw->aa, &sw->aa_cap, (size_t)a.aa_stride * max_grid)) return fail(h, BCONE_ENOMEM, "cudaMalloc acceleration workspace");
     a.aa_ws = sw->aa;
   }

@@ -84,6 +84,29 @@ __device__ __forceinline__ void apply_D(const DevStruct &S, const BwdSmem &M, co
         double *Xd = M.psdscr + warp * (3 * S.max_psd * S.max_psd + S.max_psd), *T1 = Xd + k * k, *T2 = T1 + k * k;
         svec_to_mat_warp(k, ib, Xd);
         __syncwarp();
+        if (k <= 16) {   // the two congruences V' . V and V . V' on the FP64 tensor cores (DMMA.8x8x4, common.cuh warp_mm16)
+          auto inb = [&](int i, int j) { return i < k && j < k; };
+          warp_mm16(k, [&](int i, int q) { return inb(i, q) ? Xd[i * k + q] : 0.0; }, [&](int q, int j) { return inb(q, j) ? Vm[q * k + j] : 0.0; },
+                    [&](int i, int j, double val) { if (inb(i, j)) T1[i * k + j] = val; });                       // T1 = Xd V
+          __syncwarp();
+          warp_mm16(k, [&](int i, int q) { return inb(i, q) ? Vm[q * k + i] : 0.0; }, [&](int q, int j) { return inb(q, j) ? T1[q * k + j] : 0.0; },
+                    [&](int i, int j, double val) {                                                                // T2 = B o (V' T1)
+                      if (!inb(i, j)) return;
+                      const double li = lam[i], lj = lam[j];
+                      double bij;
+                      if (li > 0 && lj > 0) bij = 1.0; else if (li <= 0 && lj <= 0) bij = 0.0;
+                      else { const double lp = li > 0 ? li : lj, ln = li > 0 ? lj : li; bij = lp / (lp - ln); }
+                      T2[i * k + j] = val * bij; });
+          __syncwarp();
+          warp_mm16(k, [&](int i, int q) { return inb(i, q) ? Vm[i * k + q] : 0.0; }, [&](int q, int j) { return inb(q, j) ? T2[q * k + j] : 0.0; },
+                    [&](int i, int j, double val) { if (inb(i, j)) T1[i * k + j] = val; });                       // T1 = V T2
+          __syncwarp();
+          warp_mm16(k, [&](int i, int q) { return inb(i, q) ? T1[i * k + q] : 0.0; }, [&](int q, int j) { return inb(q, j) ? Vm[j * k + q] : 0.0; },
+                    [&](int i, int j, double val) { if (inb(i, j)) Xd[i * k + j] = val; });                       // Xd = T1 V'
+          __syncwarp();
+          mat_to_svec_warp(k, Xd, ob);
+          continue;
+        }
         for (int e = lane; e < k * k; e += 32) {  // T1 = Xd V
           const int i = e / k, j = e % k; double acc = 0;
           for (int q = 0; q < k; q++) acc = fma(Xd[i * k + q], Vm[q * k + j], acc);
@@ -291,7 +314,11 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
           double *Xd = M.psdscr + warp * (3 * S.max_psd * S.max_psd + S.max_psd);
           svec_to_mat_warp(k, M.v + s0, Xd);
           __syncwarp();
-          jacobi_eig_warp(k, Xd, Vm);
+          if (k <= 16) {   // parallel-ordered Jacobi (common.cuh), cold start
+            for (int e = lane; e < k * k; e += 32) Vm[e] = (e / k == e % k) ? 1.0 : 0.0;
+            __syncwarp();
+            jacobi_par_warp(k, Xd, Vm);
+          } else jacobi_eig_warp(k, Xd, Vm);
           for (int i = lane; i < k; i += 32) lam[i] = Xd[i * k + i];
           __syncwarp();
           for (int e = lane; e < k * k; e += 32) {  // pi = V max(lam,0) V'

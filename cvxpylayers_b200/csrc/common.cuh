@@ -163,6 +163,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[K], double *red) {
 // the small solve runs on one warp with one matrix row per lane (partial pivoting through shuffles).
 #define BC_AA_MAXMEM 16
 #define BC_AA_HDR (8 + BC_AA_MAXMEM * BC_AA_MAXMEM + 3 * BC_AA_MAXMEM)
+#define BC_AA_LU (BC_AA_MAXMEM * (BC_AA_MAXMEM + 1))
 #define BC_AA_MAX_WEIGHT_NORM 1e10
 #define BC_AA_SAFEGUARD_FACTOR 1.0
 __host__ __device__ inline size_t aa_ws_doubles(int N, int mem) {
@@ -182,8 +183,9 @@ static __device__ __noinline__ void aa_store_prev(double *ws, int mem, const AaI
 }
 // w (the newest iterate, reached by one step from w_prev) is overwritten with the accelerated point when a
 // step is taken.  Block-uniform return value: ||gamma|| (0 nothing done, < 0 step dropped).  Starts and ends
-// with a barrier; *w.wtau must have been written before the call (any thread).
-static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, const AaIter w, double *sscr, double *red) {
+// with a barrier; *w.wtau must have been written before the call (any thread).  sscr: BC_AA_MAXMEM + 1 doubles, lu:
+// BC_AA_LU doubles of shared memory the call may use.
+static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, const AaIter w, double *sscr, double *red, double *lu) {
   const int T = blockDim.x, t = threadIdx.x, N = w.n + w.m + 1, Np = (N + 1) & ~1;
   const int mem = lookback > 0 ? lookback : -lookback;
   const bool type1 = lookback > 0;
@@ -242,51 +244,45 @@ static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, con
     }
   }
   __syncthreads();
-  if (t < 32) {   // (M + r I) gamma = work: one row per lane, Gaussian elimination with partial pivoting
-    const int lane = t;
+  if (t < 32) {   // (M + r I) gamma = work: Gaussian elimination with partial pivoting, one row per lane, the
+                  // matrix in shared memory (lu: BC_AA_MAXMEM x (BC_AA_MAXMEM + 1) doubles): a register-resident copy
+                  // would make this function -- and, through the call, the kernels' iteration loops -- register-hungry
+    const int lane = t, LD = BC_AA_MAXMEM + 1;
     double nys = 0.0;
     for (int c = 0; c < len; c++) nys += yn[c] + sn[c];
     const double r = (type1 ? 1e-6 : 1e-10) * nys;
-    double a[BC_AA_MAXMEM], rhs = lane < len ? work[lane] : 0.0;
-#pragma unroll
-    for (int k = 0; k < BC_AA_MAXMEM; k++) a[k] = (lane < len && k < len) ? Mm[lane * BC_AA_MAXMEM + k] + (k == lane ? r : 0.0) : 0.0;
+    if (lane < len) {
+      for (int k = 0; k < len; k++) lu[lane * LD + k] = Mm[lane * BC_AA_MAXMEM + k] + (k == lane ? r : 0.0);
+      lu[lane * LD + BC_AA_MAXMEM] = work[lane];
+    }
+    __syncwarp();
     int myc = -1;
     bool ok = true;
-#pragma unroll
-    for (int c = 0; c < BC_AA_MAXMEM; c++) {
-      if (c < len) {
-        const double v = (lane < len && myc < 0) ? fabs(a[c]) : -1.0;
-        const double best = warp_max(v);
-        const int p = __ffs(__ballot_sync(0xffffffffu, v == best)) - 1;
-        if (!(best > 0.0)) ok = false;
-        const double pc = __shfl_sync(0xffffffffu, a[c], p);
-        const double f = (lane < len && myc < 0 && lane != p && ok) ? a[c] / pc : 0.0;
-#pragma unroll
-        for (int k = 0; k < BC_AA_MAXMEM; k++) { const double pk = __shfl_sync(0xffffffffu, a[k], p); if (k >= c) a[k] = fma(-f, pk, a[k]); }
-        rhs = fma(-f, __shfl_sync(0xffffffffu, rhs, p), rhs);
-        if (lane == p) myc = c;
+    for (int c = 0; c < len; c++) {
+      const double v = (lane < len && myc < 0) ? fabs(lu[lane * LD + c]) : -1.0;
+      const double best = warp_max(v);
+      const int p = __ffs(__ballot_sync(0xffffffffu, v == best)) - 1;
+      if (!(best > 0.0)) ok = false;
+      if (lane < len && myc < 0 && lane != p && ok) {
+        const double f = lu[lane * LD + c] / lu[p * LD + c];
+        for (int k = c; k < len; k++) lu[lane * LD + k] = fma(-f, lu[p * LD + k], lu[lane * LD + k]);
+        lu[lane * LD + BC_AA_MAXMEM] = fma(-f, lu[p * LD + BC_AA_MAXMEM], lu[lane * LD + BC_AA_MAXMEM]);
       }
+      if (lane == p) myc = c;
+      __syncwarp();
     }
-    double xs[BC_AA_MAXMEM], nrm = 0.0;
-#pragma unroll
-    for (int c = BC_AA_MAXMEM - 1; c >= 0; c--) {
-      xs[c] = 0.0;
-      if (c < len) {
-        double acc = rhs;
-#pragma unroll
-        for (int k = c + 1; k < BC_AA_MAXMEM; k++) if (k < len) acc = fma(-a[k], xs[k], acc);
-        const double xv = acc / a[c];
-        const int p = __ffs(__ballot_sync(0xffffffffu, myc == c)) - 1;
-        xs[c] = __shfl_sync(0xffffffffu, xv, p < 0 ? 0 : p);
-        nrm = fma(xs[c], xs[c], nrm);
+    double nrm = 0.0;
+    for (int c = len - 1; c >= 0; c--) {   // the lane that pivoted on column c owns unknown c
+      if (myc == c) {
+        double acc = lu[lane * LD + BC_AA_MAXMEM];
+        for (int k = c + 1; k < len; k++) acc = fma(-lu[lane * LD + k], sscr[k], acc);
+        sscr[c] = acc / lu[lane * LD + c];
       }
+      __syncwarp();
+      nrm = fma(sscr[c], sscr[c], nrm);
     }
     nrm = sqrt(nrm);
-    if (lane == 0) {
-#pragma unroll
-      for (int c = 0; c < BC_AA_MAXMEM; c++) sscr[c] = xs[c];
-      sscr[BC_AA_MAXMEM] = (ok && nrm < BC_AA_MAX_WEIGHT_NORM) ? nrm : -1.0;
-    }
+    if (lane == 0) sscr[BC_AA_MAXMEM] = (ok && nrm < BC_AA_MAX_WEIGHT_NORM) ? nrm : -1.0;
   }
   __syncthreads();
   const double aa_norm = sscr[BC_AA_MAXMEM];
@@ -398,6 +394,9 @@ __device__ __forceinline__ double butterfly4(double a0, double a1, double a2, do
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+
+__device__ __forceinline__ double c_mul_sub(double c, double x, double s, double y) { return fma(c, x, -(s * y)); }   // c x - s y
+__device__ __forceinline__ double c_mul_add(double s, double x, double c, double y) { return fma(s, x, c * y); }      // s x + c y
 
 // out_i = sum_j M[i][j] * x[j]: one warp per row, lanes across columns (conflict-free for any
 // row stride), x held in registers (ncols <= 128), four rows reduced together.
@@ -978,22 +977,130 @@ __device__ inline void jacobi_eig_warp(int k, double *X, double *V) {
   __syncwarp();
 }
 
-__device__ inline void project_psd_warp(double *v, int k, double *scr) {
+// C(i, j) = sum_q fa(i, q) fb(q, j), i, j, q < k <= 16, by one warp on the FP64 tensor cores (DMMA.8x8x4): the
+// k x k matrices are padded to 8 x 8 output tiles and k-steps of 4 through the accessors (which must return 0
+// outside the matrix); st(i, j, value) receives every entry of the padded result once (guard inside).
+template <class FA, class FB, class ST>
+__device__ __forceinline__ void warp_mm16(int k, FA fa, FB fb, ST st) {
+  const int lane = threadIdx.x & 31, fr = lane >> 2, fc = lane & 3;
+  const int nt = (k + 7) >> 3, nk = (k + 3) >> 2;
+  for (int ti = 0; ti < nt; ti++) {
+    double d[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int ks = 0; ks < nk; ks++) {
+      const double a = fa(8 * ti + fr, 4 * ks + fc);
+#pragma unroll
+      for (int tj = 0; tj < 2; tj++) if (tj < nt) dmma884(d[tj][0], d[tj][1], a, fb(4 * ks + fc, 8 * tj + fr));
+    }
+#pragma unroll
+    for (int tj = 0; tj < 2; tj++) if (tj < nt) { st(8 * ti + fr, 8 * tj + 2 * fc, d[tj][0]); st(8 * ti + fr, 8 * tj + 2 * fc + 1, d[tj][1]); }
+  }
+}
+
+// Parallel-ordered (round-robin) Jacobi on a symmetric k x k matrix T (row-major, shared memory) by one warp:
+// every round rotates k/2 DISJOINT pairs at once -- the angles on one lane per pair, then all column updates of T and
+// of the accumulated eigenvector matrix V (V <- V J), then all row updates -- three warp barriers per round instead
+// of three per rotation.  V is updated, not reset: the caller passes the identity (cold) or the eigenvectors of a
+// nearby matrix after transforming T <- V' T V (warm start: one or two sweeps instead of six to eight).
+// A sweep whose largest |a_pq| / (|a_pp| + |a_qq|) was below 1e-8 is the last one (quadratic convergence puts the
+// remaining off-diagonal part below double precision).  k <= 32.
+__device__ inline void jacobi_par_warp(int k, double *T, double *V) {
   const int lane = threadIdx.x & 31;
-  double *X = scr, *V = scr + k * k, *lam = V + k * k;
+  const int kk = (k + 1) & ~1, np = kk >> 1, nr = kk - 1;   // players (a dummy when k is odd), pairs per round, rounds
+  for (int sweep = 0; sweep < 30; sweep++) {
+    double big = 0.0;
+    for (int r = 0; r < nr; r++) {
+      // pair of lane j < np in round r (circle method: the last player stays, the others rotate)
+      int p = 0, q = 0; double c = 1.0, s = 0.0;
+      if (lane < np) {
+        int a = lane == 0 ? kk - 1 : (r + lane) % nr, b = lane == 0 ? r : (r - lane + nr) % nr;
+        p = min(a, b); q = max(a, b);
+        if (q < k) {
+          const double apq = T[p * k + q], app = T[p * k + p], aqq = T[q * k + q];
+          const double lim = fabs(app) + fabs(aqq);
+          if (!(fabs(apq) <= 1e-17 * lim) && apq != 0.0) {
+            big = fmax(big, fabs(apq) / lim);
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = rsqrt(t * t + 1.0); s = t * c;
+          }
+        }
+      }
+      __syncwarp();   // every angle has been taken from the un-rotated matrix
+      for (int base = 0; base < k * np; base += 32) {   // columns p, q of T and V (warp-uniform trip count: shuffles inside)
+        const int e = base + lane;
+        const bool live = e < k * np;
+        const int row = live ? e / np : 0, j = live ? e - row * np : 0;
+        const int pj = __shfl_sync(0xffffffffu, p, j), qj = __shfl_sync(0xffffffffu, q, j);
+        const double cj = __shfl_sync(0xffffffffu, c, j), sj = __shfl_sync(0xffffffffu, s, j);
+        if (live && qj < k && sj != 0.0) {
+          const double xp = T[row * k + pj], xq = T[row * k + qj];
+          T[row * k + pj] = c_mul_sub(cj, xp, sj, xq); T[row * k + qj] = c_mul_add(sj, xp, cj, xq);
+          const double vp = V[row * k + pj], vq = V[row * k + qj];
+          V[row * k + pj] = c_mul_sub(cj, vp, sj, vq); V[row * k + qj] = c_mul_add(sj, vp, cj, vq);
+        }
+      }
+      __syncwarp();
+      for (int base = 0; base < k * np; base += 32) {   // rows p, q of T
+        const int e = base + lane;
+        const bool live = e < k * np;
+        const int col = live ? e / np : 0, j = live ? e - col * np : 0;
+        const int pj = __shfl_sync(0xffffffffu, p, j), qj = __shfl_sync(0xffffffffu, q, j);
+        const double cj = __shfl_sync(0xffffffffu, c, j), sj = __shfl_sync(0xffffffffu, s, j);
+        if (live && qj < k && sj != 0.0) {
+          const double xp = T[pj * k + col], xq = T[qj * k + col];
+          T[pj * k + col] = c_mul_sub(cj, xp, sj, xq); T[qj * k + col] = c_mul_add(sj, xp, cj, xq);
+        }
+      }
+      __syncwarp();
+    }
+    big = warp_max(big);
+    if (big < 1e-8) break;
+  }
+}
+
+// v (svec) <- Pi_PSD(v).  scr: 2 k^2 + k doubles of per-warp scratch.  Vp: k^2 doubles that persist across the
+// calls of one instance (eigenvectors of the previous iterate) or nullptr; warm = Vp holds them.
+// k <= 16: warm start T = Vp' X Vp and the reconstruction V diag(lam+) V' run on the tensor cores (warp_mm16).
+__device__ inline void project_psd_warp(double *v, int k, double *scr, double *Vp = nullptr, bool warm = false) {
+  const int lane = threadIdx.x & 31;
+  double *X = scr, *W = scr + k * k, *lam = W + k * k;
   svec_to_mat_warp(k, v, X);
   __syncwarp();
-  jacobi_eig_warp(k, X, V);
+  if (k > 16 || !Vp) {   // large blocks: the serial cyclic Jacobi (cold every time)
+    jacobi_eig_warp(k, X, W);
+    for (int i = lane; i < k; i += 32) lam[i] = fmax(X[i * k + i], 0.0);
+    __syncwarp();
+    for (int e = lane; e < k * k; e += 32) {
+      int i = e / k, j = e % k;
+      double a = 0;
+      for (int q = 0; q < k; q++) a = fma(W[i * k + q] * lam[q], W[j * k + q], a);
+      X[e] = a;
+    }
+    __syncwarp();
+    mat_to_svec_warp(k, X, v);
+    __syncwarp();
+    return;
+  }
+  auto inb = [&](int i, int j) { return i < k && j < k; };
+  if (warm) {   // T = Vp' (X Vp)
+    warp_mm16(k, [&](int i, int q) { return inb(i, q) ? X[i * k + q] : 0.0; }, [&](int q, int j) { return inb(q, j) ? Vp[q * k + j] : 0.0; },
+              [&](int i, int j, double val) { if (inb(i, j)) W[i * k + j] = val; });
+    __syncwarp();
+    warp_mm16(k, [&](int i, int q) { return inb(i, q) ? Vp[q * k + i] : 0.0; }, [&](int q, int j) { return inb(q, j) ? W[q * k + j] : 0.0; },
+              [&](int i, int j, double val) { if (inb(i, j)) X[i * k + j] = val; });
+    __syncwarp();
+    // (the product is symmetric up to rounding; the rotations read the upper triangle for the angles)
+  } else {
+    for (int e = lane; e < k * k; e += 32) Vp[e] = (e / k == e % k) ? 1.0 : 0.0;
+    __syncwarp();
+  }
+  jacobi_par_warp(k, X, Vp);
   for (int i = lane; i < k; i += 32) lam[i] = fmax(X[i * k + i], 0.0);
   __syncwarp();
-  for (int e = lane; e < k * k; e += 32) {
-    int i = e / k, j = e % k;
-    double a = 0;
-    for (int q = 0; q < k; q++) a = fma(V[i * k + q] * lam[q], V[j * k + q], a);
-    X[e] = a;
-  }
+  warp_mm16(k, [&](int i, int q) { return inb(i, q) ? Vp[i * k + q] * lam[q] : 0.0; }, [&](int q, int j) { return inb(q, j) ? Vp[j * k + q] : 0.0; },
+            [&](int i, int j, double val) { if (inb(i, j)) W[i * k + j] = val; });
   __syncwarp();
-  mat_to_svec_warp(k, X, v);
+  mat_to_svec_warp(k, W, v);
   __syncwarp();
 }
 
@@ -1027,13 +1134,52 @@ __device__ inline double exp_h(double r, double s, double t, double rho, double 
   *mu = *y * E - t;
   return *y + *mu * E * (1.0 - rho) - s;
 }
-// v <- Pi_{K_exp}(v); returns the case (0 inside, 1 polar, 2 analytic face, 3 iterative)
-__device__ inline int proj_exp(double *v) {
+// Newton on h(rho) = 0 (rho = x / y of the projection p = (rho y, y, y e^rho); h is the stationarity residual of the
+// y-coordinate, exp_h above) with the analytic derivative, started from *rho0 (the previous iterate's root; the
+// cone moves little between operator-splitting iterations) or from a crude guess.  Accepts only a root with y > 0,
+// mu >= 0 and |h| at rounding level; anything else (no decrease, leaving the domain) returns false and the caller falls
+// back to the bisection.  Typically 2-4 iterations warm, 5-8 cold.
+__device__ inline bool exp_newton_rho(double r, double s, double t, double *rho0, double *x) {
+  double rho = (rho0 && *rho0 == *rho0) ? *rho0 : (s > 0 ? fmin(fmax(r / s, -20.0), 20.0) : (t > 0 && r > 0 ? fmin(log(fmax(t, 1e-300) / fmax(r, 1e-300)) , 20.0) : 0.0));
+  const double scale = fmax(1.0, fmax(fabs(r), fmax(fabs(s), fabs(t))));
+  double y, mu, hv = exp_h(r, s, t, rho, &y, &mu);
+  for (int it = 0; it < 30; it++) {
+    if (!(hv == hv)) return false;
+    if (fabs(hv) <= 1e-15 * scale) break;
+    const double E = exp(rho), den = rho + E * E;
+    const double yp = (t * E * den - (r + t * E) * (1.0 + 2.0 * E * E)) / (den * den);
+    const double mup = (yp + y) * E;
+    const double hp = yp + mup * E * (1.0 - rho) - mu * E * rho;
+    if (hp == 0.0 || !(hp == hp)) return false;
+    double step = -hv / hp, rn, yn, mn, hn;
+    int bt = 0;
+    for (;; bt++) {   // damping: accept the first step that reduces |h| inside the domain
+      rn = rho + step;
+      hn = exp_h(r, s, t, rn, &yn, &mn);
+      if (hn == hn && fabs(hn) < fabs(hv) && rn + exp(2.0 * rn) > 0) break;
+      if (bt == 12) return false;
+      step *= 0.5;
+    }
+    const bool tiny = fabs(step) <= 1e-15 * fmax(1.0, fabs(rn));
+    rho = rn; hv = hn; y = yn; mu = mn;
+    if (tiny) break;
+  }
+  if (!(fabs(hv) <= 1e-12 * scale) || !(y > 0) || !(mu >= -1e-14 * scale)) return false;
+  x[0] = y * rho; x[1] = y; x[2] = y * exp(rho);
+  if (rho0) *rho0 = rho;
+  return true;
+}
+// v <- Pi_{K_exp}(v); returns the case (0 inside, 1 polar, 2 analytic face, 3 iterative).  rho0: optional warm start
+// slot of this cone (NaN = none), updated when the Newton path was taken.
+__device__ inline int proj_exp(double *v, double *rho0 = nullptr) {
   const double r = v[0], s = v[1], t = v[2];
   if ((s > 0 && s * exp(fmin(r / s, 700.0)) - t <= 1e-13) || (r <= 0 && s == 0 && t >= 0)) return 0;
   if ((r > 0 && r * exp(fmin(s / r, 700.0)) + 2.718281828459045 * t <= 1e-13) || (r == 0 && s <= 0 && t <= 0)) { v[0] = v[1] = v[2] = 0; return 1; }
   if (r < 0 && s < 0) { v[1] = 0.0; v[2] = fmax(t, 0.0); return 2; }
-  double x[3], lb = 0.0, ub = 0.125;
+  double x[3];
+  if (exp_newton_rho(r, s, t, rho0, x)) { v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; return 3; }
+  if (rho0) *rho0 = nan("");
+  double lb = 0.0, ub = 0.125;
   while (exp_calc_grad(v, x, ub) > 0 && ub < 1e300) { lb = ub; ub *= 2.0; }
   for (int i = 0; i < 200; i++) {
     const double rho = 0.5 * (ub + lb), g = exp_calc_grad(v, x, rho);
@@ -1098,9 +1244,9 @@ __device__ inline void dproj_exp_mat(const double *v, double *J) {
 }
 // y-block versions: rows whose primal cone is K_exp project onto K* (Moreau), rows whose primal
 // cone is the dual exponential cone project onto K_exp itself.
-__device__ inline void proj_exp_dualblock(double *v, bool primal_is_exp) {
-  if (primal_is_exp) { double w[3] = {-v[0], -v[1], -v[2]}; proj_exp(w); v[0] += w[0]; v[1] += w[1]; v[2] += w[2]; }
-  else proj_exp(v);
+__device__ inline void proj_exp_dualblock(double *v, bool primal_is_exp, double *rho0 = nullptr) {
+  if (primal_is_exp) { double w[3] = {-v[0], -v[1], -v[2]}; proj_exp(w, rho0); v[0] += w[0]; v[1] += w[1]; v[2] += w[2]; }
+  else proj_exp(v, rho0);
 }
 __device__ inline void dproj_exp_dualblock_mat(const double *v, bool primal_is_exp, double *J) {
   if (primal_is_exp) {
@@ -1112,13 +1258,23 @@ __device__ inline void dproj_exp_dualblock_mat(const double *v, bool primal_is_e
 }
 
 // v (y-space, length m) <- Pi_{K*}(v) for the SOC/PSD blocks; warps stride over cone blocks.
-__device__ __forceinline__ void project_cones(const DevStruct &S, double *v, double *psd_scr) {
+// psd_scr: [per-warp scratch (2 max_psd^2 + max_psd) x warps | persistent eigenvectors, max_psd^2 per PSD block |
+// one warm-start slot per exponential cone].  warm: the persistent part was written by a previous call of this instance.
+__host__ __device__ inline size_t cone_scratch_doubles(int threads, int max_psd, int ns, int nexp) {
+  return (size_t)(max_psd > 0 ? (threads / 32) * (2 * (size_t)max_psd * max_psd + max_psd) + (size_t)ns * max_psd * max_psd : 0) + (size_t)nexp;
+}
+__device__ __forceinline__ void project_cones(const DevStruct &S, double *v, double *psd_scr, bool warm) {
   const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int scr_stride = 2 * S.max_psd * S.max_psd + S.max_psd;
+  double *persist = psd_scr + (S.max_psd > 0 ? nw * scr_stride : 0);
   for (int cb = warp; cb < S.ncones; cb += nw) {
     const int ty = __ldg(S.cone_type + cb), st = __ldg(S.cone_start + cb);
     if (ty == BC_CSOC) project_soc_warp(v + st, __ldg(S.cone_size + cb));
-    else project_psd_warp(v + st, __ldg(S.cone_order + cb), psd_scr + warp * scr_stride);
+    else project_psd_warp(v + st, __ldg(S.cone_order + cb), psd_scr + warp * scr_stride, persist + (cb - S.nq) * S.max_psd * S.max_psd, warm);
   }
-  for (int e = threadIdx.x; e < S.ep + S.ed; e += blockDim.x) proj_exp_dualblock(v + S.exp_start + 3 * e, e < S.ep);
+  double *rho = persist + (S.max_psd > 0 ? S.ns * S.max_psd * S.max_psd : 0);
+  for (int e = threadIdx.x; e < S.ep + S.ed; e += blockDim.x) {
+    if (!warm) rho[e] = nan("");
+    proj_exp_dualblock(v + S.exp_start + 3 * e, e < S.ep, rho + e);
+  }
 }

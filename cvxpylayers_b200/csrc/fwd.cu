@@ -39,13 +39,15 @@ __host__ __device__ inline size_t fwd_vec_doubles(int n, int m, int indirect) {
 }
 // DIRECT: everything on chip.  INDIRECT (instances whose n x n Cholesky does not fit): the CSR values,
 // the reduction scratch and the PSD scratch stay in shared memory, the vectors move to a global slab.
-__host__ __device__ inline size_t fwd_part_doubles(int n, int threads) { return (size_t)(8 * n > threads ? 8 * n : threads); }
-__host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd, int indirect) {
+__host__ __device__ inline size_t fwd_part_doubles(int n, int threads) {   // (also the LU scratch of the Anderson step: BC_AA_LU = 272)
+  const size_t d = (size_t)(8 * n > threads ? 8 * n : threads);
+  return d > 272 ? d : 272;
+}
+__host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int threads, int max_psd, int indirect, int ns, int nexp) {
   size_t nA = ((size_t)nnzA + 1) & ~(size_t)1;
   size_t d = 4 + nA + fwd_part_doubles(n, threads) + 8 * 32;
   if (!indirect) d += (size_t)n * (n + 1) / 2 + fwd_vec_doubles(n, m, 0);
-  if (max_psd > 0) d += (size_t)(threads / 32) * (2 * (size_t)max_psd * max_psd + max_psd);
-  return d;
+  return d + cone_scratch_doubles(threads, max_psd, ns, nexp);
 }
 
 __device__ __forceinline__ void carve(FwdSmem &M, double *base, double *gws, int n, int m, int nnzA, int threads, int max_psd) {
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
 
     for (it = 1; okf && it <= st.max_iters; it++) {
       const bool aa_now = aa_lb && it > 1 && (it - 1) % aa_iv == 0;
-      if (aa_now) aa_apply_dev(aaw, aa_lb, aait, M.red + 128, M.red);
+      if (aa_now) aa_apply_dev(aaw, aa_lb, aait, M.red + 128, M.red, M.part);
       if (aa_lb && (aa_now || it % aa_iv == 0)) { aa_store_prev(aaw, aa_lb, aait, M.w[N - 1]); __syncthreads(); }
       // ---- affine step ----
       const double w_tau = M.w[N - 1];   // read before anything of this iteration can overwrite it
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
         if (fused) M.w[k] = wk + alpha * (uk - utk);
       }
       __syncthreads();
-      if (nonpoly) { project_cones(S, M.u + n, M.psd); __syncthreads(); }
+      if (nonpoly) { project_cones(S, M.u + n, M.psd, it > 1); __syncthreads(); }
 
       SUB_STAMP(pi, 28);
       pt.stamp(3);   // iteration body
@@ -618,8 +620,8 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
 }
 
 // ----------------------------------------------------------------------------- host launcher
-extern "C" size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect) {
-  return fwd_smem_doubles(n, m, nnzA, threads, max_psd, indirect) * sizeof(double);
+extern "C" size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect, int ns, int nexp) {
+  return fwd_smem_doubles(n, m, nnzA, threads, max_psd, indirect, ns, nexp) * sizeof(double);
 }
 extern "C" size_t bc_fwd_ws_doubles(int n, int m) { return (fwd_vec_doubles(n, m, 1) + 1) & ~(size_t)1; }
 

@@ -307,7 +307,7 @@ __device__ __noinline__ bool chol_cold(double *K, int n, double *tmp) { return c
 // Slots of the shared scalar block sc[] (= red + 256): values every thread agrees on but only the cold paths
 // need, kept out of the register file.
 enum { SC_SIGMA = 0, SC_NB0, SC_NC0, SC_SUMLOG, SC_PREVLR, SC_RP, SC_RD, SC_GAP, SC_UTAU, SC_NLOG, SC_LASTUP, SC_PREVIT,
-       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AASCR };   // SC_AASCR: 17 slots
+       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AADT, SC_NEXTREAL, SC_AASCR };   // SC_AASCR: 17 slots
 
 // Everything of a termination check after the two products with A (A u_x in tm, A' u_y in tn): P^ u_x, the
 // residual norms on the un-normalised data, termination and certificates, the adaptive
@@ -433,6 +433,46 @@ __device__ __noinline__ void scatter_P(const DevStruct &S, const double *Pg, dou
     const int i = __ldg(S.P_rowof + k), j = __ldg(S.P_indices + k);   // j >= i
     Pl[((j * (j + 1)) >> 1) + i] = Pg[k];
   }
+  __syncthreads();
+}
+
+// Anderson acceleration hooks of the register-tiled kernel.  Events happen at the END of iteration j (w complete),
+// which is the oracle's top of iteration j + 1 (nothing happens in between):
+//   j = 0 (mod iv): accelerate.  The iterate the last step started from is rebuilt as w - alpha (u - u~) (u, u~ are
+//                   still in shared memory), so no event is needed one iteration earlier just to remember it.
+//   j = 1 (mod iv): safeguard the step taken from an accelerated point -- scheduled only after a step was taken.
+// While the window fills (the first `lookback` events) an event is a few vector copies to the slab in L2.
+// ibuf[1] holds the next event's iteration; w_tau travels through sc[SC_AATAU], alpha (u_tau - tau~) through sc[SC_AADT].
+__device__ __noinline__ void aa_begin(const FwdArgs &a, int *ibuf) {
+  if (threadIdx.x == 0) {
+    const int iv = a.st.acceleration_interval > 0 ? a.st.acceleration_interval : 1;
+    const bool on = a.aa_ws != nullptr && a.st.acceleration_lookback != 0;
+    ibuf[1] = on ? iv : 0x7fffffff;
+    if (on) { double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride; ws[0] = 0.0; ws[1] = 0.0; }
+  }
+  __syncthreads();
+}
+__device__ __noinline__ void aa_event(const FwdArgs &a, int j, double *vxb, double *vyb, int npad, int mpad, double *sc, double *red, int *ibuf, double *lu) {
+  const int iv = a.st.acceleration_interval > 0 ? a.st.acceleration_interval : 1, lb = a.st.acceleration_lookback;
+  const int n = a.S.n, m = a.S.m, N = n + m + 1, Np = (N + 1) & ~1, t = threadIdx.x;
+  double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride;
+  const AaIter w{vxb + VX_W * npad, n, vyb + VY_W * mpad, m, sc + SC_AATAU};
+  __syncthreads();   // sc[SC_AATAU], sc[SC_AADT] written by thread 0
+  bool pending = false;
+  if (j < a.st.max_iters) {
+    bool rejected = false;
+    if (ws[1] != 0.0) rejected = aa_safeguard_dev(ws, lb, w, red);
+    if (j % iv == 0) {
+      if (!rejected) {   // w_prev = the iterate this step started from
+        double *wprev = ws + BC_AA_HDR + 3 * Np;
+        const double *ux = vxb + VX_U * npad, *utx = vxb + VX_UT * npad, *uy = vyb + VY_U * mpad, *uty = vyb + VY_UT * mpad;
+        for (int e = t; e < N; e += FT)
+          wprev[e] = e < n ? w.wx[e] - a.st.alpha * (ux[e] - utx[e]) : (e < n + m ? w.wy[e - n] - a.st.alpha * (uy[e - n] - uty[e - n]) : sc[SC_AATAU] - sc[SC_AADT]);
+      }
+      if (aa_apply_dev(ws, lb, w, sc + SC_AASCR, red, lu) > 0.0) { aa_store_prev(ws, lb, w, sc[SC_AATAU]); pending = true; }
+    }
+  }
+  if (t == 0) ibuf[1] = pending ? j + 1 : j + iv - j % iv;
   __syncthreads();
 }
 
@@ -621,22 +661,14 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     if (t < m) { vy(VY_W)[t] = 0; vy(VY_U)[t] = 0; vy(VY_UT)[t] = 0; }
     __syncthreads();
     bool refactor = true, first = true;
-    // Anderson acceleration of w (common.cuh): state and window in a global slab, touched every aa_iv iterations
-    const int aa_lb = a.aa_ws ? st.acceleration_lookback : 0, aa_iv = st.acceleration_interval > 0 ? st.acceleration_interval : 1;
-    double *const aaw = aa_lb ? a.aa_ws + (size_t)blockIdx.x * a.aa_stride : nullptr;
-    if (aa_lb) aa_reset_dev(aaw);
+    // Anderson acceleration of w (common.cuh): everything about it lives in aa_event(); the loop only compares the
+    // iteration counter with the next event kept in shared memory (ibuf[1]), so the hot path carries no extra state.
+    aa_begin(a, ibuf);
+    if (t == 0) sc[SC_NEXTREAL] = next_check;
+    __syncthreads();
+    next_check = min(next_check, ibuf[1]);
 
     for (it = 1; it <= st.max_iters; it++) {
-      if (aa_lb && (it % aa_iv == 0 || (it > 1 && (it - 1) % aa_iv == 0))) {
-        const AaIter aait{vx(VX_W), n, vy(VY_W), m, sc + SC_AATAU};
-        if (it > 1 && (it - 1) % aa_iv == 0) {
-          if (t == 0) sc[SC_AATAU] = w_tau;
-          aa_apply_dev(aaw, aa_lb, aait, sc + SC_AASCR, red);
-          w_tau = sc[SC_AATAU];
-        }
-        aa_store_prev(aaw, aa_lb, aait, w_tau);
-        __syncthreads();
-      }
       if (refactor) {
         // Factorisation at the current scale (the one place it is written, so the tiles stay in registers):
         // stage A^ from the tiles -> K -> Cholesky -> Linv -> Kinv; then g = (R_z + M)^{-1} h and g'Rg.
@@ -753,30 +785,46 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
       if (!check) w_tau += st.alpha * (u_tau - tau_t);
       __syncthreads();
       SUB_STAMP(pi, 28);
-      if (check) {
-        pt_stamp(3);
-        rt_rows(ar, ps, g, act, R, C, vx(VX_U), XR, m, [&](int i, double v) { vy(VY_TM)[i] = v; });
-        __syncthreads();   // row and column partials share one buffer
-        rt_cols(ar, ps, g, act, R, C, vy(VY_U), XC, n, [&](int j, double v) { vx(VX_TN)[j] = v; });
-        __syncthreads();
-        check_tail(a, vx(0), vy(0), red, XC, Pg ? Li : nullptr, g.npad(), g.mpad(), it, scale, u_tau);
-        next_check = st.adaptive_check ? (int)sc[SC_NEXT] : it + st.check_interval;
-        const bool done = sc[SC_DONE] != 0.0;
-        const double ns = sc[SC_NEWSCALE];
-        pt_stamp(4);
-        if (done) break;
-        if (ns != 0.0) { scale = ns; refactor = true; if (aa_lb) aa_reset_dev(aaw); }
+      if (check) {   // an event: a termination check and / or an acceleration event (both rare, both cold)
+        if (it >= (int)sc[SC_NEXTREAL] || it == st.max_iters) {
+          pt_stamp(3);
+          rt_rows(ar, ps, g, act, R, C, vx(VX_U), XR, m, [&](int i, double v) { vy(VY_TM)[i] = v; });
+          __syncthreads();   // row and column partials share one buffer
+          rt_cols(ar, ps, g, act, R, C, vy(VY_U), XC, n, [&](int j, double v) { vx(VX_TN)[j] = v; });
+          __syncthreads();
+          check_tail(a, vx(0), vy(0), red, XC, Pg ? Li : nullptr, g.npad(), g.mpad(), it, scale, u_tau);
+          if (t == 0) sc[SC_NEXTREAL] = st.adaptive_check ? sc[SC_NEXT] : (double)(it + st.check_interval);
+          const bool done = sc[SC_DONE] != 0.0;
+          const double ns = sc[SC_NEWSCALE];
+          pt_stamp(4);
+          if (done) break;
+          if (ns != 0.0) { scale = ns; refactor = true; if (a.aa_ws) aa_reset_dev(a.aa_ws + (size_t)blockIdx.x * a.aa_stride); }
+        }
         if (it < st.max_iters) {  // (the last iterate keeps w so that s = R(u - t) is recoverable)
           if (t < n) vx(VX_W)[t] += st.alpha * (vx(VX_U)[t] - vx(VX_UT)[t]);
           if (t < m) vy(VY_W)[t] += st.alpha * (vy(VY_U)[t] - vy(VY_UT)[t]);
           w_tau += st.alpha * (u_tau - tau_t);
           __syncthreads();
         }
-      }
-      if (aa_lb && it > 1 && (it - 1) % aa_iv == 0 && it < st.max_iters) {   // safeguard after the convergence check
-        const AaIter aait{vx(VX_W), n, vy(VY_W), m, sc + SC_AATAU};
-        if (t == 0) sc[SC_AATAU] = w_tau;
-        if (aa_safeguard_dev(aaw, aa_lb, aait, red)) w_tau = sc[SC_AATAU];
+        if (it >= ibuf[1]) {   // acceleration event (every acceleration_interval iterations; never when it is off)
+          // The callee chain needs more registers than the tile leaves free.  Parking the tile in the slab for the
+          // duration of the call (128 KB per CTA, L2) keeps it out of the call's live set, so the register allocation
+          // of the iteration loop is the one without acceleration; the compiler's own answer was to keep a third of
+          // the tile in local memory for the whole loop (+20 % per iteration, measured).
+          double *park = a.aa_ws + (size_t)blockIdx.x * a.aa_stride + ((aa_ws_doubles(n + m + 1, abs(st.acceleration_lookback)) + 1) & ~(size_t)1) + t;
+#pragma unroll
+          for (int r = 0; r < TR; r++)
+#pragma unroll
+            for (int c = 0; c < TCR; c++) park[(r * TCR + c) * FT] = ar[r][c];
+          if (t == 0) { sc[SC_AATAU] = w_tau; sc[SC_AADT] = st.alpha * (u_tau - tau_t); }
+          aa_event(a, it, vx(0), vy(0), g.npad(), g.mpad(), sc, red, ibuf, XC);   // (the partial-sum buffer is idle between iterations)
+          w_tau = sc[SC_AATAU];
+#pragma unroll
+          for (int r = 0; r < TR; r++)
+#pragma unroll
+            for (int c = 0; c < TCR; c++) ar[r][c] = park[(r * TCR + c) * FT];
+        }
+        next_check = min((int)sc[SC_NEXTREAL], ibuf[1]);
       }
     }
     if (it > st.max_iters) it = st.max_iters;

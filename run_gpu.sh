@@ -1,7 +1,10 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt; nproc >> gpurun_out/smi.txt
-timeout 1500 python -m pytest tests -x -q -m gpu --durations=15 > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; tail -25 gpurun_out/tests.log
+timeout 1500 python -m pytest tests -q -m gpu --durations=10 > gpurun_out/tests.log 2>&1; echo "tests rc=$?"; grep -E "passed|failed|FAILED" gpurun_out/tests.log | tail -30
 timeout 300 python bench.py --steps 5 --warmup 3 --cpu-sample 0 > gpurun_out/bench_aa.json 2>gpurun_out/bench_aa.err; python -c "
 import json;d=json.loads(open('gpurun_out/bench_aa.json').read());print('AA on ',d['value'],d['e2e']['value'],d['kernel_ms'],d['solver'])"
 timeout 300 python bench.py --steps 5 --warmup 3 --cpu-sample 0 --set acceleration_lookback=0 > gpurun_out/bench_noaa.json 2>gpurun_out/bench_noaa.err; python -c "
 import json;d=json.loads(open('gpurun_out/bench_noaa.json').read());print('AA off',d['value'],d['e2e']['value'],d['kernel_ms'],d['solver'])"
+for c in C3 C5 EXP C4 C1; do
+timeout 600 python bench.py --config $c --steps 3 --warmup 3 > gpurun_out/bench_$c.json 2>gpurun_out/bench_$c.err; python -c "
+import json;d=json.loads(open('gpurun_out/bench_$c.json').read());print('$c',round(d['value']),round(d['e2e']['value']),d['kernel_ms'],d['solver'],d.get('cpu_baseline',{}).get('value'))"
+done
