@@ -92,6 +92,19 @@ def make_workload(batch: int, seed: int):
     return bt, pr.to_boundary(bt)
 
 
+def config_block(bt, B: int, world: int, l2: str) -> dict:
+    """The `config` object of the JSON line -- identical for both arms so that the driver can tell they ran the same thing."""
+    st = bt.structure
+    return {"workload": f"{CONFIG} {bt.name}: n={st.n} m={st.m} cones={st.cones.to_dict()}, synthetic, seed = shard index",
+            "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"batch-shard x{world}", "l2": l2,
+            "solver_args": dict(SOLVER_ARGS)}
+
+
+def l2_note(st, B: int) -> str:
+    nbytes = (st.nnzA + st.m + st.n + 1 + st.nnzP) * B * 8
+    return f"inputs ({nbytes / 1e9:.2f} GB/step) vs 126 MB L2" + ("" if nbytes > 130e6 else "; NOT larger than L2 (secondary config, no flush)")
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -99,7 +112,7 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_arm(bt, sample: int, steps: int, warmup: int, threads: int = 0):
+def cpu_arm(bt, sample: int, steps: int, warmup: int, threads: int = 0, spread: bool = False, repeat: int = 1):
     """Times the oracle (reference algorithm on host cores): forward + adjoint on `sample` instances.
     The thread count is passed explicitly (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin
     the baseline to one core)."""
@@ -115,34 +128,49 @@ def cpu_arm(bt, sample: int, steps: int, warmup: int, threads: int = 0):
     args = dict(SOLVER_ARGS)
 
     def step():
-        x, y, s, status, _ = orc.solve_batch(st, sub.A_vals, sub.b, sub.c, sub.P_vals, nthreads=threads, **args)
-        orc.vjp_batch(st, sub.A_vals, sub.b, sub.c, x, y, s, dx, dy, sub.P_vals, nthreads=threads, **args)
+        for _ in range(repeat):
+            x, y, s, status, _ = orc.solve_batch(st, sub.A_vals, sub.b, sub.c, sub.P_vals, nthreads=threads, **args)
+            orc.vjp_batch(st, sub.A_vals, sub.b, sub.c, x, y, s, dx, dy, sub.P_vals, nthreads=threads, **args)
         return status
 
     for _ in range(warmup):
         step()
+    per_step = []
     t0 = time.perf_counter()
     for _ in range(steps):
+        t1 = time.perf_counter()
         status = step()
+        per_step.append(1e3 * (time.perf_counter() - t1))
     dt = (time.perf_counter() - t0) / max(steps, 1)
     cores = threads
-    return sample / dt, dt, cores, int((status == 1).sum())
+    if spread:
+        return sample * repeat / dt, dt, cores, int((status == 1).sum()), per_step
+    return sample * repeat / dt, dt, cores, int((status == 1).sum())
 
 
 def run_reference(a):
+    """The reference's algorithm on the host cores over the SAME batch as our arm (all `a.batch` instances per step,
+    every host thread, warmed up, threads bound to cores); per-step times are reported so a noisy host shows."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    bt, _ = make_workload(max(a.cpu_sample, 8), seed=0)
-    val, dt, cores, solved = cpu_arm(bt, a.cpu_sample, a.steps, a.warmup)
+    sample = a.batch if a.cpu_sample <= 0 or a.cpu_sample >= a.batch or not a.cpu_sample_given else a.cpu_sample
+    bt, _ = make_workload(a.batch, seed=0)
+    a.cpu_sample = sample
+    world = max(int(os.environ.get("WORLD_SIZE", "1")), 1)
+    # N > 1: the job's global batch is N shards; the host has no more cores for it, so a step is N passes over a shard
+    val, dt, cores, solved, per_step = cpu_arm(bt, sample, a.steps, max(a.warmup, 1), spread=True, repeat=world)
     st = bt.structure
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{CONFIG} {bt.name}: n={st.n} m={st.m} cones={st.cones.to_dict()}, synthetic, seed 0",
-                       "sample_instances": a.cpu_sample, "solver_args": SOLVER_ARGS},
+            "config": config_block(bt, a.batch, world, l2_note(st, a.batch)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{a.cpu_sample} instances of the C2 batch per step (oracle/cone_oracle.c, OpenMP over instances)"},
+                             "sample": f"{a.cpu_sample} of the {a.batch} instances of the {CONFIG} batch per step (oracle/cone_oracle.c: the reference's "
+                                       "algorithm restated in C, OpenMP over instances like diffcp's thread pool; diffcp/SCS are not installable here)",
+                             "ms_per_step_all": [round(v, 1) for v in per_step],
+                             "ms_per_step_min_max": [round(min(per_step), 1), round(max(per_step), 1)],
+                             "omp_proc_bind": os.environ.get("OMP_PROC_BIND")},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "solved": solved}
     print(json.dumps(line))
@@ -296,16 +324,16 @@ def run_ours(a):
         ach = dom_bytes / (kt[dom] * 1e-3) / 1e9
         cpu = None
         if world == 1 and a.cpu_sample > 0:
-            v, dtc, cores, solved_c = cpu_arm(bt, a.cpu_sample, 1, 0)
+            ns = min(a.cpu_sample, B)
+            v, dtc, cores, solved_c, per = cpu_arm(bt, ns, 2, 1, spread=True)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {a.cpu_sample} instances of the same batch, 1 pass ({dtc:.1f} s), oracle/cone_oracle.c with OpenMP over instances"}
+                   "sample": f"first {ns} instances of the same batch, 1 warm-up + 2 timed passes ({dtc:.2f} s each), oracle/cone_oracle.c with OpenMP over instances",
+                   "ms_per_pass": [round(x, 1) for x in per]}
         info = eng.kernel_info()
         line = {"metric": METRIC, "value": Btot / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"{CONFIG} {bt.name}: n={st.n} m={st.m} cones={st.cones.to_dict()}, synthetic, seed=rank",
-                           "batch_per_gpu": B, "global_batch": Btot, "parallelism": f"batch-shard x{world}",
-                           "l2": f"inputs ({(hA.numel() + npel) * 8 / 1e9:.2f} GB/step) vs 126 MB L2" + ("" if (hA.numel() + npel) * 8 > 130e6 else "; NOT larger than L2 (secondary config, no flush)"), "solver_args": SOLVER_ARGS},
+                "config": config_block(bt, B, world, l2_note(st, B)),
                 # value = mean over exactly `steps` timed steps (the contract's definition).  The per-step wall times and
                 # their median are diagnostics only: on shared boxes single steps sometimes take 2x (profiles/README.md).
                 "e2e": {"value": Btot / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
@@ -337,12 +365,16 @@ def main():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the BASELINE.json batch of the config)")
-    p.add_argument("--cpu-sample", type=int, default=512, help="instances per CPU-baseline pass")
+    p.add_argument("--cpu-sample", type=int, default=None,
+                   help="instances per CPU pass (default: 2048 for the cpu_baseline leg of our arm, the whole batch for --impl reference)")
     p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "C5S", "EXP"],
                    help="workload (default: the headline C2; others are secondary measurements)")
     p.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
                    help="override a solver argument for both arms, e.g. --set acceleration_lookback=0")
     a = p.parse_args()
+    a.cpu_sample_given = a.cpu_sample is not None
+    if a.cpu_sample is None:
+        a.cpu_sample = 2048
     global CONFIG, METRIC
     CONFIG = a.config
     for kv in a.set:
@@ -363,6 +395,9 @@ def main():
     os.dup2(2, 1)
     sys.stdout = os.fdopen(saved, "w", buffering=1)
     if a.impl == "reference":
+        # bind the OpenMP team to cores before libgomp initialises (the oracle is the only OpenMP user of this arm)
+        os.environ.setdefault("OMP_PROC_BIND", "spread")
+        os.environ.setdefault("OMP_PLACES", "threads")
         run_reference(a)
     else:
         run_ours(a)

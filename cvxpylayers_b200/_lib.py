@@ -16,7 +16,7 @@ _f64p = C.POINTER(C.c_double)
 
 EXPORTS = [
     "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary",
-    "bcone_ingest", "bcone_emit", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
+    "bcone_ingest", "bcone_emit", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
 
@@ -72,6 +72,12 @@ def load() -> C.CDLL:
     lib.bcone_ingest.restype = C.c_int
     lib.bcone_emit.argtypes = [vp, C.c_int32] + [vp] * 8
     lib.bcone_emit.restype = C.c_int
+    lib.bcone_set_param_maps.argtypes = [vp, C.c_int32] + [_i32p, _i32p, _f64p] * 3
+    lib.bcone_set_param_maps.restype = C.c_int
+    lib.bcone_ingest_params.argtypes = [vp, C.c_int32] + [vp] * 6
+    lib.bcone_ingest_params.restype = C.c_int
+    lib.bcone_emit_params.argtypes = [vp, C.c_int32] + [vp] * 6
+    lib.bcone_emit_params.restype = C.c_int
     lib.bcone_solve.argtypes = [vp, C.c_int32] + [vp] * 10 + [C.POINTER(BconeSettings), vp]
     lib.bcone_solve.restype = C.c_int
     lib.bcone_vjp.argtypes = [vp, C.c_int32] + [vp] * 14 + [C.POINTER(BconeSettings), vp]

@@ -37,6 +37,10 @@ cudaError_t bc_bwdb_configure(size_t smem);
 cudaError_t bc_bwdb_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
 cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
+cudaError_t bc_p2e(const double *p, const int *rptr, const int *cols, const double *vals, double *out, int K, int B, int ldo, int roff,
+                   const int *smap, const int *dmap, double sign, cudaStream_t st);
+cudaError_t bc_e2p(const double *in, const int *rptr, const int *cols, const double *vals, double *dp, int K, int B, int ldi, int roff,
+                   const int *smap, const int *dmap, double sign, int skip, cudaStream_t st);
 }
 
 namespace {
@@ -49,6 +53,10 @@ struct Handle {
   int slot = 0;
   int nnz_aug = 0, nb = 0;
   int *d_gather = nullptr, *d_bidx = nullptr;
+  // parameter -> matrix maps (bcone_set_param_maps): CSR [rows x P1] per boundary tensor, device copies
+  struct PMap { int *ptr = nullptr, *col = nullptr; double *val = nullptr; int rows = 0; };
+  PMap pmA, pmq, pmP;
+  int P1 = 0;
   int fwd_threads = 0, bwd_threads = 0, fwd_ctas = 0, bwd_ctas = 0;
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
@@ -286,6 +294,85 @@ extern "C" int bcone_set_boundary(void *handle, int32_t nnz_aug, const int32_t *
 }
 
 #define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, where); } while (0)
+
+// ---- parameter -> matrix affine map fused into ingest / emit ----
+extern "C" int bcone_set_param_maps(void *handle, int32_t P1, const int32_t *A_ptr, const int32_t *A_col, const double *A_val,
+                                    const int32_t *q_ptr, const int32_t *q_col, const double *q_val,
+                                    const int32_t *P_ptr, const int32_t *P_col, const double *P_val) {
+  Handle *h = (Handle *)handle;
+  if (!h || P1 <= 0 || !A_ptr || !q_ptr) return fail(h, BCONE_EINVAL, "set_param_maps: null argument");
+  if (h->nnz_aug == 0 && h->S.nnzA + h->nb != 0) return fail(h, BCONE_EINVAL, "set_param_maps: call bcone_set_boundary first");
+  const DevStruct &S = h->S;
+  const int rowsA = h->nnz_aug, rowsq = S.n + 1, rowsP = (P_ptr && S.nnzP > 0) ? S.nnzP : 0;
+  const int32_t *ptrs[3] = {A_ptr, q_ptr, P_ptr}, *colsv[3] = {A_col, q_col, P_col};
+  const double *valsv[3] = {A_val, q_val, P_val};
+  const int rows[3] = {rowsA, rowsq, rowsP};
+  std::vector<int> count(P1, 0);
+  for (int w = 0; w < 3; w++) {
+    if (!rows[w]) continue;
+    if (ptrs[w][0] != 0) return fail(h, BCONE_EINVAL, "set_param_maps: row pointer must start at 0");
+    for (int r = 0; r < rows[w]; r++) if (ptrs[w][r + 1] < ptrs[w][r]) return fail(h, BCONE_EINVAL, "set_param_maps: row pointer not monotone");
+    const int nz = ptrs[w][rows[w]];
+    if (nz > 0 && (!colsv[w] || !valsv[w])) return fail(h, BCONE_EINVAL, "set_param_maps: missing column / value array");
+    for (int e = 0; e < nz; e++) {
+      if (colsv[w][e] < 0 || colsv[w][e] >= P1) return fail(h, BCONE_EINVAL, "set_param_maps: parameter index out of range");
+      count[colsv[w][e]]++;
+    }
+  }
+  cudaSetDevice(h->device);
+  Handle::PMap *dst[3] = {&h->pmA, &h->pmq, &h->pmP};
+  for (int w = 0; w < 3; w++) {
+    *dst[w] = Handle::PMap();
+    if (!rows[w]) continue;
+    const int nz = ptrs[w][rows[w]];
+    std::vector<int> ptr(ptrs[w], ptrs[w] + rows[w] + 1), col(std::max(nz, 1), 0);
+    std::vector<double> val(std::max(nz, 1), 0.0);
+    for (int e = 0; e < nz; e++) { col[e] = colsv[w][e] | (count[colsv[w][e]] == 1 ? 0x40000000 : 0); val[e] = valsv[w][e]; }   // bit 30: exclusive column
+    dst[w]->ptr = upload(h, ptr); dst[w]->col = upload(h, col); dst[w]->val = upload(h, val); dst[w]->rows = rows[w];
+    if (!dst[w]->ptr || !dst[w]->col || !dst[w]->val) return fail(h, BCONE_ENOMEM, "set_param_maps: cudaMalloc");
+  }
+  h->P1 = P1;
+  return BCONE_OK;
+}
+
+extern "C" int bcone_ingest_params(void *handle, int32_t B, const double *p_stack, double *A_vals, double *P_vals, double *b, double *c, void *stream) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !p_stack || !A_vals || !b || !c) return fail(h, BCONE_EINVAL, "ingest_params: null argument");
+  if (h->P1 <= 0) return fail(h, BCONE_EINVAL, "ingest_params: call bcone_set_param_maps first");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevStruct &S = h->S;
+  CK(bc_p2e(p_stack, h->pmA.ptr, h->pmA.col, h->pmA.val, A_vals, S.nnzA, B, S.nnzA, 0, h->d_gather, nullptr, -1.0, st), "ingest_params A");
+  CK(cudaMemsetAsync(b, 0, (size_t)B * S.m * sizeof(double), st), "ingest_params b memset");
+  CK(bc_p2e(p_stack, h->pmA.ptr, h->pmA.col, h->pmA.val, b, h->nb, B, S.m, S.nnzA, nullptr, h->d_bidx, 1.0, st), "ingest_params b");
+  CK(bc_p2e(p_stack, h->pmq.ptr, h->pmq.col, h->pmq.val, c, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "ingest_params c");
+  h->launches += 3;
+  if (P_vals && S.nnzP > 0) {
+    if (!h->pmP.rows) return fail(h, BCONE_EINVAL, "ingest_params: structure has P but no parameter map for it");
+    CK(bc_p2e(p_stack, h->pmP.ptr, h->pmP.col, h->pmP.val, P_vals, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, st), "ingest_params P");
+    h->launches++;
+  }
+  return BCONE_OK;
+}
+
+extern "C" int bcone_emit_params(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db, const double *dc,
+                                 double *dp_stack, void *stream) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !dA_vals || !db || !dc || !dp_stack) return fail(h, BCONE_EINVAL, "emit_params: null argument");
+  if (h->P1 <= 0) return fail(h, BCONE_EINVAL, "emit_params: call bcone_set_param_maps first");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevStruct &S = h->S;
+  const int skip = h->P1 - 1;   // the constant-1 row of p_stack is not a parameter
+  CK(cudaMemsetAsync(dp_stack, 0, (size_t)h->P1 * B * sizeof(double), st), "emit_params memset");
+  CK(bc_e2p(dA_vals, h->pmA.ptr, h->pmA.col, h->pmA.val, dp_stack, S.nnzA, B, S.nnzA, 0, nullptr, h->d_gather, -1.0, skip, st), "emit_params dA");
+  CK(bc_e2p(db, h->pmA.ptr, h->pmA.col, h->pmA.val, dp_stack, h->nb, B, S.m, S.nnzA, h->d_bidx, nullptr, 1.0, skip, st), "emit_params db");
+  CK(bc_e2p(dc, h->pmq.ptr, h->pmq.col, h->pmq.val, dp_stack, S.n, B, S.n, 0, nullptr, nullptr, 1.0, skip, st), "emit_params dc");
+  h->launches += 3;
+  if (dP_vals && S.nnzP > 0 && h->pmP.rows) {
+    CK(bc_e2p(dP_vals, h->pmP.ptr, h->pmP.col, h->pmP.val, dp_stack, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, skip, st), "emit_params dP");
+    h->launches++;
+  }
+  return BCONE_OK;
+}
 
 extern "C" int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_eval, const double *P_eval,
                             double *A_vals, double *P_vals, double *b, double *c, void *stream) {

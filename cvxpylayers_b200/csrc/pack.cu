@@ -77,6 +77,99 @@ __global__ void __launch_bounds__(256) e2b_kernel(const double *__restrict__ in,
   }
 }
 
+// ---- parameter -> matrix affine map fused into the load stage ------------------------------------------
+// The reference materialises A_eval = A_param @ p_stack ([nnz_aug, P1] sparse x [P1, B] dense; forward at
+// src/cvxpylayers/torch/cvxpylayer.py:443-451, transpose at :33-37) in memory only for the solver interface to read it
+// once.  p2e_kernel evaluates the map straight into the engine's instance-contiguous tiles: same tile geometry as
+// b2e_kernel, but a tile row is sum_e val_e p_stack[col_e, i] over the CSR row of the parameter matrix (lanes along the
+// batch axis: every p_stack read is coalesced) instead of a copy.
+//   out[i * ldo + dmap(k)] = sign * sum_{e in row (roff + smap(k))} val[e] * p[col[e] * B + i]
+__global__ void __launch_bounds__(256) p2e_kernel(const double *__restrict__ p, const int *__restrict__ rptr, const int *__restrict__ cols,
+                                                  const double *__restrict__ vals, double *__restrict__ out, int K, int B, int ldo, int roff,
+                                                  const int *__restrict__ smap, const int *__restrict__ dmap, double sign) {
+  __shared__ double tile[TK][TI + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
+  for (int kk = ty; kk < TK; kk += 8) {
+    const int k = k0 + kk;
+    if (k >= K) continue;
+    const int r = roff + (smap ? __ldg(smap + k) : k);
+    const int e0 = __ldg(rptr + r), e1 = __ldg(rptr + r + 1);
+    const int i = i0 + tx;
+    double a0 = 0.0, a1 = 0.0;
+    for (int e = e0; e < e1; e++) {
+      const double v = __ldg(vals + e);
+      const double *col = p + (size_t)(__ldg(cols + e) & 0x3fffffff) * B;   // (bit 30: exclusive-column flag of the way back)
+      if (i < B) a0 = fma(v, col[i], a0);
+      if (i + 32 < B) a1 = fma(v, col[i + 32], a1);
+    }
+    tile[kk][tx] = a0; tile[kk][tx + 32] = a1;
+  }
+  __syncthreads();
+  const int k = k0 + tx;
+  if (k < K) {
+    const int d = dmap ? __ldg(dmap + k) : k;
+    for (int ii = ty; ii < TI; ii += 8) {
+      const int i = i0 + ii;
+      if (i < B) out[(size_t)i * ldo + d] = sign * tile[tx][ii];
+    }
+  }
+}
+// Transposed map on the way back: dp[col, i] += sign * val[e] * in[i * ldi + smap(k)] for every entry e of row
+// (roff + dmap(k)) of the parameter matrix.  One pass over the engine-layout gradient (tile transposed through shared
+// memory exactly like e2b_kernel), then lanes along the batch axis update dp: entries flagged exclusive (the only entry
+// of their parameter column, the usual "this matrix entry IS a parameter" case; flag = bit 30 of col) are plain stores,
+// the others are fp64 atomic adds (dp is zeroed by the caller).  Column `skip` (the constant 1 row of p_stack) is dropped.
+__global__ void __launch_bounds__(256) e2p_kernel(const double *__restrict__ in, const int *__restrict__ rptr, const int *__restrict__ cols,
+                                                  const double *__restrict__ vals, double *__restrict__ dp, int K, int B, int ldi, int roff,
+                                                  const int *__restrict__ smap, const int *__restrict__ dmap, double sign, int skip) {
+  __shared__ double tile[TK][TI + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
+  const int k = k0 + tx;
+  if (k < K) {
+    const int s = smap ? __ldg(smap + k) : k;
+    for (int ii = ty; ii < TI; ii += 8) {
+      const int i = i0 + ii;
+      if (i < B) tile[tx][ii] = in[(size_t)i * ldi + s];
+    }
+  }
+  __syncthreads();
+  for (int kk = ty; kk < TK; kk += 8) {
+    const int kq = k0 + kk;
+    if (kq >= K) continue;
+    const int r = roff + (dmap ? __ldg(dmap + kq) : kq);
+    const int e0 = __ldg(rptr + r), e1 = __ldg(rptr + r + 1);
+    for (int e = e0; e < e1; e++) {
+      const int cf = __ldg(cols + e), c = cf & 0x3fffffff;
+      if (c == skip) continue;
+      const double v = sign * __ldg(vals + e);
+      double *row = dp + (size_t)c * B + i0;
+      if (cf & 0x40000000) {
+        if (i0 + tx < B) row[tx] = v * tile[kk][tx];
+        if (i0 + tx + 32 < B) row[tx + 32] = v * tile[kk][tx + 32];
+      } else {
+        if (i0 + tx < B) atomicAdd(row + tx, v * tile[kk][tx]);
+        if (i0 + tx + 32 < B) atomicAdd(row + tx + 32, v * tile[kk][tx + 32]);
+      }
+    }
+  }
+}
+extern "C" cudaError_t bc_p2e(const double *p, const int *rptr, const int *cols, const double *vals, double *out, int K, int B, int ldo, int roff,
+                              const int *smap, const int *dmap, double sign, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
+  p2e_kernel<<<grid, 256, 0, st>>>(p, rptr, cols, vals, out, K, B, ldo, roff, smap, dmap, sign);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t bc_e2p(const double *in, const int *rptr, const int *cols, const double *vals, double *dp, int K, int B, int ldi, int roff,
+                              const int *smap, const int *dmap, double sign, int skip, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
+  e2p_kernel<<<grid, 256, 0, st>>>(in, rptr, cols, vals, dp, K, B, ldi, roff, smap, dmap, sign, skip);
+  return cudaGetLastError();
+}
+
 extern "C" cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap,
                               const int *dmap, double sign, cudaStream_t st) {
   if (K <= 0 || B <= 0) return cudaSuccess;

@@ -198,6 +198,58 @@ class Engine:
         self._raise(rc, "bcone_emit")
         return dA_eval, dq_eval, dP_eval
 
+    # ------------------------------------------------------------------ fused parameter -> matrix map
+    def set_param_maps(self, A_map, q_map, P_map=None):
+        """SciPy CSR matrices [rows x P1] in boundary row order (the reference's ``_A_scipy`` / ``_q_scipy`` /
+        ``_P_scipy``, ``torch/cvxpylayer.py:443-451``)."""
+        import scipy.sparse as sp  # noqa: PLC0415
+
+        def parts(M):
+            if M is None:
+                return None, None, None, []
+            M = sp.csr_matrix(M)
+            M.sort_indices()
+            ptr = np.ascontiguousarray(M.indptr, dtype=np.int32)
+            col = np.ascontiguousarray(M.indices, dtype=np.int32)
+            val = np.ascontiguousarray(M.data, dtype=np.float64)
+            return (ptr.ctypes.data_as(_lib._i32p), col.ctypes.data_as(_lib._i32p), val.ctypes.data_as(_lib._f64p), [ptr, col, val])
+
+        P1 = int(A_map.shape[1])
+        if self._boundary is None:
+            raise RuntimeError("set_boundary() has not been called")
+        if A_map.shape[0] != self._boundary[0] or q_map.shape != (self.structure.n + 1, P1):
+            raise ValueError("parameter maps do not match the boundary tensors")
+        if (P_map is not None) != bool(self.structure.nnzP) or (P_map is not None and P_map.shape != (self.structure.nnzP, P1)):
+            raise ValueError("P parameter map does not match the structure")
+        a, q, p = parts(A_map), parts(q_map), parts(P_map)
+        rc = self.lib.bcone_set_param_maps(self.h, C.c_int32(P1), a[0], a[1], a[2], q[0], q[1], q[2], p[0], p[1], p[2])
+        self._raise(rc, "bcone_set_param_maps")
+        self._P1 = P1
+
+    def ingest_params(self, p_stack: torch.Tensor, out=None):
+        """p_stack[P1, B] -> engine-layout (A_vals, P_vals, b, c) without materialising A_eval."""
+        st, dev, f64 = self.structure, self.device, torch.float64
+        B = p_stack.shape[1]
+        _chk(p_stack, (self._P1, B), f64, dev, "p_stack")
+        if out is not None:
+            A_vals, P_vals, b, c = out
+        else:
+            A_vals = torch.empty((B, st.nnzA), dtype=f64, device=dev)
+            b = torch.empty((B, st.m), dtype=f64, device=dev)
+            c = torch.empty((B, st.n), dtype=f64, device=dev)
+            P_vals = torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None
+        rc = self.lib.bcone_ingest_params(self.h, C.c_int32(B), _ptr(p_stack), _ptr(A_vals), _ptr(P_vals), _ptr(b), _ptr(c), self._stream())
+        self._raise(rc, "bcone_ingest_params")
+        return A_vals, P_vals, b, c
+
+    def emit_params(self, dA_vals, dP_vals, db, dc, out=None):
+        """engine gradients -> dp_stack[P1, B] (transposed parameter maps; the constant's row stays 0)."""
+        B = dA_vals.shape[0]
+        dp = out if out is not None else torch.empty((self._P1, B), dtype=torch.float64, device=self.device)
+        rc = self.lib.bcone_emit_params(self.h, C.c_int32(B), _ptr(dA_vals), _ptr(dP_vals), _ptr(db), _ptr(dc), _ptr(dp), self._stream())
+        self._raise(rc, "bcone_emit_params")
+        return dp
+
     # ------------------------------------------------------------------ forward / backward
     def solve(self, A_vals, b, c, P_vals=None, settings: _lib.BconeSettings | None = None, out: "Solution | None" = None) -> Solution:
         st, dev, f64 = self.structure, self.device, torch.float64

@@ -76,6 +76,23 @@ int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_
 int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
                const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *cuda_stream);
 
+/* Parameter -> matrix affine map fused into the load stage (replaces the reference's sparse x dense products around
+ * the solver interface: forward  A_eval = A_param @ p_stack etc. at src/cvxpylayers/torch/cvxpylayer.py:443-451,
+ * transposes at :33-37).  The three maps are HOST CSR matrices [rows x P1] (P1 = total parameter size + 1; the last row
+ * of p_stack is the constant 1, torch/cvxpylayer.py:84-141), rows in BOUNDARY order: A map nnz_aug rows ([A_cvx values ; b
+ * entries], exactly the rows of A_eval), q map n + 1 rows, P map nnzP rows or NULL.  Call after bcone_set_boundary.
+ * bcone_ingest_params: p_stack[P1, B] (device, batch axis contiguous) -> A_vals[B,nnzA] = -A_eval, b, c, P_vals without
+ *   materialising A_eval.  bcone_emit_params: engine gradients -> dp_stack[P1, B] = (the three maps)' applied to
+ *   [-dA ; db[b_idx]], [dc ; 0], dP; the row of the constant is left 0.  Only parameters and parameter gradients have
+ *   to cross PCIe (or NVLink, for a sharded batch) on this path. */
+int bcone_set_param_maps(void *handle, int32_t P1, const int32_t *A_ptr, const int32_t *A_col, const double *A_val,
+                         const int32_t *q_ptr, const int32_t *q_col, const double *q_val,
+                         const int32_t *P_ptr, const int32_t *P_col, const double *P_val);
+int bcone_ingest_params(void *handle, int32_t B, const double *p_stack, double *A_vals, double *P_vals, double *b,
+                        double *c, void *cuda_stream);
+int bcone_emit_params(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
+                      const double *dc, double *dp_stack, void *cuda_stream);
+
 /* Forward: instance-contiguous inputs A_vals[B,nnzA] (CSR order), P_vals[B,nnzP] or NULL, b[B,m], c[B,n];
  * outputs x[B,n], y[B,m], s[B,m], status[B], iters[B] (int32), resid[B,3] or NULL. */
 int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,

@@ -23,6 +23,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <malloc.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -1028,10 +1029,23 @@ int orc_vjp(const orc_desc *d, const double *Av, const double *Pv, const double 
 }
 
 /* ------------------------------------------------------------ batch drivers */
+/* Every instance allocates and frees a few hundred KB of scratch.  Above glibc's default mmap threshold each of those
+ * is an mmap / munmap pair, and with ~128 threads doing that concurrently the kernel's address-space lock decides the
+ * run time (the same batch took between 0.5 and 2.9 s on otherwise identical hosts).  Keep the scratch in the
+ * per-thread malloc arenas instead. */
+static void tune_malloc(void) {
+  static int done = 0;
+  if (done) return;
+  done = 1;
+  mallopt(M_MMAP_THRESHOLD, 1 << 29);
+  mallopt(M_TRIM_THRESHOLD, 1 << 29);
+  mallopt(M_TOP_PAD, 1 << 24);
+}
 void orc_solve_batch(const orc_desc *d, int32_t B, const double *Av, const double *Pv, const double *b,
                      const double *c, double *x, double *y, double *s, int32_t *status, int32_t *iters,
                      const orc_settings *st, int32_t nthreads) {
   int n = d->n, m = d->m; size_t nA = d->nnzA, nP = d->P_indptr ? d->nnzP : 0;
+  tune_malloc();
 #ifdef _OPENMP
   if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
@@ -1050,6 +1064,7 @@ void orc_vjp_batch(const orc_desc *d, int32_t B, const double *Av, const double 
                    const double *dy, double *dAv, double *dPv, double *db, double *dc, int32_t *lsqr_iters,
                    const orc_settings *st, int32_t nthreads) {
   int n = d->n, m = d->m; size_t nA = d->nnzA, nP = d->P_indptr ? d->nnzP : 0;
+  tune_malloc();
 #ifdef _OPENMP
   if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)

@@ -196,3 +196,83 @@ def test_pipelined_host_path_equals_plain_path(cuda_device, monkeypatch):
         outs.append([primal.detach().clone(), dual.detach().clone(), A.grad.clone(), q.grad.clone(), P.grad.clone()])
     for a_, b_ in zip(*outs):
         assert a_.device.type == "cpu" and torch.allclose(a_, b_, rtol=1e-9, atol=1e-11)
+
+
+# ----------------------------------------------------------------------------- fused parameter -> matrix map
+def _random_param_maps(bt, bd, rng, P1):
+    """Random affine maps p_stack -> (A_eval, q_eval, P_eval) with the three kinds of parameter columns the reference
+    produces: exclusive (one matrix entry IS the parameter), shared (a parameter feeds several entries, possibly of
+    different tensors) and the constant-1 column (last)."""
+    import scipy.sparse as sp
+
+    st = bt.structure
+    maps = []
+    for rows in (bd.A_eval.shape[0], st.n + 1, st.nnzP):
+        if rows == 0:
+            maps.append(None)
+            continue
+        nz_rows, nz_cols, nz_vals = [], [], []
+        for r in range(rows):
+            k = rng.integers(0, 4)          # 0..3 entries per row (empty rows = structural zeros of the map)
+            cols = rng.choice(P1, size=k, replace=False)
+            nz_rows += [r] * k
+            nz_cols += list(cols)
+            nz_vals += list(rng.standard_normal(k))
+        maps.append(sp.csr_matrix((nz_vals, (nz_rows, nz_cols)), shape=(rows, P1)))
+    return maps
+
+
+@pytest.mark.parametrize("name,B", [("C1", 70), ("C3", 37), ("C2", 130)])
+def test_fused_parameter_map_equals_spmm_then_ingest(name, B, cuda_device):
+    """bcone_ingest_params == (A_param @ p_stack, q_param @ p_stack, P_param @ p_stack) followed by bcone_ingest, and
+    bcone_emit_params == the transposed products applied to bcone_emit's output (torch/cvxpylayer.py:443-451, :33-37)."""
+    bt = pr.CONFIGS[name](B=B)
+    st, dev = bt.structure, cuda_device
+    ctx, bd, _ = _layer(bt)
+    eng = ctx.engine(dev)
+    rng = np.random.default_rng(3)
+    P1 = 41
+    Am, qm, Pm = _random_param_maps(bt, bd, rng, P1)
+    # make a few columns exclusive on purpose (single entry in total) and keep the last column as the constant
+    eng.set_param_maps(Am, qm, Pm)
+    p_stack = rng.standard_normal((P1, B)); p_stack[-1] = 1.0
+    A_eval, q_eval = Am @ p_stack, qm @ p_stack
+    P_eval = Pm @ p_stack if Pm is not None else None
+    ref = eng.ingest(_t(A_eval, dev), _t(q_eval, dev), _t(P_eval, dev))
+    got = eng.ingest_params(_t(p_stack, dev))
+    for r_, g_ in zip(ref, got):
+        if r_ is not None:
+            assert float((r_ - g_).abs().max()) <= 1e-13 * max(1.0, float(r_.abs().max()))
+    gA, gb, gc = rng.standard_normal(bt.A_vals.shape), rng.standard_normal(bt.b.shape), rng.standard_normal(bt.c.shape)
+    gP = rng.standard_normal(bt.P_vals.shape) if bt.P_vals is not None else None
+    dA_eval, dq_eval, dP_eval = eng.emit(_t(gA, dev), _t(gP, dev), _t(gb, dev), _t(gc, dev))
+    want = Am.T @ dA_eval.cpu().numpy() + qm.T @ dq_eval.cpu().numpy()
+    if Pm is not None:
+        want = want + Pm.T @ dP_eval.cpu().numpy()
+    want[-1] = 0.0   # the constant's row is not a parameter
+    dp = eng.emit_params(_t(gA, dev), _t(gP, dev), _t(gb, dev), _t(gc, dev)).cpu().numpy()
+    assert np.abs(dp - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_identity_parameter_map_is_the_plain_boundary(cuda_device):
+    """Every matrix entry is its own parameter (the headline workload): exclusive columns, plain stores on the way back."""
+    import scipy.sparse as sp
+
+    bt = pr.dense_qp(33, 10, 20, 3, seed=8)
+    st, dev = bt.structure, cuda_device
+    ctx, bd, _ = _layer(bt)
+    eng = ctx.engine(dev)
+    na, nq, nP = bd.A_eval.shape[0], st.n + 1, st.nnzP
+    P1 = na + nq + nP + 1
+    eye = lambda rows, off: sp.csr_matrix((np.ones(rows), (np.arange(rows), off + np.arange(rows))), shape=(rows, P1))  # noqa: E731
+    eng.set_param_maps(eye(na, 0), eye(nq, na), eye(nP, na + nq))
+    p_stack = np.concatenate([bd.A_eval, bd.q_eval, bd.P_eval, np.ones((1, bt.B))])
+    got = eng.ingest_params(_t(p_stack, dev))
+    assert np.array_equal(got[0].cpu().numpy(), bt.A_vals) and np.array_equal(got[2].cpu().numpy(), bt.b) and np.array_equal(got[3].cpu().numpy(), bt.c)
+    assert np.array_equal(got[1].cpu().numpy(), bt.P_vals)
+    rng = np.random.default_rng(0)
+    gA, gP, gb, gc = (rng.standard_normal(a.shape) for a in (bt.A_vals, bt.P_vals, bt.b, bt.c))
+    dA_eval, dq_eval, dP_eval = eng.emit(_t(gA, dev), _t(gP, dev), _t(gb, dev), _t(gc, dev))
+    dp = eng.emit_params(_t(gA, dev), _t(gP, dev), _t(gb, dev), _t(gc, dev)).cpu().numpy()
+    assert np.array_equal(dp[:na], dA_eval.cpu().numpy()) and np.array_equal(dp[na:na + nq - 1], dq_eval.cpu().numpy()[:-1])
+    assert np.array_equal(dp[na + nq:na + nq + nP], dP_eval.cpu().numpy()) and not dp[-1].any()
