@@ -15,7 +15,7 @@ _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
 
 EXPORTS = [
-    "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary",
+    "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary", "bcone_set_boundary_quad",
     "bcone_ingest", "bcone_emit", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.bcone_last_error.restype = C.c_char_p
     lib.bcone_set_boundary.argtypes = [vp, C.c_int32, _i32p, C.c_int32, _i32p]
     lib.bcone_set_boundary.restype = C.c_int
+    lib.bcone_set_boundary_quad.argtypes = [vp, C.c_int32, _i32p]
+    lib.bcone_set_boundary_quad.restype = C.c_int
     lib.bcone_ingest.argtypes = [vp, C.c_int32] + [vp] * 8
     lib.bcone_ingest.restype = C.c_int
     lib.bcone_emit.argtypes = [vp, C.c_int32] + [vp] * 8

@@ -53,6 +53,7 @@ struct Handle {
   int slot = 0;
   int nnz_aug = 0, nb = 0;
   int *d_gather = nullptr, *d_bidx = nullptr;
+  int *d_gatherP = nullptr; int nnzP_b = -1;   // boundary rows of P_eval feeding the engine's upper-triangular slots (bcone_set_boundary_quad)
   // parameter -> matrix maps (bcone_set_param_maps): CSR [rows x P1] per boundary tensor, device copies
   struct PMap { int *ptr = nullptr, *col = nullptr; double *val = nullptr; int rows = 0; };
   PMap pmA, pmq, pmP;
@@ -293,6 +294,17 @@ extern "C" int bcone_set_boundary(void *handle, int32_t nnz_aug, const int32_t *
   return BCONE_OK;
 }
 
+extern "C" int bcone_set_boundary_quad(void *handle, int32_t nnzP_boundary, const int32_t *gatherP) {
+  Handle *h = (Handle *)handle;
+  if (!h) return BCONE_EINVAL;
+  if (h->S.nnzP > 0 && (!gatherP || nnzP_boundary < 1)) return fail(h, BCONE_EINVAL, "set_boundary_P: missing gather map");
+  for (int k = 0; k < h->S.nnzP; k++) if (gatherP[k] < 0 || gatherP[k] >= nnzP_boundary) return fail(h, BCONE_EINVAL, "set_boundary_P: gather out of range");
+  cudaSetDevice(h->device);
+  h->nnzP_b = nnzP_boundary;
+  h->d_gatherP = h->S.nnzP > 0 ? upload(h, std::vector<int>(gatherP, gatherP + h->S.nnzP)) : nullptr;
+  return BCONE_OK;
+}
+
 #define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, where); } while (0)
 
 // ---- parameter -> matrix affine map fused into ingest / emit ----
@@ -303,7 +315,7 @@ extern "C" int bcone_set_param_maps(void *handle, int32_t P1, const int32_t *A_p
   if (!h || P1 <= 0 || !A_ptr || !q_ptr) return fail(h, BCONE_EINVAL, "set_param_maps: null argument");
   if (h->nnz_aug == 0 && h->S.nnzA + h->nb != 0) return fail(h, BCONE_EINVAL, "set_param_maps: call bcone_set_boundary first");
   const DevStruct &S = h->S;
-  const int rowsA = h->nnz_aug, rowsq = S.n + 1, rowsP = (P_ptr && S.nnzP > 0) ? S.nnzP : 0;
+  const int rowsA = h->nnz_aug, rowsq = S.n + 1, rowsP = (P_ptr && S.nnzP > 0) ? (h->nnzP_b > 0 ? h->nnzP_b : S.nnzP) : 0;
   const int32_t *ptrs[3] = {A_ptr, q_ptr, P_ptr}, *colsv[3] = {A_col, q_col, P_col};
   const double *valsv[3] = {A_val, q_val, P_val};
   const int rows[3] = {rowsA, rowsq, rowsP};
@@ -348,7 +360,7 @@ extern "C" int bcone_ingest_params(void *handle, int32_t B, const double *p_stac
   h->launches += 3;
   if (P_vals && S.nnzP > 0) {
     if (!h->pmP.rows) return fail(h, BCONE_EINVAL, "ingest_params: structure has P but no parameter map for it");
-    CK(bc_p2e(p_stack, h->pmP.ptr, h->pmP.col, h->pmP.val, P_vals, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, st), "ingest_params P");
+    CK(bc_p2e(p_stack, h->pmP.ptr, h->pmP.col, h->pmP.val, P_vals, S.nnzP, B, S.nnzP, 0, h->d_gatherP, nullptr, 1.0, st), "ingest_params P");
     h->launches++;
   }
   return BCONE_OK;
@@ -368,7 +380,7 @@ extern "C" int bcone_emit_params(void *handle, int32_t B, const double *dA_vals,
   CK(bc_e2p(dc, h->pmq.ptr, h->pmq.col, h->pmq.val, dp_stack, S.n, B, S.n, 0, nullptr, nullptr, 1.0, skip, st), "emit_params dc");
   h->launches += 3;
   if (dP_vals && S.nnzP > 0 && h->pmP.rows) {
-    CK(bc_e2p(dP_vals, h->pmP.ptr, h->pmP.col, h->pmP.val, dp_stack, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, skip, st), "emit_params dP");
+    CK(bc_e2p(dP_vals, h->pmP.ptr, h->pmP.col, h->pmP.val, dp_stack, S.nnzP, B, S.nnzP, 0, nullptr, h->d_gatherP, 1.0, skip, st), "emit_params dP");
     h->launches++;
   }
   return BCONE_OK;
@@ -386,7 +398,7 @@ extern "C" int bcone_ingest(void *handle, int32_t B, const double *A_eval, const
   CK(bc_b2e(A_eval, b, h->nb, B, S.m, S.nnzA, nullptr, h->d_bidx, 1.0, st), "ingest b");
   CK(bc_b2e(q_eval, c, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "ingest c");
   h->launches += 3;
-  if (P_eval && P_vals && S.nnzP > 0) { CK(bc_b2e(P_eval, P_vals, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, st), "ingest P"); h->launches++; }
+  if (P_eval && P_vals && S.nnzP > 0) { CK(bc_b2e(P_eval, P_vals, S.nnzP, B, S.nnzP, 0, h->d_gatherP, nullptr, 1.0, st), "ingest P"); h->launches++; }
   return BCONE_OK;
 }
 
@@ -401,7 +413,12 @@ extern "C" int bcone_emit(void *handle, int32_t B, const double *dA_vals, const 
   CK(bc_e2b(dc, dq_eval, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "emit dc");
   CK(cudaMemsetAsync(dq_eval + (size_t)S.n * B, 0, (size_t)B * sizeof(double), st), "emit dq tail");
   h->launches += 3;
-  if (dP_vals && dP_eval && S.nnzP > 0) { CK(bc_e2b(dP_vals, dP_eval, S.nnzP, B, S.nnzP, 0, nullptr, nullptr, 1.0, st), "emit dP"); h->launches++; }
+  if (dP_vals && dP_eval && S.nnzP > 0) {
+    // boundary rows without an engine slot (the lower triangle of a full symmetric pattern) get a zero gradient:
+    // the engine reads the upper triangle only, so that is the derivative of what was computed
+    if (h->d_gatherP && h->nnzP_b != S.nnzP) CK(cudaMemsetAsync(dP_eval, 0, (size_t)h->nnzP_b * B * sizeof(double), st), "emit dP memset");
+    CK(bc_e2b(dP_vals, dP_eval, S.nnzP, B, S.nnzP, 0, nullptr, h->d_gatherP, 1.0, st), "emit dP"); h->launches++;
+  }
   return BCONE_OK;
 }
 

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ Bwd
     const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
     const double *Pglob = (a.P_vals && S.nnzP > 0) ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
     const double *Pg = (Pglob && a.p_in_smem) ? M.Pv : Pglob;
-    const bool tmaP = a.use_tma && Pglob && a.p_in_smem && (S.nnzP % 2 == 0) && ((((size_t)inst * S.nnzP) & 1) == 0);
+    const bool tmaP = a.use_tma && Pglob && a.p_in_smem && (S.nnzP % 2 == 0) && (((uintptr_t)Pglob & 15) == 0);
     if (a.use_tma) {
       if (t == 0) {
         fence_proxy_async();

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(512, 1) bwd_fast_kernel(const __grid_constant_
     if (inst < 0) break;
     const double *Ag = a.A_vals + (size_t)inst * S.nnzA;
     const double *Pglob = hasP ? a.P_vals + (size_t)inst * S.nnzP : nullptr;
-    const bool tmaP = a.use_tma && hasP && (S.nnzP % 2 == 0);
+    const bool tmaP = a.use_tma && hasP && (S.nnzP % 2 == 0) && (((uintptr_t)a.P_vals & 15) == 0);   // bulk copies need 16-byte aligned sources
     if (a.use_tma) {
       if (t == 0) {
         fence_proxy_async();

@@ -174,7 +174,9 @@ struct AaIter {   // where the kernel keeps the iterate
   double *wx; int n; double *wy; int m; double *wtau;
   __device__ __forceinline__ double &at(int e) const { return e < n ? wx[e] : (e < n + m ? wy[e - n] : *wtau); }
 };
-__device__ __forceinline__ void aa_reset_dev(double *ws) { if (threadIdx.x == 0) { ws[0] = 0.0; ws[1] = 0.0; } }
+// header: [0] pairs seen since the last reset, [1] a step was taken and awaits its safeguard, [2] ||g|| of that step,
+// [3] the raw history of the fill phase has been turned into difference columns
+__device__ __forceinline__ void aa_reset_dev(double *ws) { if (threadIdx.x == 0) { ws[0] = 0.0; ws[1] = 0.0; ws[3] = 0.0; } }
 // w_prev <- w (tau passed by value: the register-tiled kernel keeps it in a register)
 static __device__ __noinline__ void aa_store_prev(double *ws, int mem, const AaIter w, double tau) {
   const int N = w.n + w.m + 1, Np = (N + 1) & ~1;
@@ -194,13 +196,32 @@ static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, con
   __syncthreads();
   const int iter = (int)hdr[0];
   __syncthreads();   // everybody has read the header before thread 0 rewrites it
-  if (iter == 0) {
-    for (int e = t; e < N; e += T) { const double xe = wprev[e], fe = w.at(e); ax[e] = xe; af[e] = fe; gp[e] = xe - fe; }
-    if (t == 0) { hdr[0] = 1.0; hdr[1] = 0.0; }
+  if (iter < mem) {
+    // Fill phase (SCS fills the memory before the first solve): only the raw pair (x, f) is recorded -- x in column
+    // `iter` of S, f in column `iter` of D.  Instances that converge before the window is full (the common case at
+    // 1e-4) pay two vector stores per acceleration_interval iterations and nothing else.
+    double *Sx = Sm + (size_t)iter * Np, *Df = D + (size_t)iter * Np;
+    for (int e = t; e < N; e += T) { Sx[e] = wprev[e]; Df[e] = w.at(e); }
+    if (t == 0) { hdr[0] = iter + 1; hdr[1] = 0.0; hdr[3] = 0.0; }
     __syncthreads();
     return 0.0;
   }
-  const int len = iter < mem ? iter : mem, idx = (iter - 1) % mem;
+  if (hdr[3] == 0.0) {
+    // first solve: raw pairs 0 .. mem-1 -> difference columns 0 .. mem-2 (s_k = x_k - x_{k-1}, d_k = f_k - f_{k-1},
+    // y_k = g_k - g_{k-1}, g = x - f) and the running (x, f, g) = pair mem-1: exactly what one update per pair would
+    // have left behind
+    for (int e = t; e < N; e += T) {
+      double xp = Sm[e], fp = D[e];
+      for (int k = 1; k < mem; k++) {
+        const double xk = Sm[(size_t)k * Np + e], fk = D[(size_t)k * Np + e];
+        Sm[(size_t)(k - 1) * Np + e] = xk - xp; D[(size_t)(k - 1) * Np + e] = fk - fp; Y[(size_t)(k - 1) * Np + e] = (xk - fk) - (xp - fp);
+        xp = xk; fp = fk;
+      }
+      ax[e] = xp; af[e] = fp; gp[e] = xp - fp;
+    }
+    __syncthreads();   // (thread 0 sets hdr[3] below, after everybody has read it)
+  }
+  const int len = mem, idx = (iter - 1) % mem;
   double ng[1] = {0.0};
   {
     double *Yc = Y + (size_t)idx * Np, *Sc = Sm + (size_t)idx * Np, *Dc = D + (size_t)idx * Np;
@@ -210,11 +231,6 @@ static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, con
       gp[e] = g; ax[e] = xe; af[e] = fe;
       ng[0] = fma(g, g, ng[0]);
     }
-  }
-  if (iter < mem) {   // SCS fills the memory before the first solve
-    if (t == 0) { hdr[0] = iter + 1; hdr[1] = 0.0; }
-    __syncthreads();
-    return 0.0;
   }
   block_reduce<1, false>(ng, red);   // (its barriers publish the new columns)
   const double norm_g = sqrt(ng[0]);
@@ -287,7 +303,7 @@ static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, con
   __syncthreads();
   const double aa_norm = sscr[BC_AA_MAXMEM];
   if (!(aa_norm >= 0.0)) {
-    if (t == 0) { hdr[0] = 0.0; hdr[1] = 0.0; }
+    if (t == 0) { hdr[0] = 0.0; hdr[1] = 0.0; hdr[3] = 0.0; }
     __syncthreads();
     return -1.0;
   }
@@ -296,7 +312,7 @@ static __device__ __noinline__ double aa_apply_dev(double *ws, int lookback, con
     for (int c = 0; c < len; c++) v = fma(-sscr[c], D[(size_t)c * Np + e], v);
     w.at(e) = v;
   }
-  if (t == 0) { hdr[0] = iter + 1; hdr[1] = 1.0; hdr[2] = norm_g; }
+  if (t == 0) { hdr[0] = iter + 1; hdr[1] = 1.0; hdr[2] = norm_g; hdr[3] = 1.0; }
   __syncthreads();
   return aa_norm;
 }
@@ -317,7 +333,7 @@ static __device__ __noinline__ bool aa_safeguard_dev(double *ws, int lookback, c
   const bool reject = sqrt(nd[0]) > BC_AA_SAFEGUARD_FACTOR * norm_g;
   if (reject) {
     for (int e = t; e < N; e += T) { w.at(e) = af[e]; wprev[e] = ax[e]; }
-    if (t == 0) hdr[0] = 0.0;
+    if (t == 0) { hdr[0] = 0.0; hdr[3] = 0.0; }
   }
   __syncthreads();
   return reject;
@@ -1153,19 +1169,33 @@ __device__ inline bool exp_newton_rho(double r, double s, double t, double *rho0
     if (hp == 0.0 || !(hp == hp)) return false;
     double step = -hv / hp, rn, yn, mn, hn;
     int bt = 0;
+    bool stalled = false;
     for (;; bt++) {   // damping: accept the first step that reduces |h| inside the domain
       rn = rho + step;
       hn = exp_h(r, s, t, rn, &yn, &mn);
-      if (hn == hn && fabs(hn) < fabs(hv) && rn + exp(2.0 * rn) > 0) break;
-      if (bt == 12) return false;
+      if (hn == hn && fabs(hn) < fabs(hv)) break;   // (rho + e^{2 rho} may have either sign: roots exist on both sides of its zero)
+      if (bt == 12) { stalled = true; break; }
       step *= 0.5;
+    }
+    if (stalled) {   // no decrease left: at rounding level that is convergence, anywhere else a failure
+      if (fabs(hv) <= 1e-11 * scale) break;
+      return false;
     }
     const bool tiny = fabs(step) <= 1e-15 * fmax(1.0, fabs(rn));
     rho = rn; hv = hn; y = yn; mu = mn;
     if (tiny) break;
   }
-  if (!(fabs(hv) <= 1e-12 * scale) || !(y > 0) || !(mu >= -1e-14 * scale)) return false;
-  x[0] = y * rho; x[1] = y; x[2] = y * exp(rho);
+  if (!(fabs(hv) <= 1e-11 * scale) || !(y > 0)) return false;
+  // Certificate (the projection is the unique point with p in K, v - p in the polar cone, p'(v - p) = 0): h = 0 alone can
+  // be met by a spurious root where mu = y e^rho - t is pure cancellation, so the dual part is checked on d = v - p itself.
+  const double E = exp(rho);
+  const double px = y * rho, py = y, pz = y * E;
+  const double dx = r - px, dy = s - py, dz = t - pz;           // must be mu (E, (1 - rho) E, -1), mu >= 0
+  const double mu2 = -dz;
+  if (!(mu2 >= -1e-13 * scale)) return false;
+  if (fabs(dx - mu2 * E) > 1e-9 * scale || fabs(dy - mu2 * E * (1.0 - rho)) > 1e-9 * scale) return false;
+  if (fabs(px * dx + py * dy + pz * dz) > 1e-9 * scale * scale) return false;
+  x[0] = px; x[1] = py; x[2] = pz;
   if (rho0) *rho0 = rho;
   return true;
 }
@@ -1198,7 +1228,7 @@ __device__ inline int proj_exp(double *v, double *rho0 = nullptr) {
       if (!(fabs(hn) < fabs(hv) && yn > 0 && mn >= 0)) break;
       rr = rn; hv = hn; y = yn; mu = mn;
     }
-    if (y > 0 && mu >= 0) { x[0] = y * rr; x[1] = y; x[2] = y * exp(rr); }
+    if (y > 0 && mu >= 0) { x[0] = y * rr; x[1] = y; x[2] = y * exp(rr); if (rho0) *rho0 = rr; }   // next call starts Newton from this root
   }
   v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
   return 3;

@@ -594,6 +594,9 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     // ---- write back ----
     {
       double *xo = a.x + (size_t)inst * n, *yo = a.y + (size_t)inst * m, *so = a.s + (size_t)inst * m;
+      // the iteration limit was hit without tau ever turning positive: x / tau would be garbage scaled by 1e12 (the problem
+      // is probably infeasible or unbounded but not certified yet).  SCS / diffcp raise here; so does the interface on FAILED.
+      if (status == BCONE_INACCURATE && !(M.u[N - 1] > 1e-12) && okf) status = BCONE_FAILED;
       if (status == BCONE_SOLVED || status == BCONE_INACCURATE) {
         double tau = M.u[N - 1];
         if (!(tau > 1e-12)) tau = 1e-12;

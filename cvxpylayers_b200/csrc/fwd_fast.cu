@@ -448,8 +448,24 @@ __device__ __noinline__ void aa_begin(const FwdArgs &a, int *ibuf) {
     const int iv = a.st.acceleration_interval > 0 ? a.st.acceleration_interval : 1;
     const bool on = a.aa_ws != nullptr && a.st.acceleration_lookback != 0;
     ibuf[1] = on ? iv : 0x7fffffff;
-    if (on) { double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride; ws[0] = 0.0; ws[1] = 0.0; }
+    ibuf[2] = 0;   // pairs recorded since the last reset (mirror of the slab header)
+    if (on) { double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride; ws[0] = 0.0; ws[1] = 0.0; ws[3] = 0.0; }
   }
+  __syncthreads();
+}
+// Fill-phase event (fewer than `lookback` pairs recorded, nothing to safeguard): store the raw pair -- x = the iterate the
+// last step started from, rebuilt as w - alpha (u - u~); f = w -- into column k of S / D (common.cuh aa_apply_dev turns
+// them into difference columns at the first solve).  A dozen registers: cheap to call from the iteration loop.
+__device__ __noinline__ void aa_fill_light(const FwdArgs &a, int j, const double *vxb, const double *vyb, int npad, int mpad, const double *sc, int *ibuf) {
+  const int iv = a.st.acceleration_interval > 0 ? a.st.acceleration_interval : 1, lb = a.st.acceleration_lookback, mem = lb > 0 ? lb : -lb;
+  const int n = a.S.n, m = a.S.m, N = n + m + 1, Np = (N + 1) & ~1, t = threadIdx.x, k = ibuf[2];
+  double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride;
+  double *Sx = ws + BC_AA_HDR + (size_t)(4 + mem + k) * Np, *Df = Sx + (size_t)mem * Np;
+  const double al = a.st.alpha;
+  if (t < n) { const double f = vxb[VX_W * npad + t]; Df[t] = f; Sx[t] = f - al * (vxb[VX_U * npad + t] - vxb[VX_UT * npad + t]); }
+  if (t < m) { const double f = vyb[VY_W * mpad + t]; Df[n + t] = f; Sx[n + t] = f - al * (vyb[VY_U * mpad + t] - vyb[VY_UT * mpad + t]); }
+  __syncthreads();   // everybody has read ibuf[2]
+  if (t == 0) { Df[N - 1] = sc[SC_AATAU]; Sx[N - 1] = sc[SC_AATAU] - sc[SC_AADT]; ws[0] = k + 1; ibuf[2] = k + 1; ibuf[1] = j + iv - j % iv; }
   __syncthreads();
 }
 __device__ __noinline__ void aa_event(const FwdArgs &a, int j, double *vxb, double *vyb, int npad, int mpad, double *sc, double *red, int *ibuf, double *lu) {
@@ -472,7 +488,8 @@ __device__ __noinline__ void aa_event(const FwdArgs &a, int j, double *vxb, doub
       if (aa_apply_dev(ws, lb, w, sc + SC_AASCR, red, lu) > 0.0) { aa_store_prev(ws, lb, w, sc[SC_AATAU]); pending = true; }
     }
   }
-  if (t == 0) ibuf[1] = pending ? j + 1 : j + iv - j % iv;
+  __syncthreads();
+  if (t == 0) { ibuf[1] = pending ? j + 1 : j + iv - j % iv; ibuf[2] = (int)ws[0]; }
   __syncthreads();
 }
 
@@ -798,7 +815,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
           const double ns = sc[SC_NEWSCALE];
           pt_stamp(4);
           if (done) break;
-          if (ns != 0.0) { scale = ns; refactor = true; if (a.aa_ws) aa_reset_dev(a.aa_ws + (size_t)blockIdx.x * a.aa_stride); }
+          if (ns != 0.0) { scale = ns; refactor = true; if (a.aa_ws) { aa_reset_dev(a.aa_ws + (size_t)blockIdx.x * a.aa_stride); if (t == 0) ibuf[2] = 0; } }
         }
         if (it < st.max_iters) {  // (the last iterate keeps w so that s = R(u - t) is recoverable)
           if (t < n) vx(VX_W)[t] += st.alpha * (vx(VX_U)[t] - vx(VX_UT)[t]);
@@ -806,7 +823,12 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
           w_tau += st.alpha * (u_tau - tau_t);
           __syncthreads();
         }
-        if (it >= ibuf[1]) {   // acceleration event (every acceleration_interval iterations; never when it is off)
+        if (it >= ibuf[1] && it < st.max_iters && ibuf[2] < abs(st.acceleration_lookback) && it % (st.acceleration_interval > 0 ? st.acceleration_interval : 1) == 0) {
+          // acceleration window still filling: record the pair (cheap callee, the tile stays in registers)
+          if (t == 0) { sc[SC_AATAU] = w_tau; sc[SC_AADT] = st.alpha * (u_tau - tau_t); }
+          __syncthreads();
+          aa_fill_light(a, it, vx(0), vy(0), g.npad(), g.mpad(), sc, ibuf);
+        } else if (it >= ibuf[1]) {   // acceleration event (every acceleration_interval iterations; never when it is off)
           // The callee chain needs more registers than the tile leaves free.  Parking the tile in the slab for the
           // duration of the call (128 KB per CTA, L2) keeps it out of the call's live set, so the register allocation
           // of the iteration loop is the one without acceleration; the compiler's own answer was to keep a third of
@@ -832,7 +854,8 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     pt_stamp(4);
     // ---- write back ----
     {
-      const int status = (int)sc[SC_STATUS];
+      int status = (int)sc[SC_STATUS];
+      if (status == BCONE_INACCURATE && !(sc[SC_UTAU] > 1e-12)) status = BCONE_FAILED;   // (see fwd.cu: no positive tau at the iteration limit)
       double *xo = a.x + (size_t)inst * n, *yo = a.y + (size_t)inst * m, *so = a.s + (size_t)inst * m;
       if (status == BCONE_SOLVED || status == BCONE_INACCURATE) {
         double tau = sc[SC_UTAU];

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) b2e_kernel(const double *__restrict__ in,
   __shared__ double tile[TK][TI + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
-  const bool vec = ((B & 1) == 0);
+  const bool vec = ((B & 1) == 0) && (((uintptr_t)in & 15) == 0);   // 128-bit accesses need an aligned base (the C ABI takes any pointer)
   for (int kk = ty; kk < TK; kk += 8) {
     const int k = k0 + kk;
     if (k >= K) continue;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) e2b_kernel(const double *__restrict__ in,
     }
   }
   __syncthreads();
-  const bool vec = ((B & 1) == 0);
+  const bool vec = ((B & 1) == 0) && (((uintptr_t)out & 15) == 0);
   for (int kk = ty; kk < TK; kk += 8) {
     const int kq = k0 + kk;
     if (kq >= K) continue;

@@ -161,6 +161,14 @@ class Engine:
                                          C.c_int32(b_idx.size), b_idx.ctypes.data_as(_lib._i32p))
         self._raise(rc, "bcone_set_boundary")
         self._boundary = (gather.size + b_idx.size, b_idx.size)
+        self._nnzP_b = self.structure.nnzP
+
+    def set_boundary_P(self, nnzP_boundary: int, gatherP: np.ndarray):
+        """Rows of the reference's P_eval feeding the engine's upper-triangular slots (any symmetric pattern)."""
+        gatherP = np.ascontiguousarray(gatherP, dtype=np.int32)
+        rc = self.lib.bcone_set_boundary_quad(self.h, C.c_int32(nnzP_boundary), gatherP.ctypes.data_as(_lib._i32p))
+        self._raise(rc, "bcone_set_boundary_quad")
+        self._nnzP_b = int(nnzP_boundary)
 
     def ingest(self, A_eval: torch.Tensor, q_eval: torch.Tensor, P_eval: torch.Tensor | None = None, out=None):
         """[nnz_aug,B] / [n+1,B] boundary tensors -> engine-layout (A_vals, P_vals, b, c).
@@ -171,7 +179,7 @@ class Engine:
         B = A_eval.shape[1]
         _chk(A_eval, (self._boundary[0], B), f64, dev, "A_eval")
         _chk(q_eval, (st.n + 1, B), f64, dev, "q_eval")
-        _chk(P_eval, (st.nnzP, B), f64, dev, "P_eval")
+        _chk(P_eval, (self._nnzP_b, B), f64, dev, "P_eval")
         if out is not None:
             A_vals, P_vals, b, c = out
         else:
@@ -192,7 +200,7 @@ class Engine:
         else:
             dA_eval = torch.empty((self._boundary[0], B), dtype=f64, device=dev)
             dq_eval = torch.empty((st.n + 1, B), dtype=f64, device=dev)
-            dP_eval = torch.empty((st.nnzP, B), dtype=f64, device=dev) if (dP_vals is not None and st.nnzP) else None
+            dP_eval = torch.empty((self._nnzP_b, B), dtype=f64, device=dev) if (dP_vals is not None and st.nnzP) else None
         rc = self.lib.bcone_emit(self.h, C.c_int32(B), _ptr(dA_vals), _ptr(dP_vals), _ptr(db), _ptr(dc), _ptr(dA_eval),
                                  _ptr(dq_eval), _ptr(dP_eval), self._stream())
         self._raise(rc, "bcone_emit")
@@ -219,7 +227,7 @@ class Engine:
             raise RuntimeError("set_boundary() has not been called")
         if A_map.shape[0] != self._boundary[0] or q_map.shape != (self.structure.n + 1, P1):
             raise ValueError("parameter maps do not match the boundary tensors")
-        if (P_map is not None) != bool(self.structure.nnzP) or (P_map is not None and P_map.shape != (self.structure.nnzP, P1)):
+        if (P_map is not None) != bool(self.structure.nnzP) or (P_map is not None and P_map.shape != (self._nnzP_b, P1)):
             raise ValueError("P parameter map does not match the structure")
         a, q, p = parts(A_map), parts(q_map), parts(P_map)
         rc = self.lib.bcone_set_param_maps(self.h, C.c_int32(P1), a[0], a[1], a[2], q[0], q[1], q[2], p[0], p[1], p[2])

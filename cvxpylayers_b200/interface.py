@@ -90,17 +90,31 @@ class B200_ctx:
         csr.sort_indices()
         self.gather = (csr.data - 1).astype(np.int32)
         P_indptr = P_indices = None
-        self.nnzP = 0
+        self.nnzP = 0          # engine slots (upper triangle)
+        self.nnzP_boundary = 0  # rows of P_eval
+        self.gatherP = None
         if objective_structure is not None:
+            # cvxpy's CSC structure (indices = rows, indptr over columns) of a symmetric P, exactly what DIFFCP_ctx is
+            # handed (reduced_P.problem_data_index, interfaces/__init__.py:27-34).  Any symmetric pattern is accepted:
+            # upper, lower or full.  The engine stores the upper triangle in CSR order; slot (i, j), i <= j, is fed by
+            # the boundary row of entry (i, j) if present, else by its mirror (j, i).  (The CSR upper triangle, which the
+            # CSR-route backends get, is the CSC lower triangle of the same matrix and lands on the identity map.)
             p_indices, p_ptr, _ = objective_structure
             p_indices, p_ptr = np.asarray(p_indices), np.asarray(p_ptr)
-            # accepted convention: CSR of the upper triangle (values arrive already CSR-ordered, as the
-            # reference arranges for its QP-capable backends, interfaces/__init__.py:38-42)
-            rows = np.repeat(np.arange(n), np.diff(p_ptr))
-            if np.any(p_indices < rows):
-                raise NotImplementedError("P must be passed as the CSR upper triangle")
-            P_indptr, P_indices = p_ptr.astype(np.int32), p_indices.astype(np.int32)
-            self.nnzP = int(P_indices.size)
+            nb_ = int(p_indices.size)
+            cols = np.repeat(np.arange(n), np.diff(p_ptr))
+            rows = p_indices.astype(np.int64)
+            lo, hi = np.minimum(rows, cols), np.maximum(rows, cols)
+            order = np.lexsort((rows > cols, hi, lo))   # by slot (lo, hi); the true upper entry first when both exist
+            key = lo[order] * n + hi[order]
+            first = np.ones(nb_, dtype=bool)
+            first[1:] = key[1:] != key[:-1]
+            sel = order[first]
+            P_indices = hi[sel].astype(np.int32)
+            P_indptr = np.concatenate([[0], np.cumsum(np.bincount(lo[sel], minlength=n))]).astype(np.int32)
+            self.gatherP = sel.astype(np.int32)
+            self.nnzP = int(sel.size)
+            self.nnzP_boundary = nb_
         cones = ConeSpec.from_dict(dims_to_solver_dict(dims))
         self.structure = Structure(n, m, csr.indptr.astype(np.int32), csr.indices.astype(np.int32), cones,
                                    P_indptr, P_indices)
@@ -111,8 +125,20 @@ class B200_ctx:
         if eng is None:
             eng = Engine(self.structure, device)
             eng.set_boundary(self.gather, np.asarray(self.b_idx, dtype=np.int32))
+            if self.nnzP:
+                eng.set_boundary_P(self.nnzP_boundary, self.gatherP)
+            if getattr(self, "_param_maps", None) is not None:
+                eng.set_param_maps(*self._param_maps)
             self._engines[device] = eng
         return eng
+
+    def set_param_maps(self, A_map, q_map, P_map=None):
+        """Register the layer's parameter -> matrix maps (SciPy CSR [rows x P1], boundary row order: the reference's
+        ``_A_scipy`` / ``_q_scipy`` / ``_P_scipy``, ``torch/cvxpylayer.py:443-451``) so that
+        :class:`_CvxpyLayerFused` can take ``p_stack`` instead of the evaluated matrices."""
+        self._param_maps = (A_map, q_map, P_map if self.nnzP else None)
+        for eng in self._engines.values():
+            eng.set_param_maps(*self._param_maps)
 
     def compute_device(self, t: torch.Tensor) -> torch.device:
         if t.is_cuda:
@@ -355,13 +381,26 @@ class _CvxpyLayer(torch.autograd.Function):
 
 
 def get_solver_ctx(solver, param_prob, cone_dims, data, kwargs, verbose=False):
-    """Twin of ``cvxpylayers.interfaces.get_solver_ctx`` (``interfaces/__init__.py:13-69``) for the
-    solver name "B200"; see INTEGRATION.md for the two-line patch that registers it."""
+    """Twin of ``cvxpylayers.interfaces.get_solver_ctx`` (``interfaces/__init__.py:13-69``) for the solver name
+    "B200".  Like DIFFCP it takes cvxpy's CSC structures as they are (``reduced_P/A.problem_data_index``): the CSC -> CSR
+    re-ordering and the upper-triangle selection of P happen inside the engine's ingest kernels, so the parametrisation
+    matrices need no row permutation (what ``convert_to_csr`` does for the other CSR backends)."""
     if solver != "B200":
         raise RuntimeError("Unknown solver. Check if your solver is supported by CVXPYlayers")
     options = dict(kwargs) if kwargs else {}
-    return B200_ctx(None, param_prob.reduced_A.problem_data_index, cone_dims,
-                    data.get("lower_bound"), data.get("upper_bound"), options)
+    if verbose:
+        options["verbose"] = True
+    red_P = getattr(param_prob, "reduced_P", None)
+    p_struct = getattr(red_P, "problem_data_index", None) if red_P is not None else None
+    ctx = B200_ctx(p_struct, param_prob.reduced_A.problem_data_index, cone_dims,
+                   data.get("lower_bound"), data.get("upper_bound"), options)
+    # the fused path needs the parametrisation matrices themselves (rows in boundary order, last column = constant)
+    A_mat = getattr(param_prob.reduced_A, "reduced_mat", None)
+    q_mat = getattr(param_prob, "q", getattr(param_prob, "c", None))
+    P_mat = getattr(red_P, "reduced_mat", None) if (red_P is not None and p_struct is not None) else None
+    if A_mat is not None and q_mat is not None:
+        ctx.set_param_maps(A_mat, q_mat, P_mat)
+    return ctx
 
 
 def get_torch_cvxpylayer(solver):
@@ -371,20 +410,130 @@ def get_torch_cvxpylayer(solver):
     return _CvxpyLayer
 
 
-def register() -> None:
-    """Patch an importable ``cvxpylayers`` so ``CvxpyLayer(problem, ..., solver="B200")`` dispatches
-    here (the reference's dispatch is a closed ``match``; INTEGRATION.md shows the same change as a
-    source patch).  cvxpy's canonicalisation for DIFFCP is reused (``parse_args.py:447-462``)."""
-    import cvxpylayers.interfaces as ifs  # noqa: PLC0415
+class _CvxpyLayerFused(torch.autograd.Function):
+    """``p_stack -> (primal, dual)`` with the parameter -> matrix affine map fused into the engine's load stage and its
+    transpose into the gradient write-back: replaces the three sparse products at
+    ``torch/cvxpylayer.py:443-451`` + ``_CvxpyLayer.apply`` + their transposes (``:33-37``).  ``p_stack[P1, B]`` is what
+    ``_flatten_and_batch_params`` builds (last row = 1).  Only parameters and parameter gradients cross PCIe."""
 
-    orig_ctx, orig_layer = ifs.get_solver_ctx, ifs.get_torch_cvxpylayer
+    @staticmethod
+    def forward(p_stack, cl_ctx, solver_args, needs_grad=True):
+        ctx: B200_ctx = cl_ctx.solver_ctx
+        unb = p_stack.dim() == 1
+        ps = p_stack.unsqueeze(1) if unb else p_stack
+        in_device, in_dtype = ps.device, ps.dtype
+        dev = ctx.compute_device(ps)
+        eng = ctx.engine(dev)
+        settings = make_settings({**ctx.options, **(solver_args or {})})
+        with torch.cuda.device(dev):
+            A_vals, P_vals, b, c = eng.ingest_params(_to_dev(ps, dev))
+            sol = eng.solve(A_vals, b, c, P_vals, settings)
+            status = sol.status.cpu()
+        bad = (status != 1) & (status != 2)
+        if bool(bad.any()):
+            i = int(torch.nonzero(bad)[0])
+            raise SolverError(f"instance {i}: solver returned status {STATUS.get(int(status[i]), int(status[i]))}")
+        if bool((status == 2).any()):
+            warnings.warn("Solved/Inaccurate.", stacklevel=2)
+        with torch.cuda.device(dev):
+            primal = _to_host_like(sol.x, in_device, in_dtype)
+            dual = _to_host_like(sol.y, in_device, in_dtype)
+            if in_device.type == "cpu":
+                torch.cuda.current_stream(dev).synchronize()
+        saved = _Saved(eng, settings, A_vals, P_vals, b, c, sol.x, sol.y, sol.s) if needs_grad else None
+        return primal, dual, saved, (unb, in_device, in_dtype)
+
+    @staticmethod
+    def setup_context(ctx: Any, inputs: tuple, outputs: tuple) -> None:
+        ctx.saved, ctx.backward_data = outputs[2], outputs[3]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx: Any, dprimal, ddual, _saved, _data):
+        unb, in_device, in_dtype = ctx.backward_data
+        if ctx.saved is None:
+            raise RuntimeError("backward called on a forward pass run with needs_grad=False")
+        eng, settings, A_vals, P_vals, b, c, x, y, s = ctx.saved.items
+        dev = eng.device
+        B = A_vals.shape[0]
+        with torch.cuda.device(dev):
+            dA, dP, db, dc, _ = eng.vjp(A_vals, b, c, x, y, s, _to_dev(dprimal, dev).reshape(B, -1), _to_dev(ddual, dev).reshape(B, -1), P_vals, settings)
+            dp = _to_host_like(eng.emit_params(dA, dP, db, dc), in_device, in_dtype)
+            if in_device.type == "cpu":
+                torch.cuda.current_stream(dev).synchronize()
+        return (dp.squeeze(1) if unb else dp), None, None, None
+
+
+_REGISTERED = False
+_FORCE_B200 = False
+
+
+def register(canon_solver: str = "DIFFCP", fuse: bool = True) -> None:
+    """Patch an importable ``cvxpylayers`` so that ``CvxpyLayer(problem, ..., solver="B200")`` works unmodified
+    (INTEGRATION.md shows the same change as a source patch):
+
+    * ``utils.parse_args.parse_args`` is wrapped: cvxpy does not know a solver called "B200", so the problem is
+      canonicalised for ``canon_solver`` (default "DIFFCP": quad_form -> SOC, ``_quad_form_dpp.py:29-32``; pass the name of
+      a cvxpy solver with a quadratic objective, e.g. "CLARABEL", together with a cvxpylayers whose
+      ``SUPPORTS_QUAD_OBJ`` lists it to keep ``P``), while the context that comes back carries ``solver = "B200"`` and a
+      :class:`B200_ctx` (``parse_args.py:447-462`` is where the name reaches cvxpy);
+    * ``interfaces.get_solver_ctx`` / ``get_torch_cvxpylayer`` dispatch the new name (the reference's dispatch is a closed
+      ``match``, ``interfaces/__init__.py:44-69,81-101``);
+    * with ``fuse=True`` the torch layer's ``forward`` hands ``p_stack`` to :class:`_CvxpyLayerFused` instead of evaluating
+      ``A_eval``/``q_eval``/``P_eval`` first (``torch/cvxpylayer.py:434-487``)."""
+    global _REGISTERED
+    import dataclasses  # noqa: PLC0415
+    import importlib  # noqa: PLC0415
+
+    ifs = importlib.import_module("cvxpylayers.interfaces")
+    pa = importlib.import_module("cvxpylayers.utils.parse_args")
+    if _REGISTERED and getattr(ifs.get_solver_ctx, "_b200", False):
+        return
+    orig_ctx, orig_layer, orig_parse = ifs.get_solver_ctx, ifs.get_torch_cvxpylayer, pa.parse_args
 
     def _ctx(solver, param_prob, cone_dims, data, kwargs, verbose=False):
-        if solver == "B200":
-            return get_solver_ctx(solver, param_prob, cone_dims, data, kwargs, verbose)
+        if solver == "B200" or _FORCE_B200:
+            return get_solver_ctx("B200", param_prob, cone_dims, data, kwargs, verbose)
         return orig_ctx(solver, param_prob, cone_dims, data, kwargs, verbose)
 
     def _layer(solver):
         return _CvxpyLayer if solver == "B200" else orig_layer(solver)
 
-    ifs.get_solver_ctx, ifs.get_torch_cvxpylayer = _ctx, _layer
+    def _parse(problem, variables, parameters, solver, *args, **kwargs):
+        global _FORCE_B200
+        if solver != "B200":
+            return orig_parse(problem, variables, parameters, solver, *args, **kwargs)
+        _FORCE_B200 = True
+        try:
+            ctx = orig_parse(problem, variables, parameters, canon_solver, *args, **kwargs)
+        finally:
+            _FORCE_B200 = False
+        try:
+            return dataclasses.replace(ctx, solver="B200")
+        except TypeError:   # not a dataclass (stubs): plain attribute
+            ctx.solver = "B200"
+            return ctx
+
+    _ctx._b200 = True
+    ifs.get_solver_ctx, ifs.get_torch_cvxpylayer, pa.parse_args = _ctx, _layer, _parse
+    if fuse:
+        try:
+            tl = importlib.import_module("cvxpylayers.torch.cvxpylayer")
+        except Exception:  # noqa: BLE001
+            tl = None
+        if tl is not None and hasattr(tl, "CvxpyLayer"):
+            orig_forward = tl.CvxpyLayer.forward
+
+            def _forward(self, *params, solver_args=None, warm_start=False, **kw):
+                sctx = getattr(self.ctx, "solver_ctx", None)
+                if getattr(self.ctx, "solver", None) != "B200" or getattr(sctx, "_param_maps", None) is None or warm_start:
+                    return orig_forward(self, *params, solver_args=solver_args, warm_start=warm_start, **kw)
+                batch = self.ctx.validate_params(list(params))
+                params_ = tl._apply_gp_log_transform(params, self.ctx)
+                p_stack = tl._flatten_and_batch_params(params_, self.ctx, batch)
+                needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params_)
+                primal, dual, _, _ = _CvxpyLayerFused.apply(p_stack, self.ctx, solver_args or {}, needs_grad)
+                return tl._recover_results(primal, dual, self.ctx, batch)
+
+            tl.CvxpyLayer.forward = _forward
+    _REGISTERED = True

@@ -69,6 +69,10 @@ const char *bcone_last_error(void *handle); /* handle may be NULL: last create()
  * bcone_set_boundary) is the row of A_eval feeding CSR slot k.  Outputs: A_vals[B,nnzA] = -A_eval,
  * b[B,m] (zeros off b_idx), c[B,n], P_vals[B,nnzP]. */
 int bcone_set_boundary(void *handle, int32_t nnz_aug, const int32_t *gather, int32_t nb, const int32_t *b_idx);
+/* Optional: P_eval[nnzP_boundary, B] rows in the reference's order for ANY symmetric pattern cvxpy emits (upper, lower or
+ * full); gatherP[k] (HOST int32 [nnzP]) is the row feeding the engine's upper-triangular CSR slot k.  Rows that feed no
+ * slot (the mirror entries of a full pattern) receive a zero gradient in bcone_emit.  Default: identity. */
+int bcone_set_boundary_quad(void *handle, int32_t nnzP_boundary, const int32_t *gatherP);
 int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_eval, const double *P_eval,
                  double *A_vals, double *P_vals, double *b, double *c, void *cuda_stream);
 /* Engine gradients -> boundary layout: dA_eval[nnz_aug,B] = [-dA (boundary order) ; db[b_idx]],

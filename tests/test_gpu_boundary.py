@@ -276,3 +276,39 @@ def test_identity_parameter_map_is_the_plain_boundary(cuda_device):
     dp = eng.emit_params(_t(gA, dev), _t(gP, dev), _t(gb, dev), _t(gc, dev)).cpu().numpy()
     assert np.array_equal(dp[:na], dA_eval.cpu().numpy()) and np.array_equal(dp[na:na + nq - 1], dq_eval.cpu().numpy()[:-1])
     assert np.array_equal(dp[na + nq:na + nq + nP], dP_eval.cpu().numpy()) and not dp[-1].any()
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_registered_layer_end_to_end_with_quadratic_term(fuse, cuda_device, monkeypatch):
+    """CvxpyLayer(problem, ..., solver="B200") through the registered wrappers: construction via the wrapped
+    parse_args, forward / backward via the reference's own sequence (fuse=False: sparse products + _CvxpyLayer.apply) or
+    the fused path (fuse=True: p_stack straight into the engine), native P passed through from a FULL symmetric pattern.
+    Solutions and parameter gradients against the oracle."""
+    from cvxpylayers_b200 import interface as itf
+    from tests.util import fake_param_prob, install_fake_cvxpylayers
+
+    fake = install_fake_cvxpylayers(monkeypatch)
+    bt = pr.dense_qp(5, 8, 14, 3, seed=4)
+    st = bt.structure
+    problem, params = fake_param_prob(bt)
+    itf.register(fuse=fuse)
+    args = {"eps": 1e-9, "max_iters": 100000, "lsqr_precond": 1}
+    layer = fake.tl.CvxpyLayer(problem, [], [], solver="B200", solver_args=args)
+    layer.ctx.solver_ctx.device = cuda_device
+    th = [torch.tensor(p, device=cuda_device, requires_grad=True) for p in params]
+    primal, dual = layer(*th)
+    xo, yo, so, sto, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+    assert (sto == 1).all()
+    assert np.abs(primal.detach().cpu().numpy() - xo).max() < 1e-6 and np.abs(dual.detach().cpu().numpy() - yo).max() < 1e-6
+    rng = np.random.default_rng(2)
+    dx, dy = rng.standard_normal(xo.shape), rng.standard_normal(yo.shape)
+    ((primal * torch.tensor(dx, device=cuda_device)).sum() + (dual * torch.tensor(dy, device=cuda_device)).sum()).backward()
+    gA, gP, gb, gc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, xo, yo, so, dx, dy, bt.P_vals, **args)
+    sc = layer.ctx.solver_ctx
+    dAe = th[0].grad.cpu().numpy().T            # [nnz_aug, B]: [-dA (boundary order) ; db]
+    assert rel_err(-dAe[sc.gather].T, gA) < 1e-4 and rel_err(dAe[st.nnzA:].T, gb) < 1e-4
+    assert rel_err(th[1].grad.cpu().numpy(), gc) < 1e-4
+    dPe = th[2].grad.cpu().numpy().T            # [n*n, B] rows of the full pattern: upper entries carry the gradient, mirrors 0
+    assert rel_err(dPe[sc.gatherP].T, gP) < 1e-4
+    mirror = np.setdiff1d(np.arange(st.n * st.n), sc.gatherP)
+    assert not dPe[mirror].any()

@@ -127,3 +127,36 @@ def test_gather_rows_world_size_2_gloo(B):
     port = 29500 + (os.getpid() % 500) + B
     mp.spawn(_gloo_worker, args=(2, port, B, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_register_makes_the_solver_name_constructible(monkeypatch):
+    """after ``register()`` a layer can be CONSTRUCTED with solver="B200" -- parse_args canonicalises for a
+    solver cvxpy knows while the context carries the new name and a B200_ctx with the quadratic term passed through (full
+    symmetric CSC pattern -> upper-triangular engine structure) and the parameter maps attached; other names still go to
+    the reference's own dispatch.  cvxpy is absent here, so the reference package is a stand-in (tests/util.py)."""
+    from cvxpylayers_b200 import interface as itf
+    from tests.util import fake_param_prob, install_fake_cvxpylayers
+
+    fake = install_fake_cvxpylayers(monkeypatch)
+    bt = pr.dense_qp(3, 6, 9, 2, seed=1)
+    problem, params = fake_param_prob(bt)
+    with pytest.raises(ValueError):   # before registration cvxpy's canonicalisation rejects the unknown solver
+        fake.pa.parse_args(problem, [], [], "B200")
+    itf.register()
+    ctx = fake.pa.parse_args(problem, [], [], "B200", solver_args={"eps": 1e-8})
+    assert ctx.solver == "B200" and isinstance(ctx.solver_ctx, itf.B200_ctx)
+    sc = ctx.solver_ctx
+    st = bt.structure
+    assert np.array_equal(sc.structure.A_indptr, st.A_indptr) and np.array_equal(sc.structure.A_indices, st.A_indices)
+    assert np.array_equal(sc.structure.P_indptr, st.P_indptr) and np.array_equal(sc.structure.P_indices, st.P_indices)   # upper triangle of the full pattern
+    assert sc.nnzP == st.nnzP and sc.nnzP_boundary == st.n * st.n and sc.options == {"eps": 1e-8}
+    # gatherP picks the true upper entry (row i, col j), i <= j, out of the CSC-ordered full pattern
+    pr_rows = problem["param_prob"].reduced_P.problem_data_index[0]
+    pr_cols = np.repeat(np.arange(st.n), st.n)
+    assert all(pr_rows[g] <= pr_cols[g] for g in sc.gatherP)
+    assert sc._param_maps is not None and sc._param_maps[0].shape[0] == st.nnzA + st.m
+    assert fake.ifs.get_torch_cvxpylayer("B200") is itf._CvxpyLayer
+    with pytest.raises(RuntimeError):
+        fake.ifs.get_torch_cvxpylayer("NOPE")
+    with pytest.raises(ValueError):
+        fake.pa.parse_args(problem, [], [], "NOPE")
