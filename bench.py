@@ -191,6 +191,7 @@ def run_ours(a):
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = bdist.bind_to_gpu_numa_node(local) if world > 1 else False   # pinned buffers next to the GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch
@@ -226,11 +227,81 @@ def run_ours(a):
         if timed: e[3].record()
         gA_eval, gq_eval, gP_eval = eng.emit(gA, gP, gb, gc)
         if timed: e[4].record()
-        if world > 1:  # the path's single exchange: gather solutions and gradient blocks on rank 0
-            bdist.gather_rows(torch.cat([sol.x, sol.y], dim=1), Btot, dst=0)
-            bdist.gather_rows(gA_eval.t().contiguous(), Btot, dst=0)
-            bdist.gather_rows(gq_eval.t().contiguous(), Btot, dst=0)
         return sol, its, e
+
+    # ---- sharded batch (N > 1): two-stream chunk pipeline, each chunk's results pushed to rank 0 behind the next chunk ----
+    # The path has no data-path collective; its one exchange (solutions + gradient blocks onto the rank that owns the
+    # autograd graph) runs peer-to-peer on the copy engines while the next chunk solves.
+    from cvxpylayers_b200.engine import Solution  # noqa: E402
+
+    nnz_aug = hA.shape[0]
+    offA = 0
+    offq = offA + nnz_aug * B * 8
+    offP = offq + (st.n + 1) * B * 8
+    offx = offP + st.nnzP * B * 8
+    offy = offx + B * st.n * 8
+    slot_bytes = offy + B * st.m * 8
+    xchg = bdist.PeerExchange(eng.lib, dev, slot_bytes) if world > 1 else None
+    if world > 1:
+        bufs = dict(A_vals=torch.empty((B, st.nnzA), dtype=f64, device=dev), b=torch.empty((B, st.m), dtype=f64, device=dev),
+                    c=torch.empty((B, st.n), dtype=f64, device=dev), P_vals=torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None,
+                    sol=eng.alloc_solution(B), gA=torch.empty((B, st.nnzA), dtype=f64, device=dev), gb=torch.empty((B, st.m), dtype=f64, device=dev),
+                    gc=torch.empty((B, st.n), dtype=f64, device=dev), gP=torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None,
+                    its=torch.empty(B, dtype=torch.int32, device=dev), gA_eval=torch.empty((nnz_aug, B), dtype=f64, device=dev),
+                    gq_eval=torch.empty((st.n + 1, B), dtype=f64, device=dev), gP_eval=torch.empty((st.nnzP, B), dtype=f64, device=dev) if st.nnzP else None)
+        side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        copy_stream = torch.cuda.Stream(dev)
+        chunk_events, recv_bufs = {}, {}
+
+    def chunk_list(Bs: int, chunk: int):
+        nchunk = max(1, Bs // max(chunk, 1))
+        base, extra = divmod(Bs, nchunk)
+        out, lo = [], 0
+        for k in range(nchunk):
+            hi = lo + base + (1 if k < extra else 0)
+            out.append((lo, hi)); lo = hi
+        return out
+
+    def step_sharded(Bs: int, chunk: int):
+        """One step over instances [0, Bs) of this rank's shard."""
+        u = bufs
+        cur = torch.cuda.current_stream(dev)
+        for s_ in side:
+            s_.wait_stream(cur)
+        copy_stream.wait_stream(cur)
+        sl = lambda t_, lo, hi: None if t_ is None else t_[lo:hi]  # noqa: E731
+        for k, (lo, hi) in enumerate(chunk_list(Bs, chunk)):
+            with torch.cuda.stream(side[k % 2]):
+                eng.ingest_cols(dA_, dq_, dP_, lo, hi, out=(u["A_vals"][lo:hi], sl(u["P_vals"], lo, hi), u["b"][lo:hi], u["c"][lo:hi]))
+                so = u["sol"]
+                eng.solve(u["A_vals"][lo:hi], u["b"][lo:hi], u["c"][lo:hi], sl(u["P_vals"], lo, hi), settings,
+                          out=Solution(so.x[lo:hi], so.y[lo:hi], so.s[lo:hi], so.status[lo:hi], so.iters[lo:hi], so.resid[lo:hi]))
+                eng.vjp(u["A_vals"][lo:hi], u["b"][lo:hi], u["c"][lo:hi], so.x[lo:hi], so.y[lo:hi], so.s[lo:hi], dx[lo:hi], dy[lo:hi],
+                        sl(u["P_vals"], lo, hi), settings, out=(u["gA"][lo:hi], sl(u["gP"], lo, hi), u["gb"][lo:hi], u["gc"][lo:hi], u["its"][lo:hi]))
+                eng.emit_cols(u["gA"][lo:hi], sl(u["gP"], lo, hi), u["gb"][lo:hi], u["gc"][lo:hi], lo, hi, out=(u["gA_eval"], u["gq_eval"], u["gP_eval"]))
+                evk = chunk_events.setdefault(k, torch.cuda.Event())
+                evk.record()
+            copy_stream.wait_event(evk)
+            if xchg.p2p:
+                w8 = (hi - lo) * 8
+                xchg.push(u["gA_eval"][:, lo:hi], offA + lo * 8, copy_stream, rows=nnz_aug, width_bytes=w8, dpitch=B * 8, spitch=B * 8)
+                xchg.push(u["gq_eval"][:, lo:hi], offq + lo * 8, copy_stream, rows=st.n + 1, width_bytes=w8, dpitch=B * 8, spitch=B * 8)
+                if st.nnzP:
+                    xchg.push(u["gP_eval"][:, lo:hi], offP + lo * 8, copy_stream, rows=st.nnzP, width_bytes=w8, dpitch=B * 8, spitch=B * 8)
+                xchg.push(so.x[lo:hi], offx + lo * st.n * 8, copy_stream)
+                xchg.push(so.y[lo:hi], offy + lo * st.m * 8, copy_stream)
+        for s_ in side:
+            cur.wait_stream(s_)
+        cur.wait_stream(copy_stream)
+        if not xchg.p2p:   # no peer mapping: one NCCL gather per tensor (no transposes, no concatenation afterwards)
+            for t_ in (u["gA_eval"], u["gq_eval"], u["gP_eval"], u["sol"].x, u["sol"].y):
+                if t_ is None:
+                    continue
+                if rank == 0:
+                    dist.gather(t_, recv_bufs.setdefault(id(t_), [torch.empty_like(t_) for _ in range(world)]), dst=0)
+                else:
+                    dist.gather(t_, None, dst=0)
+        return u["sol"], u["its"]
 
     def step_e2e():
         A = hA.detach().requires_grad_(True)
@@ -252,6 +323,7 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    # per-kernel times (and the N = 1 step): the plain one-launch-per-stage sequence
     for _ in range(a.warmup):
         step_device(False)
     sync()
@@ -266,7 +338,8 @@ def run_ours(a):
         evs.append(e)
     t_end.record()
     sync()
-    clocks = sampler.stop()
+    if world == 1:
+        clocks = sampler.stop()
     launches = eng.launch_count() - l0
     ms_total = t_start.elapsed_time(t_end)
     for e in evs:
@@ -276,10 +349,44 @@ def run_ours(a):
     for k in kt:
         kt[k] /= a.steps
     ms_step = ms_total / a.steps
+    strong = None
     if world > 1:
-        tt = torch.tensor([ms_step], dtype=f64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step = float(tt)
+        def timed_sharded(Bs, chunk):
+            for _ in range(a.warmup):
+                step_sharded(Bs, chunk)
+            sync()
+            lA = eng.launch_count()
+            t0_, t1_ = ev(), ev()
+            t0_.record()
+            for _ in range(a.steps):
+                sol_, its_ = step_sharded(Bs, chunk)
+            t1_.record()
+            sync()
+            tt = torch.tensor([t0_.elapsed_time(t1_) / a.steps], dtype=f64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt), sol_, its_, eng.launch_count() - lA
+        ms_step, sol, its, launches = timed_sharded(B, a.chunk)  # weak scaling: every rank its own B instances
+        clocks = sampler.stop()
+        Bs = max(1, B // world)                                  # strong scaling: the BASELINE batch split over the ranks
+        ms_strong, _, _, _ = timed_sharded(Bs, a.chunk)
+        strong = {"global_batch": Bs * world, "batch_per_gpu": Bs, "ms_per_step": ms_strong, "value": Bs * world / (ms_strong * 1e-3), "unit": UNIT,
+                  "chunks_per_gpu": len(chunk_list(Bs, a.chunk)),
+                  "note": f"{Bs} instances per GPU = {Bs / 148:.2f} waves of one CTA per SM: wave quantisation and the fixed per-launch costs bound strong scaling"}
+        if a.verify_exchange:
+            # every slot of rank 0's buffer against an NCCL gather of the same tensors
+            ok = True
+            for name_, t_, off_ in (("gA_eval", bufs["gA_eval"], offA), ("gq_eval", bufs["gq_eval"], offq), ("x", bufs["sol"].x, offx), ("y", bufs["sol"].y, offy)):
+                recv = [torch.empty_like(t_) for _ in range(world)] if rank == 0 else None
+                dist.gather(t_.contiguous(), recv, dst=0)
+                if rank == 0 and xchg.p2p:
+                    for r_ in range(world):
+                        got = xchg.read(r_, off_, torch.empty_like(t_))
+                        torch.cuda.synchronize()
+                        # (the strong-scaling pass overwrote the first Bs instances of every shard: same data, same values)
+                        ok = ok and bool(torch.equal(got, recv[r_]))
+            if rank == 0:
+                print(f"[bench] exchange verified against NCCL gather: {ok} (p2p={xchg.p2p})", file=sys.stderr)
+                assert ok
     status = sol.status.cpu().numpy()
     iters = sol.iters.cpu().numpy()
     lits = its.cpu().numpy()
@@ -343,6 +450,8 @@ def run_ours(a):
                         "diagnostic_wall_ms_per_step": [round(v, 1) for v in per_step],
                         "diagnostic_wall_ms_median": round(float(np.median(per_step)), 2)},
                 "gpu_launches": int(launches),
+                **({"strong_scaling": strong, "exchange": {"kind": "peer-to-peer copy engines (CUDA IPC over NVLink), chunked behind the solve" if xchg.p2p else "NCCL gather into preallocated slots",
+                                                          "bytes_per_rank": int(slot_bytes), "chunk": a.chunk, "numa_bound": bool(numa_bound)}} if world > 1 else {}),
                 "roofline": {"bound": "hbm", "kernel": eng.path_info()[dom], "achieved": ach, "peak": peak, "unit": "GB/s",
                              "frac": ach / peak, "traffic": (NCU_DRAM_BYTES_PER_INSTANCE.get(dom, 0) * B / 1e9 or None) if CONFIG == "C2" else None,
                              "traffic_unit": "GB per launch (ncu dram__bytes_read+write per instance, profiles/prof_*_r1*.txt, x B)",
@@ -371,6 +480,8 @@ def main():
                    help="instances per CPU pass (default: 2048 for the cpu_baseline leg of our arm, the whole batch for --impl reference)")
     p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "C5S", "EXP"],
                    help="workload (default: the headline C2; others are secondary measurements)")
+    p.add_argument("--chunk", type=int, default=1024, help="N > 1: instances per pipeline chunk (results of a chunk travel to rank 0 behind the next chunk's solve)")
+    p.add_argument("--verify-exchange", action="store_true", help="N > 1: check rank 0's gathered buffer against an NCCL gather")
     p.add_argument("--set", action="append", default=[], metavar="KEY=VALUE",
                    help="override a solver argument for both arms, e.g. --set acceleration_lookback=0")
     a = p.parse_args()

@@ -16,7 +16,8 @@ _f64p = C.POINTER(C.c_double)
 
 EXPORTS = [
     "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary", "bcone_set_boundary_quad",
-    "bcone_ingest", "bcone_emit", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
+    "bcone_ingest", "bcone_emit", "bcone_ingest_pitched", "bcone_emit_pitched", "bcone_peer_alloc", "bcone_peer_open", "bcone_peer_close",
+    "bcone_peer_free", "bcone_copy2d_async", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
 
@@ -74,6 +75,20 @@ def load() -> C.CDLL:
     lib.bcone_ingest.restype = C.c_int
     lib.bcone_emit.argtypes = [vp, C.c_int32] + [vp] * 8
     lib.bcone_emit.restype = C.c_int
+    lib.bcone_ingest_pitched.argtypes = [vp, C.c_int32, C.c_int64] + [vp] * 8
+    lib.bcone_ingest_pitched.restype = C.c_int
+    lib.bcone_emit_pitched.argtypes = [vp, C.c_int32, C.c_int64] + [vp] * 8
+    lib.bcone_emit_pitched.restype = C.c_int
+    lib.bcone_peer_alloc.argtypes = [C.c_int32, C.c_int64, C.POINTER(vp), vp]
+    lib.bcone_peer_alloc.restype = C.c_int
+    lib.bcone_peer_open.argtypes = [C.c_int32, vp, C.POINTER(vp)]
+    lib.bcone_peer_open.restype = C.c_int
+    lib.bcone_peer_close.argtypes = [vp]
+    lib.bcone_peer_close.restype = C.c_int
+    lib.bcone_peer_free.argtypes = [vp]
+    lib.bcone_peer_free.restype = C.c_int
+    lib.bcone_copy2d_async.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int64, vp]
+    lib.bcone_copy2d_async.restype = C.c_int
     lib.bcone_set_param_maps.argtypes = [vp, C.c_int32] + [_i32p, _i32p, _f64p] * 3
     lib.bcone_set_param_maps.restype = C.c_int
     lib.bcone_ingest_params.argtypes = [vp, C.c_int32] + [vp] * 6

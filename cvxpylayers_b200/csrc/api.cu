@@ -35,8 +35,8 @@ cudaError_t bc_bwdf_launch(const BwdArgs *a, int grid, int threads, size_t smem,
 size_t bc_bwdb_smem_bytes(int n, int m, int threads);
 cudaError_t bc_bwdb_configure(size_t smem);
 cudaError_t bc_bwdb_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
-cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
-cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, cudaStream_t st);
+cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, long long ldb, cudaStream_t st);
+cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, long long ldb, cudaStream_t st);
 cudaError_t bc_p2e(const double *p, const int *rptr, const int *cols, const double *vals, double *out, int K, int B, int ldo, int roff,
                    const int *smap, const int *dmap, double sign, cudaStream_t st);
 cudaError_t bc_e2p(const double *in, const int *rptr, const int *cols, const double *vals, double *dp, int K, int B, int ldi, int roff,
@@ -386,39 +386,83 @@ extern "C" int bcone_emit_params(void *handle, int32_t B, const double *dA_vals,
   return BCONE_OK;
 }
 
-extern "C" int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_eval, const double *P_eval,
-                            double *A_vals, double *P_vals, double *b, double *c, void *stream) {
+extern "C" int bcone_ingest_pitched(void *handle, int32_t B, int64_t ldb, const double *A_eval, const double *q_eval, const double *P_eval,
+                                    double *A_vals, double *P_vals, double *b, double *c, void *stream) {
   Handle *h = (Handle *)handle;
-  if (!h || B <= 0 || !A_eval || !q_eval || !A_vals || !b || !c) return fail(h, BCONE_EINVAL, "ingest: null argument");
+  if (!h || B <= 0 || ldb < B || !A_eval || !q_eval || !A_vals || !b || !c) return fail(h, BCONE_EINVAL, "ingest: null argument / bad pitch");
   if (h->nnz_aug == 0 && h->S.nnzA + h->nb != 0) return fail(h, BCONE_EINVAL, "ingest: call bcone_set_boundary first");
   cudaStream_t st = (cudaStream_t)stream;
   const DevStruct &S = h->S;
-  CK(bc_b2e(A_eval, A_vals, S.nnzA, B, S.nnzA, 0, h->d_gather, nullptr, -1.0, st), "ingest A");
+  CK(bc_b2e(A_eval, A_vals, S.nnzA, B, S.nnzA, 0, h->d_gather, nullptr, -1.0, ldb, st), "ingest A");
   CK(cudaMemsetAsync(b, 0, (size_t)B * S.m * sizeof(double), st), "ingest b memset");
-  CK(bc_b2e(A_eval, b, h->nb, B, S.m, S.nnzA, nullptr, h->d_bidx, 1.0, st), "ingest b");
-  CK(bc_b2e(q_eval, c, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "ingest c");
+  CK(bc_b2e(A_eval, b, h->nb, B, S.m, S.nnzA, nullptr, h->d_bidx, 1.0, ldb, st), "ingest b");
+  CK(bc_b2e(q_eval, c, S.n, B, S.n, 0, nullptr, nullptr, 1.0, ldb, st), "ingest c");
   h->launches += 3;
-  if (P_eval && P_vals && S.nnzP > 0) { CK(bc_b2e(P_eval, P_vals, S.nnzP, B, S.nnzP, 0, h->d_gatherP, nullptr, 1.0, st), "ingest P"); h->launches++; }
+  if (P_eval && P_vals && S.nnzP > 0) { CK(bc_b2e(P_eval, P_vals, S.nnzP, B, S.nnzP, 0, h->d_gatherP, nullptr, 1.0, ldb, st), "ingest P"); h->launches++; }
   return BCONE_OK;
 }
+extern "C" int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_eval, const double *P_eval,
+                            double *A_vals, double *P_vals, double *b, double *c, void *stream) {
+  return bcone_ingest_pitched(handle, B, B, A_eval, q_eval, P_eval, A_vals, P_vals, b, c, stream);
+}
 
-extern "C" int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
-                          const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *stream) {
+extern "C" int bcone_emit_pitched(void *handle, int32_t B, int64_t ldb, const double *dA_vals, const double *dP_vals, const double *db,
+                                  const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *stream) {
   Handle *h = (Handle *)handle;
-  if (!h || B <= 0 || !dA_vals || !db || !dc || !dA_eval || !dq_eval) return fail(h, BCONE_EINVAL, "emit: null argument");
+  if (!h || B <= 0 || ldb < B || !dA_vals || !db || !dc || !dA_eval || !dq_eval) return fail(h, BCONE_EINVAL, "emit: null argument / bad pitch");
   cudaStream_t st = (cudaStream_t)stream;
   const DevStruct &S = h->S;
-  CK(bc_e2b(dA_vals, dA_eval, S.nnzA, B, S.nnzA, 0, nullptr, h->d_gather, -1.0, st), "emit dA");
-  CK(bc_e2b(db, dA_eval, h->nb, B, S.m, S.nnzA, h->d_bidx, nullptr, 1.0, st), "emit db");
-  CK(bc_e2b(dc, dq_eval, S.n, B, S.n, 0, nullptr, nullptr, 1.0, st), "emit dc");
-  CK(cudaMemsetAsync(dq_eval + (size_t)S.n * B, 0, (size_t)B * sizeof(double), st), "emit dq tail");
+  CK(bc_e2b(dA_vals, dA_eval, S.nnzA, B, S.nnzA, 0, nullptr, h->d_gather, -1.0, ldb, st), "emit dA");
+  CK(bc_e2b(db, dA_eval, h->nb, B, S.m, S.nnzA, h->d_bidx, nullptr, 1.0, ldb, st), "emit db");
+  CK(bc_e2b(dc, dq_eval, S.n, B, S.n, 0, nullptr, nullptr, 1.0, ldb, st), "emit dc");
+  CK(cudaMemset2DAsync(dq_eval + (size_t)S.n * ldb, (size_t)ldb * sizeof(double), 0, (size_t)B * sizeof(double), 1, st), "emit dq tail");
   h->launches += 3;
   if (dP_vals && dP_eval && S.nnzP > 0) {
     // boundary rows without an engine slot (the lower triangle of a full symmetric pattern) get a zero gradient:
     // the engine reads the upper triangle only, so that is the derivative of what was computed
-    if (h->d_gatherP && h->nnzP_b != S.nnzP) CK(cudaMemsetAsync(dP_eval, 0, (size_t)h->nnzP_b * B * sizeof(double), st), "emit dP memset");
-    CK(bc_e2b(dP_vals, dP_eval, S.nnzP, B, S.nnzP, 0, nullptr, h->d_gatherP, 1.0, st), "emit dP"); h->launches++;
+    if (h->d_gatherP && h->nnzP_b != S.nnzP)
+      CK(cudaMemset2DAsync(dP_eval, (size_t)ldb * sizeof(double), 0, (size_t)B * sizeof(double), (size_t)h->nnzP_b, st), "emit dP memset");
+    CK(bc_e2b(dP_vals, dP_eval, S.nnzP, B, S.nnzP, 0, nullptr, h->d_gatherP, 1.0, ldb, st), "emit dP"); h->launches++;
   }
+  return BCONE_OK;
+}
+extern "C" int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
+                          const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *stream) {
+  return bcone_emit_pitched(handle, B, B, dA_vals, dP_vals, db, dc, dA_eval, dq_eval, dP_eval, stream);
+}
+
+// ---- peer exchange: a buffer on one GPU that every rank of the node can write (CUDA IPC over NVLink) -----------------------
+extern "C" int bcone_peer_alloc(int32_t device, int64_t bytes, void **ptr, void *ipc_handle64) {
+  if (!ptr || !ipc_handle64 || bytes <= 0) return BCONE_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return BCONE_ECUDA;
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) { g_create_err = std::string("bcone_peer_alloc: ") + cudaGetErrorString(e); return BCONE_ENOMEM; }
+  cudaIpcMemHandle_t hnd;
+  e = cudaIpcGetMemHandle(&hnd, p);
+  if (e != cudaSuccess) { cudaFree(p); g_create_err = std::string("bcone_peer_alloc (ipc handle): ") + cudaGetErrorString(e); return BCONE_ECUDA; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  memcpy(ipc_handle64, &hnd, 64);
+  *ptr = p;
+  return BCONE_OK;
+}
+extern "C" int bcone_peer_open(int32_t device, const void *ipc_handle64, void **ptr) {
+  if (!ptr || !ipc_handle64) return BCONE_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return BCONE_ECUDA;
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, ipc_handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, hnd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { g_create_err = std::string("bcone_peer_open: ") + cudaGetErrorString(e); cudaGetLastError(); return BCONE_ECUDA; }
+  return BCONE_OK;
+}
+extern "C" int bcone_peer_close(void *ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? BCONE_OK : BCONE_ECUDA; }
+extern "C" int bcone_peer_free(void *ptr) { return cudaFree(ptr) == cudaSuccess ? BCONE_OK : BCONE_ECUDA; }
+// dst / src: any device pointers of this process' address space (local or peer-mapped); pitches and width in bytes.
+// height = 1 is a plain copy.  Runs on the copy engines: no SM is taken from a solve that is in flight.
+extern "C" int bcone_copy2d_async(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t height, void *stream) {
+  cudaError_t e = height <= 1 ? cudaMemcpyAsync(dst, src, (size_t)width, cudaMemcpyDefault, (cudaStream_t)stream)
+                              : cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_err = std::string("bcone_copy2d_async: ") + cudaGetErrorString(e); return BCONE_ECUDA; }
   return BCONE_OK;
 }
 

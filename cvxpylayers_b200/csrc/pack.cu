@@ -13,19 +13,21 @@
 #define TI 64  // batch entries per tile
 
 // out[i * ldo + dmap(k)] = sign * in[(roff + smap(k)) * B + i],  k in [0,K), i in [0,B)
+// (ldb: row pitch of the boundary tensor in doubles -- B for a whole tensor, the full batch when `in` points at a column
+//  slice [lo, lo + B) of it)
 __global__ void __launch_bounds__(256) b2e_kernel(const double *__restrict__ in, double *__restrict__ out, int K, int B,
                                                   int ldo, int roff, const int *__restrict__ smap,
-                                                  const int *__restrict__ dmap, double sign) {
+                                                  const int *__restrict__ dmap, double sign, long long ldb) {
   __shared__ double tile[TK][TI + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
-  const bool vec = ((B & 1) == 0) && (((uintptr_t)in & 15) == 0);   // 128-bit accesses need an aligned base (the C ABI takes any pointer)
+  const bool vec = ((B & 1) == 0) && ((ldb & 1) == 0) && (((uintptr_t)in & 15) == 0);   // 128-bit accesses need an aligned base (the C ABI takes any pointer)
   for (int kk = ty; kk < TK; kk += 8) {
     const int k = k0 + kk;
     if (k >= K) continue;
     const int r = roff + (smap ? __ldg(smap + k) : k);
     const int i = i0 + 2 * tx;
-    const double *p = in + (size_t)r * B + i;
+    const double *p = in + (size_t)r * ldb + i;
     if (vec && i + 1 < B) {
       const double2 v = *reinterpret_cast<const double2 *>(p);
       tile[kk][2 * tx] = v.x; tile[kk][2 * tx + 1] = v.y;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) b2e_kernel(const double *__restrict__ in,
 // out[(roff + dmap(k)) * B + i] = sign * in[i * ldi + smap(k)]
 __global__ void __launch_bounds__(256) e2b_kernel(const double *__restrict__ in, double *__restrict__ out, int K, int B,
                                                   int ldi, int roff, const int *__restrict__ smap,
-                                                  const int *__restrict__ dmap, double sign) {
+                                                  const int *__restrict__ dmap, double sign, long long ldb) {
   __shared__ double tile[TK][TI + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
@@ -61,13 +63,13 @@ __global__ void __launch_bounds__(256) e2b_kernel(const double *__restrict__ in,
     }
   }
   __syncthreads();
-  const bool vec = ((B & 1) == 0) && (((uintptr_t)out & 15) == 0);
+  const bool vec = ((B & 1) == 0) && ((ldb & 1) == 0) && (((uintptr_t)out & 15) == 0);
   for (int kk = ty; kk < TK; kk += 8) {
     const int kq = k0 + kk;
     if (kq >= K) continue;
     const int r = roff + (dmap ? __ldg(dmap + kq) : kq);
     const int i = i0 + 2 * tx;
-    double *p = out + (size_t)r * B + i;
+    double *p = out + (size_t)r * ldb + i;
     if (vec && i + 1 < B) {
       *reinterpret_cast<double2 *>(p) = make_double2(sign * tile[kk][2 * tx], sign * tile[kk][2 * tx + 1]);
     } else {
@@ -171,16 +173,16 @@ extern "C" cudaError_t bc_e2p(const double *in, const int *rptr, const int *cols
 }
 
 extern "C" cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap,
-                              const int *dmap, double sign, cudaStream_t st) {
+                              const int *dmap, double sign, long long ldb, cudaStream_t st) {
   if (K <= 0 || B <= 0) return cudaSuccess;
   dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
-  b2e_kernel<<<grid, 256, 0, st>>>(in, out, K, B, ldo, roff, smap, dmap, sign);
+  b2e_kernel<<<grid, 256, 0, st>>>(in, out, K, B, ldo, roff, smap, dmap, sign, ldb);
   return cudaGetLastError();
 }
 extern "C" cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap,
-                              const int *dmap, double sign, cudaStream_t st) {
+                              const int *dmap, double sign, long long ldb, cudaStream_t st) {
   if (K <= 0 || B <= 0) return cudaSuccess;
   dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
-  e2b_kernel<<<grid, 256, 0, st>>>(in, out, K, B, ldi, roff, smap, dmap, sign);
+  e2b_kernel<<<grid, 256, 0, st>>>(in, out, K, B, ldi, roff, smap, dmap, sign, ldb);
   return cudaGetLastError();
 }

@@ -192,6 +192,26 @@ class Engine:
         self._raise(rc, "bcone_ingest")
         return A_vals, P_vals, b, c
 
+    def ingest_cols(self, A_eval, q_eval, P_eval, lo: int, hi: int, out):
+        """Column slice [lo, hi) of full boundary tensors -> the engine-layout views in ``out`` (no staging copy)."""
+        Bfull = A_eval.shape[1]
+        A_vals, P_vals, b, c = out
+        off = lo * 8
+        pp = lambda t: C.c_void_p(0 if t is None else t.data_ptr() + off)  # noqa: E731
+        rc = self.lib.bcone_ingest_pitched(self.h, C.c_int32(hi - lo), C.c_int64(Bfull), pp(A_eval), pp(q_eval), pp(P_eval), _ptr(A_vals),
+                                           _ptr(P_vals), _ptr(b), _ptr(c), self._stream())
+        self._raise(rc, "bcone_ingest_pitched")
+
+    def emit_cols(self, dA_vals, dP_vals, db, dc, lo: int, hi: int, out):
+        """Engine gradients of instances [lo, hi) -> columns [lo, hi) of the full boundary gradient tensors in ``out``."""
+        dA_eval, dq_eval, dP_eval = out
+        Bfull = dA_eval.shape[1]
+        off = lo * 8
+        pp = lambda t: C.c_void_p(0 if t is None else t.data_ptr() + off)  # noqa: E731
+        rc = self.lib.bcone_emit_pitched(self.h, C.c_int32(hi - lo), C.c_int64(Bfull), _ptr(dA_vals), _ptr(dP_vals), _ptr(db), _ptr(dc),
+                                         pp(dA_eval), pp(dq_eval), pp(dP_eval), self._stream())
+        self._raise(rc, "bcone_emit_pitched")
+
     def emit(self, dA_vals, dP_vals, db, dc, out=None):
         st, dev, f64 = self.structure, self.device, torch.float64
         B = dA_vals.shape[0]
@@ -285,8 +305,8 @@ class Engine:
         self._raise(rc, "bcone_solve")
         return Solution(x, y, s, status, iters, resid)
 
-    def vjp(self, A_vals, b, c, x, y, s, dx, dy, P_vals=None, settings: _lib.BconeSettings | None = None):
-        """-> dA_vals[B,nnzA], dP_vals[B,nnzP]|None, db[B,m], dc[B,n], lsqr_iters[B]"""
+    def vjp(self, A_vals, b, c, x, y, s, dx, dy, P_vals=None, settings: _lib.BconeSettings | None = None, out=None):
+        """-> dA_vals[B,nnzA], dP_vals[B,nnzP]|None, db[B,m], dc[B,n], lsqr_iters[B]  (``out``: the same five, preallocated)"""
         st, dev, f64 = self.structure, self.device, torch.float64
         B = A_vals.shape[0]
         for name, t, shp in (("A_vals", A_vals, (B, st.nnzA)), ("b", b, (B, st.m)), ("c", c, (B, st.n)),
@@ -294,11 +314,14 @@ class Engine:
                              ("dx", dx, (B, st.n)), ("dy", dy, (B, st.m))):
             _chk(t, shp, f64, dev, name)
         settings = settings or _lib.default_settings()
-        dA = torch.empty((B, st.nnzA), dtype=f64, device=dev)
-        db = torch.empty((B, st.m), dtype=f64, device=dev)
-        dc = torch.empty((B, st.n), dtype=f64, device=dev)
-        dP = torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None
-        its = torch.empty(B, dtype=torch.int32, device=dev)
+        if out is not None:
+            dA, dP, db, dc, its = out
+        else:
+            dA = torch.empty((B, st.nnzA), dtype=f64, device=dev)
+            db = torch.empty((B, st.m), dtype=f64, device=dev)
+            dc = torch.empty((B, st.n), dtype=f64, device=dev)
+            dP = torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None
+            its = torch.empty(B, dtype=torch.int32, device=dev)
         rc = self.lib.bcone_vjp(self.h, C.c_int32(B), _ptr(A_vals), _ptr(P_vals if st.nnzP else None), _ptr(b), _ptr(c),
                                 _ptr(x), _ptr(y), _ptr(s), _ptr(dx), _ptr(dy), _ptr(dA), _ptr(dP), _ptr(db), _ptr(dc),
                                 _ptr(its), C.byref(settings), self._stream())

@@ -80,6 +80,25 @@ int bcone_ingest(void *handle, int32_t B, const double *A_eval, const double *q_
 int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
                const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *cuda_stream);
 
+/* Same as bcone_ingest / bcone_emit on a COLUMN SLICE of the boundary tensors: the pointers address column lo of tensors whose
+ * rows are ldb doubles apart (ldb = the full batch), B = hi - lo instances.  A sharded or pipelined caller reads its slice of
+ * A_eval in place and writes its slice of dA_eval straight into the full gradient tensor (no staging copy, no concatenation). */
+int bcone_ingest_pitched(void *handle, int32_t B, int64_t ldb, const double *A_eval, const double *q_eval, const double *P_eval,
+                         double *A_vals, double *P_vals, double *b, double *c, void *cuda_stream);
+int bcone_emit_pitched(void *handle, int32_t B, int64_t ldb, const double *dA_vals, const double *dP_vals, const double *db,
+                       const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *cuda_stream);
+
+/* Peer exchange for a batch sharded over the GPUs of one node (one exchange of solutions + gradients).  The
+ * rank that owns the autograd graph allocates the destination with bcone_peer_alloc and passes the 64-byte CUDA IPC handle
+ * to the other ranks (any host channel: torch.distributed, MPI, a pipe); they map it with bcone_peer_open and push their
+ * shard with bcone_copy2d_async -- peer-to-peer over NVLink on the copy engines, chunk by chunk behind the solve, so the
+ * transfer takes no SM and hides behind the next chunk's kernels.  bcone_copy2d_async also serves local strided copies. */
+int bcone_peer_alloc(int32_t device, int64_t bytes, void **ptr, void *ipc_handle64);
+int bcone_peer_open(int32_t device, const void *ipc_handle64, void **ptr);
+int bcone_peer_close(void *ptr);
+int bcone_peer_free(void *ptr);
+int bcone_copy2d_async(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t height, void *cuda_stream);
+
 /* Parameter -> matrix affine map fused into the load stage (replaces the reference's sparse x dense products around
  * the solver interface: forward  A_eval = A_param @ p_stack etc. at src/cvxpylayers/torch/cvxpylayer.py:443-451,
  * transposes at :33-37).  The three maps are HOST CSR matrices [rows x P1] (P1 = total parameter size + 1; the last row

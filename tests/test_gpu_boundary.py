@@ -312,3 +312,57 @@ def test_registered_layer_end_to_end_with_quadratic_term(fuse, cuda_device, monk
     assert rel_err(dPe[sc.gatherP].T, gP) < 1e-4
     mirror = np.setdiff1d(np.arange(st.n * st.n), sc.gatherP)
     assert not dPe[mirror].any()
+
+
+def test_column_slice_ingest_and_emit_equal_the_whole_tensor_calls(cuda_device):
+    """bcone_ingest_pitched / bcone_emit_pitched on column slices of the full boundary tensors (what a sharded or
+    pipelined caller uses: no staging copy, no concatenation) == bcone_ingest / bcone_emit on the whole batch."""
+    bt = pr.dense_qp(37, 10, 20, 3, seed=10)
+    st, dev = bt.structure, cuda_device
+    ctx, bd, _ = _layer(bt)
+    eng = ctx.engine(dev)
+    A_eval, q_eval, P_eval = _t(bd.A_eval, dev), _t(bd.q_eval, dev), _t(bd.P_eval, dev)
+    ref = eng.ingest(A_eval, q_eval, P_eval)
+    B = bt.B
+    f64 = torch.float64
+    out = (torch.zeros((B, st.nnzA), dtype=f64, device=dev), torch.zeros((B, st.nnzP), dtype=f64, device=dev),
+           torch.zeros((B, st.m), dtype=f64, device=dev), torch.zeros((B, st.n), dtype=f64, device=dev))
+    cuts = [(0, 9), (9, 10), (10, 26), (26, 37)]   # odd offsets: the 128-bit fast path must fall back where it is misaligned
+    for lo, hi in cuts:
+        eng.ingest_cols(A_eval, q_eval, P_eval, lo, hi, out=tuple(o[lo:hi] for o in out))
+    for r_, g_ in zip(ref, out):
+        assert torch.equal(r_, g_)
+    rng = np.random.default_rng(1)
+    gA, gP, gb, gc = (_t(rng.standard_normal(a.shape), dev) for a in (bt.A_vals, bt.P_vals, bt.b, bt.c))
+    want = eng.emit(gA, gP, gb, gc)
+    got = (torch.full_like(want[0], 7.0), torch.full_like(want[1], 7.0), torch.full_like(want[2], 7.0))
+    for lo, hi in cuts:
+        eng.emit_cols(gA[lo:hi], gP[lo:hi], gb[lo:hi], gc[lo:hi], lo, hi, out=got)
+    for w_, g_ in zip(want, got):
+        assert torch.equal(w_, g_)
+
+
+def test_pipelined_host_path_on_the_workspace_backed_kernels(cuda_device, monkeypatch):
+    """Two chunks in flight on two streams for a structure whose forward keeps its iterate vectors in a global-memory slab
+    (indirect / CG path) and whose backward keeps the LSQR vectors there too: the slabs are per stream (ADVICE round 1:
+    a single per-handle slab was shared by concurrent launches), so the pipelined result equals the single-shot one."""
+    import cvxpylayers_b200.interface as itf
+
+    bt = pr.sparse_qp(B=6, seed=2)
+    args = {"eps": 1e-8, "max_iters": 100000, "lsqr_precond": 1, "lsqr_iter_lim": 20000}
+    outs = []
+    for chunk in (2, 10**9):
+        monkeypatch.setattr(itf, "PIPE_CHUNK", chunk)
+        ctx, bd, cl = _layer(bt, **args)
+        ctx.device = cuda_device
+        info = ctx.engine(cuda_device).path_info()
+        assert "indirect" in info["fwd"]
+        A = torch.tensor(bd.A_eval).pin_memory().requires_grad_(True)
+        q = torch.tensor(bd.q_eval).pin_memory().requires_grad_(True)
+        P = torch.tensor(bd.P_eval).pin_memory().requires_grad_(True)
+        primal, dual, saved, _ = _CvxpyLayer.apply(P, q, A, cl, {}, True, None)
+        assert saved.items[9] == (chunk == 2)
+        (primal.sum() + (dual * dual).sum()).backward()
+        outs.append([primal.detach().clone(), dual.detach().clone(), A.grad.clone(), q.grad.clone(), P.grad.clone()])
+    for a_, b_ in zip(*outs):
+        assert torch.allclose(a_, b_, rtol=1e-9, atol=1e-11)
