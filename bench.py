@@ -478,7 +478,7 @@ def main():
     p.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the BASELINE.json batch of the config)")
     p.add_argument("--cpu-sample", type=int, default=None,
                    help="instances per CPU pass (default: 2048 for the cpu_baseline leg of our arm, the whole batch for --impl reference)")
-    p.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5", "C5S", "EXP"],
+    p.add_argument("--config", default="C2", choices=["C1", "C2", "C2SOC", "C3", "C4", "C5", "C5S", "EXP"],
                    help="workload (default: the headline C2; others are secondary measurements)")
     p.add_argument("--chunk", type=int, default=1024, help="N > 1: instances per pipeline chunk (results of a chunk travel to rank 0 behind the next chunk's solve)")
     p.add_argument("--verify-exchange", action="store_true", help="N > 1: check rank 0's gathered buffer against an NCCL gather")
@@ -494,11 +494,11 @@ def main():
         k, v = kv.split("=", 1)
         SOLVER_ARGS[k] = float(v) if ("." in v or "e" in v.lower()) else int(v)
     if a.batch <= 0:
-        a.batch = {"C1": 4096, "C2": 4096, "C3": 2048, "C4": 512, "C5": 256, "C5S": 256, "EXP": 1024}[CONFIG]
+        a.batch = {"C1": 4096, "C2": 4096, "C2SOC": 1024, "C3": 2048, "C4": 512, "C5": 256, "C5S": 256, "EXP": 1024}[CONFIG]
     if CONFIG != "C2":
         METRIC = f"problems/sec fwd+bwd, BASELINE config {CONFIG} (secondary measurement)"
         a.cpu_sample = min(a.cpu_sample, a.batch)
-        if CONFIG == "C4":   # LP: no quadratic term for the block factorisation; thousands of iterations per instance
+        if CONFIG in ("C4", "C2SOC"):   # no quadratic term for the block factorisation; LPs need thousands of iterations
             SOLVER_ARGS.update({"lsqr_precond": 1, "max_iters": 100000})
     # The contract is ONE JSON line on stdout.  Libraries write there behind Python's back (NCCL prints its version
     # banner on fd 1 when NCCL_DEBUG is set), so fd 1 points at stderr while the run is in progress and the

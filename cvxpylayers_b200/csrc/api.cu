@@ -466,10 +466,19 @@ extern "C" int bcone_copy2d_async(void *dst, int64_t dpitch, const void *src, in
   return BCONE_OK;
 }
 
+extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
+                                const double *x0, const double *y0, const double *s0, double *x, double *y, double *s, int32_t *status,
+                                int32_t *iters, double *resid, const bcone_settings *stg, void *stream);
 extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,
                            const double *c, double *x, double *y, double *s, int32_t *status, int32_t *iters,
                            double *resid, const bcone_settings *stg, void *stream) {
+  return bcone_solve_warm(handle, B, A_vals, P_vals, b, c, nullptr, nullptr, nullptr, x, y, s, status, iters, resid, stg, stream);
+}
+extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
+                                const double *x0, const double *y0, const double *s0, double *x, double *y, double *s, int32_t *status,
+                                int32_t *iters, double *resid, const bcone_settings *stg, void *stream) {
   Handle *h = (Handle *)handle;
+  if (h && ((x0 != nullptr) != (y0 != nullptr) || (x0 != nullptr) != (s0 != nullptr))) return fail(h, BCONE_EINVAL, "solve: warm start needs x0, y0 and s0 together");
   if (!h || B <= 0 || !A_vals || !b || !c || !x || !y || !s || !status || !iters || !stg) return fail(h, BCONE_EINVAL, "solve: null argument");
   if (h->S.nnzP > 0 && !P_vals) return fail(h, BCONE_EINVAL, "solve: structure has P but P_vals is NULL");
   if (stg->check_interval <= 0 || stg->max_iters <= 0) return fail(h, BCONE_EINVAL, "solve: check_interval and max_iters must be positive");
@@ -480,6 +489,7 @@ extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const 
   FwdArgs a;
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
+  a.x0 = x0; a.y0 = y0; a.s0 = s0;
   int *ctr = h->counters + 4 * (h->slot++ % Handle::RING);
   a.counter = ctr; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
   const int grid = std::min(B, h->num_sms * h->fwd_ctas);

@@ -426,6 +426,14 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
     int status = BCONE_INACCURATE, it = 0;
     bool okf = factor_and_g<DENSE, INDIRECT>(a, M, Pg, scale, rho_x, gRg, plA, plN);
     for (int k = t; k < N; k += T) { M.w[k] = (k == N - 1) ? 1.0 : 0.0; M.u[k] = 0; M.ut[k] = 0; }
+    if (a.x0) {
+      // Warm start (the reference exposes it for one backend only, torch/cvxpylayer.py:464-487): start the
+      // splitting at the fixed point a previous solution (x0, y0, s0) would be for this instance -- w = u + R^{-1} v with
+      // u = (x0 sigma / E, y0 sigma / D, 1), v_y = s0 D sigma (the inverse of the write-back below at tau = 1).
+      const double *x0 = a.x0 + (size_t)inst * n, *y0 = a.y0 + (size_t)inst * m, *s0 = a.s0 + (size_t)inst * m;
+      for (int j = t; j < n; j += T) M.w[j] = x0[j] * sigma / M.En[j];
+      for (int i = t; i < m; i += T) M.w[n + i] = y0[i] * sigma / M.Dm[i] + s0[i] * M.Dm[i] * sigma * inv_ry(S, i, scale);
+    }
     if (INDIRECT) for (int j = t; j < n; j += T) M.cx[j] = 0.0;
     __syncthreads();
     pt.stamp(2);   // K formation + Cholesky + inverse + g

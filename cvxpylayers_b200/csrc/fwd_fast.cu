@@ -676,6 +676,11 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     int it = 0, next_check = st.adaptive_check ? (st.check_interval < 10 ? st.check_interval : 10) : st.check_interval;
     if (t < n) { vx(VX_W)[t] = 0; vx(VX_U)[t] = 0; vx(VX_UT)[t] = 0; }
     if (t < m) { vy(VY_W)[t] = 0; vy(VY_U)[t] = 0; vy(VY_UT)[t] = 0; }
+    if (a.x0) {   // warm start: w = u + R^{-1} v at the previous solution (see fwd.cu)
+      const double sg = sc[SC_SIGMA];
+      if (t < n) vx(VX_W)[t] = a.x0[(size_t)inst * n + t] * sg / vx(VX_EN)[t];
+      if (t < m) { const double d = vy(VY_DM)[t]; vy(VY_W)[t] = a.y0[(size_t)inst * m + t] * sg / d + a.s0[(size_t)inst * m + t] * d * sg * inv_ry_f(z, t, scale); }
+    }
     __syncthreads();
     bool refactor = true, first = true;
     // Anderson acceleration of w (common.cuh): everything about it lives in aa_event(); the loop only compares the

@@ -26,7 +26,7 @@ _ARG_MAP = {
     "lsqr_iter_lim": "lsqr_iter_lim", "lsqr_precond": "lsqr_precond", "adaptive_check": "adaptive_check",
     "acceleration_lookback": "acceleration_lookback", "acceleration_interval": "acceleration_interval",
 }
-_IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "warm_starts", "raise_on_error"}
+_IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "warm_starts", "raise_on_error", "warm_start"}
 
 
 def make_settings(args: dict | None) -> _lib.BconeSettings:
@@ -279,7 +279,8 @@ class Engine:
         return dp
 
     # ------------------------------------------------------------------ forward / backward
-    def solve(self, A_vals, b, c, P_vals=None, settings: _lib.BconeSettings | None = None, out: "Solution | None" = None) -> Solution:
+    def solve(self, A_vals, b, c, P_vals=None, settings: _lib.BconeSettings | None = None, out: "Solution | None" = None,
+              warm: "tuple | Solution | None" = None) -> Solution:
         st, dev, f64 = self.structure, self.device, torch.float64
         B = A_vals.shape[0]
         _chk(A_vals, (B, st.nnzA), f64, dev, "A_vals")
@@ -299,9 +300,14 @@ class Engine:
             status = torch.empty(B, dtype=torch.int32, device=dev)
             iters = torch.empty(B, dtype=torch.int32, device=dev)
             resid = torch.empty((B, 3), dtype=f64, device=dev)
-        rc = self.lib.bcone_solve(self.h, C.c_int32(B), _ptr(A_vals), _ptr(P_vals if st.nnzP else None), _ptr(b), _ptr(c),
-                                  _ptr(x), _ptr(y), _ptr(s), _ptr(status), _ptr(iters), _ptr(resid), C.byref(settings),
-                                  self._stream())
+        x0 = y0 = s0 = None
+        if warm is not None:   # a previous solution of a nearby problem (training loops re-solve almost the same programs)
+            x0, y0, s0 = (warm.x, warm.y, warm.s) if isinstance(warm, Solution) else warm
+            for name, t_, shp in (("x0", x0, (B, st.n)), ("y0", y0, (B, st.m)), ("s0", s0, (B, st.m))):
+                _chk(t_, shp, f64, dev, name)
+        rc = self.lib.bcone_solve_warm(self.h, C.c_int32(B), _ptr(A_vals), _ptr(P_vals if st.nnzP else None), _ptr(b), _ptr(c),
+                                       _ptr(x0), _ptr(y0), _ptr(s0), _ptr(x), _ptr(y), _ptr(s), _ptr(status), _ptr(iters), _ptr(resid),
+                                       C.byref(settings), self._stream())
         self._raise(rc, "bcone_solve")
         return Solution(x, y, s, status, iters, resid)
 

@@ -140,6 +140,24 @@ class B200_ctx:
         for eng in self._engines.values():
             eng.set_param_maps(*self._param_maps)
 
+    # ---- warm starts: the previous call's solution seeds the next one ({"warm_start": True}) ----
+    def warm_for(self, dev: torch.device, B: int, warm_start, merged: dict):
+        """What to start from: an explicit (x0, y0, s0) / Solution passed as ``warm_start``, else -- when the option
+        ``warm_start`` is on -- the cached solution of the previous call with the same batch size on this device (the
+        reference's rule for its one warm-startable backend, ``torch/cvxpylayer.py:464-473``)."""
+        if warm_start is not None and not isinstance(warm_start, bool):
+            ws = (warm_start.x, warm_start.y, warm_start.s) if hasattr(warm_start, "x") else tuple(warm_start)
+            return tuple(t.detach().to(device=dev, dtype=torch.float64).contiguous() for t in ws)
+        if warm_start is True or merged.get("warm_start"):
+            return getattr(self, "_last_solution", {}).get((dev, B))
+        return None
+
+    def remember(self, dev: torch.device, B: int, sol, merged: dict, warm_start) -> None:
+        if warm_start is True or merged.get("warm_start"):
+            if not hasattr(self, "_last_solution"):
+                self._last_solution = {}
+            self._last_solution[(dev, B)] = (sol.x.detach(), sol.y.detach(), sol.s.detach())
+
     def compute_device(self, t: torch.Tensor) -> torch.device:
         if t.is_cuda:
             return t.device
@@ -214,7 +232,7 @@ def _side_streams(eng: Engine, dev):
     return ss
 
 
-def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P):
+def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P, warm=None):
     st = eng.structure
     B = A_eval.shape[1]
     f64 = torch.float64
@@ -243,7 +261,8 @@ def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P
             eng.ingest(A_c, q_c, P_c, out=(A_vals[lo:hi], P_vals[lo:hi] if use_P else None, b[lo:hi], c[lo:hi]))
             from .engine import Solution  # noqa: PLC0415
             eng.solve(A_vals[lo:hi], b[lo:hi], c[lo:hi], P_vals[lo:hi] if use_P else None, settings,
-                      out=Solution(sol.x[lo:hi], sol.y[lo:hi], sol.s[lo:hi], sol.status[lo:hi], sol.iters[lo:hi], sol.resid[lo:hi]))
+                      out=Solution(sol.x[lo:hi], sol.y[lo:hi], sol.s[lo:hi], sol.status[lo:hi], sol.iters[lo:hi], sol.resid[lo:hi]),
+                      warm=None if warm is None else tuple(w_[lo:hi] for w_ in warm))
             primal[lo:hi].copy_(sol.x[lo:hi], non_blocking=True)
             dual[lo:hi].copy_(sol.y[lo:hi], non_blocking=True)
     for s_ in streams:
@@ -314,16 +333,18 @@ class _CvxpyLayer(torch.autograd.Function):
             merged.update(solver_args)
         settings = make_settings(merged)
         use_P = P_eval is not None and ctx.nnzP > 0
+        warm = ctx.warm_for(dev, batch_size, warm_start, merged)
         piped = _pipe_ok(eng, batch_size, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None)
         with torch.cuda.device(dev):
             if piped:
                 A_vals, P_vals, b, c, sol, primal, dual = _forward_pipelined(
-                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P)
+                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P, warm)
             else:
                 A_vals, P_vals, b, c = eng.ingest(_to_dev(A_eval, dev), _to_dev(q_eval, dev),
                                                   _to_dev(P_eval, dev) if use_P else None)
-                sol = eng.solve(A_vals, b, c, P_vals, settings)
+                sol = eng.solve(A_vals, b, c, P_vals, settings, warm=warm)
             status = sol.status.cpu()  # the one host sync of the forward: per-instance status
+        ctx.remember(dev, batch_size, sol, merged, warm_start)
         bad = (status != 1) & (status != 2)
         if bool(bad.any()):
             i = int(torch.nonzero(bad)[0])
@@ -417,18 +438,21 @@ class _CvxpyLayerFused(torch.autograd.Function):
     ``_flatten_and_batch_params`` builds (last row = 1).  Only parameters and parameter gradients cross PCIe."""
 
     @staticmethod
-    def forward(p_stack, cl_ctx, solver_args, needs_grad=True):
+    def forward(p_stack, cl_ctx, solver_args, needs_grad=True, warm_start=None):
         ctx: B200_ctx = cl_ctx.solver_ctx
         unb = p_stack.dim() == 1
         ps = p_stack.unsqueeze(1) if unb else p_stack
         in_device, in_dtype = ps.device, ps.dtype
         dev = ctx.compute_device(ps)
         eng = ctx.engine(dev)
-        settings = make_settings({**ctx.options, **(solver_args or {})})
+        merged = {**ctx.options, **(solver_args or {})}
+        settings = make_settings(merged)
+        B = ps.shape[1]
         with torch.cuda.device(dev):
             A_vals, P_vals, b, c = eng.ingest_params(_to_dev(ps, dev))
-            sol = eng.solve(A_vals, b, c, P_vals, settings)
+            sol = eng.solve(A_vals, b, c, P_vals, settings, warm=ctx.warm_for(dev, B, warm_start, merged))
             status = sol.status.cpu()
+        ctx.remember(dev, B, sol, merged, warm_start)
         bad = (status != 1) & (status != 2)
         if bool(bad.any()):
             i = int(torch.nonzero(bad)[0])
@@ -461,7 +485,7 @@ class _CvxpyLayerFused(torch.autograd.Function):
             dp = _to_host_like(eng.emit_params(dA, dP, db, dc), in_device, in_dtype)
             if in_device.type == "cpu":
                 torch.cuda.current_stream(dev).synchronize()
-        return (dp.squeeze(1) if unb else dp), None, None, None
+        return (dp.squeeze(1) if unb else dp), None, None, None, None
 
 
 _REGISTERED = False
@@ -526,13 +550,14 @@ def register(canon_solver: str = "DIFFCP", fuse: bool = True) -> None:
 
             def _forward(self, *params, solver_args=None, warm_start=False, **kw):
                 sctx = getattr(self.ctx, "solver_ctx", None)
-                if getattr(self.ctx, "solver", None) != "B200" or getattr(sctx, "_param_maps", None) is None or warm_start:
+                if getattr(self.ctx, "solver", None) != "B200" or getattr(sctx, "_param_maps", None) is None:
                     return orig_forward(self, *params, solver_args=solver_args, warm_start=warm_start, **kw)
                 batch = self.ctx.validate_params(list(params))
                 params_ = tl._apply_gp_log_transform(params, self.ctx)
                 p_stack = tl._flatten_and_batch_params(params_, self.ctx, batch)
                 needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params_)
-                primal, dual, _, _ = _CvxpyLayerFused.apply(p_stack, self.ctx, solver_args or {}, needs_grad)
+                # (the reference refuses warm_start for every backend but one, torch/cvxpylayer.py:416-420; this one takes it)
+                primal, dual, _, _ = _CvxpyLayerFused.apply(p_stack, self.ctx, solver_args or {}, needs_grad, True if warm_start else None)
                 return tl._recover_results(primal, dual, self.ctx, batch)
 
             tl.CvxpyLayer.forward = _forward

@@ -196,6 +196,57 @@ def dense_lp(B: int, n: int, m: int, seed: int = 0) -> Batch:
     return Batch(st, A, b, c, None, x, y, s, f"dense_lp_n{n}_m{m}")
 
 
+def qp_as_socp(bt: Batch) -> Batch:
+    """The same QPs in the form the reference's DIFFCP path hands over: DIFFCP cannot take a quadratic objective
+    (``/root/reference/src/cvxpylayers/_quad_form_dpp.py:29-32``: "DIFFCP decomposes quad_form to SOC"), so cvxpy
+    canonicalises ``1/2 x'Px`` with ``P = R'R`` through an epigraph variable and one second-order cone of size n + 2,
+
+        min c'x + t   s.t.  (original rows),   (t + 1, t - 1, sqrt2 R x) in SOC     [<=> x'Px <= 2t],
+
+    variables (x, t).  ``R`` is the upper-triangular Cholesky factor here (cvxpy's ``decomp_quad`` returns a dense factor of
+    the same product; with a dense n x n block the instance's values, 30,002 doubles at n = 100 / m = 200, exceed the 227 KB
+    a CTA can hold, the triangular factor's 25,052 fit).  Planted optimum carried over: t* = 1/2 x*'Px*, cone dual from the
+    KKT conditions."""
+    st = bt.structure
+    n, m, B = st.n, st.m, bt.B
+    assert st.P_indptr is not None and not st.cones.q and not st.cones.s
+    Pd = np.stack([bt.P_dense(i) for i in range(B)])
+    R = np.swapaxes(np.linalg.cholesky(Pd), 1, 2)            # upper triangular, P = R'R
+    iu = np.triu_indices(n)
+    # rows: original m rows (columns 0..n-1), then SOC rows: [t+1], [t-1], sqrt2 R x
+    rows, cols = [], []
+    for i in range(m):
+        lo, hi = st.A_indptr[i], st.A_indptr[i + 1]
+        rows += [i] * (hi - lo)
+        cols += list(st.A_indices[lo:hi])
+    rows += [m, m + 1]
+    cols += [n, n]
+    for r_, c_ in zip(*iu):
+        rows.append(m + 2 + r_)
+        cols.append(c_)
+    pat = sp.csr_matrix((np.arange(1, len(rows) + 1), (rows, cols)), shape=(m + n + 2, n + 1))
+    pat.sort_indices()
+    order = pat.data - 1                                     # CSR slot -> position in the construction order above
+    st2 = Structure(n + 1, m + n + 2, pat.indptr, pat.indices, ConeSpec(z=st.cones.z, l=st.cones.l, q=[n + 2]))
+    vals = np.concatenate([bt.A_vals, -np.ones((B, 2)), -SQRT2 * R[:, iu[0], iu[1]]], axis=1)   # A x + s = b with s = (t+1, t-1, sqrt2 R x)
+    A_vals = np.ascontiguousarray(vals[:, order])
+    b = np.concatenate([bt.b, np.ones((B, 1)), -np.ones((B, 1)), np.zeros((B, n))], axis=1)
+    c = np.concatenate([bt.c, np.ones((B, 1))], axis=1)
+    out = Batch(st2, A_vals, b, c, None, name=bt.name + "_as_socp")
+    if bt.x_star is not None:
+        x = bt.x_star
+        Rx = np.einsum("bij,bj->bi", R, x)
+        t = 0.5 * (Rx * Rx).sum(1)
+        s_soc = np.concatenate([(t + 1)[:, None], (t - 1)[:, None], SQRT2 * Rx], axis=1)
+        # dual of the cone from stationarity: the x-columns need -sqrt2 R'y_rest = Px = R'Rx, the t-column 1 - y0 - y1 = 0:
+        # y = 1/2 (s0, -s1, -s_rest), on the cone boundary and orthogonal to s
+        y_soc = 0.5 * np.concatenate([s_soc[:, :1], -s_soc[:, 1:]], axis=1)
+        out.x_star = np.concatenate([x, t[:, None]], axis=1)
+        out.y_star = np.concatenate([bt.y_star, y_soc], axis=1)
+        out.s_star = np.concatenate([bt.s_star, s_soc], axis=1)
+    return out
+
+
 def config_c1(seed: int = 0) -> Batch:
     return dense_qp(1, 10, 20, 0, seed)
 
@@ -347,6 +398,8 @@ def exp_sum(B: int = 64, p: int = 6, k: int = 12, lam: float = 1.0, seed: int = 
 CONFIGS = {
     "C1": lambda B=1, seed=0: dense_qp(B, 10, 20, 0, seed),
     "C2": lambda B=4096, seed=0: dense_qp(B, 100, 200, 50, seed),
+    # C2 in the form the reference's DIFFCP canonicalisation emits (quad_form -> one SOC of size n + 2)
+    "C2SOC": lambda B=4096, seed=0: qp_as_socp(dense_qp(B, 100, 200, 50, seed)),
     "C3": lambda B=2048, seed=0: socp_portfolio(B, seed=seed),
     "C4": lambda B=512, seed=0: sparse_lp(B, seed=seed),
     # C5: 20 equalities and a rank-5 planted optimum (unique, differentiable); C5S is SURVEY.md 8d's literal default

@@ -122,6 +122,13 @@ int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_v
                 const double *c, double *x, double *y, double *s, int32_t *status, int32_t *iters,
                 double *resid, const bcone_settings *st, void *cuda_stream);
 
+/* Warm-started forward (the reference has the API for one backend only, torch/cvxpylayer.py:464-487,
+ * interfaces/moreau_if.py:237-256): x0[B,n], y0[B,m], s0[B,m] = a solution of a nearby problem (typically the previous call of
+ * a training loop); the operator splitting starts at the fixed point that solution would be.  All three NULL = bcone_solve. */
+int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
+                     const double *x0, const double *y0, const double *s0, double *x, double *y, double *s,
+                     int32_t *status, int32_t *iters, double *resid, const bcone_settings *st, void *cuda_stream);
+
 /* Backward (stateless): adjoint of the solution map at (x,y,s) applied to (dx,dy), ds = 0.
  * Outputs dA_vals[B,nnzA] (every structural entry), dP_vals[B,nnzP] or NULL, db[B,m], dc[B,n],
  * lsqr_iters[B] or NULL. */

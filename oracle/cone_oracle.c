@@ -228,6 +228,12 @@ static int exp_newton_rho(double r, double s, double t, double *rho0, double *x)
   if (rho0) *rho0 = rho;
   return 1;
 }
+static int exp_newton_multi(double r, double s, double t, double *x) {
+  if (exp_newton_rho(r, s, t, NULL, x)) return 1;
+  const double starts[6] = {0.0, -1.0, 1.0, -3.0, 3.0, 8.0};
+  for (int k = 0; k < 6; k++) { double g = starts[k]; if (exp_newton_rho(r, s, t, &g, x)) return 1; }
+  return 0;
+}
 /* returns the case: 0 in K, 1 in polar (-> 0), 2 analytic face, 3 iterative.  The iterative case first tries the Newton
  * iteration above (certified by the Moreau conditions, more accurate than the bisection near the y = 0 face) and only
  * then the bisection of Parikh & Boyd. */
@@ -237,7 +243,7 @@ static int proj_exp(double *v) {
   if ((r > 0 && r * exp(fmin(s / r, 700.0)) + 2.718281828459045 * t <= 1e-13) || (r == 0 && s <= 0 && t <= 0)) { v[0] = v[1] = v[2] = 0; return 1; }
   if (r < 0 && s < 0) { v[1] = 0.0; v[2] = fmax(t, 0.0); return 2; }
   double x[3];
-  if (exp_newton_rho(r, s, t, NULL, x)) { v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; return 3; }
+  if (exp_newton_multi(r, s, t, x)) { v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; return 3; }
   double lb = 0.0, ub = 0.125;
   while (exp_calc_grad(v, x, ub) > 0 && ub < 1e300) { lb = ub; ub *= 2.0; }
   for (int i = 0; i < 200; i++) {
@@ -575,8 +581,23 @@ static void set_ry(fwd_ws *w, double scale) {
   for (int i = 0; i < w->m; i++) w->ry[i] = (i < w->d->z) ? 1.0 / (ZERO_CONE_FACTOR * scale) : 1.0 / scale;
 }
 
+static int solve_impl(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
+                      const double *x0, const double *y0, const double *s0,
+                      double *x, double *y, double *s, int32_t *iters, double *resid, const orc_settings *st);
 int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
               double *x, double *y, double *s, int32_t *iters, double *resid, const orc_settings *st) {
+  return solve_impl(d, Av, Pv, b, c, NULL, NULL, NULL, x, y, s, iters, resid, st);
+}
+/* x0, y0, s0: a solution of a nearby problem (all three or none): the splitting starts at the fixed point it would be,
+ * w = u + R^{-1} v with u = (x0 sigma / E, y0 sigma / D, 1), v_y = s0 D sigma (the inverse of the final un-scaling at tau = 1). */
+int orc_solve_warm(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
+                   const double *x0, const double *y0, const double *s0,
+                   double *x, double *y, double *s, int32_t *iters, double *resid, const orc_settings *st) {
+  return solve_impl(d, Av, Pv, b, c, x0, y0, s0, x, y, s, iters, resid, st);
+}
+static int solve_impl(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
+                      const double *x0, const double *y0, const double *s0,
+                      double *x, double *y, double *s, int32_t *iters, double *resid, const orc_settings *st) {
   int n = d->n, m = d->m, N = n + m + 1, nnzA = d->nnzA, nnzP = d->P_indptr ? d->nnzP : 0;
   size_t tot = (size_t)nnzA + nnzP + 3 * m + 3 * n + (size_t)n * n + (n + m) + n + m + 6 * (size_t)N + 2 * m + 2 * n;
   double *buf = (double *)calloc(tot + 16, sizeof(double)), *q = buf;
@@ -634,6 +655,10 @@ int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const doubl
   double rp = NAN, rd = NAN, gap = NAN;
   if (factor(&W)) { status = ORC_FAILED; goto done; }
   w[N - 1] = 1.0;
+  if (x0 && y0 && s0) {
+    for (int j = 0; j < n; j++) w[j] = x0[j] * sigma / W.E[j];
+    for (int i = 0; i < m; i++) w[n + i] = y0[i] * sigma / W.D[i] + s0[i] * W.D[i] * sigma / W.ry[i];
+  }
   aa = aa_init(N, st->acceleration_lookback);
   if (aa) wprev = (double *)calloc(N, sizeof(double));
   const int aa_iv = st->acceleration_interval > 0 ? st->acceleration_interval : 1;
@@ -1108,6 +1133,25 @@ void orc_solve_batch(const orc_desc *d, int32_t B, const double *Av, const doubl
     int32_t itc = 0;
     int stt = orc_solve(d, Av + i * nA, nP ? Pv + i * nP : NULL, b + (size_t)i * m, c + (size_t)i * n,
                         x + (size_t)i * n, y + (size_t)i * m, s + (size_t)i * m, &itc, NULL, st);
+    if (status) status[i] = stt;
+    if (iters) iters[i] = itc;
+  }
+}
+
+void orc_solve_batch_warm(const orc_desc *d, int32_t B, const double *Av, const double *Pv, const double *b,
+                          const double *c, const double *x0, const double *y0, const double *s0, double *x, double *y, double *s,
+                          int32_t *status, int32_t *iters, const orc_settings *st, int32_t nthreads) {
+  int n = d->n, m = d->m; size_t nA = d->nnzA, nP = d->P_indptr ? d->nnzP : 0;
+  tune_malloc();
+#ifdef _OPENMP
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+  for (int i = 0; i < B; i++) {
+    int32_t itc = 0;
+    int stt = solve_impl(d, Av + i * nA, nP ? Pv + i * nP : NULL, b + (size_t)i * m, c + (size_t)i * n,
+                         x0 ? x0 + (size_t)i * n : NULL, y0 ? y0 + (size_t)i * m : NULL, s0 ? s0 + (size_t)i * m : NULL,
+                         x + (size_t)i * n, y + (size_t)i * m, s + (size_t)i * m, &itc, NULL, st);
     if (status) status[i] = stt;
     if (iters) iters[i] = itc;
   }

@@ -58,6 +58,14 @@ int orc_solve(const orc_desc *d, const double *Av, const double *Pv, const doubl
               const double *c, double *x, double *y, double *s, int32_t *iters,
               double *resid, const orc_settings *st);
 
+/* Warm-started variants (a previous solution x0, y0, s0 of a nearby problem). */
+int orc_solve_warm(const orc_desc *d, const double *Av, const double *Pv, const double *b, const double *c,
+                   const double *x0, const double *y0, const double *s0,
+                   double *x, double *y, double *s, int32_t *iters, double *resid, const orc_settings *st);
+void orc_solve_batch_warm(const orc_desc *d, int32_t B, const double *Av, const double *Pv, const double *b,
+                          const double *c, const double *x0, const double *y0, const double *s0, double *x, double *y,
+                          double *s, int32_t *status, int32_t *iters, const orc_settings *st, int32_t nthreads);
+
 /* Adjoint of the solution map at (x,y,s): given dx,dy (ds = 0, as the reference
  * always passes, diffcp_if.py:84) produce dA (all nnzA structural entries),
  * dP (nnzP upper-tri entries, may be NULL), db, dc. Returns LSQR iterations. */

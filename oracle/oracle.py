@@ -96,9 +96,18 @@ def _c(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def solve_batch(st: Structure, A_vals, b, c, P_vals=None, nthreads: int = 0, **settings):
-    """-> x[B,n], y[B,m], s[B,m], status[B], iters[B]"""
+def solve_batch(st: Structure, A_vals, b, c, P_vals=None, nthreads: int = 0, warm=None, **settings):
+    """-> x[B,n], y[B,m], s[B,m], status[B], iters[B]   (warm = (x0, y0, s0): start from a previous solution)"""
     A_vals, b, c, P_vals = _c(A_vals), _c(b), _c(c), _c(P_vals)
+    if warm is not None:
+        x0, y0, s0 = map(_c, warm)
+        B = A_vals.shape[0]
+        x = np.empty((B, st.n)); y = np.empty((B, st.m)); s = np.empty((B, st.m))
+        status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+        D = _Desc(st); S = make_settings(**settings)
+        lib().orc_solve_batch_warm(C.byref(D.d), C.c_int32(B), _p(A_vals), _p(P_vals), _p(b), _p(c), _p(x0), _p(y0), _p(s0), _p(x), _p(y), _p(s),
+                                   _p(status, _i32p), _p(iters, _i32p), C.byref(S), C.c_int32(nthreads))
+        return x, y, s, status, iters
     B = A_vals.shape[0]
     x = np.empty((B, st.n)); y = np.empty((B, st.m)); s = np.empty((B, st.m))
     status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)

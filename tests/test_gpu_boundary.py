@@ -366,3 +366,37 @@ def test_pipelined_host_path_on_the_workspace_backed_kernels(cuda_device, monkey
         outs.append([primal.detach().clone(), dual.detach().clone(), A.grad.clone(), q.grad.clone(), P.grad.clone()])
     for a_, b_ in zip(*outs):
         assert torch.allclose(a_, b_, rtol=1e-9, atol=1e-11)
+
+
+def test_warm_start_through_the_layer_matches_the_oracle(cuda_device):
+    """{"warm_start": True} re-uses the previous call's solution as the starting point (the rule the
+    reference applies for its one warm-startable backend, torch/cvxpylayer.py:464-487).  A training-loop step changes the
+    data a little: the warm-started solve takes the oracle's (smaller) iteration count and reaches the same optimum;
+    started at its own solution it stops at the first check."""
+    bt = pr.dense_qp(40, 100, 200, 50, seed=13)
+    st, dev = bt.structure, cuda_device
+    args = {"eps": 1e-6, "max_iters": 100000, "warm_start": True}
+    ctx, bd, cl = _layer(bt, **args)
+    A, q, P = _t(bd.A_eval, dev), _t(bd.q_eval, dev), _t(bd.P_eval, dev)
+    eng = ctx.engine(dev)
+    p1, d1, _, _ = _CvxpyLayer.apply(P, q, A, cl, {}, False, None)              # cold: nothing cached yet
+    it_cold = None
+    x0, y0, s0 = (t_.clone() for t_ in ctx._last_solution[(dev, bt.B)])
+    rng = np.random.default_rng(1)
+    b2 = bt.b + 1e-4 * rng.standard_normal(bt.b.shape)
+    c2 = bt.c + 1e-4 * rng.standard_normal(bt.c.shape)
+    bt2 = pr.Batch(st, bt.A_vals, b2, c2, bt.P_vals)
+    bd2 = pr.to_boundary(bt2)
+    p2, d2, _, _ = _CvxpyLayer.apply(P, _t(bd2.q_eval, dev), _t(bd2.A_eval, dev), cl, {}, False, None)   # warm from call 1
+    o_args = dict(eps=1e-6, max_iters=100000)
+    xw, yw, sw, stw, it_w = orc.solve_batch(st, bt.A_vals, b2, c2, bt.P_vals, warm=(x0.cpu().numpy(), y0.cpu().numpy(), s0.cpu().numpy()), **o_args)
+    xc, yc, sc_, stc, it_c = orc.solve_batch(st, bt.A_vals, b2, c2, bt.P_vals, **o_args)
+    assert (stw == 1).all() and np.abs(p2.cpu().numpy() - xw).max() < 1e-5 and np.abs(p2.cpu().numpy() - xc).max() < 1e-4
+    # iteration counts through the engine directly (the layer does not return them)
+    sol_w = eng.solve(_t(bt.A_vals, dev), _t(b2, dev), _t(c2, dev), _t(bt.P_vals, dev), make_settings(o_args), warm=(x0, y0, s0))
+    sol_c = eng.solve(_t(bt.A_vals, dev), _t(b2, dev), _t(c2, dev), _t(bt.P_vals, dev), make_settings(o_args))
+    iw, ic = sol_w.iters.cpu().numpy(), sol_c.iters.cpu().numpy()
+    assert np.abs(iw - it_w).max() <= 25 and np.abs(ic - it_c).max() <= 25
+    assert iw.mean() < 0.7 * ic.mean(), (iw.mean(), ic.mean())
+    sol_f = eng.solve(_t(bt.A_vals, dev), _t(b2, dev), _t(c2, dev), _t(bt.P_vals, dev), make_settings(o_args), warm=sol_w)
+    assert int(sol_f.iters.max()) <= 25 and float((sol_f.x - sol_w.x).abs().max()) < 1e-5

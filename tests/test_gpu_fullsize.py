@@ -274,3 +274,35 @@ def test_lsqr_variants_against_exact_least_squares(name, B, cuda_device):
     assert err[0] < 5e-3 and err_o < 5e-3, (name, err, err_o)
     if err[0] > 1e-4:   # the deviation is the recurrence's: the oracle running the same recurrence shows it too
         assert 0.1 < err[0] / err_o < 10.0, (name, err[0], err_o)
+
+
+# ----------------------------------------------------------------------------- the QP in the form the reference's DIFFCP path produces
+def test_c2_in_soc_form_through_the_generic_kernels(cuda_device):
+    """C2-sized instances (n = 100, m = 200) as quad_form -> SOC (one cone of size n + 2, problems.qp_as_socp): what the
+    reference's DIFFCP canonicalisation would really hand over (_quad_form_dpp.py:29-32).  25,052 values per instance: the
+    generic kernels (CG forward, LSQR backward) take it.  Forward vs the native-P solve and the oracle; backward vs the
+    oracle on the same inputs."""
+    B = 32
+    bq = pr.dense_qp(B, 100, 200, 50, seed=3)
+    bt = pr.qp_as_socp(bq)
+    st, dev = bt.structure, cuda_device
+    eps = 1e-8
+    eng = Engine(st, dev)
+    assert eng.path_info()["fwd"].startswith("fwd_kernel")
+    A, b, c = _t(bt.A_vals, dev), _t(bt.b, dev), _t(bt.c, dev)
+    sol = eng.solve(A, b, c, None, make_settings({"eps": eps, "max_iters": 200000}))
+    torch.cuda.synchronize()
+    assert int((sol.status == 1).sum()) == B, (sol.status, sol.iters)
+    x = sol.x.cpu().numpy()
+    assert np.abs(x[:, :100] - bq.x_star).max() < 1e-5 and np.abs(x - bt.x_star).max() < 1e-4
+    xo, yo, so, sto, ito = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, None, nthreads=NT, eps=eps, max_iters=200000)
+    assert (sto == 1).all() and np.abs(x - xo).max() < 1e-5 * max(1.0, np.abs(xo).max())
+    rng = np.random.default_rng(8)
+    dx, dy = rng.standard_normal(xo.shape), rng.standard_normal(yo.shape)
+    bwd = {"lsqr_precond": 1, "lsqr_iter_lim": 20 * (st.n + st.m + 1)}
+    g = eng.vjp(A, b, c, _t(xo, dev), _t(yo, dev), _t(so, dev), _t(dx, dev), _t(dy, dev), None, make_settings(bwd))
+    torch.cuda.synchronize()
+    r = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, xo, yo, so, dx, dy, None, nthreads=NT, **bwd)
+    for g_, r_ in ((g[0], r[0]), (g[2], r[2]), (g[3], r[3])):
+        e = _rel_rows(g_, r_)
+        assert e.max() < 1e-4, (e.max(), int(e.argmax()))

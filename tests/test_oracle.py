@@ -151,6 +151,34 @@ def test_anderson_acceleration_safeguard_keeps_lps_convergent():
             assert np_ref.is_converged(np_ref.kkt_residuals(bt.A_dense(i), None, bt.b[i], bt.c[i], x[i], y[i], s[i]), 1e-6, 1e-6, 1.0001)
 
 
+# ----------------------------------------------------------------------------- warm start
+@pytest.mark.parametrize("name,B", [("C2", 4), ("C3", 4), ("C5", 3)])
+def test_warm_start_is_a_fixed_point_and_speeds_up_nearby_problems(name, B):
+    """SURVEY.md 8f.2 (the reference offers warm starts for one backend only, torch/cvxpylayer.py:464-487): started at its own
+    solution the splitting stops at the first check with the same answer; started at the solution of a slightly perturbed
+    problem (a training-loop step, examples/torch/algorithms.py:34-41) it needs fewer iterations than from cold and reaches
+    the same certified optimum."""
+    bt = pr.CONFIGS[name](B=B)
+    st = bt.structure
+    args = dict(eps=1e-8, max_iters=100000)
+    x, y, s, status, it_cold = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+    assert (status == 1).all()
+    x2, y2, s2, status2, it_fix = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, warm=(x, y, s), **args)
+    assert (status2 == 1).all() and (it_fix <= 25).all() and np.abs(x2 - x).max() < 1e-6 * max(1.0, np.abs(x).max())
+    rng = np.random.default_rng(0)
+    b2 = bt.b + 1e-4 * rng.standard_normal(bt.b.shape) * (np.abs(bt.b) > 0)
+    c2 = bt.c + 1e-4 * rng.standard_normal(bt.c.shape)
+    args = dict(eps=1e-6, max_iters=100000)   # (the start is ~1e-4 from the new optimum: two decades to go instead of six)
+    xc, yc, sc, stc, it_c = orc.solve_batch(st, bt.A_vals, b2, c2, bt.P_vals, **args)
+    xw, yw, sw, stw, it_w = orc.solve_batch(st, bt.A_vals, b2, c2, bt.P_vals, warm=(x, y, s), **args)
+    assert (stc == 1).all() and (stw == 1).all()
+    assert it_w.mean() < 0.7 * it_c.mean(), (it_w, it_c)
+    for i in range(B):
+        P = bt.P_dense(i) if bt.P_vals is not None else None
+        assert np_ref.is_converged(np_ref.kkt_residuals(bt.A_dense(i), P, b2[i], c2[i], xw[i], yw[i], sw[i]), 1e-6, 1e-6, 1.0001)
+    assert np.abs((c2 * xw).sum(1) - (c2 * xc).sum(1)).max() < 1e-5 * max(1.0, np.abs((c2 * xc).sum(1)).max())
+
+
 # ----------------------------------------------------------------------------- cones
 def test_cone_projection_and_jacobian_against_numpy():
     cones = ConeSpec(z=2, l=3, q=[4, 1, 5], s=[3, 2])
@@ -299,6 +327,28 @@ def test_soc_adjoint_matches_finite_differences(precond):
         dA, dP, db, dc, _ = orc.vjp_batch(st, bt.A_vals, bt.b, bt.c, x, y, s, dx[None], dy[None], bt.P_vals, lsqr_precond=precond,
                                           lsqr_iter_lim=20000, lsqr_atol=1e-12, lsqr_btol=1e-12)
         _fd_check(make, p0, "c,t", args, dx, dy, np.concatenate([dc[0], db[0, :1]]))
+
+
+def test_qp_in_the_reference_soc_form_matches_the_native_quadratic_form():
+    """The reference's DIFFCP path never sees P: cvxpy turns 1/2 x'Px into an epigraph variable and one SOC of size
+    n + 2 (_quad_form_dpp.py:29-32, tests/test_torch.py:1005-1020).  Same optimum, same derivative of the solution with
+    respect to the data both forms share (b and c of the original rows), through two different programs."""
+    bt = pr.dense_qp(3, 8, 14, 3, seed=6)
+    bs = pr.qp_as_socp(bt)
+    args = dict(eps=1e-11, max_iters=400000)
+    x, y, s, st1, _ = orc.solve_batch(bt.structure, bt.A_vals, bt.b, bt.c, bt.P_vals, **args)
+    xs, ys, ss, st2, _ = orc.solve_batch(bs.structure, bs.A_vals, bs.b, bs.c, None, **args)
+    assert (st1 == 1).all() and (st2 == 1).all()
+    n, m = bt.structure.n, bt.structure.m
+    assert np.abs(xs[:, :n] - x).max() < 1e-8 and np.abs(ys[:, :m] - y).max() < 1e-7
+    assert np.abs(xs[:, n] - 0.5 * np.einsum("bi,bi->b", x, np.stack([bt.P_dense(i) @ x[i] for i in range(bt.B)]))).max() < 1e-8   # t* = 1/2 x'Px
+    rng = np.random.default_rng(3)
+    dx, dy = rng.standard_normal(x.shape), rng.standard_normal(y.shape)
+    g1 = orc.vjp_batch(bt.structure, bt.A_vals, bt.b, bt.c, x, y, s, dx, dy, bt.P_vals, lsqr_precond=1, lsqr_iter_lim=50000, lsqr_atol=1e-12, lsqr_btol=1e-12)
+    dxs = np.concatenate([dx, np.zeros((bt.B, 1))], axis=1)
+    dys = np.concatenate([dy, np.zeros((bt.B, n + 2))], axis=1)
+    g2 = orc.vjp_batch(bs.structure, bs.A_vals, bs.b, bs.c, xs, ys, ss, dxs, dys, None, lsqr_precond=1, lsqr_iter_lim=50000, lsqr_atol=1e-12, lsqr_btol=1e-12)
+    assert rel_err(g2[2][:, :m], g1[2]) < 1e-5 and rel_err(g2[3][:, :n], g1[3]) < 1e-5   # db, dc of the shared rows / columns
 
 
 # ----------------------------------------------------------------------------- golden fixtures
