@@ -254,12 +254,20 @@ def run_ours(a):
         chunk_events, recv_bufs = {}, {}
 
     def chunk_list(Bs: int, chunk: int):
-        nchunk = max(1, Bs // max(chunk, 1))
-        base, extra = divmod(Bs, nchunk)
+        """Full chunks first, then a tapered tail (half, quarter, quarter of a chunk, never below 256): the only transfer that
+        cannot hide behind a later chunk's solve is the last one, so the last chunk is kept small."""
+        sizes, rem = [], Bs
+        while rem > chunk:
+            sizes.append(chunk); rem -= chunk
+        if world > 1 and rem >= 1024:
+            sizes += [rem // 2, rem // 4, rem - rem // 2 - rem // 4]
+        elif world > 1 and rem >= 512:
+            sizes += [rem // 2, rem - rem // 2]
+        elif rem > 0:
+            sizes.append(rem)
         out, lo = [], 0
-        for k in range(nchunk):
-            hi = lo + base + (1 if k < extra else 0)
-            out.append((lo, hi)); lo = hi
+        for sz in sizes:
+            out.append((lo, lo + sz)); lo += sz
         return out
 
     def step_sharded(Bs: int, chunk: int):

@@ -13,7 +13,7 @@
 // ---- kernels / launchers implemented in fwd.cu, bwd.cu, pack.cu ----
 extern "C" {
 size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect, int ns, int nexp);
-size_t bc_fwd_ws_doubles(int n, int m);
+size_t bc_fwd_ws_doubles(int n, int m, int with_factor);
 cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem);
 cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas);
 cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t st);
@@ -62,6 +62,7 @@ struct Handle {
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
   int fwd_indirect = 0, bwd_vec_global = 0;   // large instances: CG instead of Cholesky, vectors in a global slab
+  int fwd_factor_global = 0;                  // in between: values on chip, vectors + packed Cholesky factor in the slab (direct solve from L2 / HBM)
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   // Per-stream scratch slabs (one per CTA of the grid): launches on different streams may overlap, launches on one
   // stream cannot, so the stream is the unit of ownership.  Allocated on first use.
@@ -207,11 +208,20 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   int threads = d->nnzA >= 8192 ? 512 : (d->nnzA >= 1024 ? 256 : 128);
   while (threads < 512 && threads < n) threads *= 2;  // transposed products want one lane per column
   const int npoly = d->z + d->l;
-  auto pick_fwd = [&]() -> bool {   // DIRECT (Cholesky on chip) if the instance fits, else INDIRECT (CG, vectors in L2)
+  // DIRECT (everything on chip) if the instance fits; else values on chip with the vectors and the packed Cholesky factor
+  // in a per-CTA slab of global memory (two triangular products per iteration read it from L2 / HBM: n <= 2048, i.e. <= 16 MB
+  // per CTA); else INDIRECT (conjugate gradients, SCS's "indirect" mode).  BCONE_FWD_MODE=indirect forces the last one.
+  const char *fm = getenv("BCONE_FWD_MODE");
+  const bool force_indirect = fm && std::string(fm) == "indirect";
+  auto pick_fwd = [&]() -> bool {
     for (int ind = 0; ind <= 1; ind++)
       for (int tt = threads; tt >= 64; tt /= 2) {
         size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd, ind, d->ns, d->ep + d->ed);
-        if (sm <= smem_cap) { h->fwd_threads = tt; h->fwd_smem = sm; h->fwd_indirect = ind; return true; }
+        if (sm <= smem_cap) {
+          h->fwd_threads = tt; h->fwd_smem = sm; h->fwd_indirect = ind;
+          if (ind && !force_indirect && n <= 2048) { h->fwd_indirect = 0; h->fwd_factor_global = 1; }
+          return true;
+        }
       }
     return false;
   };
@@ -247,7 +257,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   }
   cudaError_t e;
   // register-tiled forward (fwd_fast.cu) when the structure allows it; BCONE_NO_FAST_FWD=1 keeps the generic kernel
-  if (S.dense && S.ncones == 0 && d->ep + d->ed == 0 && !h->fwd_indirect && bc_fwdf_eligible(n, m) &&
+  if (S.dense && S.ncones == 0 && d->ep + d->ed == 0 && !h->fwd_indirect && !h->fwd_factor_global && bc_fwdf_eligible(n, m) &&
       bc_fwdf_smem_bytes(n, m) <= smem_cap && !(getenv("BCONE_NO_FAST_FWD") && atoi(getenv("BCONE_NO_FAST_FWD")))) {
     if (bc_fwdf_configure(n, m, bc_fwdf_smem_bytes(n, m)) == cudaSuccess) {
       h->fast_fwd = 1; h->fwd_threads = bc_fwdf_threads(); h->fwd_smem = bc_fwdf_smem_bytes(n, m);
@@ -266,7 +276,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;
-  if (h->fwd_indirect) h->fwd_ws_stride = bc_fwd_ws_doubles(n, m);
+  if (h->fwd_indirect || h->fwd_factor_global) h->fwd_ws_stride = bc_fwd_ws_doubles(n, m, h->fwd_factor_global);
   if (h->bwd_vec_global && !h->fast_bwd) h->bwd_ws_stride = bc_bwd_ws_doubles(n, m, npoly);
   h->tma_ok = (d->nnzA > 0 && (d->nnzA % 2) == 0 && (size_t)d->nnzA * 8 < (1u << 20)) ? 1 : 0;
   *out = h;
@@ -496,7 +506,7 @@ extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, c
   const size_t max_grid = (size_t)h->num_sms * h->fwd_ctas;
   Handle::StreamWs *sw = stream_ws(h, st);
   a.ws = nullptr; a.ws_stride = (long long)h->fwd_ws_stride; a.prof = h->prof;
-  if (h->fwd_indirect) {
+  if (h->fwd_indirect || h->fwd_factor_global) {
     if (!ensure_slab(h, &sw->fwd, nullptr, h->fwd_ws_stride * max_grid)) return fail(h, BCONE_ENOMEM, "cudaMalloc forward workspace");
     a.ws = sw->fwd;
   }
@@ -593,7 +603,7 @@ extern "C" int64_t bcone_launch_count(void *handle) { return handle ? ((Handle *
 extern "C" int bcone_path_info(void *handle, int32_t *fwd_path, int32_t *bwd_path) {
   Handle *h = (Handle *)handle;
   if (!h) return BCONE_EINVAL;
-  if (fwd_path) *fwd_path = h->fast_fwd ? 2 : (h->fwd_indirect ? 1 : 0);
+  if (fwd_path) *fwd_path = h->fast_fwd ? 2 : (h->fwd_indirect ? 1 : (h->fwd_factor_global ? 3 : 0));
   if (bwd_path) *bwd_path = h->block_bwd ? 2 : (h->fast_bwd ? 1 : 0);
   return BCONE_OK;
 }

@@ -50,7 +50,10 @@ __host__ __device__ inline size_t fwd_smem_doubles(int n, int m, int nnzA, int t
   return d + cone_scratch_doubles(threads, max_psd, ns, nexp);
 }
 
-__device__ __forceinline__ void carve(FwdSmem &M, double *base, double *gws, int n, int m, int nnzA, int threads, int max_psd) {
+// gws != nullptr: the vectors live in the per-CTA global slab; li_global: the packed Cholesky factor follows them there
+// (mode 2: instances whose values fit on chip but whose factor does not -- the factor is then read from L2 / HBM twice per
+// iteration, which is still far cheaper than the conjugate-gradient solve of the indirect mode).
+__device__ __forceinline__ void carve(FwdSmem &M, double *base, double *gws, int n, int m, int nnzA, int threads, int max_psd, bool li_global = false) {
   const int N = n + m + 1;
   double *q = base;
   M.bar = (uint64_t *)q; q += 2;
@@ -62,7 +65,7 @@ __device__ __forceinline__ void carve(FwdSmem &M, double *base, double *gws, int
   M.w = v; v += N; M.u = v; v += N; M.ut = v; v += N;
   M.g = v; v += n + m; M.bh = v; v += m; M.ch = v; v += n; M.Dm = v; v += m; M.En = v; v += n;
   M.tn = v; v += n; M.tn2 = v; v += n; M.tn3 = v; v += n; M.tm = v; v += m;
-  if (gws) { M.cr = v; v += n; M.cp = v; v += n; M.cq = v; v += n; M.kd = v; v += n; M.cx = v; v += n; }
+  if (gws) { M.cr = v; v += n; M.cp = v; v += n; M.cq = v; v += n; M.kd = v; v += n; M.cx = v; v += n; if (li_global) { v += ((size_t)(v - gws) & 1); M.Li = v; } }
   else { M.cr = M.cp = M.cq = M.kd = M.cx = nullptr; q = v; }
   M.psd = q;
 }
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
   const bcone_settings &st = a.st;
   FwdSmem M;
-  carve(M, smem, INDIRECT ? a.ws + (size_t)blockIdx.x * a.ws_stride : nullptr, n, m, S.nnzA, T, S.max_psd);
+  carve(M, smem, a.ws ? a.ws + (size_t)blockIdx.x * a.ws_stride : nullptr, n, m, S.nnzA, T, S.max_psd, !INDIRECT && a.ws != nullptr);
   if (t == 0) { mbar_init(M.bar, 1); fence_mbar_init(); }
   __syncthreads();
   uint32_t tma_phase = 0;
@@ -634,7 +637,10 @@ __global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ Fwd
 extern "C" size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect, int ns, int nexp) {
   return fwd_smem_doubles(n, m, nnzA, threads, max_psd, indirect, ns, nexp) * sizeof(double);
 }
-extern "C" size_t bc_fwd_ws_doubles(int n, int m) { return (fwd_vec_doubles(n, m, 1) + 1) & ~(size_t)1; }
+// per-CTA slab: the vectors (+ the packed factor in mode 2)
+extern "C" size_t bc_fwd_ws_doubles(int n, int m, int with_factor) {
+  return ((fwd_vec_doubles(n, m, 1) + 1) & ~(size_t)1) + (with_factor ? (((size_t)n * (n + 1) / 2 + 1) & ~(size_t)1) : 0);
+}
 
 #define FWD_DISPATCH(EXPR)                                        \
   do {                                                            \

@@ -151,7 +151,8 @@ int64_t bcone_launch_count(void *handle);
 int bcone_kernel_info(void *handle, int32_t *fwd_threads, int32_t *fwd_smem, int32_t *fwd_ctas_per_sm,
                       int32_t *bwd_threads, int32_t *bwd_smem, int32_t *bwd_ctas_per_sm);
 /* Which kernels the structure selected.  fwd_path: 0 generic on-chip Cholesky (fwd.cu), 1 generic indirect (CG),
- * 2 register-tiled dense/polyhedral (fwd_fast.cu).  bwd_path: 0 generic LSQR (bwd.cu), 1 fused single-pass LSQR
+ * 2 register-tiled dense/polyhedral (fwd_fast.cu), 3 generic with the values on chip and the Cholesky factor + vectors in a
+ * per-CTA slab of global memory (instances between the two; BCONE_FWD_MODE=indirect in the environment forces 1 instead).  bwd_path: 0 generic LSQR (bwd.cu), 1 fused single-pass LSQR
  * (bwd_fast.cu), 2 KKT-block preconditioned (bwd_block.cu, used when lsqr_precond = 2; falls back to 1 per instance). */
 int bcone_path_info(void *handle, int32_t *fwd_path, int32_t *bwd_path);
 

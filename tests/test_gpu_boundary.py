@@ -356,7 +356,7 @@ def test_pipelined_host_path_on_the_workspace_backed_kernels(cuda_device, monkey
         ctx, bd, cl = _layer(bt, **args)
         ctx.device = cuda_device
         info = ctx.engine(cuda_device).path_info()
-        assert "indirect" in info["fwd"]
+        assert "slab" in info["fwd"] or "indirect" in info["fwd"]   # a workspace-backed forward path
         A = torch.tensor(bd.A_eval).pin_memory().requires_grad_(True)
         q = torch.tensor(bd.q_eval).pin_memory().requires_grad_(True)
         P = torch.tensor(bd.P_eval).pin_memory().requires_grad_(True)

@@ -109,14 +109,16 @@ def test_backward_matches_oracle(name, B, precond, cuda_device):
         assert rel(dP, rP) < tol
 
 
-def test_sparse_lp_c4_indirect_forward(cuda_device):
+def test_sparse_lp_c4_indirect_forward(cuda_device, monkeypatch):
     """BASELINE config C4 (sparse LP, n=1000, m=2000, 1% dense): the n x n Cholesky does not fit on
     chip, so the engine switches to CG on the reduced KKT system with the iterate vectors in L2.
     Un-accelerated operator splitting needs thousands of iterations on LPs, so the check
     is the solver's own termination certificate at the SCS default tolerance."""
     B, eps = 4, 1e-4
     bt = pr.sparse_lp(B=B, seed=3)
+    monkeypatch.setenv("BCONE_FWD_MODE", "indirect")   # (the default for this size is the factor-in-slab direct mode, test_gpu_fullsize.py)
     eng, sol = _solve_gpu(bt, cuda_device, eps=eps, max_iters=100000)
+    assert "indirect" in eng.path_info()["fwd"]
     assert eng.kernel_info()["fwd_smem"] < 232448
     assert (sol.status.cpu().numpy() == 1).all(), (sol.status, sol.iters)
     x, y, s = sol.x.cpu().numpy(), sol.y.cpu().numpy(), sol.s.cpu().numpy()
@@ -126,11 +128,19 @@ def test_sparse_lp_c4_indirect_forward(cuda_device):
     assert (s >= -1e-12).all() and (y >= -1e-12).all() and np.abs((s * y).sum(1)).max() < 1e-8
 
 
-def test_large_sparse_qp_indirect_forward_and_l2_backward(cuda_device):
-    """n=300, m=600 sparse QP: CG forward + L2-resident LSQR vectors, against the oracle."""
+@pytest.mark.parametrize("mode", ["slab", "indirect"])
+def test_large_sparse_qp_indirect_forward_and_l2_backward(mode, cuda_device, monkeypatch):
+    """n=300, m=600 sparse QP -- too large for the all-on-chip forward: values on chip with the Cholesky factor in a global
+    slab (default) or conjugate gradients (SCS's indirect mode, forced through BCONE_FWD_MODE); L2-resident LSQR vectors in
+    the backward; against the oracle."""
     bt = pr.sparse_qp(B=5, seed=2)
     st, dev = bt.structure, cuda_device
+    if mode == "indirect":
+        monkeypatch.setenv("BCONE_FWD_MODE", "indirect")
+    else:
+        monkeypatch.delenv("BCONE_FWD_MODE", raising=False)
     eng, sol = _solve_gpu(bt, dev, eps=1e-8, max_iters=100000)
+    assert mode in eng.path_info()["fwd"]
     assert (sol.status.cpu().numpy() == 1).all(), (sol.status, sol.iters)
     assert np.abs(sol.x.cpu().numpy() - bt.x_star).max() < 1e-5
     xo, yo, so, sto, _ = orc.solve_batch(st, bt.A_vals, bt.b, bt.c, bt.P_vals, eps=1e-10, max_iters=400000)
