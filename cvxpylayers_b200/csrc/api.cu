@@ -209,7 +209,7 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   while (threads < 512 && threads < n) threads *= 2;  // transposed products want one lane per column
   const int npoly = d->z + d->l;
   // DIRECT (everything on chip) if the instance fits; else values on chip with the vectors and the packed Cholesky factor
-  // in a per-CTA slab of global memory (two triangular products per iteration read it from L2 / HBM: n <= 2048, i.e. <= 16 MB
+  // in a per-CTA slab of global memory (two triangular products per iteration read it from L2: n <= 512, i.e. <= 1 MB
   // per CTA); else INDIRECT (conjugate gradients, SCS's "indirect" mode).  BCONE_FWD_MODE=indirect forces the last one.
   const char *fm = getenv("BCONE_FWD_MODE");
   const bool force_indirect = fm && std::string(fm) == "indirect";
@@ -219,7 +219,10 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
         size_t sm = bc_fwd_smem_bytes(n, m, d->nnzA, tt, max_psd, ind, d->ns, d->ep + d->ed);
         if (sm <= smem_cap) {
           h->fwd_threads = tt; h->fwd_smem = sm; h->fwd_indirect = ind;
-          if (ind && !force_indirect && n <= 2048) { h->fwd_indirect = 0; h->fwd_factor_global = 1; }
+          // (n <= 512: one thread per column in the transposed triangular product; measured on the sparse LP with n = 1000 the
+          //  slab mode streams 8 MB of factor per iteration and CTA from HBM and loses to conjugate gradients, 12.6 s vs 5.8 s per
+          //  512-batch, while at n = 101 it wins 37x)
+          if (ind && !force_indirect && n <= 512) { h->fwd_indirect = 0; h->fwd_factor_global = 1; }
           return true;
         }
       }

@@ -1018,8 +1018,8 @@ __device__ __forceinline__ void warp_mm16(int k, FA fa, FB fb, ST st) {
 // of the accumulated eigenvector matrix V (V <- V J), then all row updates -- three warp barriers per round instead
 // of three per rotation.  V is updated, not reset: the caller passes the identity (cold) or the eigenvectors of a
 // nearby matrix after transforming T <- V' T V (warm start: one or two sweeps instead of six to eight).
-// A sweep whose largest |a_pq| / (|a_pp| + |a_qq|) was below 1e-8 is the last one (quadratic convergence puts the
-// remaining off-diagonal part below double precision).  k <= 32.
+// A sweep that met no |a_pq| above 1e-7 (|a_pp| + |a_qq|) is the last one: quadratic convergence leaves the off-diagonal
+// part below 1e-13 of the diagonal after it.  k <= 16.
 // 1 / x by the hardware approximation + two Newton steps (a couple of ulp; a third of the latency of the IEEE division).
 __device__ __forceinline__ double rcp_nr(double x) {
   double y;
@@ -1046,7 +1046,7 @@ __device__ inline void jacobi_par_warp(int k, double *T, double *V) {
     p = min(a, b); q = max(a, b);
   };
   for (int sweep = 0; sweep < 30; sweep++) {
-    double big = 0.0;
+    bool big = false;
     for (int r = 0; r < nr; r++) {
       double c = 1.0, s = 0.0;
       if (lane < np) {
@@ -1056,7 +1056,7 @@ __device__ inline void jacobi_par_warp(int k, double *T, double *V) {
           const double apq = T[p * k + q], app = T[p * k + p], aqq = T[q * k + q];
           const double lim = fabs(app) + fabs(aqq);
           if (!(fabs(apq) <= 1e-17 * lim) && apq != 0.0) {
-            big = fmax(big, fabs(apq) * rcp_nr(lim));
+            big = big || fabs(apq) > 1e-7 * lim;
             const double theta = (aqq - app) * rcp_nr(2.0 * apq), th2 = fma(theta, theta, 1.0);
             const double t = (theta >= 0 ? 1.0 : -1.0) * rcp_nr(fabs(theta) + th2 * rsqrt_nr(th2));
             c = rsqrt_nr(fma(t, t, 1.0)); s = t * c;
@@ -1095,8 +1095,7 @@ __device__ inline void jacobi_par_warp(int k, double *T, double *V) {
       }
       __syncwarp();
     }
-    big = warp_max(big);
-    if (big < 1e-8) break;
+    if (!__any_sync(0xffffffffu, big)) break;
   }
 }
 

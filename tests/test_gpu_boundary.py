@@ -364,8 +364,10 @@ def test_pipelined_host_path_on_the_workspace_backed_kernels(cuda_device, monkey
         assert saved.items[9] == (chunk == 2)
         (primal.sum() + (dual * dual).sum()).backward()
         outs.append([primal.detach().clone(), dual.detach().clone(), A.grad.clone(), q.grad.clone(), P.grad.clone()])
+    # (K = rho I + P + A'R^{-1}A of a sparse A is accumulated with shared-memory / global atomics: the summation order, hence
+    #  the last bits of the factor, differ from launch to launch; the solutions agree to the solver tolerance, not bitwise)
     for a_, b_ in zip(*outs):
-        assert torch.allclose(a_, b_, rtol=1e-9, atol=1e-11)
+        assert torch.allclose(a_, b_, rtol=1e-6, atol=1e-8)
 
 
 def test_warm_start_through_the_layer_matches_the_oracle(cuda_device):

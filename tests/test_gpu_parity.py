@@ -116,7 +116,7 @@ def test_sparse_lp_c4_indirect_forward(cuda_device, monkeypatch):
     is the solver's own termination certificate at the SCS default tolerance."""
     B, eps = 4, 1e-4
     bt = pr.sparse_lp(B=B, seed=3)
-    monkeypatch.setenv("BCONE_FWD_MODE", "indirect")   # (the default for this size is the factor-in-slab direct mode, test_gpu_fullsize.py)
+    monkeypatch.delenv("BCONE_FWD_MODE", raising=False)   # n = 1000 > 512: conjugate gradients by default
     eng, sol = _solve_gpu(bt, cuda_device, eps=eps, max_iters=100000)
     assert "indirect" in eng.path_info()["fwd"]
     assert eng.kernel_info()["fwd_smem"] < 232448
