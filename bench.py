@@ -398,6 +398,7 @@ def run_ours(a):
     status = sol.status.cpu().numpy()
     iters = sol.iters.cpu().numpy()
     lits = its.cpu().numpy()
+    n_fallback = eng.fallback_count()   # block solver -> equilibrated LSQR fallbacks of the last backward (-1: block solver not in use)
 
     # ---- end-to-end through the reference-facing call with HOST buffers ----
     # Warm-up with the same object lifetimes as the timed loop.  The first two calls pay ~360 ms each for the pinned
@@ -468,7 +469,8 @@ def run_ours(a):
                 "kernel_ms": {k: round(v, 3) for k, v in kt.items()},
                 "kernel_geometry": info, "kernel_paths": eng.path_info(),
                 "solver": {"solved": int((status == 1).sum()), "of": int(status.size), "fwd_iters_mean": float(iters.mean()),
-                           "fwd_iters_max": int(iters.max()), "lsqr_iters_mean": float(lits.mean()), "lsqr_iters_max": int(lits.max())},
+                           "fwd_iters_max": int(iters.max()), "lsqr_iters_mean": float(lits.mean()), "lsqr_iters_max": int(lits.max()),
+                           "lsqr_fallback": n_fallback, "lsqr_fallback_of": int(lits.size)},
                 "clocks": clocks}
         if cpu:
             line["cpu_baseline"] = cpu

@@ -17,7 +17,7 @@ _f64p = C.POINTER(C.c_double)
 EXPORTS = [
     "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary", "bcone_set_boundary_quad",
     "bcone_ingest", "bcone_emit", "bcone_ingest_pitched", "bcone_emit_pitched", "bcone_peer_alloc", "bcone_peer_open", "bcone_peer_close",
-    "bcone_peer_free", "bcone_copy2d_async", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_solve_warm", "bcone_vjp", "bcone_launch_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
+    "bcone_peer_free", "bcone_copy2d_async", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_solve_warm", "bcone_vjp", "bcone_launch_count", "bcone_fallback_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
 
@@ -107,6 +107,8 @@ def load() -> C.CDLL:
     lib.bcone_set_profile.restype = C.c_int
     lib.bcone_launch_count.argtypes = [vp]
     lib.bcone_launch_count.restype = C.c_int64
+    lib.bcone_fallback_count.argtypes = [vp, _i32p]
+    lib.bcone_fallback_count.restype = C.c_int
     lib.bcone_kernel_info.argtypes = [vp] + [_i32p] * 6
     lib.bcone_kernel_info.restype = C.c_int
     lib.bcone_path_info.argtypes = [vp, _i32p, _i32p]

@@ -14,9 +14,9 @@
 extern "C" {
 size_t bc_fwd_smem_bytes(int n, int m, int nnzA, int threads, int max_psd, int indirect, int ns, int nexp);
 size_t bc_fwd_ws_doubles(int n, int m, int with_factor);
-cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem);
-cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas);
-cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem, int small_cta);
+cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas, int small_cta);
+cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t st, int small_cta);
 size_t bc_fwdf_smem_bytes(int n, int m);
 int bc_fwdf_threads(void);
 int bc_fwdf_eligible(int n, int m);
@@ -25,9 +25,9 @@ cudaError_t bc_fwdf_occupancy(int n, int m, size_t smem, int *ctas);
 cudaError_t bc_fwdf_launch(const FwdArgs *a, int grid, size_t smem, cudaStream_t st);
 size_t bc_bwd_ws_doubles(int n, int m, int npoly);
 size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_smem, int threads, int max_psd, int psd_total, int nexp, int vec_global);
-cudaError_t bc_bwd_configure(int dense, size_t smem);
-cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas);
-cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t bc_bwd_configure(int dense, size_t smem, int small_cta);
+cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas, int small_cta);
+cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st, int small_cta);
 size_t bc_bwdf_smem_bytes(int n, int m, int nnzA, int nnzP, int threads);
 cudaError_t bc_bwdf_configure(int n, size_t smem);
 cudaError_t bc_bwdf_occupancy(int n, int threads, size_t smem, int *ctas);
@@ -62,6 +62,7 @@ struct Handle {
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
   int fwd_indirect = 0, bwd_vec_global = 0;   // large instances: CG instead of Cholesky, vectors in a global slab
+  int fwd_small = 0, bwd_small = 0;           // <= 256-thread instances: kernels compiled for four resident CTAs per SM (BCONE_SMALL_CTA=0 disables)
   int fwd_factor_global = 0;                  // in between: values on chip, vectors + packed Cholesky factor in the slab (direct solve from L2 / HBM)
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   // Per-stream scratch slabs (one per CTA of the grid): launches on different streams may overlap, launches on one
@@ -73,6 +74,7 @@ struct Handle {
   int fast_fwd = 0;  // dense A, polyhedral cones, direct mode: register-tiled forward (fwd_fast.cu)
   int fast_bwd = 0;  // dense A, polyhedral cones, dense-or-no P: fused single-pass backward (bwd_fast.cu)
   long long launches = 0;
+  int last_block_slot = -1;   // ring slot of the last block-preconditioned vjp (its fallback counter is read by bcone_fallback_count)
   unsigned long long *prof = nullptr;   // device [32] phase cycle counters (bcone_set_profile)
   std::string err;
 };
@@ -266,17 +268,23 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
       h->fast_fwd = 1; h->fwd_threads = bc_fwdf_threads(); h->fwd_smem = bc_fwdf_smem_bytes(n, m);
     }
   }
-  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect, d->ns, d->ep + d->ed) : h->fwd_smem)) != cudaSuccess ||
-      (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem))) != cudaSuccess) {
+  {
+    const char *sc = getenv("BCONE_SMALL_CTA");
+    const bool allow = !(sc && atoi(sc) == 0);
+    h->fwd_small = allow && !h->fast_fwd && !h->fwd_indirect && h->fwd_threads <= 256 && h->fwd_smem <= 56 * 1024;
+    h->bwd_small = allow && !h->fast_bwd && h->bwd_threads <= 256 && h->bwd_smem <= 56 * 1024;
+  }
+  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect, d->ns, d->ep + d->ed) : h->fwd_smem, h->fwd_small)) != cudaSuccess ||
+      (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem, h->bwd_small))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
   if (h->block_bwd && (e = bc_bwdb_configure(h->blk_smem)) != cudaSuccess) h->block_bwd = 0;
   if (h->fast_fwd) bc_fwdf_occupancy(n, m, h->fwd_smem, &h->fwd_ctas);
-  else bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas);
+  else bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas, h->fwd_small);
   if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
-  else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
+  else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas, h->bwd_small);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;
   if (h->fwd_indirect || h->fwd_factor_global) h->fwd_ws_stride = bc_fwd_ws_doubles(n, m, h->fwd_factor_global);
@@ -523,7 +531,7 @@ extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, c
   }
   CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   if (h->fast_fwd) CK(bc_fwdf_launch(&a, grid, h->fwd_smem, st), "solve launch (fast)");
-  else CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st), "solve launch");
+  else CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st, h->fwd_small), "solve launch");
   h->launches++;
   return BCONE_OK;
 }
@@ -560,6 +568,7 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
       h->allocs.push_back(p); h->fail_list[slot] = p; h->fail_cap[slot] = B;
     }
     CK(cudaMemsetAsync(ctr + 1, 0, 3 * sizeof(int), st), "vjp counters");
+    h->last_block_slot = slot;
     a.fail_list = h->fail_list[slot]; a.fail_count = ctr + 2;
     CK(bc_bwdb_launch(&a, std::min(B, h->num_sms), h->blk_threads, h->blk_smem, st), "vjp launch (block)");
     BwdArgs f = a;
@@ -573,7 +582,7 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   CK(cudaMemsetAsync(ctr + 1, 0, sizeof(int), st), "vjp counter");
   const int grid = std::min(B, h->num_sms * h->bwd_ctas);
   if (h->fast_bwd) CK(bc_bwdf_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch (fast)");
-  else CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch");
+  else CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st, h->bwd_small), "vjp launch");
   h->launches++;
   return BCONE_OK;
 }
@@ -598,6 +607,21 @@ extern "C" int bcone_set_profile(void *handle, int32_t on, uint64_t *out) {
   if (out && h->prof) { cudaDeviceSynchronize(); cudaMemcpy(out, h->prof, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost); cudaMemset(h->prof, 0, 32 * sizeof(uint64_t)); }
   if (on && !h->prof) { if (cudaMalloc((void **)&h->prof, 32 * sizeof(uint64_t)) != cudaSuccess) return BCONE_ENOMEM; h->allocs.push_back(h->prof); cudaMemset(h->prof, 0, 32 * sizeof(uint64_t)); }
   if (!on) h->prof = nullptr;
+  return BCONE_OK;
+}
+
+// Instances of the last block-preconditioned bcone_vjp (lsqr_precond = 2) that the block factorisation rejected and the
+// equilibrated LSQR solved instead.  Synchronises the device.  -1: no such call yet.
+extern "C" int bcone_fallback_count(void *handle, int32_t *out) {
+  Handle *h = (Handle *)handle;
+  if (!h || !out) return BCONE_EINVAL;
+  *out = -1;
+  if (h->last_block_slot < 0) return BCONE_OK;
+  cudaSetDevice(h->device);
+  if (cudaDeviceSynchronize() != cudaSuccess) return BCONE_ECUDA;
+  int v = 0;
+  if (cudaMemcpy(&v, h->counters + 4 * h->last_block_slot + 2, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return BCONE_ECUDA;
+  *out = v;
   return BCONE_OK;
 }
 

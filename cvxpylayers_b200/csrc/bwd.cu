@@ -251,8 +251,8 @@ __device__ void equilibrate(const BwdArgs &a, const BwdSmem &M, const double *Pg
   }
 }
 
-template <bool DENSE>
-__global__ void __launch_bounds__(512, 1) bwd_kernel(const __grid_constant__ BwdArgs a) {
+template <bool DENSE, bool SMALL = false>   // SMALL: <= 256 threads, four resident CTAs per SM (see fwd.cu)
+__global__ void __launch_bounds__(SMALL ? 256 : 512, SMALL ? 4 : 1) bwd_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
@@ -495,16 +495,23 @@ extern "C" size_t bc_bwd_smem_bytes(int n, int m, int npoly, int nnzA, int nnzP_
   return bwd_smem_doubles(n, m, npoly, nnzA, nnzP_smem, threads, max_psd, psd_total, nexp, vec_global) * sizeof(double);
 }
 extern "C" size_t bc_bwd_ws_doubles(int n, int m, int npoly) { return (bwd_vec_doubles(n, m, npoly) + 1) & ~(size_t)1; }
-extern "C" cudaError_t bc_bwd_configure(int dense, size_t smem) {
-  if (dense) return cudaFuncSetAttribute(bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  return cudaFuncSetAttribute(bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define BWD_DISPATCH(EXPR)                                                     \
+  do {                                                                         \
+    if (small_cta) { if (dense) { auto k = bwd_kernel<true, true>; EXPR; } else { auto k = bwd_kernel<false, true>; EXPR; } } \
+    else { if (dense) { auto k = bwd_kernel<true, false>; EXPR; } else { auto k = bwd_kernel<false, false>; EXPR; } }         \
+  } while (0)
+extern "C" cudaError_t bc_bwd_configure(int dense, size_t smem, int small_cta) {
+  cudaError_t e = cudaSuccess;
+  BWD_DISPATCH(e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return e;
 }
-extern "C" cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas_per_sm) {
-  if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_kernel<true>, threads, smem);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bwd_kernel<false>, threads, smem);
+extern "C" cudaError_t bc_bwd_occupancy(int dense, int threads, size_t smem, int *ctas_per_sm, int small_cta) {
+  cudaError_t e = cudaSuccess;
+  BWD_DISPATCH(e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k, threads, smem));
+  return e;
 }
-extern "C" cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t stream) {
-  if (a->S.dense) bwd_kernel<true><<<grid, threads, smem, stream>>>(*a);
-  else bwd_kernel<false><<<grid, threads, smem, stream>>>(*a);
+extern "C" cudaError_t bc_bwd_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t stream, int small_cta) {
+  const int dense = a->S.dense;
+  BWD_DISPATCH((k<<<grid, threads, smem, stream>>>(*a)));
   return cudaGetLastError();
 }

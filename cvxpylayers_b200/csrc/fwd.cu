@@ -248,8 +248,11 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
   return true;
 }
 
-template <bool DENSE, bool INDIRECT>
-__global__ void __launch_bounds__(512, 1) fwd_kernel(const __grid_constant__ FwdArgs a) {
+// SMALL: instances that run with <= 256 threads per CTA and a few tens of KB of shared memory are bound by the latency of one
+// CTA's dependent chain (barriers, reductions, a single projecting warp); compiled for four resident CTAs per SM (64 registers)
+// they overlap each other's stalls.  The large variant keeps 128 registers and one CTA of up to 512 threads per SM.
+template <bool DENSE, bool INDIRECT, bool SMALL = false>
+__global__ void __launch_bounds__(SMALL ? 256 : 512, SMALL ? 4 : 1) fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(16) double smem[];
   const DevStruct &S = a.S;
   const int n = S.n, m = S.m, N = n + m + 1, T = blockDim.x, t = threadIdx.x;
@@ -644,23 +647,27 @@ extern "C" size_t bc_fwd_ws_doubles(int n, int m, int with_factor) {
 
 #define FWD_DISPATCH(EXPR)                                        \
   do {                                                            \
-    if (dense && indirect) { auto k = fwd_kernel<true, true>; EXPR; }        \
+    if (small_cta && !indirect) {                                 \
+      if (dense) { auto k = fwd_kernel<true, false, true>; EXPR; }             \
+      else { auto k = fwd_kernel<false, false, true>; EXPR; }                  \
+    }                                                             \
+    else if (dense && indirect) { auto k = fwd_kernel<true, true>; EXPR; }   \
     else if (dense) { auto k = fwd_kernel<true, false>; EXPR; }              \
     else if (indirect) { auto k = fwd_kernel<false, true>; EXPR; }           \
     else { auto k = fwd_kernel<false, false>; EXPR; }                        \
   } while (0)
 
-extern "C" cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem) {
+extern "C" cudaError_t bc_fwd_configure(int dense, int indirect, size_t smem, int small_cta) {
   cudaError_t e = cudaSuccess;
   FWD_DISPATCH(e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return e;
 }
-extern "C" cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas_per_sm) {
+extern "C" cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, int *ctas_per_sm, int small_cta) {
   cudaError_t e = cudaSuccess;
   FWD_DISPATCH(e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k, threads, smem));
   return e;
 }
-extern "C" cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t stream) {
+extern "C" cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t stream, int small_cta) {
   const int dense = a->S.dense;
   FWD_DISPATCH((k<<<grid, threads, smem, stream>>>(*a)));
   return cudaGetLastError();

@@ -120,6 +120,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bcone_launch_count(self.h))
 
+    def fallback_count(self) -> int:
+        v = C.c_int32()
+        self.lib.bcone_fallback_count(self.h, C.byref(v))
+        return int(v.value)
+
     def kernel_info(self) -> dict:
         v = [C.c_int32() for _ in range(6)]
         self.lib.bcone_kernel_info(self.h, *[C.byref(x) for x in v])

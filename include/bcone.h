@@ -148,6 +148,9 @@ int bcone_set_profile(void *handle, int32_t on, uint64_t *out16);
 /* Introspection for benchmarks/tests: kernel launches issued by this handle so far, and the
  * launch geometry chosen for the forward / backward kernels. */
 int64_t bcone_launch_count(void *handle);
+/* instances of the last lsqr_precond = 2 bcone_vjp that fell back from the block factorisation to the equilibrated LSQR
+ * (device synchronising; -1 before the first such call) */
+int bcone_fallback_count(void *handle, int32_t *out);
 int bcone_kernel_info(void *handle, int32_t *fwd_threads, int32_t *fwd_smem, int32_t *fwd_ctas_per_sm,
                       int32_t *bwd_threads, int32_t *bwd_smem, int32_t *bwd_ctas_per_sm);
 /* Which kernels the structure selected.  fwd_path: 0 generic on-chip Cholesky (fwd.cu), 1 generic indirect (CG),
