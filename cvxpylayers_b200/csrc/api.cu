@@ -62,7 +62,11 @@ struct Handle {
   size_t fwd_smem = 0, bwd_smem = 0;
   int tma_ok = 0, psd_total = 0, p_in_smem = 0;
   int fwd_indirect = 0, bwd_vec_global = 0;   // large instances: CG instead of Cholesky, vectors in a global slab
-  int fwd_small = 0, bwd_small = 0;           // <= 256-thread instances: kernels compiled for four resident CTAs per SM (BCONE_SMALL_CTA=0 disables)
+  // <= 256-thread instances have a second build of the generic kernels for four resident CTAs per SM (64 registers).  It wins
+  // when the batch exceeds what the 128-register build keeps resident (more CTAs overlap each other's stalls: exp-cone workload
+  // +24 %) and loses when every instance is resident anyway and only its own latency counts (SDP at B = 256: -25 %), so the
+  // choice is made per launch from the batch size.  BCONE_SMALL_CTA=0 disables, =2 forces.
+  int fwd_small = 0, bwd_small = 0, fwd_ctas_small = 0, bwd_ctas_small = 0, small_mode = 1;
   int fwd_factor_global = 0;                  // in between: values on chip, vectors + packed Cholesky factor in the slab (direct solve from L2 / HBM)
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   // Per-stream scratch slabs (one per CTA of the grid): launches on different streams may overlap, launches on one
@@ -270,23 +274,28 @@ extern "C" int bcone_create(const bcone_desc *d, void **out) {
   }
   {
     const char *sc = getenv("BCONE_SMALL_CTA");
-    const bool allow = !(sc && atoi(sc) == 0);
+    h->small_mode = sc ? atoi(sc) : 1;
+    const bool allow = h->small_mode != 0;
     h->fwd_small = allow && !h->fast_fwd && !h->fwd_indirect && h->fwd_threads <= 256 && h->fwd_smem <= 56 * 1024;
     h->bwd_small = allow && !h->fast_bwd && h->bwd_threads <= 256 && h->bwd_smem <= 56 * 1024;
   }
-  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect, d->ns, d->ep + d->ed) : h->fwd_smem, h->fwd_small)) != cudaSuccess ||
-      (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem, h->bwd_small))) != cudaSuccess) {
+  if (h->fwd_small && bc_fwd_configure(S.dense, 0, h->fwd_smem, 1) != cudaSuccess) h->fwd_small = 0;
+  if (h->bwd_small && bc_bwd_configure(S.dense, h->bwd_smem, 1) != cudaSuccess) h->bwd_small = 0;
+  if ((e = bc_fwd_configure(S.dense, h->fwd_indirect, h->fast_fwd ? bc_fwd_smem_bytes(n, m, d->nnzA, 64, max_psd, h->fwd_indirect, d->ns, d->ep + d->ed) : h->fwd_smem, 0)) != cudaSuccess ||
+      (e = (h->fast_bwd ? bc_bwdf_configure(n, h->bwd_smem) : bc_bwd_configure(S.dense, h->bwd_smem, 0))) != cudaSuccess) {
     std::string msg = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
     bcone_destroy(h);
     return fail(nullptr, BCONE_ECUDA, msg);
   }
   if (h->block_bwd && (e = bc_bwdb_configure(h->blk_smem)) != cudaSuccess) h->block_bwd = 0;
   if (h->fast_fwd) bc_fwdf_occupancy(n, m, h->fwd_smem, &h->fwd_ctas);
-  else bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas, h->fwd_small);
+  else bc_fwd_occupancy(S.dense, h->fwd_indirect, h->fwd_threads, h->fwd_smem, &h->fwd_ctas, 0);
   if (h->fast_bwd) bc_bwdf_occupancy(n, h->bwd_threads, h->bwd_smem, &h->bwd_ctas);
-  else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas, h->bwd_small);
+  else bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas, 0);
   if (h->fwd_ctas < 1) h->fwd_ctas = 1;
   if (h->bwd_ctas < 1) h->bwd_ctas = 1;
+  if (h->fwd_small) { bc_fwd_occupancy(S.dense, 0, h->fwd_threads, h->fwd_smem, &h->fwd_ctas_small, 1); if (h->fwd_ctas_small <= h->fwd_ctas) h->fwd_small = 0; }
+  if (h->bwd_small) { bc_bwd_occupancy(S.dense, h->bwd_threads, h->bwd_smem, &h->bwd_ctas_small, 1); if (h->bwd_ctas_small <= h->bwd_ctas) h->bwd_small = 0; }
   if (h->fwd_indirect || h->fwd_factor_global) h->fwd_ws_stride = bc_fwd_ws_doubles(n, m, h->fwd_factor_global);
   if (h->bwd_vec_global && !h->fast_bwd) h->bwd_ws_stride = bc_bwd_ws_doubles(n, m, npoly);
   h->tma_ok = (d->nnzA > 0 && (d->nnzA % 2) == 0 && (size_t)d->nnzA * 8 < (1u << 20)) ? 1 : 0;
@@ -513,8 +522,11 @@ extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, c
   a.x0 = x0; a.y0 = y0; a.s0 = s0;
   int *ctr = h->counters + 4 * (h->slot++ % Handle::RING);
   a.counter = ctr; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
-  const int grid = std::min(B, h->num_sms * h->fwd_ctas);
-  const size_t max_grid = (size_t)h->num_sms * h->fwd_ctas;
+  // the 4-CTA/SM build only when the batch does not fit the resident capacity of the 128-register build
+  const int use_small = h->fwd_small && (h->small_mode == 2 || B > h->num_sms * h->fwd_ctas);
+  const int ctas = use_small ? h->fwd_ctas_small : h->fwd_ctas;
+  const int grid = std::min(B, h->num_sms * ctas);
+  const size_t max_grid = (size_t)h->num_sms * std::max(h->fwd_ctas, h->fwd_ctas_small);
   Handle::StreamWs *sw = stream_ws(h, st);
   a.ws = nullptr; a.ws_stride = (long long)h->fwd_ws_stride; a.prof = h->prof;
   if (h->fwd_indirect || h->fwd_factor_global) {
@@ -531,7 +543,7 @@ extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, c
   }
   CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   if (h->fast_fwd) CK(bc_fwdf_launch(&a, grid, h->fwd_smem, st), "solve launch (fast)");
-  else CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st, h->fwd_small), "solve launch");
+  else CK(bc_fwd_launch(&a, h->fwd_indirect, grid, h->fwd_threads, h->fwd_smem, st, use_small), "solve launch");
   h->launches++;
   return BCONE_OK;
 }
@@ -556,7 +568,7 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   a.ws = nullptr; a.ws_stride = (long long)h->bwd_ws_stride;
   if (h->bwd_vec_global && !h->fast_bwd) {
     Handle::StreamWs *sw = stream_ws(h, st);
-    if (!ensure_slab(h, &sw->bwd, nullptr, h->bwd_ws_stride * (size_t)h->num_sms * h->bwd_ctas)) return fail(h, BCONE_ENOMEM, "cudaMalloc backward workspace");
+    if (!ensure_slab(h, &sw->bwd, nullptr, h->bwd_ws_stride * (size_t)h->num_sms * std::max(h->bwd_ctas, h->bwd_ctas_small))) return fail(h, BCONE_ENOMEM, "cudaMalloc backward workspace");
     a.ws = sw->bwd;
   }
   a.inst_list = nullptr; a.B_dev = nullptr; a.fail_list = nullptr; a.fail_count = nullptr; a.prof = h->prof;
@@ -580,9 +592,10 @@ extern "C" int bcone_vjp(void *handle, int32_t B, const double *A_vals, const do
   }
   if (a.st.lsqr_precond == 2) a.st.lsqr_precond = 1;   // block factorisation not available for this structure
   CK(cudaMemsetAsync(ctr + 1, 0, sizeof(int), st), "vjp counter");
-  const int grid = std::min(B, h->num_sms * h->bwd_ctas);
+  const int use_small = h->bwd_small && (h->small_mode == 2 || B > h->num_sms * h->bwd_ctas);
+  const int grid = std::min(B, h->num_sms * (use_small ? h->bwd_ctas_small : h->bwd_ctas));
   if (h->fast_bwd) CK(bc_bwdf_launch(&a, grid, h->bwd_threads, h->bwd_smem, st), "vjp launch (fast)");
-  else CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st, h->bwd_small), "vjp launch");
+  else CK(bc_bwd_launch(&a, grid, h->bwd_threads, h->bwd_smem, st, use_small), "vjp launch");
   h->launches++;
   return BCONE_OK;
 }
