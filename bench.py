@@ -311,10 +311,11 @@ def run_ours(a):
                     dist.gather(t_, None, dst=0)
         return u["sol"], u["its"]
 
-    def step_e2e():
-        A = hA.detach().requires_grad_(True)
-        q = hq.detach().requires_grad_(True)
-        P = hP.detach().requires_grad_(True) if hP is not None else None
+    def step_e2e(pageable: bool = False):
+        srcA, srcq, srcP = (pA, pq, pP) if pageable else (hA, hq, hP)
+        A = srcA.detach().requires_grad_(True)
+        q = srcq.detach().requires_grad_(True)
+        P = srcP.detach().requires_grad_(True) if srcP is not None else None
         t0 = time.perf_counter()
         primal, dual, _, _ = _CvxpyLayer.apply(P, q, A, cl_ctx, {}, True, None)
         t1 = time.perf_counter()
@@ -423,6 +424,22 @@ def run_ours(a):
         tt = torch.tensor([ms_e2e], dtype=f64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e2e = float(tt)
+    # the same call with PAGEABLE host tensors -- what an unmodified reference layer hands over on CPU (its sparse products
+    # return torch.from_numpy arrays, torch/cvxpylayer.py:21-24): no two-stream pipeline, staged copies
+    e2e_pageable = None
+    if world == 1 and CONFIG == "C2":
+        pA, pq, pP = hA.clone(), hq.clone(), (hP.clone() if hP is not None else None)   # clone() of a pinned tensor is pageable
+        assert not pA.is_pinned()
+        for _ in range(2):
+            step_e2e(True)
+        sync()
+        tw = time.perf_counter()
+        for _ in range(3):
+            step_e2e(True)
+        sync()
+        e2e_pageable = {"value": Btot / ((time.perf_counter() - tw) / 3), "unit": UNIT, "steps": 3,
+                        "note": "pageable host inputs (the reference's CPU tensors): non-overlapped staged copies instead of the pinned two-stream pipeline"}
+        del pA, pq, pP
     npel = hP.numel() if hP is not None else 0
     h2d = (hA.numel() + hq.numel() + npel + dxh.numel() + dyh.numel()) * 8
     d2h = (gAh.numel() + gqh.numel() + npel + B * (st.n + st.m)) * 8
@@ -457,7 +474,8 @@ def run_ours(a):
                 "e2e": {"value": Btot / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "warmup_steps": e2e_warm,
                         "diagnostic_wall_ms_per_step": [round(v, 1) for v in per_step],
-                        "diagnostic_wall_ms_median": round(float(np.median(per_step)), 2)},
+                        "diagnostic_wall_ms_median": round(float(np.median(per_step)), 2),
+                        "inputs": "pinned host tensors", **({"pageable_inputs": e2e_pageable} if e2e_pageable else {})},
                 "gpu_launches": int(launches),
                 **({"strong_scaling": strong, "exchange": {"kind": "peer-to-peer copy engines (CUDA IPC over NVLink), chunked behind the solve" if xchg.p2p else "NCCL gather into preallocated slots",
                                                           "bytes_per_rank": int(slot_bytes), "chunk": a.chunk, "numa_bound": bool(numa_bound)}} if world > 1 else {}),
