@@ -17,7 +17,7 @@ _f64p = C.POINTER(C.c_double)
 EXPORTS = [
     "bcone_default_settings", "bcone_create", "bcone_destroy", "bcone_last_error", "bcone_set_boundary", "bcone_set_boundary_quad",
     "bcone_ingest", "bcone_emit", "bcone_ingest_pitched", "bcone_emit_pitched", "bcone_peer_alloc", "bcone_peer_open", "bcone_peer_close",
-    "bcone_peer_free", "bcone_copy2d_async", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_solve_warm", "bcone_vjp", "bcone_launch_count", "bcone_fallback_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
+    "bcone_peer_free", "bcone_copy2d_async", "bcone_rows_from_param", "bcone_param_from_rows", "bcone_gather_cols", "bcone_scatter_cols", "bcone_set_param_maps", "bcone_ingest_params", "bcone_emit_params", "bcone_solve", "bcone_solve_warm", "bcone_vjp", "bcone_launch_count", "bcone_fallback_count", "bcone_kernel_info", "bcone_path_info", "bcone_memcpy2d", "bcone_set_profile",
 ]
 
 
@@ -89,6 +89,14 @@ def load() -> C.CDLL:
     lib.bcone_peer_free.restype = C.c_int
     lib.bcone_copy2d_async.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int64, C.c_int64, vp]
     lib.bcone_copy2d_async.restype = C.c_int
+    lib.bcone_rows_from_param.argtypes = [vp, C.c_int64, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    lib.bcone_rows_from_param.restype = C.c_int
+    lib.bcone_param_from_rows.argtypes = [vp, vp, C.c_int64, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    lib.bcone_param_from_rows.restype = C.c_int
+    lib.bcone_gather_cols.argtypes = [vp, C.c_int64, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    lib.bcone_gather_cols.restype = C.c_int
+    lib.bcone_scatter_cols.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    lib.bcone_scatter_cols.restype = C.c_int
     lib.bcone_set_param_maps.argtypes = [vp, C.c_int32] + [_i32p, _i32p, _f64p] * 3
     lib.bcone_set_param_maps.restype = C.c_int
     lib.bcone_ingest_params.argtypes = [vp, C.c_int32] + [vp] * 6

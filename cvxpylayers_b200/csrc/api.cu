@@ -37,6 +37,10 @@ cudaError_t bc_bwdb_configure(size_t smem);
 cudaError_t bc_bwdb_launch(const BwdArgs *a, int grid, int threads, size_t smem, cudaStream_t st);
 cudaError_t bc_b2e(const double *in, double *out, int K, int B, int ldo, int roff, const int *smap, const int *dmap, double sign, long long ldb, cudaStream_t st);
 cudaError_t bc_e2b(const double *in, double *out, int K, int B, int ldi, int roff, const int *smap, const int *dmap, double sign, long long ldb, cudaStream_t st);
+cudaError_t bc_rows_from_param(const double *param, long long stride, const int *map, int K, int B, int op, double *rows, cudaStream_t st);
+cudaError_t bc_param_from_rows(const double *grows, const double *param, long long stride, const int *map, int K, int B, int op, double *gparam, cudaStream_t st);
+cudaError_t bc_gather_cols(const double *in, long long ld, const int *map, const double *scale, int K, int B, int op, double *out, cudaStream_t st);
+cudaError_t bc_scatter_cols(const double *gout, const double *out, long long ld, const int *map, const double *scale, int K, int B, int op, double *gin, cudaStream_t st);
 cudaError_t bc_p2e(const double *p, const int *rptr, const int *cols, const double *vals, double *out, int K, int B, int ldo, int roff,
                    const int *smap, const int *dmap, double sign, cudaStream_t st);
 cudaError_t bc_e2p(const double *in, const int *rptr, const int *cols, const double *vals, double *dp, int K, int B, int ldi, int roff,
@@ -459,6 +463,32 @@ extern "C" int bcone_emit_pitched(void *handle, int32_t B, int64_t ldb, const do
 extern "C" int bcone_emit(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
                           const double *dc, double *dA_eval, double *dq_eval, double *dP_eval, void *stream) {
   return bcone_emit_pitched(handle, B, B, dA_vals, dP_vals, db, dc, dA_eval, dq_eval, dP_eval, stream);
+}
+
+// ---- layer prologue / epilogue: index maps instead of the reference's reshape / permute / cat chains ----
+// All pointers are DEVICE pointers (maps: int32, scales: double); no handle, no state.  op: 0 identity, 1 exp, 2 log.
+#define CKG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_err = std::string(__func__) + ": " + cudaGetErrorString(e_); return BCONE_ECUDA; } } while (0)
+extern "C" int bcone_rows_from_param(const double *param, int64_t stride, const int32_t *map, int32_t K, int32_t B, int32_t op, double *rows, void *stream) {
+  if (!param || !rows || K < 0 || B < 0) return BCONE_EINVAL;
+  CKG(bc_rows_from_param(param, stride, map, K, B, op, rows, (cudaStream_t)stream));
+  return BCONE_OK;
+}
+extern "C" int bcone_param_from_rows(const double *grows, const double *param, int64_t stride, const int32_t *map, int32_t K, int32_t B, int32_t op,
+                                     double *gparam, void *stream) {
+  if (!grows || !gparam || K < 0 || B < 0 || (op == 2 && !param)) return BCONE_EINVAL;
+  CKG(bc_param_from_rows(grows, param, stride, map, K, B, op, gparam, (cudaStream_t)stream));
+  return BCONE_OK;
+}
+extern "C" int bcone_gather_cols(const double *in, int64_t ld, const int32_t *map, const double *scale, int32_t K, int32_t B, int32_t op, double *out, void *stream) {
+  if (!in || !out || !map || K < 0 || B < 0) return BCONE_EINVAL;
+  CKG(bc_gather_cols(in, ld, map, scale, K, B, op, out, (cudaStream_t)stream));
+  return BCONE_OK;
+}
+extern "C" int bcone_scatter_cols(const double *gout, const double *out, int64_t ld, const int32_t *map, const double *scale, int32_t K, int32_t B, int32_t op,
+                                  double *gin, void *stream) {
+  if (!gout || !gin || !map || K < 0 || B < 0 || (op == 1 && !out)) return BCONE_EINVAL;
+  CKG(bc_scatter_cols(gout, out, ld, map, scale, K, B, op, gin, (cudaStream_t)stream));
+  return BCONE_OK;
 }
 
 // ---- peer exchange: a buffer on one GPU that every rank of the node can write (CUDA IPC over NVLink) -----------------------

@@ -157,6 +157,90 @@ __global__ void __launch_bounds__(256) e2p_kernel(const double *__restrict__ in,
     }
   }
 }
+// ---- layer prologue / epilogue on the device ----------------------------------------------------------------
+// The reference builds p_stack with a chain of expand / permute / reshape / cat / transpose per call
+// (_flatten_and_batch_params, src/cvxpylayers/torch/cvxpylayer.py:84-141) and takes the requested variables apart with slices,
+// Fortran reshapes and a symmetric scatter (_recover_results, :225-282).  Both are index maps; one launch each:
+//   rows_from_param : p_stack[(row0 + k), b] = f(param[b * stride + map[k]])   (stride = 0: an unbatched parameter is broadcast;
+//                     map = the Fortran-order flattening; f = log for GP parameters)
+//   param_from_rows : its adjoint (sum over the batch for an unbatched parameter; x 1/p for log)
+//   gather_cols     : out[b, k] = f(scale[k] * in[b * ld + map[k]])   (slice + svec unpack + reshape of one variable; f = exp for GP)
+//   scatter_cols    : its adjoint (atomic: the two triangles of a symmetric variable read the same entry)
+__global__ void __launch_bounds__(256) rows_from_param_kernel(const double *__restrict__ param, long long stride, const int *__restrict__ map,
+                                                             int K, int B, int op, double *__restrict__ rows) {
+  __shared__ double tile[TK][TI + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * TK, i0 = blockIdx.y * TI;
+  const int k = k0 + tx;
+  if (k < K) {
+    const int src = map ? __ldg(map + k) : k;
+    for (int ii = ty; ii < TI; ii += 8) {
+      const int i = i0 + ii;
+      if (i < B) { const double v = param[(size_t)i * stride + src]; tile[tx][ii] = op == 2 ? log(v) : v; }
+    }
+  }
+  __syncthreads();
+  for (int kk = ty; kk < TK; kk += 8) {
+    const int kq = k0 + kk;
+    if (kq >= K) continue;
+    for (int ii = tx; ii < TI; ii += 32) { const int i = i0 + ii; if (i < B) rows[(size_t)kq * B + i] = tile[kk][ii]; }
+  }
+}
+__global__ void __launch_bounds__(256) param_from_rows_kernel(const double *__restrict__ grows, const double *__restrict__ param, long long stride,
+                                                             const int *__restrict__ map, int K, int B, int op, double *__restrict__ gparam) {
+  // one thread per (k, b) with b fastest: coalesced reads of the gradient rows; writes are strided (parameters are small) and,
+  // for an unbatched parameter (stride 0), reduced over the batch with atomics
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)K * B) return;
+  const int k = (int)(e / B), b = (int)(e - (long long)k * B);
+  const int dst = map ? __ldg(map + k) : k;
+  double g = grows[e];
+  if (op == 2) g /= param[(size_t)b * stride + dst];
+  if (stride == 0) atomicAdd(gparam + dst, g); else gparam[(size_t)b * stride + dst] = g;
+}
+__global__ void __launch_bounds__(256) gather_cols_kernel(const double *__restrict__ in, long long ld, const int *__restrict__ map,
+                                                         const double *__restrict__ scale, int K, int B, int op, double *__restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)K * B) return;
+  const int b = (int)(e / K), k = (int)(e - (long long)b * K);
+  double v = in[(size_t)b * ld + __ldg(map + k)] * (scale ? __ldg(scale + k) : 1.0);
+  out[e] = op == 1 ? exp(v) : v;
+}
+__global__ void __launch_bounds__(256) scatter_cols_kernel(const double *__restrict__ gout, const double *__restrict__ out, long long ld,
+                                                          const int *__restrict__ map, const double *__restrict__ scale, int K, int B, int op,
+                                                          double *__restrict__ gin) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)K * B) return;
+  const int b = (int)(e / K), k = (int)(e - (long long)b * K);
+  double g = gout[e] * (scale ? __ldg(scale + k) : 1.0);
+  if (op == 1) g *= out[e];   // d exp(v) = exp(v) dv
+  atomicAdd(gin + (size_t)b * ld + __ldg(map + k), g);
+}
+extern "C" cudaError_t bc_rows_from_param(const double *param, long long stride, const int *map, int K, int B, int op, double *rows, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  dim3 grid((K + TK - 1) / TK, (B + TI - 1) / TI);
+  rows_from_param_kernel<<<grid, 256, 0, st>>>(param, stride, map, K, B, op, rows);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t bc_param_from_rows(const double *grows, const double *param, long long stride, const int *map, int K, int B, int op, double *gparam, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  const long long tot = (long long)K * B;
+  param_from_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(grows, param, stride, map, K, B, op, gparam);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t bc_gather_cols(const double *in, long long ld, const int *map, const double *scale, int K, int B, int op, double *out, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  const long long tot = (long long)K * B;
+  gather_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(in, ld, map, scale, K, B, op, out);
+  return cudaGetLastError();
+}
+extern "C" cudaError_t bc_scatter_cols(const double *gout, const double *out, long long ld, const int *map, const double *scale, int K, int B, int op, double *gin, cudaStream_t st) {
+  if (K <= 0 || B <= 0) return cudaSuccess;
+  const long long tot = (long long)K * B;
+  scatter_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(gout, out, ld, map, scale, K, B, op, gin);
+  return cudaGetLastError();
+}
+
 extern "C" cudaError_t bc_p2e(const double *p, const int *rptr, const int *cols, const double *vals, double *out, int K, int B, int ldo, int roff,
                               const int *smap, const int *dmap, double sign, cudaStream_t st) {
   if (K <= 0 || B <= 0) return cudaSuccess;

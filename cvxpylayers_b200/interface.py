@@ -553,11 +553,18 @@ def register(canon_solver: str = "DIFFCP", fuse: bool = True) -> None:
                 if getattr(self.ctx, "solver", None) != "B200" or getattr(sctx, "_param_maps", None) is None:
                     return orig_forward(self, *params, solver_args=solver_args, warm_start=warm_start, **kw)
                 batch = self.ctx.validate_params(list(params))
-                params_ = tl._apply_gp_log_transform(params, self.ctx)
-                p_stack = tl._flatten_and_batch_params(params_, self.ctx, batch)
-                needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params_)
+                on_dev = all(p.is_cuda and p.dtype == torch.float64 for p in params) and hasattr(self.ctx, "batch_sizes")
+                if on_dev:   # prologue as index-map launches (layer_io.py), GP log folded in
+                    from . import layer_io  # noqa: PLC0415
+                    p_stack = layer_io.flatten_and_batch_params(tuple(params), self.ctx, batch)
+                else:
+                    params_ = tl._apply_gp_log_transform(params, self.ctx)
+                    p_stack = tl._flatten_and_batch_params(params_, self.ctx, batch)
+                needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
                 # (the reference refuses warm_start for every backend but one, torch/cvxpylayer.py:416-420; this one takes it)
                 primal, dual, _, _ = _CvxpyLayerFused.apply(p_stack, self.ctx, solver_args or {}, needs_grad, True if warm_start else None)
+                if on_dev and hasattr(self.ctx, "var_recover"):
+                    return layer_io.recover_results(primal, dual, self.ctx, batch)
                 return tl._recover_results(primal, dual, self.ctx, batch)
 
             tl.CvxpyLayer.forward = _forward

@@ -116,6 +116,24 @@ int bcone_ingest_params(void *handle, int32_t B, const double *p_stack, double *
 int bcone_emit_params(void *handle, int32_t B, const double *dA_vals, const double *dP_vals, const double *db,
                       const double *dc, double *dp_stack, void *cuda_stream);
 
+/* Layer prologue / epilogue on the device: what the reference does per call with expand / permute / reshape /
+ * cat / transpose chains (_flatten_and_batch_params, src/cvxpylayers/torch/cvxpylayer.py:84-141) and with slices, Fortran
+ * reshapes and a symmetric scatter (_recover_results, :225-282) are index maps, one launch each.  DEVICE pointers throughout
+ * (maps int32, scales fp64), no handle.  op: 0 identity, 1 exp (GP variables), 2 log (GP parameters).
+ *   rows_from_param: rows[k, b] = f(param[b * stride + map[k]]), k < K -- the K rows of p_stack[.., B] that one parameter owns
+ *                    (stride 0 broadcasts an unbatched parameter; map = Fortran-order flattening, NULL = identity)
+ *   param_from_rows: the adjoint (batch-sum for stride 0, x 1/p for log); gparam must be zeroed by the caller when stride = 0
+ *   gather_cols    : out[b, k] = f(scale[k] * in[b * ld + map[k]]) -- one requested variable out of primal[B, n] / dual[B, m]
+ *   scatter_cols   : the adjoint, accumulated into gin (zeroed by the caller) */
+int bcone_rows_from_param(const double *param, int64_t stride, const int32_t *map, int32_t K, int32_t B, int32_t op, double *rows,
+                          void *cuda_stream);
+int bcone_param_from_rows(const double *grows, const double *param, int64_t stride, const int32_t *map, int32_t K, int32_t B,
+                          int32_t op, double *gparam, void *cuda_stream);
+int bcone_gather_cols(const double *in, int64_t ld, const int32_t *map, const double *scale, int32_t K, int32_t B, int32_t op,
+                      double *out, void *cuda_stream);
+int bcone_scatter_cols(const double *gout, const double *out, int64_t ld, const int32_t *map, const double *scale, int32_t K,
+                       int32_t B, int32_t op, double *gin, void *cuda_stream);
+
 /* Forward: instance-contiguous inputs A_vals[B,nnzA] (CSR order), P_vals[B,nnzP] or NULL, b[B,m], c[B,n];
  * outputs x[B,n], y[B,m], s[B,m], status[B], iters[B] (int32), resid[B,3] or NULL. */
 int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,

@@ -402,3 +402,92 @@ def test_warm_start_through_the_layer_matches_the_oracle(cuda_device):
     assert iw.mean() < 0.7 * ic.mean(), (iw.mean(), ic.mean())
     sol_f = eng.solve(_t(bt.A_vals, dev), _t(b2, dev), _t(c2, dev), _t(bt.P_vals, dev), make_settings(o_args), warm=sol_w)
     assert int(sol_f.iters.max()) <= 25 and float((sol_f.x - sol_w.x).abs().max()) < 1e-4   # (two points inside the 1e-6 termination ball)
+
+
+# ----------------------------------------------------------------------------- layer prologue / epilogue on the device
+def _reshape_fortran(array, shape):
+    """The reference's helper, restated (torch/cvxpylayer.py:40-56): reshape in column-major order via permutes."""
+    x = array.permute(*reversed(range(len(array.shape))))
+    return x.reshape(*reversed(shape)).permute(*reversed(range(len(shape))))
+
+
+def test_device_flatten_and_recover_equal_the_reference_tensor_chains(cuda_device):
+    """cvxpylayers_b200.layer_io vs the reference's own tensor-op chains restated here: _flatten_and_batch_params
+    (torch/cvxpylayer.py:84-141: expand, Fortran reshape, cat in column order, ones row, transpose; GP log :58-81) and
+    _recover_results (:225-282: slices, svec unpacking :143-222, Fortran reshape, GP exp) -- values and gradients."""
+    from types import SimpleNamespace
+
+    from cvxpylayers_b200 import layer_io
+
+    dev, B = cuda_device, 7
+    g = torch.Generator(device="cpu").manual_seed(3)
+    mk = lambda *shape: (torch.rand(shape, dtype=torch.float64, generator=g) + 0.5).to(dev).requires_grad_(True)  # noqa: E731
+    params = (mk(B, 3, 2), mk(4), mk(B, 5), mk(2, 2))                   # batched matrix, unbatched vector, batched vector, unbatched matrix
+    lctx = SimpleNamespace(batch_sizes=[B, 0, B, 0], user_order_to_col_order=(2, 0, 3, 1), gp=True, gp_log_mask=(False, True, False, True))
+    p_dev = layer_io.flatten_and_batch_params(params, lctx, (B,))
+    # reference chain
+    flat = [None] * 5
+    for i, p in enumerate(params):
+        q = torch.log(p) if lctx.gp_log_mask[i] else p
+        if lctx.batch_sizes[i] == 0:
+            q = q.unsqueeze(0).expand((B,) + q.shape)
+        flat[lctx.user_order_to_col_order[i]] = _reshape_fortran(q, (B, -1))
+    flat[-1] = torch.ones((B, 1), dtype=torch.float64, device=dev)
+    p_ref = torch.cat(flat, -1).T
+    assert p_dev.shape == p_ref.shape and torch.allclose(p_dev, p_ref, rtol=0, atol=1e-15)
+    w = torch.randn(p_ref.shape, dtype=torch.float64, generator=g).to(dev)
+    g_dev = torch.autograd.grad((p_dev * w).sum(), params)
+    g_ref = torch.autograd.grad((p_ref * w).sum(), params)
+    for a_, b_ in zip(g_dev, g_ref):
+        assert torch.allclose(a_, b_, rtol=1e-13, atol=1e-13)
+    # unbatched call: 1-D p_stack
+    p1 = layer_io.flatten_and_batch_params((params[1], params[3]), SimpleNamespace(batch_sizes=[0, 0], user_order_to_col_order=(1, 0), gp=False), ())
+    ref1 = torch.cat([_reshape_fortran(params[3].unsqueeze(0), (1, -1)), _reshape_fortran(params[1].unsqueeze(0), (1, -1)), torch.ones((1, 1), dtype=torch.float64, device=dev)], -1).T.reshape(-1)
+    assert p1.shape == ref1.shape and torch.equal(p1, ref1)
+
+    # ---- recover ----
+    n, m = 20, 15
+    primal = torch.randn((B, n), dtype=torch.float64, generator=g).to(dev).requires_grad_(True)
+    dual = torch.randn((B, m), dtype=torch.float64, generator=g).to(dev).requires_grad_(True)
+    V = lambda **kw: SimpleNamespace(**{"primal": None, "dual": None, **kw})  # noqa: E731
+    rctx = SimpleNamespace(gp=False, var_recover=[
+        V(primal=slice(2, 8), shape=(2, 3), source="primal", unpack_fn="reshape"),
+        V(primal=slice(8, 14), shape=(3, 3), source="primal", unpack_fn="svec_primal"),
+        V(dual=slice(4, 10), shape=(3, 3), source="dual", unpack_fn="svec_dual"),
+        V(dual=slice(0, 4), shape=(4,), source="dual", unpack_fn="reshape")])
+    outs = layer_io.recover_results(primal, dual, rctx, (B,))
+
+    def ref_recover():
+        res = []
+        for var in rctx.var_recover:
+            data = primal[..., var.primal] if var.source == "primal" else dual[..., var.dual]
+            if var.unpack_fn == "reshape":
+                r = _reshape_fortran(data, (B,) + var.shape)
+            else:
+                k = var.shape[0]
+                if var.unpack_fn == "svec_primal":
+                    rows, cols = np.triu_indices(k); sc = None
+                else:
+                    rr, cc = np.tril_indices(k); o = np.lexsort((rr, cc)); rows, cols = rr[o], cc[o]
+                    sc = torch.tensor(np.where(rows == cols, 1.0, 1.0 / np.sqrt(2.0)), device=dev)
+                d = data * sc if sc is not None else data
+                r = torch.zeros((B, k, k), dtype=torch.float64, device=dev)
+                r[..., torch.tensor(rows, device=dev), torch.tensor(cols, device=dev)] = d
+                r[..., torch.tensor(cols, device=dev), torch.tensor(rows, device=dev)] = d
+            res.append(r)
+        return res
+
+    refs = ref_recover()
+    ws = [torch.randn(r.shape, dtype=torch.float64, generator=g).to(dev) for r in refs]
+    for o_, r_ in zip(outs, refs):
+        assert o_.shape == r_.shape and torch.allclose(o_, r_, rtol=0, atol=1e-15)
+    gd = torch.autograd.grad(sum((o_ * w_).sum() for o_, w_ in zip(outs, ws)), (primal, dual))
+    gr = torch.autograd.grad(sum((r_ * w_).sum() for r_, w_ in zip(refs, ws)), (primal, dual))
+    for a_, b_ in zip(gd, gr):
+        assert torch.allclose(a_, b_, rtol=1e-13, atol=1e-13)
+    # GP: exp on primal variables only
+    rctx.gp = True
+    og = layer_io.recover_results(primal, dual, rctx, (B,))
+    assert torch.allclose(og[0], torch.exp(refs[0])) and torch.allclose(og[2], refs[2])
+    gg = torch.autograd.grad((og[0] * ws[0]).sum(), primal)[0]
+    assert torch.allclose(gg, torch.autograd.grad((torch.exp(_reshape_fortran(primal[..., 2:8], (B, 2, 3))) * ws[0]).sum(), primal)[0], rtol=1e-13, atol=1e-13)

@@ -105,16 +105,26 @@ def install_fake_cvxpylayers(monkeypatch):
         cone_dims: object
         solver_ctx: object
         solver: str
+        var_recover: list = dataclasses.field(default_factory=list)
+        user_order_to_col_order: tuple = ()
+        batch_sizes: list = None
+        gp: bool = False
 
-        def validate_params(self, params):
-            return (params[0].shape[0],) if params[0].dim() > 1 else ()
+        def validate_params(self, params):   # (the reference records the per-parameter batch sizes here, parse_args.py:102-139)
+            batch = (params[0].shape[0],) if params[0].dim() > 1 else ()
+            self.batch_sizes = [p.shape[0] if batch else 0 for p in params]
+            self.user_order_to_col_order = tuple(range(len(params)))
+            return batch
 
     def parse_args(problem, variables, parameters, solver, gp=False, verbose=False, canon_backend=None, solver_args=None):
         if solver not in ("DIFFCP", "CLARABEL", "SCS"):   # cvxpy: "The solver B200 is not installed"
             raise ValueError(f"The solver {solver} is not installed.")
         pp = problem["param_prob"]
         sctx = ifs.get_solver_ctx(solver, pp, problem["dims"], {}, solver_args, verbose=verbose)
-        return LayersContext(parameters, pp.reduced_P, pp.q, pp.reduced_A, problem["dims"], sctx, solver)
+        n_, m_ = pp.q.shape[0] - 1, pp.reduced_A.problem_data_index[2][0]
+        rec = [SimpleNamespace(primal=slice(0, n_), dual=None, shape=(n_,), source="primal", unpack_fn="reshape"),
+               SimpleNamespace(primal=None, dual=slice(0, m_), shape=(m_,), source="dual", unpack_fn="reshape")]
+        return LayersContext(parameters, pp.reduced_P, pp.q, pp.reduced_A, problem["dims"], sctx, solver, var_recover=rec)
 
     pa.parse_args = parse_args
 
