@@ -928,10 +928,11 @@ __device__ __forceinline__ void project_soc_warp(double *v, int sz) {
   for (int i = 1 + lane; i < sz; i += 32) ss += v[i] * v[i];
   ss = warp_sum(ss);
   const double nx = sqrt(ss), t = v[0];
+  __syncwarp();   // every lane holds t before lane 0 may overwrite v[0] in either branch below (with independent thread scheduling a
+                  // lane that ran ahead made its neighbours read the NEW v[0] and take a different branch: a rare wrong projection)
   if (nx <= t) return;
   if (nx <= -t) { for (int i = lane; i < sz; i += 32) v[i] = 0; return; }
   const double a = 0.5 * (1.0 + t / nx);
-  __syncwarp();
   for (int i = 1 + lane; i < sz; i += 32) v[i] *= a;
   if (lane == 0) v[0] = a * nx;
 }
