@@ -177,7 +177,7 @@ struct AaIter {   // where the kernel keeps the iterate
 };
 // header: [0] pairs seen since the last reset, [1] a step was taken and awaits its safeguard, [2] ||g|| of that step,
 // [3] the raw history of the fill phase has been turned into difference columns
-__device__ __forceinline__ void aa_reset_dev(double *ws) { if (threadIdx.x == 0) { ws[0] = 0.0; ws[1] = 0.0; ws[3] = 0.0; } }
+__device__ __forceinline__ void aa_reset_dev(double *ws) { if (threadIdx.x == 0) { ws[0] = 0.0; ws[1] = 0.0; ws[2] = 0.0; ws[3] = 0.0; } }
 // w_prev <- w (tau passed by value: the register-tiled kernel keeps it in a register)
 static __device__ __noinline__ void aa_store_prev(double *ws, int mem, const AaIter w, double tau) {
   const int N = w.n + w.m + 1, Np = (N + 1) & ~1;

@@ -205,6 +205,12 @@ __device__ bool factor_and_g(const FwdArgs &a, FwdSmem &M, const double *Pv, dou
     for (int e = t; e < npk; e += T) K[e] = 0.0;
     __syncthreads();
     for (int e = t; e < n; e += T) K[e * (e + 1) / 2 + e] = rho_x;
+    // The diagonal must be in place before ANY thread accumulates into it: without this barrier a fast thread's atomicAdd on a
+    // diagonal entry could land before the plain store above and be overwritten by it -- K then lacks a_jj^2 terms, may lose
+    // positive definiteness, and the instance is reported FAILED.  (Round 1's code had the race; it surfaced as an
+    // intermittent failure of one in ~2000 SOCP instances once two launches shared the SMs; compute-sanitizer racecheck named
+    // this line and no other.)
+    __syncthreads();
     for (int k = t; k < S.nnzA; k += T) {
       const int i = __ldg(S.A_rowof + k), ja = __ldg(S.A_indices + k);
       const double va = M.Av[k] * inv_ry(S, i, scale);

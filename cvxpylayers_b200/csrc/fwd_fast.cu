@@ -449,7 +449,7 @@ __device__ __noinline__ void aa_begin(const FwdArgs &a, int *ibuf) {
     const bool on = a.aa_ws != nullptr && a.st.acceleration_lookback != 0;
     ibuf[1] = on ? iv : 0x7fffffff;
     ibuf[2] = 0;   // pairs recorded since the last reset (mirror of the slab header)
-    if (on) { double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride; ws[0] = 0.0; ws[1] = 0.0; ws[3] = 0.0; }
+    if (on) { double *ws = a.aa_ws + (size_t)blockIdx.x * a.aa_stride; ws[0] = 0.0; ws[1] = 0.0; ws[2] = 0.0; ws[3] = 0.0; }
   }
   __syncthreads();
 }
