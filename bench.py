@@ -216,16 +216,27 @@ def run_ours(a):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     kt = {"fwd": 0.0, "bwd": 0.0, "pack": 0.0}
 
+    # Every stage writes into buffers allocated once (the engine's `out=` arguments): no allocator call -- and so no
+    # cudaMalloc / cudaFree, which one run in five otherwise slipped between two event records -- inside the timed region.
+    nb_aug = hA.shape[0]
+    dbuf = dict(inp=(torch.empty((B, st.nnzA), dtype=f64, device=dev), torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None,
+                     torch.empty((B, st.m), dtype=f64, device=dev), torch.empty((B, st.n), dtype=f64, device=dev)),
+                sol=eng.alloc_solution(B),
+                g=(torch.empty((B, st.nnzA), dtype=f64, device=dev), torch.empty((B, st.nnzP), dtype=f64, device=dev) if st.nnzP else None,
+                   torch.empty((B, st.m), dtype=f64, device=dev), torch.empty((B, st.n), dtype=f64, device=dev), torch.empty(B, dtype=torch.int32, device=dev)),
+                ev=(torch.empty((nb_aug, B), dtype=f64, device=dev), torch.empty((st.n + 1, B), dtype=f64, device=dev),
+                    torch.empty((dP_.shape[0], B), dtype=f64, device=dev) if (st.nnzP and dP_ is not None) else None))
+
     def step_device(timed: bool):
         e = [ev() for _ in range(5)] if timed else None
         if timed: e[0].record()
-        A_vals, P_vals, b, c = eng.ingest(dA_, dq_, dP_)
+        A_vals, P_vals, b, c = eng.ingest(dA_, dq_, dP_, out=dbuf["inp"])
         if timed: e[1].record()
-        sol = eng.solve(A_vals, b, c, P_vals, settings)
+        sol = eng.solve(A_vals, b, c, P_vals, settings, out=dbuf["sol"])
         if timed: e[2].record()
-        gA, gP, gb, gc, its = eng.vjp(A_vals, b, c, sol.x, sol.y, sol.s, dx, dy, P_vals, settings)
+        gA, gP, gb, gc, its = eng.vjp(A_vals, b, c, sol.x, sol.y, sol.s, dx, dy, P_vals, settings, out=dbuf["g"])
         if timed: e[3].record()
-        gA_eval, gq_eval, gP_eval = eng.emit(gA, gP, gb, gc)
+        gA_eval, gq_eval, gP_eval = eng.emit(gA, gP, gb, gc, out=dbuf["ev"])
         if timed: e[4].record()
         return sol, its, e
 

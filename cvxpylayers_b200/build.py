@@ -34,10 +34,12 @@ def stale() -> bool:
     return any(p.stat().st_mtime > t for p in [*(CSRC / s for s in SOURCES), *HEADERS])
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple = (), out: "Path | None" = None) -> Path:
+    """``defines`` / ``out``: development variants (e.g. ``-DBC_SUBPROF`` into another file, loaded with BCONE_LIB=...)."""
+    target = Path(out) if out else LIB
+    if not force and not defines and not out and not stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *defines, "-o", str(target), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
@@ -46,8 +48,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = sys.argv[sys.argv.index("-o") + 1] if "-o" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=tuple(a for a in sys.argv[1:] if a.startswith("-D")), out=_out))

@@ -19,6 +19,7 @@ cudaError_t bc_fwd_occupancy(int dense, int indirect, int threads, size_t smem, 
 cudaError_t bc_fwd_launch(const FwdArgs *a, int indirect, int grid, int threads, size_t smem, cudaStream_t st, int small_cta);
 size_t bc_fwdf_smem_bytes(int n, int m);
 int bc_fwdf_threads(void);
+size_t bc_fwdf_cache_doubles(int n, int m);
 int bc_fwdf_eligible(int n, int m);
 cudaError_t bc_fwdf_configure(int n, int m, size_t smem);
 cudaError_t bc_fwdf_occupancy(int n, int m, size_t smem, int *ctas);
@@ -526,18 +527,30 @@ extern "C" int bcone_copy2d_async(void *dst, int64_t dpitch, const void *src, in
   return BCONE_OK;
 }
 
+extern "C" int bcone_solve_cached(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
+                                  const double *x0, const double *y0, const double *s0, double *x, double *y, double *s, int32_t *status,
+                                  int32_t *iters, double *resid, void *cache, int32_t reuse, const bcone_settings *stg, void *stream);
 extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
                                 const double *x0, const double *y0, const double *s0, double *x, double *y, double *s, int32_t *status,
-                                int32_t *iters, double *resid, const bcone_settings *stg, void *stream);
+                                int32_t *iters, double *resid, const bcone_settings *stg, void *stream) {
+  return bcone_solve_cached(handle, B, A_vals, P_vals, b, c, x0, y0, s0, x, y, s, status, iters, resid, nullptr, 0, stg, stream);
+}
+extern "C" size_t bcone_cache_bytes(void *handle, int32_t B) {
+  Handle *h = (Handle *)handle;
+  if (!h || B <= 0 || !h->fast_fwd) return 0;
+  return (size_t)B * bc_fwdf_cache_doubles(h->S.n, h->S.m) * sizeof(double);
+}
 extern "C" int bcone_solve(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b,
                            const double *c, double *x, double *y, double *s, int32_t *status, int32_t *iters,
                            double *resid, const bcone_settings *stg, void *stream) {
   return bcone_solve_warm(handle, B, A_vals, P_vals, b, c, nullptr, nullptr, nullptr, x, y, s, status, iters, resid, stg, stream);
 }
-extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
-                                const double *x0, const double *y0, const double *s0, double *x, double *y, double *s, int32_t *status,
-                                int32_t *iters, double *resid, const bcone_settings *stg, void *stream) {
+extern "C" int bcone_solve_cached(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
+                                  const double *x0, const double *y0, const double *s0, double *x, double *y, double *s, int32_t *status,
+                                  int32_t *iters, double *resid, void *cache, int32_t reuse, const bcone_settings *stg, void *stream) {
   Handle *h = (Handle *)handle;
+  if (h && cache && !h->fast_fwd) return fail(h, BCONE_EINVAL, "solve: this structure has no cached set-up path (bcone_cache_bytes() is 0)");
+  if (h && cache && ((uintptr_t)cache & 15)) return fail(h, BCONE_EINVAL, "solve: cache must be 16-byte aligned");
   if (h && ((x0 != nullptr) != (y0 != nullptr) || (x0 != nullptr) != (s0 != nullptr))) return fail(h, BCONE_EINVAL, "solve: warm start needs x0, y0 and s0 together");
   if (!h || B <= 0 || !A_vals || !b || !c || !x || !y || !s || !status || !iters || !stg) return fail(h, BCONE_EINVAL, "solve: null argument");
   if (h->S.nnzP > 0 && !P_vals) return fail(h, BCONE_EINVAL, "solve: structure has P but P_vals is NULL");
@@ -550,6 +563,7 @@ extern "C" int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, c
   a.S = h->S; a.B = B; a.A_vals = A_vals; a.P_vals = h->S.nnzP > 0 ? P_vals : nullptr; a.b = b; a.c = c;
   a.x = x; a.y = y; a.s = s; a.status = status; a.iters = iters; a.resid = resid; a.st = *stg;
   a.x0 = x0; a.y0 = y0; a.s0 = s0;
+  a.cache = (double *)cache; a.cache_stride = h->fast_fwd ? (long long)bc_fwdf_cache_doubles(h->S.n, h->S.m) : 0; a.cache_reuse = cache && reuse;
   int *ctr = h->counters + 4 * (h->slot++ % Handle::RING);
   a.counter = ctr; a.use_tma = h->tma_ok && (((uintptr_t)A_vals & 15) == 0);
   // the 4-CTA/SM build only when the batch does not fit the resident capacity of the 128-register build

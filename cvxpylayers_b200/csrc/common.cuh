@@ -55,6 +55,10 @@ struct FwdArgs {
   double *aa_ws;         // Anderson acceleration: per-CTA slab of global memory (L2-resident), or NULL when off
   long long aa_stride;   // doubles per CTA
   const double *x0, *y0, *s0;   // warm start [B, n] / [B, m] / [B, m] (a previous solution of a nearby problem), or NULL
+  // cached set-up (register-tiled kernel only): per instance [8 header | E npad | D mpad | Kinv n x npad], see bc_fwdf_cache_doubles
+  double *cache;         // NULL = off
+  long long cache_stride;  // doubles per instance
+  int cache_reuse;       // 0: write the set-up of this solve; 1: A and P are unchanged since the solve that wrote it -> skip it
 };
 
 struct BwdArgs {

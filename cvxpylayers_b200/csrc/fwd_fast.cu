@@ -65,6 +65,12 @@ struct Geo {
   __host__ __device__ __forceinline__ int oRed() const { return oVy() + 7 * mpad(); }
   __host__ __device__ __forceinline__ int oCh() const { return oRed() + 256 + 64; }   // Cholesky scratch (4 x 4 block inverses)
   __host__ __device__ __forceinline__ int total() const { return oCh() + ((chol_scratch_doubles(npad()) + 1) & ~1); }
+  // cached set-up of one instance (global memory): [header 8 | E npad | D mpad | Kinv npad x npad]; header = {scale of the
+  // stored Kinv, 1.0 once Kinv is stored, rho_x it was built with, ...}
+  __host__ __device__ __forceinline__ int cE() const { return 8; }
+  __host__ __device__ __forceinline__ int cD() const { return cE() + npad(); }
+  __host__ __device__ __forceinline__ int cK() const { return cD() + mpad(); }
+  __host__ __device__ __forceinline__ int cTotal() const { return (cK() + npad() * npad() + 1) & ~1; }
   __host__ __device__ __forceinline__ bool ok(int n, int m) const {
     return n <= FT && m <= FT && CT() * RTu() <= FT && ((npad() + KR() - 1) / KR()) * CT() <= FT;
   }
@@ -198,7 +204,10 @@ __device__ __forceinline__ void reduce4_lead(double (&v)[4], double *red, int nw
     v[0] = __shfl_sync(0xffffffffu, a0, 0); v[1] = __shfl_sync(0xffffffffu, a0, 16);
     v[2] = __shfl_sync(0xffffffffu, a1, 0); v[3] = __shfl_sync(0xffffffffu, a1, 16);
   }
+#ifndef BC_OPT_BAR7
   __syncthreads();   // red may be rewritten by the next reduction
+#endif
+  // (BC_OPT_BAR7: the caller's next barrier -- the one that closes the iteration -- precedes every later write of red)
 }
 
 // K = rho_x I + sum_i r_i a_i a_i' (r_i = scale, x 1000 on zero-cone rows) (+ P^ when haveP: K then holds the
@@ -307,7 +316,7 @@ __device__ __noinline__ bool chol_cold(double *K, int n, double *tmp) { return c
 // Slots of the shared scalar block sc[] (= red + 256): values every thread agrees on but only the cold paths
 // need, kept out of the register file.
 enum { SC_SIGMA = 0, SC_NB0, SC_NC0, SC_SUMLOG, SC_PREVLR, SC_RP, SC_RD, SC_GAP, SC_UTAU, SC_NLOG, SC_LASTUP, SC_PREVIT,
-       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AADT, SC_NEXTREAL, SC_AASCR };   // SC_AASCR: 17 slots
+       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AADT, SC_NEXTREAL, SC_AASCR, SC_INV2QA = SC_AASCR + 17 };   // SC_AASCR: 17 slots
 
 // Everything of a termination check after the two products with A (A u_x in tm, A' u_y in tn): P^ u_x, the
 // residual norms on the un-normalised data, termination and certificates, the adaptive
@@ -436,6 +445,20 @@ __device__ __noinline__ void scatter_P(const DevStruct &S, const double *Pg, dou
   __syncthreads();
 }
 
+// Cached set-up (global memory, one record per instance; layout in Geo): cold, out of line.
+template <bool PUT>
+__device__ __noinline__ void cache_vectors(double *rec, double *En, int n, int npad, double *Dm, int m) {
+  const int t = threadIdx.x;
+  if (PUT) { if (t < n) rec[t] = En[t]; if (t < m) rec[npad + t] = Dm[t]; }
+  else { if (t < n) En[t] = rec[t]; if (t < m) Dm[t] = rec[npad + t]; __syncthreads(); }
+}
+__device__ __noinline__ void cache_put_kinv(double *hd, int offK, const double *Kinv, int n2, double scale, double rho_x) {
+  double2 *dst = reinterpret_cast<double2 *>(hd + offK);
+  const double2 *src = reinterpret_cast<const double2 *>(Kinv);
+  for (int k = threadIdx.x; k < n2; k += blockDim.x) dst[k] = src[k];
+  if (threadIdx.x == 0) { hd[0] = scale; hd[1] = 1.0; hd[2] = rho_x; }
+}
+
 // Anderson acceleration hooks of the register-tiled kernel.  Events happen at the END of iteration j (w complete),
 // which is the oracle's top of iteration j + 1 (nothing happens in between):
 //   j = 0 (mod iv): accelerate.  The iterate the last step started from is rebuilt as w - alpha (u - u~) (u, u~ are
@@ -521,7 +544,17 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
   double ar[TR][TCR];
 
   for (;;) {
-    if (t == 0) ibuf[0] = atomicAdd(a.counter, 1);
+    if (t == 0) {
+      const int k = atomicAdd(a.counter, 1);
+      ibuf[0] = k;
+      int ru = 0;   // cached set-up usable: written by a completed factorisation with the same rho_x
+      if (k < a.B && a.cache) {
+        double *hd = a.cache + (size_t)k * a.cache_stride;
+        ru = a.cache_reuse && hd[1] == 1.0 && hd[2] == a.st.rho_x;
+        if (!ru) hd[1] = 0.0;
+      }
+      ibuf[3] = ru;
+    }
     __syncthreads();
     const int inst = ibuf[0];
     if (inst >= a.B) break;
@@ -556,7 +589,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         sc[SC_RP] = nan(""); sc[SC_RD] = nan(""); sc[SC_GAP] = nan(""); sc[SC_UTAU] = 0; sc[SC_STATUS] = BCONE_INACCURATE;
       }
     }
-    if (Pg) scatter_P(S, Pg, Li, g.npk());
+    if (Pg && !ibuf[3]) scatter_P(S, Pg, Li, g.npk());   // (a cached set-up needs P only in CSR order, for the checks)
     if (a.use_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }
     __syncthreads();
     // ---- register tiles ----
@@ -580,8 +613,9 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     pt_stamp(0);
 
     // ---- Ruiz equilibration: A^ = D A E, P^ = E P E ----
+    if (ibuf[3]) cache_vectors<false>(a.cache + (size_t)inst * a.cache_stride + g.cE(), vx(VX_EN), n, g.npad(), vy(VY_DM), m);   // E and D of the solve that wrote it
     if (st.normalize) {
-      for (int pass = 0; pass < st.ruiz_passes; pass++) {
+      for (int pass = ibuf[3] ? st.ruiz_passes : 0; pass < st.ruiz_passes; pass++) {
         SUB_SKIP(pi);
         if (act) {
           double e[TC], d[TR], rowp[TR];
@@ -658,6 +692,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         }
       }
     }
+    if (a.cache && !ibuf[3]) cache_vectors<true>(a.cache + (size_t)inst * a.cache_stride + g.cE(), vx(VX_EN), n, g.npad(), vy(VY_DM), m);
     {
       double v[2] = {0, 0};
       if (t < m) { const double q = vy(VY_DM)[t] * vy(VY_BH)[t]; vy(VY_BH)[t] = q; v[0] = fabs(q); }
@@ -672,7 +707,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     }
     pt_stamp(1);
 
-    double scale = st.scale, w_tau = 1.0;
+    double scale = ibuf[3] ? a.cache[(size_t)inst * a.cache_stride] : st.scale, w_tau = 1.0;
     int it = 0, next_check = st.adaptive_check ? (st.check_interval < 10 ? st.check_interval : 10) : st.check_interval;
     if (t < n) { vx(VX_W)[t] = 0; vx(VX_U)[t] = 0; vx(VX_UT)[t] = 0; }
     if (t < m) { vy(VY_W)[t] = 0; vy(VY_U)[t] = 0; vy(VY_UT)[t] = 0; }
@@ -695,6 +730,9 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         // Factorisation at the current scale (the one place it is written, so the tiles stay in registers):
         // stage A^ from the tiles -> K -> Cholesky -> Linv -> Kinv; then g = (R_z + M)^{-1} h and g'Rg.
         SUB_DECL(pf);
+        const bool from_cache = first && ibuf[3];   // Kinv at this scale comes from the cached set-up: no staging, K, Cholesky
+        const bool c_tma = from_cache && a.use_tma && (((uintptr_t)a.cache & 15) == 0);
+        if (!from_cache) {
         if (!first && Pg) scatter_P(S, Pg, Li, g.npk());   // the factor's buffer held P in CSR order for the checks
         {
           double2 sl[TR];
@@ -725,22 +763,27 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         load_tile();
         __syncthreads();
         form_Kinv(Li, n, g.npad(), Kinv);
-        if (Pg) {   // the factor's buffer now carries P (CSR order) for the termination checks
-          if (p_tma) {
-            if (t == 0) {
-              fence_proxy_async();
-              mbar_expect_tx(bar, (uint32_t)(S.nnzP * sizeof(double)));
-              tma_bulk_g2s(Li, Pg, (uint32_t)(S.nnzP * sizeof(double)), bar);
-            }
-          } else {
-            for (int k = t; k < S.nnzP; k += FT) Li[k] = Pg[k];
+        if (a.cache) cache_put_kinv(a.cache + (size_t)inst * a.cache_stride, g.cK(), Kinv, (n * g.npad()) >> 1, scale, st.rho_x);
+        }
+        {   // asynchronous loads behind one barrier phase: P in CSR order into the factor's buffer (for the termination
+            // checks) and, with a cached set-up, Kinv
+          const double *ck = from_cache ? a.cache + (size_t)inst * a.cache_stride + g.cK() : nullptr;
+          const uint32_t pb = (Pg && p_tma) ? (uint32_t)(S.nnzP * sizeof(double)) : 0u, kb = c_tma ? (uint32_t)(n * g.npad() * sizeof(double)) : 0u;
+          if (t == 0 && pb + kb) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, pb + kb);
+            if (pb) tma_bulk_g2s(Li, Pg, pb, bar);
+            if (kb) tma_bulk_g2s(Kinv, ck, kb, bar);
           }
+          if (Pg && !p_tma) for (int k = t; k < S.nnzP; k += FT) Li[k] = Pg[k];
+          if (from_cache && !c_tma) for (int k = t; k < n * g.npad(); k += FT) Kinv[k] = ck[k];
         }
         SUB_STAMP(pf, 20);
         if (t == 0) { sc[SC_RYZ] = 1.0 / (BC_ZERO_CONE_FACTOR * scale); sc[SC_RYL] = 1.0 / scale; }
         if (t < m) vy(VY_TM)[t] = vy(VY_BH)[t] * inv_ry_f(z, t, scale);
         __syncthreads();
         rt_cols(ar, ps, g, act, R, C, vy(VY_TM), XC, n, [&](int j, double v) { vx(VX_TN)[j] = vx(VX_CH)[j] - v; });
+        if (c_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }   // Kinv (and P) have landed
         __syncthreads();
         kinv_mul(Kinv, g, n, R, C, vx(VX_TN), XR, [&](int j, double v) { vx(VX_G)[j] = v; });
         __syncthreads();
@@ -750,8 +793,8 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
           vy(VY_G)[i] = gi; acc[0] = fma((1.0 / iry) * gi, gi, acc[0]); });
         if (t < n) acc[0] = fma(st.rho_x * vx(VX_G)[t], vx(VX_G)[t], acc[0]);
         block_reduce<1, false>(acc, red);
-        if (t == 0) sc[SC_GRG] = acc[0];
-        if (Pg && p_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }
+        if (t == 0) { sc[SC_GRG] = acc[0]; sc[SC_INV2QA] = 0.5 / (BC_TAU_FACTOR + acc[0]); }
+        if (Pg && p_tma && !c_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }
         __syncthreads();
         SUB_STAMP(pf, 22);
         pt_stamp(2);
@@ -788,7 +831,11 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
       const double qa = BC_TAU_FACTOR + sc[SC_GRG], qb = d4[0] - 2.0 * d4[1] - BC_TAU_FACTOR * w_tau, qc = d4[2] - d4[3];
       double disc = qb * qb - 4.0 * qa * qc;
       if (disc < 0) disc = 0;
+#ifdef BC_OPT_INV2QA
+      const double tau_t = (-qb + sqrt(disc)) * sc[SC_INV2QA];   // (qa only changes with a factorisation)
+#else
       const double tau_t = (-qb + sqrt(disc)) / (2.0 * qa);
+#endif
       const bool check = it >= next_check || it == st.max_iters;
       // cone step + relaxation (the relaxation is fused here unless a check needs the plain iterate)
       if (ti < n) {
@@ -901,6 +948,7 @@ extern "C" size_t bc_fwdf_smem_bytes(int n, int m) {
   return (size_t)g.total() * sizeof(double);
 }
 extern "C" int bc_fwdf_threads(void) { return FT; }
+extern "C" size_t bc_fwdf_cache_doubles(int n, int m) { const Geo<0, 0> g(n, m); return (size_t)g.cTotal(); }
 // Eligibility beyond "dense A, polyhedral cones, direct mode" (checked by the caller): the tile grid has to
 // cover the matrix with at least half of the threads busy.
 extern "C" int bc_fwdf_eligible(int n, int m) {

@@ -26,7 +26,7 @@ _ARG_MAP = {
     "lsqr_iter_lim": "lsqr_iter_lim", "lsqr_precond": "lsqr_precond", "adaptive_check": "adaptive_check",
     "acceleration_lookback": "acceleration_lookback", "acceleration_interval": "acceleration_interval",
 }
-_IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "warm_starts", "raise_on_error", "warm_start"}
+_IGNORED = {"verbose", "n_jobs_forward", "n_jobs_backward", "solve_method", "warm_starts", "raise_on_error", "warm_start", "reuse_setup"}   # (warm_start / reuse_setup are handled by the layer)
 
 
 def make_settings(args: dict | None) -> _lib.BconeSettings:
@@ -285,8 +285,19 @@ class Engine:
         return dp
 
     # ------------------------------------------------------------------ forward / backward
+    def cache_bytes(self, B: int) -> int:
+        """Bytes of the set-up cache of a batch of B instances; 0 = this structure has no cached set-up path."""
+        return int(self.lib.bcone_cache_bytes(self.h, C.c_int32(B)))
+
+    def new_cache(self, B: int):
+        """A zero-filled set-up cache for ``solve(..., cache=)`` (``None`` when the structure has no such path)."""
+        nb = self.cache_bytes(B)
+        return torch.zeros(nb // 8, dtype=torch.float64, device=self.device) if nb else None
+
     def solve(self, A_vals, b, c, P_vals=None, settings: _lib.BconeSettings | None = None, out: "Solution | None" = None,
-              warm: "tuple | Solution | None" = None) -> Solution:
+              warm: "tuple | Solution | None" = None, cache=None, reuse: bool = False) -> Solution:
+        """``cache`` (from :meth:`new_cache`): keep the equilibration and the factorisation of every instance; ``reuse=True``
+        states that ``A_vals`` / ``P_vals`` are those of the call that filled it (``b`` and ``c`` may differ) and skips them."""
         st, dev, f64 = self.structure, self.device, torch.float64
         B = A_vals.shape[0]
         _chk(A_vals, (B, st.nnzA), f64, dev, "A_vals")
@@ -311,9 +322,11 @@ class Engine:
             x0, y0, s0 = (warm.x, warm.y, warm.s) if isinstance(warm, Solution) else warm
             for name, t_, shp in (("x0", x0, (B, st.n)), ("y0", y0, (B, st.m)), ("s0", s0, (B, st.m))):
                 _chk(t_, shp, f64, dev, name)
-        rc = self.lib.bcone_solve_warm(self.h, C.c_int32(B), _ptr(A_vals), _ptr(P_vals if st.nnzP else None), _ptr(b), _ptr(c),
-                                       _ptr(x0), _ptr(y0), _ptr(s0), _ptr(x), _ptr(y), _ptr(s), _ptr(status), _ptr(iters), _ptr(resid),
-                                       C.byref(settings), self._stream())
+        if cache is not None and (cache.dtype != f64 or cache.device != dev or cache.numel() * 8 < self.cache_bytes(B) or not cache.is_contiguous()):
+            raise ValueError("cache: need a contiguous float64 tensor of cache_bytes(B) bytes on the engine's device (engine.new_cache(B))")
+        rc = self.lib.bcone_solve_cached(self.h, C.c_int32(B), _ptr(A_vals), _ptr(P_vals if st.nnzP else None), _ptr(b), _ptr(c),
+                                         _ptr(x0), _ptr(y0), _ptr(s0), _ptr(x), _ptr(y), _ptr(s), _ptr(status), _ptr(iters), _ptr(resid),
+                                         _ptr(cache), C.c_int32(1 if (cache is not None and reuse) else 0), C.byref(settings), self._stream())
         self._raise(rc, "bcone_solve")
         return Solution(x, y, s, status, iters, resid)
 

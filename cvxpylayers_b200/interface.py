@@ -137,6 +137,14 @@ class B200_ctx:
         ``_A_scipy`` / ``_q_scipy`` / ``_P_scipy``, ``torch/cvxpylayer.py:443-451``) so that
         :class:`_CvxpyLayerFused` can take ``p_stack`` instead of the evaluated matrices."""
         self._param_maps = (A_map, q_map, P_map if self.nnzP else None)
+        # The reference's `PA_is_constant` (interfaces/moreau_if.py:233-241): no entry of A or P depends on a parameter (only the
+        # constant column of their rows is populated), so the equilibration and the factorisation of a call stay valid for
+        # the next one.  (The trailing rows of A_map feed b and may depend on parameters.)
+        try:
+            nA = A_map.shape[0] - len(self.b_idx)
+            self.PA_is_constant = bool(A_map.tocsr()[:nA, :-1].nnz == 0 and (P_map is None or not self.nnzP or P_map.tocsr()[:, :-1].nnz == 0))
+        except Exception:  # noqa: BLE001  (a map that is not a SciPy matrix: no claim)
+            self.PA_is_constant = False
         for eng in self._engines.values():
             eng.set_param_maps(*self._param_maps)
 
@@ -157,6 +165,20 @@ class B200_ctx:
             if not hasattr(self, "_last_solution"):
                 self._last_solution = {}
             self._last_solution[(dev, B)] = (sol.x.detach(), sol.y.detach(), sol.s.detach())
+
+    # ---- cached set-up: equilibration + factorisation kept across calls while A and P do not change ----
+    def setup_cache(self, eng: Engine, dev: torch.device, B: int, merged: dict):
+        """The set-up cache of (device, batch size) when the option ``reuse_setup`` is on -- explicitly (the caller states that
+        A and P are the same on every call), or by default when the parameter maps show it (``PA_is_constant``) -- else None.
+        The engine validates every record itself, so a fresh (zero-filled) cache is simply filled by its first solve."""
+        if not merged.get("reuse_setup", getattr(self, "PA_is_constant", False)):
+            return None
+        if not hasattr(self, "_setup_cache"):
+            self._setup_cache = {}
+        key = (dev, B)
+        if key not in self._setup_cache:
+            self._setup_cache[key] = eng.new_cache(B)   # None: this structure has no cached path
+        return self._setup_cache[key]
 
     def compute_device(self, t: torch.Tensor) -> torch.device:
         if t.is_cuda:
@@ -232,9 +254,10 @@ def _side_streams(eng: Engine, dev):
     return ss
 
 
-def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P, warm=None):
+def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P, warm=None, cache=None):
     st = eng.structure
     B = A_eval.shape[1]
+    cstride = (cache.numel() // B) if cache is not None else 0
     f64 = torch.float64
     A_vals = torch.empty((B, st.nnzA), dtype=f64, device=dev)
     b = torch.empty((B, st.m), dtype=f64, device=dev)
@@ -262,7 +285,8 @@ def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P
             from .engine import Solution  # noqa: PLC0415
             eng.solve(A_vals[lo:hi], b[lo:hi], c[lo:hi], P_vals[lo:hi] if use_P else None, settings,
                       out=Solution(sol.x[lo:hi], sol.y[lo:hi], sol.s[lo:hi], sol.status[lo:hi], sol.iters[lo:hi], sol.resid[lo:hi]),
-                      warm=None if warm is None else tuple(w_[lo:hi] for w_ in warm))
+                      warm=None if warm is None else tuple(w_[lo:hi] for w_ in warm),
+                      cache=None if cache is None else cache[lo * cstride:hi * cstride], reuse=True)
             primal[lo:hi].copy_(sol.x[lo:hi], non_blocking=True)
             dual[lo:hi].copy_(sol.y[lo:hi], non_blocking=True)
     for s_ in streams:
@@ -334,15 +358,16 @@ class _CvxpyLayer(torch.autograd.Function):
         settings = make_settings(merged)
         use_P = P_eval is not None and ctx.nnzP > 0
         warm = ctx.warm_for(dev, batch_size, warm_start, merged)
+        cache = ctx.setup_cache(eng, dev, batch_size, merged)
         piped = _pipe_ok(eng, batch_size, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None)
         with torch.cuda.device(dev):
             if piped:
                 A_vals, P_vals, b, c, sol, primal, dual = _forward_pipelined(
-                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P, warm)
+                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P, warm, cache)
             else:
                 A_vals, P_vals, b, c = eng.ingest(_to_dev(A_eval, dev), _to_dev(q_eval, dev),
                                                   _to_dev(P_eval, dev) if use_P else None)
-                sol = eng.solve(A_vals, b, c, P_vals, settings, warm=warm)
+                sol = eng.solve(A_vals, b, c, P_vals, settings, warm=warm, cache=cache, reuse=True)
             status = sol.status.cpu()  # the one host sync of the forward: per-instance status
         ctx.remember(dev, batch_size, sol, merged, warm_start)
         bad = (status != 1) & (status != 2)
@@ -450,7 +475,8 @@ class _CvxpyLayerFused(torch.autograd.Function):
         B = ps.shape[1]
         with torch.cuda.device(dev):
             A_vals, P_vals, b, c = eng.ingest_params(_to_dev(ps, dev))
-            sol = eng.solve(A_vals, b, c, P_vals, settings, warm=ctx.warm_for(dev, B, warm_start, merged))
+            sol = eng.solve(A_vals, b, c, P_vals, settings, warm=ctx.warm_for(dev, B, warm_start, merged),
+                            cache=ctx.setup_cache(eng, dev, B, merged), reuse=True)
             status = sol.status.cpu()
         ctx.remember(dev, B, sol, merged, warm_start)
         bad = (status != 1) & (status != 2)

@@ -147,6 +147,23 @@ int bcone_solve_warm(void *handle, int32_t B, const double *A_vals, const double
                      const double *x0, const double *y0, const double *s0, double *x, double *y, double *s,
                      int32_t *status, int32_t *iters, double *resid, const bcone_settings *st, void *cuda_stream);
 
+/* Forward with a cached set-up (second half; the reference's template is the one-time `setup()` of
+ * interfaces/moreau_if.py:237-256, `PA_is_constant`): the equilibration (D, E) and the factorisation (K^-1 at its final scale)
+ * of every instance are kept in `cache` -- caller-owned device memory of bcone_cache_bytes(handle, B) bytes, 16-byte aligned.
+ *   reuse = 0: solve as bcone_solve_warm and write the set-up;
+ *   reuse = 1: the caller states that A_vals and P_vals are the ones of the call that wrote `cache` (same B, same order; b and c
+ *              are free to change): the kernel skips the Ruiz passes, the formation of K, its Cholesky factorisation and
+ *              inverse, and starts at the cached scale.  A record that was never completed (or was written with another
+ *              rho_x) is rebuilt in place, so reuse = 1 on a fresh zero-filled buffer is safe.
+ * An adaptive re-scaling inside a solve re-factorises as usual and refreshes the record.  Only the register-tiled dense kernel
+ * (dense A, zero + nonneg rows, direct mode) has this path: bcone_cache_bytes returns 0 for every other structure, and
+ * bcone_solve_cached then requires cache = NULL (it is bcone_solve_warm). */
+size_t bcone_cache_bytes(void *handle, int32_t B);
+int bcone_solve_cached(void *handle, int32_t B, const double *A_vals, const double *P_vals, const double *b, const double *c,
+                       const double *x0, const double *y0, const double *s0, double *x, double *y, double *s,
+                       int32_t *status, int32_t *iters, double *resid, void *cache, int32_t reuse,
+                       const bcone_settings *st, void *cuda_stream);
+
 /* Backward (stateless): adjoint of the solution map at (x,y,s) applied to (dx,dy), ds = 0.
  * Outputs dA_vals[B,nnzA] (every structural entry), dP_vals[B,nnzP] or NULL, db[B,m], dc[B,n],
  * lsqr_iters[B] or NULL. */

@@ -160,3 +160,29 @@ def test_register_makes_the_solver_name_constructible(monkeypatch):
         fake.ifs.get_torch_cvxpylayer("NOPE")
     with pytest.raises(ValueError):
         fake.pa.parse_args(problem, [], [], "NOPE")
+
+
+def test_constant_matrices_are_detected_from_the_parameter_maps():
+    """the reference's ``PA_is_constant`` rule (interfaces/moreau_if.py:233-241) -- no entry of A or P depends on
+    a parameter -- switches the cached set-up on by default; rows of the constraint map that feed b may depend on parameters."""
+    import scipy.sparse as sp
+
+    from cvxpylayers_b200 import interface as itf
+    from tests.util import fake_param_prob
+
+    bt = pr.dense_qp(2, 6, 9, 2, seed=3)
+    problem, _ = fake_param_prob(bt)
+    pp = problem["param_prob"]
+    ctx = itf.get_solver_ctx("B200", pp, problem["dims"], {}, None)
+    assert ctx.PA_is_constant is False                     # every entry of A, b, c, P is a parameter in that stand-in
+    assert ctx.setup_cache(None, "cpu", 2, {}) is None      # ... so no cache unless asked for
+    A_map, q_map, P_map = pp.reduced_A.reduced_mat, pp.q, pp.reduced_P.reduced_mat
+    nA, P1 = bt.structure.nnzA, A_map.shape[1]
+    const = lambda rows: sp.csr_matrix((np.ones(rows), (np.arange(rows), np.full(rows, P1 - 1))), shape=(rows, P1))  # noqa: E731
+    A_const_b_param = sp.vstack([const(nA), A_map.tocsr()[nA:]]).tocsr()       # A entries constant, b entries still parameters
+    ctx.set_param_maps(A_const_b_param, q_map, const(P_map.shape[0]))
+    assert ctx.PA_is_constant is True
+    ctx.set_param_maps(A_const_b_param, q_map, P_map)      # P still parametrised
+    assert ctx.PA_is_constant is False
+    ctx.set_param_maps(A_map, q_map, const(P_map.shape[0]))
+    assert ctx.PA_is_constant is False
