@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 400 python bench.py --steps 10 --warmup 3 --cpu-sample 0 > gpurun_out/bench_v.json 2>gpurun_out/bench_v.err; python -c "
-import json;d=json.loads(open('gpurun_out/bench_v.json').read());print('C2',d['value'],d['e2e']['value'],d['kernel_ms']);print(json.dumps(d['e2e'].get('fused_params'))[:2500])"
-tail -3 gpurun_out/bench_v.err
+timeout 500 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_sweep.py C2 > gpurun_out/san3_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "^C2|RACECHECK SUMMARY|Race reported" gpurun_out/san3_racecheck.log | cut -c1-250 | head
+timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_sweep.py C2 > gpurun_out/san3_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "^C2|ERROR SUMMARY|Invalid" gpurun_out/san3_memcheck.log | cut -c1-250 | head
+timeout 300 compute-sanitizer --tool initcheck --print-limit 20 python tools/sanitize_sweep.py C2 > gpurun_out/san3_initcheck.log 2>&1; echo "initcheck rc=$?"; grep -E "^C2|ERROR SUMMARY|Uninitialized" gpurun_out/san3_initcheck.log | cut -c1-250 | head

@@ -24,3 +24,10 @@ for name, bt, precond in cases:
     out = eng.vjp(A, b, c, sol.x, sol.y, sol.s, dx, dy, P, make_settings({"lsqr_precond": precond, "lsqr_iter_lim": 400}))
     torch.cuda.synchronize()
     print(name, eng.path_info(), "status", sol.status.tolist(), "iters", sol.iters.tolist(), "lsqr", out[4].tolist(), flush=True)
+    if name == "C2":   # the cached set-up: fill, then reuse with a warm start (Kinv + E + D come back through the cache; P by TMA)
+        S = make_settings({"eps": 1e-9, "max_iters": 3000})
+        cache = eng.new_cache(bt.B)
+        one = eng.solve(A, b, c, P, S, cache=cache, reuse=False)
+        two = eng.solve(A, b * 1.001, c, P, S, warm=one, cache=cache, reuse=True)
+        torch.cuda.synchronize()
+        print("C2 cached", "status", two.status.tolist(), "iters", two.iters.tolist(), "valid", cache.view(bt.B, -1)[:, 1].tolist(), flush=True)
