@@ -76,7 +76,7 @@ struct Handle {
   size_t fwd_ws_stride = 0, bwd_ws_stride = 0;
   // Per-stream scratch slabs (one per CTA of the grid): launches on different streams may overlap, launches on one
   // stream cannot, so the stream is the unit of ownership.  Allocated on first use.
-  struct StreamWs { cudaStream_t s; double *fwd = nullptr, *bwd = nullptr, *aa = nullptr; size_t aa_cap = 0; };
+  struct StreamWs { cudaStream_t s; double *fwd = nullptr, *bwd = nullptr, *aa = nullptr, *park = nullptr; size_t aa_cap = 0; };
   std::vector<StreamWs> sws;
   int block_bwd = 0, blk_threads = 0; size_t blk_smem = 0;   // KKT-block preconditioned backward (lsqr_precond = 2)
   int *fail_list[RING] = {nullptr}; int fail_cap[RING] = {0};
@@ -581,9 +581,13 @@ extern "C" int bcone_solve_cached(void *handle, int32_t B, const double *A_vals,
   if (stg->acceleration_lookback != 0 && stg->max_iters > 1) {
     const int mem = std::abs(stg->acceleration_lookback);
     a.aa_stride = (long long)((aa_ws_doubles(h->S.n + h->S.m + 1, mem) + 1) & ~(size_t)1);
-    if (h->fast_fwd) a.aa_stride += 32 * 512;   // the register-tiled kernel parks its tile here during an acceleration event
     if (!ensure_slab(h, &sw->aa, &sw->aa_cap, (size_t)a.aa_stride * max_grid)) return fail(h, BCONE_ENOMEM, "cudaMalloc acceleration workspace");
     a.aa_ws = sw->aa;
+  }
+  a.park = nullptr;
+  if (h->fast_fwd) {   // where the register tile waits while a termination check or an acceleration event runs (128 KB per CTA, L2)
+    if (!ensure_slab(h, &sw->park, nullptr, (size_t)32 * 512 * max_grid)) return fail(h, BCONE_ENOMEM, "cudaMalloc tile parking slab");
+    a.park = sw->park;
   }
   CK(cudaMemsetAsync(ctr, 0, sizeof(int), st), "solve counter");
   if (h->fast_fwd) CK(bc_fwdf_launch(&a, grid, h->fwd_smem, st), "solve launch (fast)");

@@ -58,6 +58,7 @@ struct FwdArgs {
   // cached set-up (register-tiled kernel only): per instance [8 header | E npad | D mpad | Kinv n x npad], see bc_fwdf_cache_doubles
   double *cache;         // NULL = off
   long long cache_stride;  // doubles per instance
+  double *park;          // register-tiled kernel: per-CTA slab (4 x 8 x 512 doubles, L2) where the A tile waits out heavy cold calls
   int cache_reuse;       // 0: write the set-up of this solve; 1: A and P are unchanged since the solve that wrote it -> skip it
 };
 

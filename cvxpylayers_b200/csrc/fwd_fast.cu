@@ -56,7 +56,9 @@ struct Geo {
   // Row stride of Kinv.  The 2 x 10 tiles of kinv_rows are read as double2 by quarter-warps that straddle two tile rows
   // (10 tiles per row, 8 lanes per quarter); with 16-byte units u = KR R kst / 2 + 5 C + c / 2 the two halves collide unless
   // KR kst / 2 = 2 (mod 8): stride 100 costs 60 % extra wavefronts on the 80 KB that every iteration reads, 106 none.
-  __host__ __device__ __forceinline__ int kst() const { return KR() == 2 ? npad() + ((10 - (npad() & 7)) & 7) : npad(); }
+  // (Compile-time geometries only: in the runtime-geometry instantiation one more loop-invariant value pushed the tile products of
+  //  the iteration loop into local memory, +6-9 % per solve measured, more than the conflicts cost.)
+  __host__ __device__ __forceinline__ int kst() const { return (CT_ != 0 && KR() == 2) ? npad() + ((10 - (npad() & 7)) & 7) : npad(); }
   __host__ __device__ __forceinline__ int oXC() const { return npad() * kst(); }
   __host__ __device__ __forceinline__ int szPart() const { const int a = RTu() * npad(), b = rowsR() * CT(); return ((a > b ? a : b) + 1) & ~1; }
   __host__ __device__ __forceinline__ int oPS() const { return oXC() + szPart(); }
@@ -286,19 +288,52 @@ __device__ __noinline__ void form_K(const double *Av, int m, int n, int z, doubl
 // Tensor-core tiles: Kinv(I, J) = sum over k >= 8 I of X(k, I)' X(k, J) in steps of four rows k (DMMA 8 x 8 x 4); a warp owns
 // one block row I (the A fragment) and up to eight tiles J <= I of it, rows dealt round-robin; entries above the diagonal of
 // X (not stored) and rows past n enter as zeros.  The mirror image is written with the tile.
+#ifdef BC_KINV_SCALAR   // the round-1 version (2 x 2 register tiles on the DFMA pipe), kept for A/B timing
+__device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, int kst, double *Kinv) {
+  const int T = blockDim.x, t = threadIdx.x;
+  const int nb = (n + 1) >> 1, ntile = (nb * (nb + 1)) >> 1;
+  for (int e = t; e < ntile; e += T) {
+    int I = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+    while (((I + 1) * (I + 2)) >> 1 <= e) I++;
+    while ((I * (I + 1)) >> 1 > e) I--;
+    const int J = e - ((I * (I + 1)) >> 1);
+    const int i0 = 2 * I, j0 = 2 * J;
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+    {   // k = i0: X[k][i0 + 1] is above the diagonal
+      const double *row = Xp + ((i0 * (i0 + 1)) >> 1);
+      const double a0 = row[i0], b0 = row[j0], b1 = (j0 + 1 <= i0) ? row[j0 + 1] : 0.0;
+      c00 = a0 * b0; c01 = a0 * b1;
+    }
+    for (int k = i0 + 1; k < n; k++) {
+      const double *row = Xp + ((k * (k + 1)) >> 1);
+      const double a0 = row[i0], a1 = row[i0 + 1], b0 = row[j0], b1 = row[j0 + 1];
+      c00 = fma(a0, b0, c00); c01 = fma(a0, b1, c01); c10 = fma(a1, b0, c10); c11 = fma(a1, b1, c11);
+    }
+    const bool i1 = i0 + 1 < n, j1 = j0 + 1 < n;
+    Kinv[i0 * kst + j0] = c00; Kinv[j0 * kst + i0] = c00;
+    if (j1) { Kinv[i0 * kst + j0 + 1] = c01; Kinv[(j0 + 1) * kst + i0] = c01; }
+    if (i1) { Kinv[(i0 + 1) * kst + j0] = c10; Kinv[j0 * kst + i0 + 1] = c10; }
+    if (i1 && j1) { Kinv[(i0 + 1) * kst + j0 + 1] = c11; Kinv[(j0 + 1) * kst + i0 + 1] = c11; }
+  }
+  __syncthreads();
+  for (int k = t; k < n * (npad - n); k += T) { const int i = k / (npad - n), c = n + k % (npad - n); Kinv[i * kst + c] = 0.0; }
+  __syncthreads();
+}
+#else
 __device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, int kst, double *Kinv) {
   const int T = blockDim.x, t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5, nw = T >> 5;
   const int fr = lane >> 2, fc = lane & 3;
   const int nb = (n + 7) >> 3;
+  constexpr int KJ = 4;   // tiles per work item: 8 accumulator registers (this runs with the A tile of the caller live)
   int cnt = 0;
   for (int I = 0; I < nb; I++)
-    for (int J0 = 0; J0 <= I; J0 += 8) {
+    for (int J0 = 0; J0 <= I; J0 += KJ) {
       if ((cnt++ % nw) != warp) continue;
-      const int nJ = min(I - J0 + 1, 8);
-      double acc[8][2];
+      const int nJ = min(I - J0 + 1, KJ);
+      double acc[KJ][2];
 #pragma unroll
-      for (int v = 0; v < 8; v++) acc[v][0] = acc[v][1] = 0.0;
+      for (int v = 0; v < KJ; v++) acc[v][0] = acc[v][1] = 0.0;
       const int ia = 8 * I + fr;
       for (int k0 = 8 * I; k0 < n; k0 += 4) {
         const int k = k0 + fc;
@@ -306,7 +341,7 @@ __device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, int ks
         const double *row = Xp + ((k * (k + 1)) >> 1);
         const double fa = (kv && ia <= k) ? row[ia] : 0.0;
 #pragma unroll
-        for (int v = 0; v < 8; v++)
+        for (int v = 0; v < KJ; v++)
           if (v < nJ) {   // (warp-uniform)
             const int jb = 8 * (J0 + v) + fr;
             const double fb = (kv && jb <= k) ? row[jb] : 0.0;
@@ -314,7 +349,7 @@ __device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, int ks
           }
       }
 #pragma unroll
-      for (int v = 0; v < 8; v++)
+      for (int v = 0; v < KJ; v++)
         if (v < nJ && ia < n) {
           const int j = 8 * (J0 + v) + 2 * fc;
           const bool mirror = (J0 + v) != I;   // a diagonal tile is complete by itself
@@ -327,13 +362,14 @@ __device__ __noinline__ void form_Kinv(const double *Xp, int n, int npad, int ks
   for (int k = t; k < n * (npad - n); k += T) { const int i = k / (npad - n), c = n + k % (npad - n); Kinv[i * kst + c] = 0.0; }
   __syncthreads();
 }
+#endif
 
 __device__ __noinline__ bool chol_cold(double *K, int n, double *tmp) { return chol_inv_packed(K, n, tmp); }
 
 // Slots of the shared scalar block sc[] (= red + 256): values every thread agrees on but only the cold paths
 // need, kept out of the register file.
 enum { SC_SIGMA = 0, SC_NB0, SC_NC0, SC_SUMLOG, SC_PREVLR, SC_RP, SC_RD, SC_GAP, SC_UTAU, SC_NLOG, SC_LASTUP, SC_PREVIT,
-       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AADT, SC_NEXTREAL, SC_AASCR, SC_INV2QA = SC_AASCR + 17 };   // SC_AASCR: 17 slots
+       SC_NEXT, SC_STATUS, SC_DONE, SC_NEWSCALE, SC_RYZ, SC_RYL, SC_GRG, SC_COUNT, SC_AATAU, SC_AADT, SC_NEXTREAL, SC_AASCR };   // SC_AASCR: 17 slots
 
 // Everything of a termination check after the two products with A (A u_x in tm, A' u_y in tn): P^ u_x, the
 // residual norms on the un-normalised data, termination and certificates, the adaptive
@@ -754,6 +790,11 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         SUB_DECL(pf);
         const bool from_cache = first && ibuf[3];   // Kinv at this scale comes from the cached set-up: no staging, K, Cholesky
         const bool c_tma = from_cache && a.use_tma && (((uintptr_t)a.cache & 15) == 0);
+        // (the record's address is derived HERE, from a value the compiler cannot prove loop-invariant: hoisted out of the iteration
+        //  loop it cost the runtime-geometry instantiation three tile values in local memory)
+        int inst_c = ibuf[0];
+        asm volatile("" : "+r"(inst_c));
+        double *const rec = a.cache ? a.cache + (size_t)inst_c * a.cache_stride : nullptr;
         if (!from_cache) {
         if (!first && Pg) scatter_P(S, Pg, Li, g.npk());   // the factor's buffer held P in CSR order for the checks
         {
@@ -785,11 +826,11 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
         load_tile();
         __syncthreads();
         form_Kinv(Li, n, g.npad(), g.kst(), Kinv);
-        if (a.cache) cache_put_kinv(a.cache + (size_t)inst * a.cache_stride, g.cK(), Kinv, (n * g.kst()) >> 1, scale, st.rho_x);
+        if (rec) cache_put_kinv(rec, g.cK(), Kinv, (n * g.kst()) >> 1, scale, st.rho_x);
         }
         {   // asynchronous loads behind one barrier phase: P in CSR order into the factor's buffer (for the termination
             // checks) and, with a cached set-up, Kinv
-          const double *ck = from_cache ? a.cache + (size_t)inst * a.cache_stride + g.cK() : nullptr;
+          const double *ck = from_cache ? rec + g.cK() : nullptr;
           const uint32_t pb = (Pg && p_tma) ? (uint32_t)(S.nnzP * sizeof(double)) : 0u, kb = c_tma ? (uint32_t)(n * g.kst() * sizeof(double)) : 0u;
           if (t == 0 && pb + kb) {
             fence_proxy_async();
@@ -815,7 +856,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
           vy(VY_G)[i] = gi; acc[0] = fma((1.0 / iry) * gi, gi, acc[0]); });
         if (t < n) acc[0] = fma(st.rho_x * vx(VX_G)[t], vx(VX_G)[t], acc[0]);
         block_reduce<1, false>(acc, red);
-        if (t == 0) { sc[SC_GRG] = acc[0]; sc[SC_INV2QA] = 0.5 / (BC_TAU_FACTOR + acc[0]); }
+        if (t == 0) sc[SC_GRG] = acc[0];
         if (Pg && p_tma && !c_tma) { mbar_wait(bar, tma_phase); tma_phase ^= 1; }
         __syncthreads();
         SUB_STAMP(pf, 22);
@@ -853,11 +894,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
       const double qa = BC_TAU_FACTOR + sc[SC_GRG], qb = d4[0] - 2.0 * d4[1] - BC_TAU_FACTOR * w_tau, qc = d4[2] - d4[3];
       double disc = qb * qb - 4.0 * qa * qc;
       if (disc < 0) disc = 0;
-#ifdef BC_OPT_INV2QA
-      const double tau_t = (-qb + sqrt(disc)) * sc[SC_INV2QA];   // (qa only changes with a factorisation)
-#else
       const double tau_t = (-qb + sqrt(disc)) / (2.0 * qa);
-#endif
       const bool check = it >= next_check || it == st.max_iters;
       // cone step + relaxation (the relaxation is fused here unless a check needs the plain iterate)
       if (ti < n) {
@@ -883,7 +920,18 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
           __syncthreads();   // row and column partials share one buffer
           rt_cols(ar, ps, g, act, R, C, vy(VY_U), XC, n, [&](int j, double v) { vx(VX_TN)[j] = v; });
           __syncthreads();
-          check_tail(a, vx(0), vy(0), red, XC, Pg ? Li : nullptr, g.npad(), g.mpad(), it, scale, u_tau);
+          {   // the check's register footprint would otherwise keep part of the tile in local memory for the whole loop
+            double *pk = a.park + (size_t)blockIdx.x * (TR * TCR * FT) + t;
+#pragma unroll
+            for (int r = 0; r < TR; r++)
+#pragma unroll
+              for (int c = 0; c < TCR; c++) pk[(r * TCR + c) * FT] = ar[r][c];
+            check_tail(a, vx(0), vy(0), red, XC, Pg ? Li : nullptr, g.npad(), g.mpad(), it, scale, u_tau);
+#pragma unroll
+            for (int r = 0; r < TR; r++)
+#pragma unroll
+              for (int c = 0; c < TCR; c++) ar[r][c] = pk[(r * TCR + c) * FT];
+          }
           if (t == 0) sc[SC_NEXTREAL] = st.adaptive_check ? sc[SC_NEXT] : (double)(it + st.check_interval);
           const bool done = sc[SC_DONE] != 0.0;
           const double ns = sc[SC_NEWSCALE];
@@ -907,7 +955,7 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
           // duration of the call (128 KB per CTA, L2) keeps it out of the call's live set, so the register allocation
           // of the iteration loop is the one without acceleration; the compiler's own answer was to keep a third of
           // the tile in local memory for the whole loop (+20 % per iteration, measured).
-          double *park = a.aa_ws + (size_t)blockIdx.x * a.aa_stride + ((aa_ws_doubles(n + m + 1, abs(st.acceleration_lookback)) + 1) & ~(size_t)1) + t;
+          double *park = a.park + (size_t)blockIdx.x * (TR * TCR * FT) + t;
 #pragma unroll
           for (int r = 0; r < TR; r++)
 #pragma unroll
@@ -964,13 +1012,22 @@ __global__ void __launch_bounds__(FT, 1) fwd_fast_kernel(const __grid_constant__
     else { auto k = fwd_fast_kernel<0, 0>; EXPR; }                                     \
   } while (0)
 
+// (sizes come from the geometry type the launch will instantiate: the padded Kinv stride exists only in the compile-time one)
+#define FWDF_GEO(n, m, EXPR)                                                                 \
+  do {                                                                                       \
+    const Geo<0, 0> g0(n, m);                                                                \
+    if (g0.CT() == 10 && g0.RTu() == 50) { const Geo<10, 50> g(n, m); EXPR; }                \
+    else { const Geo<0, 0> g(n, m); EXPR; }                                                  \
+  } while (0)
 extern "C" size_t bc_fwdf_smem_bytes(int n, int m) {
-  const Geo<0, 0> g(n, m);
-  if (!g.ok(n, m)) return (size_t)1 << 40;
-  return (size_t)g.total() * sizeof(double);
+  const Geo<0, 0> g0(n, m);
+  if (!g0.ok(n, m)) return (size_t)1 << 40;
+  size_t r = 0;
+  FWDF_GEO(n, m, r = (size_t)g.total() * sizeof(double));
+  return r;
 }
 extern "C" int bc_fwdf_threads(void) { return FT; }
-extern "C" size_t bc_fwdf_cache_doubles(int n, int m) { const Geo<0, 0> g(n, m); return (size_t)g.cTotal(); }
+extern "C" size_t bc_fwdf_cache_doubles(int n, int m) { size_t r = 0; FWDF_GEO(n, m, r = (size_t)g.cTotal()); return r; }
 // Eligibility beyond "dense A, polyhedral cones, direct mode" (checked by the caller): the tile grid has to
 // cover the matrix with at least half of the threads busy.
 extern "C" int bc_fwdf_eligible(int n, int m) {

@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-timeout 500 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_sweep.py C2 > gpurun_out/san3_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "^C2|RACECHECK SUMMARY|Race reported" gpurun_out/san3_racecheck.log | cut -c1-250 | head
-timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_sweep.py C2 > gpurun_out/san3_memcheck.log 2>&1; echo "memcheck rc=$?"; grep -E "^C2|ERROR SUMMARY|Invalid" gpurun_out/san3_memcheck.log | cut -c1-250 | head
-timeout 300 compute-sanitizer --tool initcheck --print-limit 20 python tools/sanitize_sweep.py C2 > gpurun_out/san3_initcheck.log 2>&1; echo "initcheck rc=$?"; grep -E "^C2|ERROR SUMMARY|Uninitialized" gpurun_out/san3_initcheck.log | cut -c1-250 | head
+timeout 200 python tools/bench_shapes.py > gpurun_out/shapes.jsonl 2>gpurun_out/shapes.err; python - <<'PY'
+import json
+for l in open('gpurun_out/shapes.jsonl'):
+    d=json.loads(l); print('  ',d['n'],d['m'],d['geometry'],d['fwd_ms_per_4096'],d['us_per_instance_iteration'])
+PY
+timeout 200 python bench.py --steps 10 --warmup 3 --cpu-sample 0 > gpurun_out/v_default.json 2>gpurun_out/v_default.err
+python -c "
+import json;d=json.loads(open('gpurun_out/v_default.json').read().strip().splitlines()[-1]);print('default', round(d['value']), d['kernel_ms'], round(d['e2e']['value']))"
+timeout 300 python -m pytest tests/test_gpu_cached.py tests/test_gpu_parity.py -q -x 2>&1 | tail -2
