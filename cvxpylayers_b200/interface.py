@@ -19,6 +19,7 @@ entry of ``A`` (the reference's ``dA.data`` drops exact zeros, SURVEY.md 8a note
 from __future__ import annotations
 
 import os
+from types import SimpleNamespace
 import sys
 import time
 import warnings
@@ -244,6 +245,31 @@ def _pipe_ok(eng: Engine, B: int, *tensors) -> bool:
     return info["fwd_smem"] > 0
 
 
+def _stage_ok(B: int, *tensors) -> bool:
+    """Host-resident but NOT pinned inputs (what the reference's own CPU path hands over: ``torch.from_numpy`` results of its sparse
+    products, ``torch/cvxpylayer.py:21-24``) and a batch worth splitting: batch slices are gathered into a small ring of pinned
+    staging buffers by a background thread while the previous slice is copied and solved."""
+    if B < 2 * PIPE_CHUNK or PIPE_CHUNK <= 0 or os.environ.get("B200_NO_STAGING"):
+        return False
+    return all(t is None or (t.device.type == "cpu" and t.dim() == 2 and t.dtype == torch.float64) for t in tensors)
+
+
+_STAGE_SLOTS = 3
+
+
+def _stager(eng: Engine):
+    sg = getattr(eng, "_stager", None)
+    if sg is None:
+        from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
+
+        nthr = int(os.environ.get("B200_STAGE_THREADS", "8"))
+        sg = SimpleNamespace(pool=ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200-stage"),          # one slice at a time, in order
+                             copiers=ThreadPoolExecutor(max_workers=nthr, thread_name_prefix="b200-copy"),   # ... gathered by row blocks
+                             nthr=nthr, bufs={})
+        eng._stager = sg
+    return sg
+
+
 def _side_streams(eng: Engine, dev):
     """The two pipeline streams of an engine, created once: torch's device allocator keeps one block pool per
     stream, so fresh streams per call would cudaMalloc every chunk buffer again (tens of ms per step)."""
@@ -254,7 +280,7 @@ def _side_streams(eng: Engine, dev):
     return ss
 
 
-def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P, warm=None, cache=None):
+def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P, warm=None, cache=None, staged: bool = False):
     st = eng.structure
     B = A_eval.shape[1]
     cstride = (cache.numel() // B) if cache is not None else 0
@@ -270,17 +296,70 @@ def _forward_pipelined(eng: Engine, dev, A_eval, q_eval, P_eval, settings, use_P
     streams = _side_streams(eng, dev)
     for s_ in streams:
         s_.wait_stream(cur)
-    for k, (lo, hi) in enumerate(_chunks(B)):
+    chunks = list(_chunks(B))
+    futs = enq = cev = None
+    if staged:
+        # Pageable (or non-fp64) host inputs: a background thread gathers slice k into pinned staging buffers (the gather is
+        # split over a few copy threads) while slice k-1 is on its way; a slot of the ring is rewritten only after the device copy that read
+        # it has completed (per-call handshake: the main thread publishes the event, the stager waits for it).
+        import threading  # noqa: PLC0415
+
+        sg = _stager(eng)
+        enq = [threading.Event() for _ in chunks]
+        cev = [None] * len(chunks)
+        abort = threading.Event()   # set when the main thread leaves early (an exception): the stager must not wait for it
+        srcs = (("A", A_eval), ("q", q_eval), ("P", P_eval if use_P else None))
+
+        def stage(k, lo, hi):
+            if k >= _STAGE_SLOTS:
+                while not enq[k - _STAGE_SLOTS].wait(0.05):
+                    if abort.is_set():
+                        return None
+                cev[k - _STAGE_SLOTS].synchronize()
+            out = []
+            for name, src in srcs:
+                if src is None:
+                    out.append(None)
+                    continue
+                key = (k % _STAGE_SLOTS, name, src.shape[0], hi - lo)
+                buf = sg.bufs.get(key)
+                if buf is None:
+                    buf = torch.empty((src.shape[0], hi - lo), dtype=f64, pin_memory=True)
+                    sg.bufs[key] = buf
+                rows = src.shape[0]
+                step = max(256, -(-rows // sg.nthr))   # a strided gather is one core's memcpy: split it by row blocks
+                if rows <= step:
+                    buf.copy_(src[:, lo:hi])
+                else:
+                    list(sg.copiers.map(lambda r0, buf=buf, src=src: buf[r0:r0 + step].copy_(src[r0:r0 + step, lo:hi]), range(0, rows, step)))
+                out.append(buf)
+            return out
+
+        futs = [sg.pool.submit(stage, k, lo, hi) for k, (lo, hi) in enumerate(chunks)]
+    for k, (lo, hi) in enumerate(chunks):
         with torch.cuda.stream(streams[k % 2]):
             Bc = hi - lo
             A_c = torch.empty((A_eval.shape[0], Bc), dtype=f64, device=dev)
             q_c = torch.empty((q_eval.shape[0], Bc), dtype=f64, device=dev)
-            eng.copy2d(A_c, A_eval, lo, hi, True)
-            eng.copy2d(q_c, q_eval, lo, hi, True)
-            P_c = None
-            if use_P:
-                P_c = torch.empty((P_eval.shape[0], Bc), dtype=f64, device=dev)
-                eng.copy2d(P_c, P_eval, lo, hi, True)
+            P_c = torch.empty((P_eval.shape[0], Bc), dtype=f64, device=dev) if use_P else None
+            if staged:
+                try:
+                    hA_, hq_, hP_ = futs[k].result()
+                    A_c.copy_(hA_, non_blocking=True)
+                    q_c.copy_(hq_, non_blocking=True)
+                    if use_P:
+                        P_c.copy_(hP_, non_blocking=True)
+                    cev[k] = torch.cuda.Event()
+                    cev[k].record(streams[k % 2])
+                    enq[k].set()
+                except BaseException:
+                    abort.set()
+                    raise
+            else:
+                eng.copy2d(A_c, A_eval, lo, hi, True)
+                eng.copy2d(q_c, q_eval, lo, hi, True)
+                if use_P:
+                    eng.copy2d(P_c, P_eval, lo, hi, True)
             eng.ingest(A_c, q_c, P_c, out=(A_vals[lo:hi], P_vals[lo:hi] if use_P else None, b[lo:hi], c[lo:hi]))
             from .engine import Solution  # noqa: PLC0415
             eng.solve(A_vals[lo:hi], b[lo:hi], c[lo:hi], P_vals[lo:hi] if use_P else None, settings,
@@ -360,10 +439,12 @@ class _CvxpyLayer(torch.autograd.Function):
         warm = ctx.warm_for(dev, batch_size, warm_start, merged)
         cache = ctx.setup_cache(eng, dev, batch_size, merged)
         piped = _pipe_ok(eng, batch_size, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None)
+        staged = (not piped) and eng.kernel_info()["fwd_smem"] > 0 and _stage_ok(batch_size, A_eval, q_eval, P_eval if use_P else None)
+        piped = piped or staged
         with torch.cuda.device(dev):
             if piped:
                 A_vals, P_vals, b, c, sol, primal, dual = _forward_pipelined(
-                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P, warm, cache)
+                    eng, dev, A_eval.detach(), q_eval.detach(), P_eval.detach() if use_P else None, settings, use_P, warm, cache, staged)
             else:
                 A_vals, P_vals, b, c = eng.ingest(_to_dev(A_eval, dev), _to_dev(q_eval, dev),
                                                   _to_dev(P_eval, dev) if use_P else None)

@@ -491,3 +491,31 @@ def test_device_flatten_and_recover_equal_the_reference_tensor_chains(cuda_devic
     assert torch.allclose(og[0], torch.exp(refs[0])) and torch.allclose(og[2], refs[2])
     gg = torch.autograd.grad((og[0] * ws[0]).sum(), primal)[0]
     assert torch.allclose(gg, torch.autograd.grad((torch.exp(_reshape_fortran(primal[..., 2:8], (B, 2, 3))) * ws[0]).sum(), primal)[0], rtol=1e-13, atol=1e-13)
+
+
+def test_pageable_host_inputs_take_the_staged_pipeline(cuda_device, monkeypatch):
+    """What the reference's CPU path hands over is pageable memory (torch.from_numpy, torch/cvxpylayer.py:21-24).  Those inputs go
+    through a ring of pinned staging buffers filled by a background thread; results and gradients must be those of the plain path
+    (device-resident inputs), for a batch that is not a multiple of the slice and over several calls (the ring is re-used)."""
+    from cvxpylayers_b200 import interface as itf
+
+    monkeypatch.setattr(itf, "PIPE_CHUNK", 8)
+    dev = cuda_device
+    bt = pr.dense_qp(46, 20, 40, 10, seed=6)
+    ctx, bd, cl = _layer(bt, eps=1e-8, max_iters=100000, lsqr_precond=2)
+    rng = np.random.default_rng(0)
+    for call in range(3):
+        A_np = bd.A_eval * (1.0 + 1e-3 * call)
+        q_np = bd.q_eval + 1e-3 * call * rng.standard_normal(bd.q_eval.shape)
+        outs = []
+        for where in ("cpu", "cuda"):
+            mk = (lambda a: torch.tensor(a)) if where == "cpu" else (lambda a: _t(a, dev))
+            A, q, P = mk(A_np).requires_grad_(True), mk(q_np).requires_grad_(True), mk(bd.P_eval).requires_grad_(True)
+            assert where == "cuda" or (not A.is_pinned() and itf._stage_ok(bt.B, A, q, P))
+            primal, dual, _, _ = _CvxpyLayer.apply(P, q, A, cl, {}, True, None)
+            assert primal.device.type == where
+            (primal.square().sum() + dual.sum()).backward()
+            outs.append([t_.detach().cpu() for t_ in (primal, dual, A.grad, q.grad, P.grad)])
+        for a_, b_ in zip(*outs):
+            assert float((a_ - b_).abs().max()) <= 1e-9 * max(1.0, float(b_.abs().max()))
+    assert len(ctx.engine(dev)._stager.bufs) == 4 * 3   # slices 10, 9, 9, 9, 9 on 3 slots: (slot 0, 10), (1, 9), (2, 9), (0, 9); x (A, q, P)
