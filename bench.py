@@ -45,15 +45,41 @@ def algo_bytes(n, m, nnzA, nnzP):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region.  Two sources started together: an in-process NVML thread
+    (a sample every 5 ms from the first millisecond -- the timed region of the default run is ~150 ms, less than `nvidia-smi`
+    sometimes needs to start up) and an `nvidia-smi -lms 100` child as the fallback; `stop()` reports NVML's samples when it has any."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nv_sm, self.nv_max, self.nv_mask, self.nv_thread, self.nv_stop = [], None, 0, None, threading.Event()
+
+    def _nvml_loop(self, nv, handle):
+        try:
+            while not self.nv_stop.is_set():
+                self.nv_sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
+                try:
+                    self.nv_mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                except Exception:  # noqa: BLE001
+                    pass
+                self.nv_stop.wait(0.005)
+        except Exception:  # noqa: BLE001  (a failed query ends this source; nvidia-smi remains)
+            pass
 
     def start(self):
+        try:
+            import pynvml as nv  # noqa: PLC0415
+
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nv_max = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.nv_thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.nv_thread.start()
+        except Exception:  # noqa: BLE001
+            self.nv_thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -63,23 +89,37 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        try:
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
         try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+            self.nv_stop.set()
+            if self.nv_thread is not None:
+                self.nv_thread.join(timeout=1)
+            if self.proc is not None:
+                self.proc.terminate()
+                try:
+                    self.proc.wait(timeout=2)
+                except Exception:  # noqa: BLE001
+                    self.proc.kill()
+            if self.nv_sm:
+                bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+                return {"sm_mhz": float(np.median(self.nv_sm)), "sm_max_mhz": self.nv_max,
+                        "reasons": [nm for nm in self.NAMES if self.nv_mask & bits[nm]], "samples": len(self.nv_sm), "source": "nvml"}
+            if self.proc is None:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+            rows = list(self.rows)
+            sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+            mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+            reasons = [nm for k, nm in enumerate(self.NAMES) if any(len(r) >= 6 and r[2 + k].lower().startswith("active") for r in rows)]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
+        except Exception as ex:  # noqa: BLE001  (the sampler must never take the bench line down)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler error: {ex!r}"[:120]], "samples": 0}
 
 
 CONFIG = "C2"   # BASELINE.json configs[1] is the headline; the others are parity-test cases that can be timed too
