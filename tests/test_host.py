@@ -186,3 +186,48 @@ def test_constant_matrices_are_detected_from_the_parameter_maps():
     assert ctx.PA_is_constant is False
     ctx.set_param_maps(A_map, q_map, const(P_map.shape[0]))
     assert ctx.PA_is_constant is False
+
+
+def test_layer_epilogue_index_maps_restate_the_reference_unpacking():
+    """SURVEY.md 8f.3 on the host: the index / scale maps that drive `bcone_gather_cols` are the composition of the reference's
+    slice, symmetric unpacking and Fortran reshape (`torch/cvxpylayer.py:143-222, 225-282`), restated here with NumPy scatter
+    exactly as the reference writes them, for vectors, matrices, 3-D arrays and both symmetric packings."""
+    from types import SimpleNamespace
+
+    from cvxpylayers_b200.layer_io import _var_map, fortran_map
+
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal(200)
+
+    def svec_to_symmetric(v, n, rows, cols, scale=None):   # the reference's _svec_to_symmetric for one instance
+        out = np.zeros((n, n))
+        d = v * scale if scale is not None else v
+        out[rows, cols] = d
+        out[cols, rows] = d
+        return out
+
+    def apply(var):
+        imap, scale = _var_map(var)
+        got = data[imap] * (scale if scale is not None else 1.0)
+        return got.reshape(var.shape)
+
+    for shape in [(7,), (3, 4), (2, 3, 4), ()]:
+        size = int(np.prod(shape)) if shape else 1
+        var = SimpleNamespace(source="primal", primal=slice(11, 11 + size), dual=None, shape=shape, unpack_fn="reshape")
+        want = data[11:11 + size].reshape(shape, order="F") if shape else data[11:12].reshape(())
+        assert np.array_equal(apply(var), want), shape
+    n = 5
+    k = n * (n + 1) // 2
+    var = SimpleNamespace(source="primal", primal=slice(3, 3 + k), dual=None, shape=(n, n), unpack_fn="svec_primal")
+    rows, cols = np.triu_indices(n)
+    assert np.array_equal(apply(var), svec_to_symmetric(data[3:3 + k], n, rows, cols))
+    var = SimpleNamespace(source="dual", primal=None, dual=slice(40, 40 + k), shape=(n, n), unpack_fn="svec_dual")
+    rows_rm, cols_rm = np.tril_indices(n)
+    order = np.lexsort((rows_rm, cols_rm))
+    rows, cols = rows_rm[order], cols_rm[order]
+    scale = np.where(rows == cols, 1.0, 1.0 / np.sqrt(2.0))
+    assert np.allclose(apply(var), svec_to_symmetric(data[40:40 + k], n, rows, cols, scale), rtol=0, atol=0)
+    # the prologue's map: Fortran-order flattening of a parameter (torch/cvxpylayer.py:40-56, 84-141)
+    for shape in [(6,), (3, 5), (2, 3, 4)]:
+        x = rng.standard_normal(shape)
+        assert np.array_equal(x.reshape(-1)[fortran_map(shape)], x.reshape(-1, order="F")), shape
