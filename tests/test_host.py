@@ -231,3 +231,24 @@ def test_layer_epilogue_index_maps_restate_the_reference_unpacking():
     for shape in [(6,), (3, 5), (2, 3, 4)]:
         x = rng.standard_normal(shape)
         assert np.array_equal(x.reshape(-1)[fortran_map(shape)], x.reshape(-1, order="F")), shape
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): exactly one JSON line on stdout carrying the same
+    metric / unit / config block as our arm, `impl`, a `cpu_baseline` describing the run and an `e2e` with no PCIe traffic."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--config", "C1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "problems/s" and d["n_gpus"] == 1
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
