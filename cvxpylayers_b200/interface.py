@@ -258,6 +258,9 @@ _STAGE_SLOTS = 3
 
 
 def _stager(eng: Engine):
+    """The staging state of one engine (ring buffers + two thread pools), created on first use.  Like the engine itself it serves one
+    forward call at a time: concurrent calls on the SAME engine from several Python threads would share the ring (one engine per
+    thread, or a lock around the call, as for every other per-engine resource -- INTEGRATION.md)."""
     sg = getattr(eng, "_stager", None)
     if sg is None:
         from concurrent.futures import ThreadPoolExecutor  # noqa: PLC0415
