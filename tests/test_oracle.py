@@ -62,6 +62,25 @@ def test_equality_qp_known_answer():
     assert abs(db[0, 0] - 1.0) < 1e-6
 
 
+def test_dual_variables_known_answers():
+    """The two closed-form dual-variable cases of the reference (tests/test_dual_variables.py:14-42 and :45-71), in solver form
+    `A x + s = b, s in K` with the SCS sign convention (y = the multiplier of `A x + s - b`):
+      min c'x s.t. sum(x) = b, x >= 0, c = [1, 2], b = 1   ->  x* = [1, 0], nu = -1, lambda = [0, 1];
+      min c'x + ||x||^2 s.t. x >= 0, c = [1, -1]            ->  x* = [0, 1/2], lambda = c + 2 x* = [1, 0]."""
+    st = Structure(2, 3, [0, 2, 3, 4], [0, 1, 0, 1], ConeSpec(z=1, l=2))   # rows: sum(x) = b | -x1 <= 0 | -x2 <= 0
+    A = np.array([[1.0, 1.0, -1.0, -1.0]]); b = np.array([[1.0, 0.0, 0.0]]); c = np.array([[1.0, 2.0]])
+    x, y, s, status, _ = orc.solve_batch(st, A, b, c, None, eps=1e-10, max_iters=200000)
+    assert status[0] == 1
+    assert np.abs(x[0] - [1.0, 0.0]).max() < 1e-6 and np.abs(y[0] - [-1.0, 0.0, 1.0]).max() < 1e-6
+    # the dual's sensitivity (reference :177-206 differentiates through it): d(c'x*)/db = -nu = 1 here, and d x*/d b = e1
+    dA, dP, db, dc, _ = orc.vjp_batch(st, A, b, c, x, y, s, np.array([[1.0, 0.0]]), np.zeros((1, 3)), None)
+    assert abs(db[0, 0] - 1.0) < 1e-5
+    st2 = Structure(2, 2, [0, 1, 2], [0, 1], ConeSpec(l=2), [0, 1, 2], [0, 1])
+    A2 = np.array([[-1.0, -1.0]]); b2 = np.zeros((1, 2)); c2 = np.array([[1.0, -1.0]]); P2 = np.array([[2.0, 2.0]])
+    x, y, s, status, _ = orc.solve_batch(st2, A2, b2, c2, P2, eps=1e-10)
+    assert status[0] == 1 and np.abs(x[0] - [0.0, 0.5]).max() < 1e-7 and np.abs(y[0] - [1.0, 0.0]).max() < 1e-7
+
+
 def test_ridge_closed_form_and_gradient():
     """Least squares with closed-form solution and gradient (reference tests/test_torch.py:90-118:
     x* = (A'A + I)^{-1} A'b, grads atol 1e-6 at eps 1e-10), written as a QP with P = 2(A'A + I)."""
